@@ -1,0 +1,148 @@
+/* pct_b200 — C ABI of the B200-native batched PCT environment (drop-in boundary).
+ *
+ * The reference (alexfrom0815/Online-3D-BPP-PCT @ 5e088f2) has no native interface: its
+ * environment is a Python gym.Env (pct_envs/PctDiscrete0/bin3D.py:8-188,
+ * pct_envs/PctContinuous0/bin3D.py:8-207) fanned out over forked workers by
+ * wrapper/shmem_vec_env.py:20-156.  This header is what a ctypes binding of that path binds
+ * instead: every entry point names the reference interface it replaces.
+ *
+ * Conventions
+ *   - plain C types only; device pointers are raw CUDA device addresses (e.g. tensor.data_ptr()),
+ *     `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - every function returns 0 on success or a negative pct_status; pct_last_error() gives text.
+ *   - the library owns the per-environment state; the caller owns action / observation / reward /
+ *     done / info buffers.  No host synchronisation happens inside pct_reset / pct_step /
+ *     pct_policy_random: they only enqueue work on `stream` (CUDA-graph capturable).
+ *   - one host thread per handle.
+ *
+ * Observation layout (identical to D:bin3D.py:86-93 after the float32 cast of envs.py:168,180):
+ *   row-major (internal_node_holder + leaf_node_holder + 1, 9)
+ *   rows [0, NB)        placed boxes  [x1,y1,z1,x2,y2,z2,density,0,valid]   (row 0 col 8 is always 1)
+ *   rows [NB, NB+NL)    leaf nodes    [x1,y1,z1,x2,y2,BIN_H,0,0,valid]
+ *   row  NB+NL          next item     [density,0,0,d0<=d1<=d2,0,0,1]
+ */
+#ifndef PCT_B200_H
+#define PCT_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pct_env_batch *pct_handle;
+
+enum pct_status {
+    PCT_OK = 0,
+    PCT_ERR_INVALID = -1,   /* bad argument / unsupported configuration            */
+    PCT_ERR_CUDA = -2,      /* CUDA runtime error (text in pct_last_error)          */
+    PCT_ERR_NO_DEVICE = -3, /* no usable sm_100 device: the library has NO CPU fallback */
+    PCT_ERR_STATE = -4      /* call sequence error (e.g. step before reset)         */
+};
+
+enum pct_domain { PCT_DISCRETE = 0, PCT_CONTINUOUS = 1 };
+enum pct_obs_dtype { PCT_F32 = 0, PCT_F64 = 1 };
+enum pct_item_mode {
+    PCT_ITEMS_RANDOM = 0, /* uniform over item_set with the counter-based generator (RandomBoxCreator, */
+                          /*   D:binCreator.py:24-39); continuous + sample_from_distribution: C:bin3D.py:103-115 */
+    PCT_ITEMS_STREAM = 1  /* caller-supplied per-env draw sequence (pct_set_item_stream)              */
+};
+
+/* Per-environment flag bits reported in pct_step_info.flags (sticky until the env resets). */
+enum pct_env_flags {
+    PCT_FLAG_BOX_OVERFLOW = 1,      /* more than internal_node_holder boxes (IndexError in D:space.py:385) */
+    PCT_FLAG_BAD_ACTION = 2,        /* leaf row does not match the item (ValueError in D:bin3D.py:144-145) */
+    PCT_FLAG_EMS_OVERFLOW = 4,      /* EMS list exceeded the fixed capacity                                */
+    PCT_FLAG_CAND_OVERFLOW = 8,     /* candidate set exceeded the fixed capacity                           */
+    PCT_FLAG_EDGE_OVERFLOW = 16,    /* support-edge pool exceeded the fixed capacity                       */
+    PCT_FLAG_SUPPORT_OVERFLOW = 32  /* more supports under one box than the stability routine handles      */
+};
+
+/* Constructor arguments = the kwargs of PackingDiscrete / PackingContinuous.__init__
+ * (D:bin3D.py:9-15, C:bin3D.py:9-17) forwarded by envs.make_env (envs.py:33-47). */
+typedef struct pct_config {
+    int32_t domain;               /* pct_domain                                                   */
+    int32_t setting;              /* 1, 2 or 3                                                    */
+    double container_size[3];     /* W, L, H (integers for the discrete domain)                   */
+    int32_t internal_node_holder; /* <= 80 in this build                                          */
+    int32_t leaf_node_holder;     /* <= 64 in this build                                          */
+    int32_t obs_dtype;            /* pct_obs_dtype: float32 (VecPyTorch contract) or float64      */
+    int32_t item_mode;            /* pct_item_mode                                                */
+    double size_minimum;          /* np.min(item_set) (D:bin3D.py:23) / sample_left_bound (C:bin3D.py:26) */
+    int32_t sample_from_distribution; /* continuous only (C:bin3D.py:14)                          */
+    double sample_left_bound, sample_right_bound;
+    uint64_t seed;                /* item generator seed (PCT_ITEMS_RANDOM)                       */
+    int64_t env_id_base;          /* global index of env 0 of this handle (multi-GPU sharding:    */
+                                  /*   per-env streams depend on the GLOBAL index only)           */
+} pct_config;
+
+/* Terminal-step info (the dict built at D:bin3D.py:163-164 plus what Monitor adds, wrapper/monitor.py:58-77) */
+typedef struct pct_step_info {
+    int32_t counter;    /* len(space.boxes)                                      */
+    int32_t flags;      /* pct_env_flags                                         */
+    float ratio;        /* space.get_ratio()  (valid when done)                  */
+    float ep_reward;    /* sum of rewards of the finished episode (Monitor 'r')  */
+    int32_t ep_len;     /* number of steps of the finished episode (Monitor 'l') */
+    int32_t n_leaf;     /* number of valid leaf rows in the new observation      */
+    int32_t n_cand;     /* number of candidate placements generated (before the feasibility test) */
+    int32_t n_ems;      /* EMS count after the step                              */
+} pct_step_info;
+
+/* Host-side dump of one environment (parity tests; replaces poking at env.space.* in Python). */
+typedef struct pct_state_dump {
+    int32_t n_boxes, n_ems, n_leaf, flags;
+    int64_t draw_pos;
+    double next_box[3];
+    double next_den;
+    double boxes[80][7]; /* lx,ly,lz,hx,hy,hz,density */
+    double ems[256][6];
+} pct_state_dump;
+
+/* gym.make('PctDiscrete-v0' | 'PctContinuous-v0', **kwargs) x n_envs   (envs.py:84-108, tools.py:232-240) */
+int pct_create(const pct_config *cfg, int32_t n_envs, int32_t device, pct_handle *out);
+/* VecEnv.close()  (wrapper/vec_env.py:93-99) */
+void pct_destroy(pct_handle h);
+/* text of the last error on this handle (NULL handle: last pct_create error) */
+const char *pct_last_error(pct_handle h);
+
+/* item_set kwarg (givenData.py:4-14): host array (n,3) of item sizes used by PCT_ITEMS_RANDOM */
+int pct_set_item_set(pct_handle h, const double *items_xyz, int32_t n_items);
+/* replaces box_creator (D:binCreator.py): host array (n_envs, len, 4) of (x,y,z,density) draws per env,
+ * consumed one per reset and one per successful placement, cyclically. Switches the handle to PCT_ITEMS_STREAM. */
+int pct_set_item_stream(pct_handle h, const double *items_xyzd, int32_t len);
+
+/* VecEnv.reset()  (wrapper/shmem_vec_env.py:61-68 -> D:bin3D.py:61-67): resets every env, writes d_obs
+ * (n_envs x obs_len elements of cfg.obs_dtype). */
+int pct_reset(pct_handle h, void *d_obs, void *stream);
+
+/* VecEnv.step_async + step_wait  (wrapper/shmem_vec_env.py:70-81,139-143 -> D:bin3D.py:151-188):
+ * applies one action per env, auto-resets finished envs (the returned observation of a finished env is
+ * its reset observation; reward/done/info are the terminal ones).
+ *   d_actions  : n_envs x 9 leaf rows (float32 if action_f64==0 else float64), or NULL
+ *   d_leaf_idx : n_envs int32 indices into the previous observation's leaf rows (fast path), or NULL;
+ *                an index >= the env's n_leaf selects the all-zero row.  Exactly one of the two is non-NULL.
+ *   d_reward   : n_envs float32;  d_done: n_envs uint8;  d_info: n_envs pct_step_info (may be NULL) */
+int pct_step(pct_handle h, const void *d_actions, int32_t action_f64, const int32_t *d_leaf_idx, void *d_obs,
+             float *d_reward, uint8_t *d_done, pct_step_info *d_info, void *stream);
+
+/* Same call with HOST buffers (what the reference's VecEnv.step exchanges over its pipes):
+ * copies actions host->device, steps, copies obs/reward/done/info back, synchronises. */
+int pct_step_host(pct_handle h, const void *h_actions, int32_t action_f64, const int32_t *h_leaf_idx, void *h_obs,
+                  float *h_reward, uint8_t *h_done, pct_step_info *h_info);
+int pct_reset_host(pct_handle h, void *h_obs);
+
+/* Uniform-random choice among the valid leaf rows of each env (the synthetic policy of SURVEY.md §8(d)):
+ * d_leaf_idx[e] = rnd(seed, env_id_base+e, t) % n_leaf[e]  (0 when there is no valid leaf). */
+int pct_policy_random(pct_handle h, int32_t *d_leaf_idx, uint64_t seed, int64_t t, void *stream);
+
+/* introspection */
+int pct_get_state(pct_handle h, int32_t env, pct_state_dump *out);
+int32_t pct_obs_len(pct_handle h);       /* (NB + NL + 1) * 9 */
+int32_t pct_num_envs(pct_handle h);
+int64_t pct_state_bytes_per_env(pct_handle h); /* HBM bytes of library-owned state per env (roofline accounting) */
+int64_t pct_kernel_launches(pct_handle h);     /* kernels launched by this handle so far */
+const char *pct_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

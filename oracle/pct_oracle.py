@@ -1,0 +1,161 @@
+"""TEST INFRASTRUCTURE — ctypes binding of the CPU oracle (oracle/_build/libpct_oracle.so).
+
+Only tests/, __graft_entry__.smoke() and bench.py (cpu_baseline / --impl reference) may import this.
+The product path (pct_b200) never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "_build", "libpct_oracle.so")
+
+
+def build(force=False):
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".c", ".h"))]
+    if force or not os.path.exists(_LIB) or any(os.path.getmtime(s) > os.path.getmtime(_LIB) for s in srcs):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return _LIB
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_LIB)
+        dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
+        L.pcto_create.restype = C.c_void_p
+        L.pcto_create.argtypes = [C.c_int] * 6 + [C.c_double]
+        L.pcto_destroy.argtypes = [C.c_void_p]
+        L.pcto_set_stream.argtypes = [C.c_void_p, dp, C.c_int]
+        L.pcto_obs_len.argtypes = [C.c_void_p]
+        L.pcto_reset.argtypes = [C.c_void_p, dp]
+        L.pcto_step.argtypes = [C.c_void_p, dp, C.c_int, dp, dp, ip, dp]
+        L.pcto_get_ems.argtypes = [C.c_void_p, ip, C.c_int]
+        L.pcto_get_candidates.argtypes = [C.c_void_p, ip, ip, C.c_int]
+        L.pcto_get_packed.argtypes = [C.c_void_p, ip, C.c_int]
+        for f in ("pcto_n_lstsq", "pcto_n_boxes", "pcto_stream_pos"):
+            getattr(L, f).argtypes = [C.c_void_p]
+        L.pcto_set_order6.argtypes = [C.POINTER(C.c_int64), C.c_int, ip]
+        L.pcto_hull_shrunk.argtypes = [dp, C.c_int, dp]
+        L.pcto_pip.argtypes = [C.c_double, C.c_double, dp, C.c_int]
+        L.pcto_lstsq.argtypes = [dp, C.c_int, C.c_int, dp, dp]
+        L.pcto_hash_double.argtypes = [C.c_double]
+        L.pcto_hash_double.restype = C.c_uint64
+        _lib = L
+    return _lib
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+class OracleDiscrete(object):
+    """Single discrete env, same call surface as the reference's PackingDiscrete
+    (pct_envs/PctDiscrete0/bin3D.py:8-188) restricted to LNES='EMS', shuffle=False and an injected
+    item stream (array (n,4): x, y, z, density)."""
+
+    def __init__(self, setting, container_size=(10, 10, 10), internal_node_holder=80, leaf_node_holder=50,
+                 size_minimum=1, stream=None):
+        self.L = lib()
+        self.h = self.L.pcto_create(setting, *[int(c) for c in container_size], internal_node_holder,
+                                    leaf_node_holder, float(size_minimum))
+        self.nb, self.nl = internal_node_holder, leaf_node_holder
+        self.obs_len = self.L.pcto_obs_len(self.h)
+        self._stream = None
+        if stream is not None:
+            self.set_stream(stream)
+
+    def set_stream(self, stream):
+        s = np.ascontiguousarray(stream, dtype=np.float64)
+        if s.shape[1] == 3:
+            s = np.concatenate([s, np.ones((len(s), 1))], axis=1)
+        self._stream = np.ascontiguousarray(s)
+        self.L.pcto_set_stream(self.h, _dp(self._stream), len(self._stream))
+
+    def reset(self):
+        obs = np.zeros(self.obs_len)
+        self.L.pcto_reset(self.h, _dp(obs))
+        return obs
+
+    def step(self, action):
+        a = np.ascontiguousarray(action, dtype=np.float64)
+        obs = np.zeros(self.obs_len)
+        rew = C.c_double()
+        done = C.c_int()
+        info = np.zeros(3)
+        err = self.L.pcto_step(self.h, _dp(a), len(a), _dp(obs), C.byref(rew), C.byref(done), _dp(info))
+        d = {"counter": int(info[0])}
+        if done.value:
+            d.update(ratio=float(info[1]), reward=float(info[2]))
+        if err:
+            d["error"] = err
+        return obs, rew.value, bool(done.value), d
+
+    def ems(self):
+        buf = np.zeros((4096, 6), dtype=np.int32)
+        n = self.L.pcto_get_ems(self.h, _ip(buf), 4096)
+        return buf[:n].copy()
+
+    def candidates(self):
+        buf = np.zeros((8192, 6), dtype=np.int32)
+        feas = np.zeros(8192, dtype=np.int32)
+        n = self.L.pcto_get_candidates(self.h, _ip(buf), _ip(feas), 8192)
+        return buf[:n].copy(), feas[:n].copy()
+
+    @property
+    def packed(self):
+        buf = np.zeros((256, 7), dtype=np.int32)
+        n = self.L.pcto_get_packed(self.h, _ip(buf), 256)
+        return buf[:n].tolist()
+
+    @property
+    def n_lstsq(self):
+        return self.L.pcto_n_lstsq(self.h)
+
+    @property
+    def stream_pos(self):
+        return self.L.pcto_stream_pos(self.h)
+
+    def __del__(self):
+        try:
+            self.L.pcto_destroy(self.h)
+        except Exception:
+            pass
+
+
+# ---- shared deterministic test policy / item streams -------------------------------------------
+M64 = (1 << 64) - 1
+
+
+def splitmix64(x):
+    x = (x + 0x9E3779B97F4A7C15) & M64
+    z = x
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & M64
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & M64
+    return z ^ (z >> 31)
+
+
+def rnd_u64(seed, a, b):
+    """Counter-based generator shared by host tests, the oracle harness and the device code
+    (csrc/pct_rng.cuh): splitmix64(splitmix64(seed ^ a*GOLD) + b)."""
+    return splitmix64((splitmix64((seed ^ (a * 0x9E3779B97F4A7C15)) & M64) + b) & M64)
+
+
+def policy_pick(obs, nb, nl, seed, env, t):
+    """Uniform choice among valid leaf rows (all-zero leaf row if none): returns (index, row)."""
+    leaf = obs.reshape(-1, 9)[nb:nb + nl]
+    nvalid = int((leaf[:, 8] == 1).sum())
+    if nvalid == 0:
+        return 0, np.zeros(9)
+    k = rnd_u64(seed, env, t) % nvalid
+    return int(k), leaf[k].copy()
