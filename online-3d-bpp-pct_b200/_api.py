@@ -1,0 +1,12 @@
+"""Public surface of pct_b200."""
+from . import _lib
+from ._lib import build, LIB_PATH
+from .batch import PctBatch, PctError
+
+__all__ = ["PctBatch", "PctError", "build", "LIB_PATH"]
+try:  # host-side mirror of the reference's gym.Env / VecEnv surface
+    from .vec_env import PctVecEnv
+    from .envs import PackingDiscrete, PackingContinuous, make_vec_envs, registration_envs
+    __all__ += ["PctVecEnv", "PackingDiscrete", "PackingContinuous", "make_vec_envs", "registration_envs"]
+except ImportError:  # pragma: no cover - during bring-up
+    pass

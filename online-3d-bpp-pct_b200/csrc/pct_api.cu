@@ -1,0 +1,270 @@
+// C-ABI layer (include/pct_b200.h): owns the per-environment device state, validates arguments, enqueues
+// the kernels on the caller's stream.  No torch types, no exceptions across the boundary, no CPU fallback.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "pct_kernels.h"
+#include "pct_handle.h"
+
+using namespace pct;
+
+static thread_local std::string g_create_err;
+
+#define CK(h, call)                                                                                        \
+    do {                                                                                                   \
+        cudaError_t e_ = (call);                                                                           \
+        if (e_ != cudaSuccess) {                                                                           \
+            (h)->err = std::string(#call) + ": " + cudaGetErrorString(e_);                                 \
+            return PCT_ERR_CUDA;                                                                           \
+        }                                                                                                  \
+    } while (0)
+
+namespace pct {
+// continuous domain (pct_continuous.cu)
+int continuous_create(pct_env_batch *h);
+void continuous_destroy(pct_env_batch *h);
+int continuous_launch(pct_env_batch *h, int mode, const void *actions, int action_f64, const int32_t *leaf_idx, void *obs, float *rew,
+                      uint8_t *done, pct_step_info *info, cudaStream_t st);
+int continuous_policy_random(pct_env_batch *h, int32_t *leaf_idx, uint64_t seed, int64_t t, cudaStream_t st);
+int continuous_get_state(pct_env_batch *h, int env, pct_state_dump *out);
+int64_t continuous_state_bytes();
+}  // namespace pct
+
+extern "C" {
+
+const char *pct_version(void) { return "pct_b200 0.1 (sm_100a)"; }
+
+const char *pct_last_error(pct_handle h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+int pct_create(const pct_config *cfg, int32_t n_envs, int32_t device, pct_handle *out) {
+    if (!cfg || !out || n_envs <= 0) { g_create_err = "pct_create: bad arguments"; return PCT_ERR_INVALID; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        g_create_err = "pct_create: no CUDA device — this library has no CPU fallback";
+        return PCT_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= ndev) { g_create_err = "pct_create: bad device index"; return PCT_ERR_INVALID; }
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    if (prop.major != 10) {
+        g_create_err = std::string("pct_create: device '") + prop.name + "' is not sm_100 (kernels are built for sm_100a only)";
+        return PCT_ERR_NO_DEVICE;
+    }
+    if (cfg->setting < 1 || cfg->setting > 3) { g_create_err = "pct_create: setting must be 1, 2 or 3"; return PCT_ERR_INVALID; }
+    if (cfg->internal_node_holder < 1 || cfg->internal_node_holder > NB_MAX || cfg->leaf_node_holder < 1 || cfg->leaf_node_holder > NL_MAX) {
+        g_create_err = "pct_create: holder sizes out of range (internal <= 80, leaf <= 64)";
+        return PCT_ERR_INVALID;
+    }
+    if (cfg->domain == PCT_DISCRETE) {
+        for (int i = 0; i < 3; i++)
+            if (cfg->container_size[i] < 1 || cfg->container_size[i] > 255 || cfg->container_size[i] != (int)cfg->container_size[i]) {
+                g_create_err = "pct_create: discrete container sizes must be integers in [1,255]";
+                return PCT_ERR_INVALID;
+            }
+    } else if (cfg->domain != PCT_CONTINUOUS) {
+        g_create_err = "pct_create: unknown domain";
+        return PCT_ERR_INVALID;
+    }
+    pct_env_batch *h = new pct_env_batch();
+    h->cfg = *cfg;
+    h->n_envs = n_envs;
+    h->device = device;
+    h->obs_len = (cfg->internal_node_holder + cfg->leaf_node_holder + 1) * 9;
+    h->item_mode = cfg->item_mode;
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) {
+        if (cfg->domain == PCT_DISCRETE) {
+            e = cudaMalloc(&h->d_hot, sizeof(DEnvHot) * (size_t)n_envs);
+            if (e == cudaSuccess) e = cudaMalloc(&h->d_cold, sizeof(DEnvCold) * (size_t)n_envs);
+            if (e == cudaSuccess) e = cudaMemset(h->d_hot, 0, sizeof(DEnvHot) * (size_t)n_envs);
+            if (e == cudaSuccess) e = cudaMemset(h->d_cold, 0, sizeof(DEnvCold) * (size_t)n_envs);
+        } else {
+            int rc = continuous_create(h);
+            if (rc != PCT_OK) { g_create_err = h->err; delete h; return rc; }
+        }
+    }
+    if (e != cudaSuccess) {
+        g_create_err = std::string("pct_create: ") + cudaGetErrorString(e);
+        pct_destroy(h);
+        return PCT_ERR_CUDA;
+    }
+    *out = h;
+    return PCT_OK;
+}
+
+void pct_destroy(pct_handle h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->cfg.domain == PCT_CONTINUOUS) continuous_destroy(h);
+    cudaFree(h->d_hot); cudaFree(h->d_cold); cudaFree(h->d_item_set); cudaFree(h->d_stream);
+    cudaFree(h->d_obs); cudaFree(h->d_act); cudaFree(h->d_idx); cudaFree(h->d_rew); cudaFree(h->d_done); cudaFree(h->d_info);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+}
+
+int pct_set_item_set(pct_handle h, const double *items_xyz, int32_t n_items) {
+    if (!h || !items_xyz || n_items <= 0) return PCT_ERR_INVALID;
+    CK(h, cudaSetDevice(h->device));
+    cudaFree(h->d_item_set);
+    h->d_item_set = nullptr;
+    CK(h, cudaMalloc(&h->d_item_set, sizeof(double) * 3 * (size_t)n_items));
+    CK(h, cudaMemcpy(h->d_item_set, items_xyz, sizeof(double) * 3 * (size_t)n_items, cudaMemcpyHostToDevice));
+    h->n_items = n_items;
+    return PCT_OK;
+}
+
+int pct_set_item_stream(pct_handle h, const double *items_xyzd, int32_t len) {
+    if (!h || !items_xyzd || len <= 0) return PCT_ERR_INVALID;
+    CK(h, cudaSetDevice(h->device));
+    cudaFree(h->d_stream);
+    h->d_stream = nullptr;
+    const size_t bytes = sizeof(double) * 4 * (size_t)len * (size_t)h->n_envs;
+    CK(h, cudaMalloc(&h->d_stream, bytes));
+    CK(h, cudaMemcpy(h->d_stream, items_xyzd, bytes, cudaMemcpyHostToDevice));
+    h->stream_len = len;
+    h->item_mode = PCT_ITEMS_STREAM;
+    return PCT_OK;
+}
+
+static int launch(pct_handle h, int mode, const void *actions, int action_f64, const int32_t *leaf_idx, void *obs, float *rew, uint8_t *done,
+                  pct_step_info *info, cudaStream_t st) {
+    if (h->item_mode == PCT_ITEMS_RANDOM && !(h->cfg.domain == PCT_CONTINUOUS && h->cfg.sample_from_distribution) && !h->d_item_set) {
+        h->err = "no item source: call pct_set_item_set or pct_set_item_stream first";
+        return PCT_ERR_STATE;
+    }
+    if (h->item_mode == PCT_ITEMS_STREAM && !h->d_stream) { h->err = "item stream not set"; return PCT_ERR_STATE; }
+    CK(h, cudaSetDevice(h->device));
+    if (h->cfg.domain == PCT_CONTINUOUS) {
+        int rc = continuous_launch(h, mode, actions, action_f64, leaf_idx, obs, rew, done, info, st);
+        if (rc == PCT_OK) h->launches++;
+        return rc;
+    }
+    DParams p{};
+    p.hot = h->d_hot; p.cold = h->d_cold; p.n_envs = h->n_envs;
+    p.W = (int)h->cfg.container_size[0]; p.L = (int)h->cfg.container_size[1]; p.H = (int)h->cfg.container_size[2];
+    p.nb = h->cfg.internal_node_holder; p.nl = h->cfg.leaf_node_holder; p.setting = h->cfg.setting;
+    p.low_bound = h->cfg.size_minimum;
+    p.item_mode = h->item_mode; p.item_set = h->d_item_set; p.n_items = h->n_items;
+    p.stream = h->d_stream; p.stream_len = h->stream_len;
+    p.seed = h->cfg.seed; p.env_id_base = h->cfg.env_id_base;
+    p.actions = actions; p.action_f64 = action_f64; p.leaf_idx = leaf_idx;
+    p.obs = obs; p.obs_f64 = h->cfg.obs_dtype == PCT_F64;
+    p.reward = rew; p.done = done; p.info = info; p.mode = mode;
+    CK(h, launch_discrete(p, st));
+    h->launches++;
+    return PCT_OK;
+}
+
+int pct_reset(pct_handle h, void *d_obs, void *stream) {
+    if (!h || !d_obs) return PCT_ERR_INVALID;
+    int rc = launch(h, 0, nullptr, 0, nullptr, d_obs, nullptr, nullptr, nullptr, (cudaStream_t)stream);
+    if (rc == PCT_OK) h->did_reset = true;
+    return rc;
+}
+
+int pct_step(pct_handle h, const void *d_actions, int32_t action_f64, const int32_t *d_leaf_idx, void *d_obs, float *d_reward,
+             uint8_t *d_done, pct_step_info *d_info, void *stream) {
+    if (!h || !d_obs || !d_reward || !d_done) return PCT_ERR_INVALID;
+    if ((d_actions == nullptr) == (d_leaf_idx == nullptr)) { h->err = "pct_step: pass exactly one of d_actions / d_leaf_idx"; return PCT_ERR_INVALID; }
+    if (!h->did_reset) { h->err = "pct_step before pct_reset"; return PCT_ERR_STATE; }
+    return launch(h, 1, d_actions, action_f64, d_leaf_idx, d_obs, d_reward, d_done, d_info, (cudaStream_t)stream);
+}
+
+static int ensure_staging(pct_handle h) {
+    if (h->d_obs) return PCT_OK;
+    const size_t n = (size_t)h->n_envs;
+    CK(h, cudaMalloc(&h->d_obs, n * h->obs_len * (h->cfg.obs_dtype == PCT_F64 ? 8 : 4)));
+    CK(h, cudaMalloc(&h->d_act, n * 9 * 8));
+    CK(h, cudaMalloc(&h->d_idx, n * 4));
+    CK(h, cudaMalloc(&h->d_rew, n * 4));
+    CK(h, cudaMalloc(&h->d_done, n));
+    CK(h, cudaMalloc(&h->d_info, n * sizeof(pct_step_info)));
+    return PCT_OK;
+}
+
+int pct_reset_host(pct_handle h, void *h_obs) {
+    if (!h || !h_obs) return PCT_ERR_INVALID;
+    CK(h, cudaSetDevice(h->device));
+    int rc = ensure_staging(h);
+    if (rc) return rc;
+    rc = pct_reset(h, h->d_obs, h->own_stream);
+    if (rc) return rc;
+    const size_t ob = (size_t)h->n_envs * h->obs_len * (h->cfg.obs_dtype == PCT_F64 ? 8 : 4);
+    CK(h, cudaMemcpyAsync(h_obs, h->d_obs, ob, cudaMemcpyDeviceToHost, h->own_stream));
+    CK(h, cudaStreamSynchronize(h->own_stream));
+    return PCT_OK;
+}
+
+int pct_step_host(pct_handle h, const void *h_actions, int32_t action_f64, const int32_t *h_leaf_idx, void *h_obs, float *h_reward,
+                  uint8_t *h_done, pct_step_info *h_info) {
+    if (!h || !h_obs || !h_reward || !h_done) return PCT_ERR_INVALID;
+    if ((h_actions == nullptr) == (h_leaf_idx == nullptr)) { h->err = "pct_step_host: pass exactly one of actions / leaf_idx"; return PCT_ERR_INVALID; }
+    CK(h, cudaSetDevice(h->device));
+    int rc = ensure_staging(h);
+    if (rc) return rc;
+    const size_t n = (size_t)h->n_envs;
+    cudaStream_t st = h->own_stream;
+    if (h_actions) CK(h, cudaMemcpyAsync(h->d_act, h_actions, n * 9 * (action_f64 ? 8 : 4), cudaMemcpyHostToDevice, st));
+    else CK(h, cudaMemcpyAsync(h->d_idx, h_leaf_idx, n * 4, cudaMemcpyHostToDevice, st));
+    rc = pct_step(h, h_actions ? h->d_act : nullptr, action_f64, h_actions ? nullptr : h->d_idx, h->d_obs, h->d_rew, h->d_done, h->d_info, st);
+    if (rc) return rc;
+    const size_t ob = n * h->obs_len * (h->cfg.obs_dtype == PCT_F64 ? 8 : 4);
+    CK(h, cudaMemcpyAsync(h_obs, h->d_obs, ob, cudaMemcpyDeviceToHost, st));
+    CK(h, cudaMemcpyAsync(h_reward, h->d_rew, n * 4, cudaMemcpyDeviceToHost, st));
+    CK(h, cudaMemcpyAsync(h_done, h->d_done, n, cudaMemcpyDeviceToHost, st));
+    if (h_info) CK(h, cudaMemcpyAsync(h_info, h->d_info, n * sizeof(pct_step_info), cudaMemcpyDeviceToHost, st));
+    CK(h, cudaStreamSynchronize(st));
+    return PCT_OK;
+}
+
+int pct_policy_random(pct_handle h, int32_t *d_leaf_idx, uint64_t seed, int64_t t, void *stream) {
+    if (!h || !d_leaf_idx) return PCT_ERR_INVALID;
+    if (!h->did_reset) { h->err = "pct_policy_random before pct_reset"; return PCT_ERR_STATE; }
+    CK(h, cudaSetDevice(h->device));
+    if (h->cfg.domain == PCT_CONTINUOUS) {
+        int rc = continuous_policy_random(h, d_leaf_idx, seed, t, (cudaStream_t)stream);
+        if (rc == PCT_OK) h->launches++;
+        return rc;
+    }
+    CK(h, launch_policy_random_discrete(h->d_hot, h->n_envs, h->cfg.env_id_base, seed, t, d_leaf_idx, (cudaStream_t)stream));
+    h->launches++;
+    return PCT_OK;
+}
+
+int pct_get_state(pct_handle h, int32_t env, pct_state_dump *out) {
+    if (!h || !out || env < 0 || env >= h->n_envs) return PCT_ERR_INVALID;
+    CK(h, cudaSetDevice(h->device));
+    CK(h, cudaDeviceSynchronize());
+    if (h->cfg.domain == PCT_CONTINUOUS) return continuous_get_state(h, env, out);
+    DEnvHot hot;
+    std::vector<double> den(NB_MAX);
+    CK(h, cudaMemcpy(&hot, h->d_hot + env, sizeof(hot), cudaMemcpyDeviceToHost));
+    CK(h, cudaMemcpy(den.data(), (const char *)(h->d_cold + env) + offsetof(DEnvCold, density), sizeof(double) * NB_MAX, cudaMemcpyDeviceToHost));
+    memset(out, 0, sizeof(*out));
+    out->n_boxes = hot.h.n_box; out->n_ems = hot.h.n_ems; out->n_leaf = hot.h.n_leaf; out->flags = hot.h.flags;
+    out->draw_pos = hot.h.draw_pos;
+    for (int i = 0; i < 3; i++) out->next_box[i] = hot.h.next_box[i];
+    out->next_den = hot.h.next_den;
+    for (int i = 0; i < hot.h.n_box && i < 80; i++) {
+        for (int t = 0; t < 6; t++) out->boxes[i][t] = hot.box[i][t];
+        out->boxes[i][6] = h->cfg.setting == 3 ? den[i] : 1.0;
+    }
+    for (int i = 0; i < hot.h.n_ems && i < 256 && i < E_MAX; i++)
+        for (int t = 0; t < 6; t++) out->ems[i][t] = hot.ems[i][t];
+    return PCT_OK;
+}
+
+int32_t pct_obs_len(pct_handle h) { return h ? h->obs_len : 0; }
+int32_t pct_num_envs(pct_handle h) { return h ? h->n_envs : 0; }
+int64_t pct_state_bytes_per_env(pct_handle h) {
+    if (!h) return 0;
+    if (h->cfg.domain == PCT_CONTINUOUS) return continuous_state_bytes();
+    return (int64_t)(sizeof(DEnvHot) + sizeof(DEnvCold));
+}
+int64_t pct_kernel_launches(pct_handle h) { return h ? h->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,115 @@
+// Shared device helpers: counter-based RNG, CPython tuple-hash / set-probe emulation, TMA (1-D bulk copy)
+// and mbarrier wrappers for sm_100a.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace pct {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+// ---- counter-based generator shared with the host tests (oracle/pct_oracle.py rnd_u64) ----------------
+__host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    uint64_t z = x;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__host__ __device__ __forceinline__ uint64_t rnd_u64(uint64_t seed, uint64_t a, uint64_t b) {
+    return splitmix64(splitmix64(seed ^ (a * 0x9E3779B97F4A7C15ull)) + b);
+}
+constexpr uint64_t DENSITY_SALT = 0xABCDEFull;
+// uniform in (0,1): np.random.random() re-drawn while == 0 (D:bin3D.py:82-84)
+__host__ __device__ __forceinline__ double rnd_density(uint64_t seed, uint64_t a, uint64_t b) {
+    uint64_t r = rnd_u64(seed ^ DENSITY_SALT, a, b) >> 11;
+    if (r == 0) r = 1;
+    return (double)r * (1.0 / 9007199254740992.0);
+}
+
+// ---- CPython 3.12 tuple hash of a 6-tuple (Objects/tupleobject.c, xxHash-derived) --------------------
+// Call sites in the reference: the `posVec` sets of D:space.py:535,565-569 / C:space.py:532,563-567.
+constexpr uint64_t XXP1 = 11400714785074694791ull, XXP2 = 14029467366897019727ull, XXP5 = 2870177450012600261ull;
+__device__ __forceinline__ uint64_t tuple_hash6(const uint64_t lane[6]) {
+    uint64_t acc = XXP5;
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        acc += lane[i] * XXP2;
+        acc = (acc << 31) | (acc >> 33);
+        acc *= XXP1;
+    }
+    acc += 6ull ^ (XXP5 ^ 3527539ull);
+    if (acc == ~0ull) return 1546275796ull;
+    return acc;
+}
+// _Py_HashDouble (Python/pyhash.c) for finite doubles: value mod (2^61 - 1) with sign, -1 -> -2
+__device__ __forceinline__ uint64_t hash_double(double v) {
+    const uint64_t MOD = (1ull << 61) - 1;
+    if (v == 0.0) return 0;
+    int e;
+    double m = frexp(v, &e);
+    int sign = 1;
+    if (m < 0) { sign = -1; m = -m; }
+    uint64_t x = 0;
+    while (m != 0.0) {
+        x = ((x << 28) & MOD) | (x >> (61 - 28));
+        m *= 268435456.0;
+        e -= 28;
+        uint64_t y = (uint64_t)m;
+        m -= (double)y;
+        x += y;
+        if (x >= MOD) x -= MOD;
+    }
+    e = e >= 0 ? e % 61 : 61 - 1 - ((-1 - e) % 61);
+    x = ((x << e) & MOD) | (x >> (61 - e));
+    int64_t r = (int64_t)x * sign;
+    if (r == -1) r = -2;
+    return (uint64_t)r;
+}
+
+// ---- TMA 1-D bulk copies + mbarrier (PTX ISA 8.x; SASS: UBLKCP / SYNCS) ---------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_1d(void *gmem_dst, const void *smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit_wait() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
+__device__ __forceinline__ int warp_incl_scan(int v, int lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int t = __shfl_up_sync(FULL, v, d);
+        if (lane >= d) v += t;
+    }
+    return v;
+}
+
+}  // namespace pct

@@ -1,0 +1,30 @@
+// Internal: the object behind pct_handle.
+#pragma once
+#include <string>
+#include "pct_kernels.h"
+
+struct pct_env_batch {
+    pct_config cfg;
+    int n_envs = 0, device = 0;
+    int obs_len = 0;
+    bool did_reset = false;
+    int64_t launches = 0;
+    std::string err;
+    // device state
+    pct::DEnvHot *d_hot = nullptr;
+    pct::DEnvCold *d_cold = nullptr;
+    void *c_state = nullptr;  // continuous-domain state (pct_continuous.cu)
+    double *d_item_set = nullptr;
+    int n_items = 0;
+    double *d_stream = nullptr;
+    int stream_len = 0;
+    int item_mode = 0;
+    // staging for the host-buffer entry points
+    void *d_obs = nullptr, *d_act = nullptr;
+    int32_t *d_idx = nullptr;
+    float *d_rew = nullptr;
+    uint8_t *d_done = nullptr;
+    pct_step_info *d_info = nullptr;
+    cudaStream_t own_stream = nullptr;
+};
+

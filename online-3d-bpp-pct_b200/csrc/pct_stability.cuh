@@ -22,30 +22,10 @@
 #pragma once
 #include <cstdint>
 #include <math.h>
+#include <math_constants.h>
+#include "pct_kernels.h"
 
 namespace pct {
-
-constexpr int KSUP_SMALL = 8;    // supports handled with lane-local scratch
-constexpr int KSUP_MAX = 32;     // supports handled with the per-env scratch in HBM (serialised by a lock)
-constexpr int STAB_DEPTH = 14;   // DFS depth (levels of boxes on top of each other)
-constexpr int STAB_SUP_POOL = 48;
-constexpr int EDGE_MAX = 256;
-
-struct Stack4 { double cx, cy, cz, m; };
-
-struct EdgePool {          // per-env, global memory
-    uint8_t *upper;        // [EDGE_MAX]
-    uint8_t *lower;        // [EDGE_MAX]
-    Stack4 *st;            // [EDGE_MAX]
-    int n;                 // current count (lane-local copy; the REAL path writes it back)
-};
-
-// per-env HBM scratch for the rare big cases (k > KSUP_SMALL)
-struct BigScratch {
-    double px[4 * KSUP_MAX], py[4 * KSUP_MAX];
-    uint8_t order[4 * KSUP_MAX], hl[8 * KSUP_MAX], hu[4 * KSUP_MAX + 4];
-    double R[KSUP_MAX * KSUP_MAX], V[KSUP_MAX * KSUP_MAX], y[KSUP_MAX], row[KSUP_MAX], x[KSUP_MAX];
-};
 
 __device__ __forceinline__ double dot2(double u0, double u1, double v0, double v1) { return fma(u1, v1, u0 * v0); }
 

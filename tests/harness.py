@@ -1,0 +1,44 @@
+"""Shared helpers for the parity tests (test infrastructure)."""
+import numpy as np
+
+from pct_oracle import OracleDiscrete, policy_pick, rnd_u64  # noqa: F401  (oracle/ is on sys.path via conftest)
+
+ITEM_SET = [(i, j, k) for i in range(1, 6) for j in range(1, 6) for k in range(1, 6)]  # givenData.py:7-14
+
+
+def make_stream(seed, env, n, setting):
+    """Deterministic per-env draw sequence (x,y,z,density) over the 125-item set."""
+    s = np.zeros((n, 4))
+    for d in range(n):
+        s[d, :3] = ITEM_SET[rnd_u64(seed, env, d) % 125]
+        s[d, 3] = max((rnd_u64(seed ^ 0xABCDEF, env, d) >> 11), 1) / float(1 << 53) if setting == 3 else 1.0
+    return s
+
+
+class OracleVec(object):
+    """N independent oracle envs with the ShmemVecEnv worker semantics (auto-reset on done,
+    wrapper/shmem_vec_env.py:139-143) and the shared deterministic policy."""
+
+    def __init__(self, n, setting, streams, nb=80, nl=50, container=(10, 10, 10)):
+        self.envs = [OracleDiscrete(setting, container_size=container, internal_node_holder=nb, leaf_node_holder=nl, stream=streams[i])
+                     for i in range(n)]
+        self.n, self.nb, self.nl = n, nb, nl
+
+    def reset(self):
+        return np.stack([e.reset() for e in self.envs])
+
+    def step(self, actions):
+        obs, rew, done, infos = [], [], [], []
+        for e, a in zip(self.envs, actions):
+            o, r, d, i = e.step(a)
+            if d:
+                o = e.reset()
+            obs.append(o); rew.append(r); done.append(d); infos.append(i)
+        return np.stack(obs), np.array(rew), np.array(done), infos
+
+    def pick(self, obs, seed, t, env_id_base=0):
+        idx, rows = [], []
+        for e in range(self.n):
+            k, row = policy_pick(obs[e], self.nb, self.nl, seed, env_id_base + e, t)
+            idx.append(k); rows.append(row)
+        return np.array(idx, dtype=np.int32), np.stack(rows)
