@@ -159,3 +159,46 @@ def policy_pick(obs, nb, nl, seed, env, t):
         return 0, np.zeros(9)
     k = rnd_u64(seed, env, t) % nvalid
     return int(k), leaf[k].copy()
+
+
+class OracleBatch(object):
+    """N oracle envs stepped by host threads with the synthetic policy (oracle/pct_oracle_batch.c)."""
+
+    def __init__(self, n_envs, setting, item_set, item_seed, policy_seed, container_size=(10, 10, 10), nb=80, nl=50,
+                 size_minimum=1, gid_base=0, threads=None):
+        L = lib()
+        L.pcto_batch_create.restype = C.c_void_p
+        L.pcto_batch_create.argtypes = [C.c_int] * 6 + [C.c_double, C.POINTER(C.c_double), C.c_int, C.c_uint64, C.c_uint64,
+                                                          C.c_int64, C.c_int, C.c_int]
+        L.pcto_batch_run.restype = C.c_double
+        L.pcto_batch_run.argtypes = [C.c_void_p, C.c_int]
+        L.pcto_batch_get.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]
+        L.pcto_batch_destroy.argtypes = [C.c_void_p]
+        self.L = L
+        self.n, self.obs_len = n_envs, (nb + nl + 1) * 9
+        self.threads = threads or os.cpu_count() or 1
+        its = np.ascontiguousarray(np.array(item_set, dtype=np.float64).reshape(-1, 3))
+        self.h = L.pcto_batch_create(setting, int(container_size[0]), int(container_size[1]), int(container_size[2]), nb, nl,
+                                     float(size_minimum), _dp(its), len(its), item_seed, policy_seed, gid_base, n_envs, self.threads)
+
+    def run(self, steps):
+        """returns elapsed seconds for `steps` vector steps"""
+        return self.L.pcto_batch_run(self.h, steps)
+
+    def get(self):
+        obs = np.zeros((self.n, self.obs_len))
+        rew = np.zeros(self.n)
+        nd = np.zeros(self.n, dtype=np.int32)
+        self.L.pcto_batch_get(self.h, _dp(obs), _dp(rew), _ip(nd))
+        return obs, rew, nd
+
+    def close(self):
+        if self.h:
+            self.L.pcto_batch_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
