@@ -36,6 +36,7 @@ struct EdgePool {          // per-env, global memory
 
 // per-env HBM scratch for the rare big cases (k > KSUP_SMALL)
 struct BigScratch {
+    double rect[KSUP_MAX][4];
     double px[4 * KSUP_MAX], py[4 * KSUP_MAX];
     uint8_t order[4 * KSUP_MAX], hl[8 * KSUP_MAX], hu[4 * KSUP_MAX + 4];
     double R[KSUP_MAX * KSUP_MAX], V[KSUP_MAX * KSUP_MAX], y[KSUP_MAX], row[KSUP_MAX], x[KSUP_MAX];

@@ -18,7 +18,10 @@
 //     is carried in the frame, and the real edge of that path member is skipped (== the `involved`
 //     gating of D:space.py:55-63);
 //   * all FP64 arithmetic is one IEEE operation per source operator (file is compiled with
-//     -fmad=false); fma() appears only where it reproduces OpenBLAS ddot on 2-vectors.
+//     -fmad=false); fma() appears only where it reproduces OpenBLAS ddot on 2-vectors;
+//   * the step kernel is instruction-fetch bound (ncu: stalled_no_instruction), so this file is written
+//     for SMALL CODE: one runtime-flag routine for real and virtual checks, FP64 division / sqrt and the
+//     helpers are shared __noinline__ functions, loops are not unrolled.
 #pragma once
 #include <cstdint>
 #include <math.h>
@@ -27,10 +30,12 @@
 
 namespace pct {
 
+__device__ __noinline__ double ddiv(double a, double b) { return a / b; }
+__device__ __noinline__ double dsqrt(double a) { return sqrt(a); }
 __device__ __forceinline__ double dot2(double u0, double u1, double v0, double v1) { return fma(u1, v1, u0 * v0); }
 
 __device__ __forceinline__ double slope_of(double ax, double ay, double bx, double by) {
-    if (bx != ax) return (by - ay) / (bx - ax);
+    if (bx != ax) return ddiv(by - ay, bx - ax);
     return (by - ay) * CUDART_INF;  // 0*inf = nan like the reference (convex_hull.py:14)
 }
 __device__ __forceinline__ int orient_of(double s1, double s2) {
@@ -44,38 +49,39 @@ __device__ __forceinline__ int orient_of(double s1, double s2) {
 // ConvexHull (convex_hull.py:39-95) on n points already perturbed (x += y*1e-6).
 // Writes the hull as indices: lower chain (minus last) then upper chain (minus last) into `hl` (returns count).
 __device__ __noinline__ int hull_indices(const double *px, const double *py, int n, uint8_t *order, uint8_t *hl, uint8_t *hu) {
-    for (int i = 0; i < n; i++) order[i] = (uint8_t)i;
-    for (int i = 1; i < n; i++) {  // stable insertion sort by x (sorted(key=x[0]), :34-37)
-        uint8_t o = order[i];
-        double kx = px[o];
+#pragma unroll 1
+    for (int i = 0; i < n; i++) {  // stable insertion sort by x (sorted(key=x[0]), :34-37)
+        const double kx = px[i];
         int j = i - 1;
+#pragma unroll 1
         while (j >= 0 && px[order[j]] > kx) { order[j + 1] = order[j]; j--; }
-        order[j + 1] = o;
+        order[j + 1] = (uint8_t)i;
     }
-    int cnt[2];
+    int m = 0;
+#pragma unroll 1
     for (int pass = 0; pass < 2; pass++) {
         uint8_t *H = pass == 0 ? hl : hu;
         int nh = 0;
-        double s1 = 0, s2 = 0;
+#pragma unroll 1
         for (int k = 0; k < n; k++) {
-            int p = order[pass == 0 ? k : n - 1 - k];
-            double qx = px[p], qy = py[p];
-            if (nh >= 2) {
-                s1 = slope_of(px[H[nh - 2]], py[H[nh - 2]], px[H[nh - 1]], py[H[nh - 1]]);
-                s2 = slope_of(px[H[nh - 1]], py[H[nh - 1]], qx, qy);
-            }
-            while (nh >= 2 && orient_of(s1, s2) != -1) {
-                nh--;
+            const int p = order[pass == 0 ? k : n - 1 - k];
+            const double qx = px[p], qy = py[p];
+#pragma unroll 1
+            while (nh >= 2) {
+                const double s1 = slope_of(px[H[nh - 2]], py[H[nh - 2]], px[H[nh - 1]], py[H[nh - 1]]);
+                const double s2 = slope_of(px[H[nh - 1]], py[H[nh - 1]], qx, qy);
+                if (orient_of(s1, s2) == -1) break;
+                nh--;                                                                // pop
                 if (px[H[0]] == px[H[nh - 1]] && py[H[0]] == py[H[nh - 1]]) break;  // list equality :58-59
-                s1 = slope_of(px[H[nh - 2]], py[H[nh - 2]], px[H[nh - 1]], py[H[nh - 1]]);
-                s2 = slope_of(px[H[nh - 1]], py[H[nh - 1]], qx, qy);
             }
             H[nh++] = (uint8_t)p;
         }
-        cnt[pass] = nh;
+        if (pass == 0) m = nh - 1;  // drop the last of each chain (:89-92)
+        else {
+#pragma unroll 1
+            for (int i = 0; i < nh - 1; i++) hl[m++] = hu[i];
+        }
     }
-    int m = cnt[0] - 1;
-    for (int i = 0; i < cnt[1] - 1; i++) hl[m++] = hu[i];
     return m;
 }
 
@@ -83,21 +89,30 @@ __device__ __noinline__ int hull_indices(const double *px, const double *py, int
 // never stored, its vertices are produced on the fly from the hull indices.
 __device__ __noinline__ bool pip_shrunk(const double *px, const double *py, const uint8_t *hull, int m, double lat, double lon) {
     double sx = 0, sy = 0;
+#pragma unroll 1
     for (int i = 0; i < m; i++) { sx += px[hull[i]]; sy += py[hull[i]]; }
-    double cx = sx / (double)m, cy = sy / (double)m;
-    auto vx = [&](int i) { double v = px[hull[i]]; double d = v - cx; return v - d * 0.1; };
-    auto vy = [&](int i) { double v = py[hull[i]]; double d = v - cy; return v - d * 0.1; };
-    double jx = vx(m - 1), jy = vy(m - 1);
+    const double cx = ddiv(sx, (double)m), cy = ddiv(sy, (double)m);
+    double jx, jy;
+    {
+        double v = px[hull[m - 1]], d = v - cx;
+        jx = v - d * 0.1;
+        v = py[hull[m - 1]]; d = v - cy;
+        jy = v - d * 0.1;
+    }
     bool odd = false;
+#pragma unroll 1
     for (int i = 0; i < m; i++) {
-        double ix = vx(i), iy = vy(i);
-        double a0 = ix - lat, a1 = iy - lon;
-        double b0 = lat - jx, b1 = lon - jy;
-        double m1 = a0 * b1, m2 = a1 * b0;
+        double v = px[hull[i]], d = v - cx;
+        const double ix = v - d * 0.1;
+        v = py[hull[i]]; d = v - cy;
+        const double iy = v - d * 0.1;
+        const double a0 = ix - lat, a1 = iy - lon;
+        const double b0 = lat - jx, b1 = lon - jy;
+        const double m1 = a0 * b1, m2 = a1 * b0;
         if (m1 - m2 == 0) return false;
         if ((iy < lon && jy >= lon) || (jy < lon && iy >= lon)) {
-            double t = (lon - iy) / (jy - iy);
-            double u = t * (jx - ix);
+            const double t = ddiv(lon - iy, jy - iy);
+            const double u = t * (jx - ix);
             if (ix + u < lat) odd = !odd;
         }
         jx = ix; jy = iy;
@@ -109,25 +124,21 @@ __device__ __noinline__ bool pip_shrunk(const double *px, const double *py, cons
 // identical operation order to oracle/pct_oracle_common.h po_ls_*).  ld = leading dimension of R and V.
 struct LsWork { double *R, *V, *y, *row, *x; int ld; };
 
-__device__ __noinline__ void ls_init(const LsWork &w, int k) {
-    for (int i = 0; i < k; i++) {
-        w.y[i] = 0;
-        for (int j = 0; j < k; j++) w.R[i * w.ld + j] = 0;
-    }
-}
 __device__ __noinline__ void ls_add_row(const LsWork &w, int k, double rhs) {
+#pragma unroll 1
     for (int i = 0; i < k; i++) {
-        double b = w.row[i];
+        const double b = w.row[i];
         if (b == 0) continue;
-        double a = w.R[i * w.ld + i];
-        double r = sqrt(a * a + b * b);
-        double c = a / r, sn = b / r;
+        const double a = w.R[i * w.ld + i];
+        const double r = dsqrt(a * a + b * b);
+        const double c = ddiv(a, r), sn = ddiv(b, r);
+#pragma unroll 1
         for (int j = i; j < k; j++) {
-            double rij = w.R[i * w.ld + j], vj = w.row[j];
+            const double rij = w.R[i * w.ld + j], vj = w.row[j];
             w.R[i * w.ld + j] = c * rij + sn * vj;
             w.row[j] = c * vj - sn * rij;
         }
-        double yi = w.y[i];
+        const double yi = w.y[i];
         w.y[i] = c * yi + sn * rhs;
         rhs = c * rhs - sn * yi;
     }
@@ -135,270 +146,287 @@ __device__ __noinline__ void ls_add_row(const LsWork &w, int k, double rhs) {
 __device__ __noinline__ void ls_solve(const LsWork &w, int k, int rows) {
     double *G = w.R, *V = w.V;
     const int ld = w.ld;
+#pragma unroll 1
     for (int i = 0; i < k; i++)
+#pragma unroll 1
         for (int j = 0; j < k; j++) V[i * ld + j] = (i == j) ? 1.0 : 0.0;
+#pragma unroll 1
     for (int sweep = 0; sweep < 60; sweep++) {
         bool rotated = false;
+#pragma unroll 1
         for (int p = 0; p < k - 1; p++)
+#pragma unroll 1
             for (int q = p + 1; q < k; q++) {
                 double alpha = 0, beta = 0, gamma = 0;
+#pragma unroll 1
                 for (int i = 0; i < k; i++) {
-                    double gp = G[i * ld + p], gq = G[i * ld + q];
+                    const double gp = G[i * ld + p], gq = G[i * ld + q];
                     alpha += gp * gp;
                     beta += gq * gq;
                     gamma += gp * gq;
                 }
-                if (gamma == 0 || fabs(gamma) <= 1e-15 * sqrt(alpha * beta)) continue;
+                if (gamma == 0 || fabs(gamma) <= 1e-15 * dsqrt(alpha * beta)) continue;
                 rotated = true;
-                double zeta = (beta - alpha) / (2.0 * gamma);
-                double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-                double c = 1.0 / sqrt(1.0 + t * t), sn = c * t;
+                const double zeta = ddiv(beta - alpha, 2.0 * gamma);
+                const double t = ddiv(zeta >= 0 ? 1.0 : -1.0, fabs(zeta) + dsqrt(1.0 + zeta * zeta));
+                const double c = ddiv(1.0, dsqrt(1.0 + t * t)), sn = c * t;
+#pragma unroll 1
                 for (int i = 0; i < k; i++) {
-                    double gp = G[i * ld + p], gq = G[i * ld + q];
+                    const double gp = G[i * ld + p], gq = G[i * ld + q];
                     G[i * ld + p] = c * gp - sn * gq;
                     G[i * ld + q] = sn * gp + c * gq;
-                    double vp = V[i * ld + p], vq = V[i * ld + q];
+                    const double vp = V[i * ld + p], vq = V[i * ld + q];
                     V[i * ld + p] = c * vp - sn * vq;
                     V[i * ld + q] = sn * vp + c * vq;
                 }
             }
         if (!rotated) break;
     }
-    // singular values; reuse w.row for sigma
-    double smax = 0;
+    double smax = 0;  // singular values (kept in w.row)
+#pragma unroll 1
     for (int j = 0; j < k; j++) {
         double a = 0;
+#pragma unroll 1
         for (int i = 0; i < k; i++) a += G[i * ld + j] * G[i * ld + j];
-        double s = sqrt(a);
+        const double s = dsqrt(a);
         w.row[j] = s;
         if (s > smax) smax = s;
     }
-    int M = rows > k ? rows : k;
-    double cutoff = 2.220446049250313e-16 * (double)M * smax;
+    const int M = rows > k ? rows : k;
+    const double cutoff = 2.220446049250313e-16 * (double)M * smax;
+#pragma unroll 1
     for (int i = 0; i < k; i++) w.x[i] = 0;
+#pragma unroll 1
     for (int j = 0; j < k; j++) {
-        double sg = w.row[j];
+        const double sg = w.row[j];
         if (!(sg > cutoff)) continue;
         double uy = 0;
+#pragma unroll 1
         for (int i = 0; i < k; i++) uy += G[i * ld + j] * w.y[i];
-        double coef = uy / (sg * sg);
+        const double coef = ddiv(uy, sg * sg);
+#pragma unroll 1
         for (int i = 0; i < k; i++) w.x[i] += V[i * ld + j] * coef;
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// Geometry policy G must provide (all per lane):
-//   int  n_boxes() const
-//   void node_box(int id, StabNode &out) const                                          (real box id)
-//   bool support_rect(const StabNode &node, int t, double &x1,&y1,&x2,&y2) const        (is box t a support?)
-//   bool strictly_inside(cx, cy, x1,y1,x2,y2) const                                     (direct-edge test)
-// ---------------------------------------------------------------------------------------------
-struct StabNode { double lx, ly, lz, dx, dy, dz, mass; };  // corner + dims (centre = l + d/2, D:space.py:35)
+// lstsq load split for k >= 3 supports without a direct edge (D:space.py:134-152 / 231-250):
+// c2x/c2y = contact-rectangle centres, (cx,cy) = stack COM; writes the k assignment ratios to w.x
+__device__ __noinline__ void lstsq_ratios(const LsWork &w, int k, const double *c2x, const double *c2y, double cx, double cy) {
+#pragma unroll 1
+    for (int i = 0; i < k; i++) {
+        w.y[i] = 0;
+#pragma unroll 1
+        for (int j = 0; j < k; j++) w.R[i * w.ld + j] = 0;
+    }
+    int rows = 0;
+#pragma unroll 1
+    for (int a = 0; a < k - 1; a++)
+#pragma unroll 1
+        for (int b = a + 1; b < k; b++) {
+#pragma unroll 1
+            for (int t = 0; t < k; t++) w.row[t] = 0;
+            const double lx = c2x[a] - c2x[b], ly = c2y[a] - c2y[b];
+            const double molecular = dot2(cx - c2x[a], cy - c2y[a], lx, ly);
+            if (molecular != 0) {
+                const double r = ddiv(fabs(dot2(cx - c2x[b], cy - c2y[b], lx, ly)), molecular);
+                w.row[a] = 1;
+                w.row[b] = -r;
+            }
+            ls_add_row(w, k, 0.0);
+            rows++;
+        }
+#pragma unroll 1
+    for (int t = 0; t < k; t++) w.row[t] = 1;
+    ls_add_row(w, k, 1.0);
+    rows++;
+    ls_solve(w, k, rows);
+}
 
+// ---------------------------------------------------------------------------------------------
+// Geometry policy G (per lane) provides:
+//   typedef Node            footprint corner + dims of a box (ints for discrete, doubles for continuous) + mass
+//   int  n_boxes() const
+//   void node_box(int id, Node &out) const                       (real box id)
+//   void centre(const Node&, double &cx,&cy,&cz) const            (D:space.py:35)
+//   bool support(const Node &node, int t, double r[4]) const      (is box t a support? contact rect x1,y1,x2,y2)
+//   bool strictly_inside(cx, cy, const double r[4]) const         (direct-edge test)
+// ---------------------------------------------------------------------------------------------
 struct StabFrame {
     Stack4 st;        // this node's (virtual) stack for this visit
     uint8_t node;     // real box index, or NODE_NEW
     uint8_t base, k, i;
-    uint8_t whole;    // 1: children receive the whole stack centre (k==1 / direct edge); 0: (c2d_i, st.cz)
+    uint8_t whole;    // 1: whole stack to the single support; 2: direct edge (others zero); 0: (c2d_i, st.cz) split
 };
 constexpr int NODE_NEW = 255;
 
-enum StabResult { STAB_FALSE = 0, STAB_TRUE = 1 };
-
-template <bool REAL, class G>
-__device__ __noinline__ int stability_check(const G &g, const StabNode &root, EdgePool &pool, BigScratch *big, int *lock,
-                                            int new_id, int &flags) {
-    // new_id: index the new box gets if REAL placement succeeds (== n_boxes); virtual candidates use NODE_NEW
+template <class G>
+__device__ __noinline__ int stability_check(const G &g, const typename G::Node &root, EdgePool &pool, BigScratch *big, int *lock,
+                                            const bool real, const int new_id, int &flags) {
+    typedef typename G::Node Node;
     StabFrame fr[STAB_DEPTH];
     uint8_t sup_id[STAB_SUP_POOL];
     double sup_m[STAB_SUP_POOL];
+    // lane-local scratch for up to KSUP_SMALL supports
+    double lrect[KSUP_SMALL][4], lpx[4 * KSUP_SMALL], lpy[4 * KSUP_SMALL];
+    uint8_t lorder[4 * KSUP_SMALL], lhl[8 * KSUP_SMALL], lhu[4 * KSUP_SMALL + 4];
+    const int root_id = real ? new_id : NODE_NEW;
     int depth = 0;
-    fr[0].st = Stack4{root.lx + root.dx / 2, root.ly + root.dy / 2, root.lz + root.dz / 2, root.mass};
-    fr[0].node = REAL ? (uint8_t)new_id : (uint8_t)NODE_NEW;
+    g.centre(root, fr[0].st.cx, fr[0].st.cy, fr[0].st.cz);
+    fr[0].st.m = root.mass;
+    fr[0].node = (uint8_t)root_id;
     fr[0].base = 0; fr[0].k = 0xFF; fr[0].i = 0; fr[0].whole = 1;
-    StabNode cur = root;
 
+#pragma unroll 1
     while (depth >= 0) {
         StabFrame &f = fr[depth];
+        Node cur;
+        if (f.node != root_id) g.node_box(f.node, cur);
+        else cur = root;
         if (f.k == 0xFF) {
             // ---------------- ENTER: supports, hull, PIP, load distribution ----------------
-            if (f.node != (REAL ? new_id : NODE_NEW)) g.node_box(f.node, cur);
-            else cur = root;
-            const int limit = (f.node == (REAL ? new_id : NODE_NEW)) ? g.n_boxes() : (int)f.node;
-            int k = 0;
+            const int limit = (f.node == root_id) ? g.n_boxes() : (int)f.node;
             const int base = f.base;
-            bool overflow = false;
+            int k = 0;
+            double r[4];
+#pragma unroll 1
             for (int t = 0; t < limit; t++) {
-                double x1, y1, x2, y2;
-                if (g.support_rect(cur, t, x1, y1, x2, y2)) {
-                    if (base + k >= STAB_SUP_POOL || k >= KSUP_MAX) { overflow = true; break; }
-                    sup_id[base + k] = (uint8_t)t;
-                    k++;
-                }
+                if (!g.support(cur, t, r)) continue;
+                if (base + k >= STAB_SUP_POOL || k >= KSUP_MAX) { flags |= PCT_FLAG_SUPPORT_OVERFLOW; return 0; }
+                sup_id[base + k] = (uint8_t)t;
+                if (k < KSUP_SMALL) { lrect[k][0] = r[0]; lrect[k][1] = r[1]; lrect[k][2] = r[2]; lrect[k][3] = r[3]; }
+                k++;
             }
-            if (overflow) { flags |= 32; return STAB_FALSE; }
             f.k = (uint8_t)k;
             f.i = 0;
             if (k == 0) { depth--; continue; }  // return True
-            // --- polygon test ---
-            bool inside;
-            {
-                double lpx[4 * KSUP_SMALL], lpy[4 * KSUP_SMALL];
-                uint8_t lorder[4 * KSUP_SMALL], lhl[8 * KSUP_SMALL], lhu[4 * KSUP_SMALL + 4];
-                const bool small = k <= KSUP_SMALL;
-                if (!small) { while (atomicCAS(lock, 0, 1) != 0) { } __threadfence_block(); }
-                double *px = small ? lpx : big->px, *py = small ? lpy : big->py;
-                uint8_t *order = small ? lorder : big->order, *hl = small ? lhl : big->hl, *hu = small ? lhu : big->hu;
-                for (int s = 0; s < k; s++) {
-                    double x1, y1, x2, y2;
-                    g.support_rect(cur, sup_id[base + s], x1, y1, x2, y2);
-                    // combine_contact_points order: (x1,y1) (x1,y2) (x2,y1) (x2,y2); perturb x += y*1e-6 (convex_hull.py:43)
-                    double t1 = y1 * 1e-6, t2 = y2 * 1e-6;
-                    px[4 * s + 0] = x1 + t1; py[4 * s + 0] = y1;
-                    px[4 * s + 1] = x1 + t2; py[4 * s + 1] = y2;
-                    px[4 * s + 2] = x2 + t1; py[4 * s + 2] = y1;
-                    px[4 * s + 3] = x2 + t2; py[4 * s + 3] = y2;
-                }
-                int m = hull_indices(px, py, 4 * k, order, hl, hu);
-                inside = pip_shrunk(px, py, hl, m, f.st.cx, f.st.cy);
-                if (!small) { __threadfence_block(); atomicExch(lock, 0); }
+            const bool small = k <= KSUP_SMALL;
+            double (*rect)[4] = lrect;
+            double *px = lpx, *py = lpy;
+            uint8_t *order = lorder, *hl = lhl, *hu = lhu;
+            if (!small) {  // rare: serialise the lanes of this env on the per-env HBM scratch
+                while (atomicCAS(lock, 0, 1) != 0) { }
+                __threadfence_block();
+                rect = big->rect; px = big->px; py = big->py; order = big->order; hl = big->hl; hu = big->hu;
+#pragma unroll 1
+                for (int s = 0; s < k; s++) g.support(cur, sup_id[base + s], rect[s]);
             }
-            if (!inside) return STAB_FALSE;
-            // --- distribution ---
-            f.whole = 1;
-            if (k == 1) {
-                sup_m[base] = f.st.m;
-            } else {
-                int direct = -1;
-                for (int s = 0; s < k; s++) {
-                    double x1, y1, x2, y2;
-                    g.support_rect(cur, sup_id[base + s], x1, y1, x2, y2);
-                    if (g.strictly_inside(f.st.cx, f.st.cy, x1, y1, x2, y2)) { direct = s; break; }
-                }
-                if (direct >= 0) {
-                    for (int s = 0; s < k; s++) sup_m[base + s] = (s == direct) ? f.st.m : 0.0;
-                    f.whole = 2;  // non-direct supports get a zero-mass load (centre irrelevant numerically)
-                } else if (k == 2) {
-                    f.whole = 0;
-                    double x1, y1, x2, y2;
-                    g.support_rect(cur, sup_id[base + 0], x1, y1, x2, y2);
-                    double c0x = (x1 + x2) / 2, c0y = (y1 + y2) / 2;
-                    g.support_rect(cur, sup_id[base + 1], x1, y1, x2, y2);
-                    double c1x = (x1 + x2) / 2, c1y = (y1 + y2) / 2;
-                    double lx = c0x - c1x, ly = c0y - c1y;
-                    double len = sqrt(fma(ly, ly, lx * lx));
-                    double len2 = len * len;
-                    lx = lx / len2; ly = ly / len2;
-                    double r0 = fabs(dot2(f.st.cx - c1x, f.st.cy - c1y, lx, ly));
-                    double r1 = fabs(dot2(f.st.cx - c0x, f.st.cy - c0y, lx, ly));
-                    sup_m[base + 0] = f.st.m * r0;
-                    sup_m[base + 1] = f.st.m * r1;
-                } else {
-                    f.whole = 0;
-                    double lR[KSUP_SMALL * KSUP_SMALL], lV[KSUP_SMALL * KSUP_SMALL], ly_[KSUP_SMALL], lrow[KSUP_SMALL], lx_[KSUP_SMALL];
-                    const bool small = k <= KSUP_SMALL;
-                    if (!small) { while (atomicCAS(lock, 0, 1) != 0) { } __threadfence_block(); }
-                    LsWork w;
-                    w.R = small ? lR : big->R; w.V = small ? lV : big->V; w.y = small ? ly_ : big->y;
-                    w.row = small ? lrow : big->row; w.x = small ? lx_ : big->x; w.ld = small ? KSUP_SMALL : KSUP_MAX;
-                    ls_init(w, k);
-                    int rows = 0;
-                    for (int a = 0; a < k - 1; a++) {
-                        double x1, y1, x2, y2;
-                        g.support_rect(cur, sup_id[base + a], x1, y1, x2, y2);
-                        double cax = (x1 + x2) / 2, cay = (y1 + y2) / 2;
-                        for (int b = a + 1; b < k; b++) {
-                            g.support_rect(cur, sup_id[base + b], x1, y1, x2, y2);
-                            double cbx = (x1 + x2) / 2, cby = (y1 + y2) / 2;
-                            for (int t = 0; t < k; t++) w.row[t] = 0;
-                            double lx = cax - cbx, ly = cay - cby;
-                            double molecular = dot2(f.st.cx - cax, f.st.cy - cay, lx, ly);
-                            if (molecular != 0) {
-                                double r = fabs(dot2(f.st.cx - cbx, f.st.cy - cby, lx, ly)) / molecular;
-                                w.row[a] = 1;
-                                w.row[b] = -r;
-                            }
-                            ls_add_row(w, k, 0.0);
-                            rows++;
+            // combine_contact_points order: (x1,y1) (x1,y2) (x2,y1) (x2,y2); perturb x += y*1e-6 (convex_hull.py:43)
+#pragma unroll 1
+            for (int s = 0; s < k; s++) {
+                const double x1 = rect[s][0], y1 = rect[s][1], x2 = rect[s][2], y2 = rect[s][3];
+                const double t1 = y1 * 1e-6, t2 = y2 * 1e-6;
+                px[4 * s + 0] = x1 + t1; py[4 * s + 0] = y1;
+                px[4 * s + 1] = x1 + t2; py[4 * s + 1] = y2;
+                px[4 * s + 2] = x2 + t1; py[4 * s + 2] = y1;
+                px[4 * s + 3] = x2 + t2; py[4 * s + 3] = y2;
+            }
+            const int m = hull_indices(px, py, 4 * k, order, hl, hu);
+            bool ok = pip_shrunk(px, py, hl, m, f.st.cx, f.st.cy);
+            if (ok) {
+                // --- distribution ---
+                f.whole = 1;
+                if (k == 1) sup_m[base] = f.st.m;
+                else {
+                    int direct = -1;
+#pragma unroll 1
+                    for (int s = 0; s < k; s++)
+                        if (g.strictly_inside(f.st.cx, f.st.cy, rect[s])) { direct = s; break; }
+                    if (direct >= 0) {
+#pragma unroll 1
+                        for (int s = 0; s < k; s++) sup_m[base + s] = (s == direct) ? f.st.m : 0.0;
+                        f.whole = 2;
+                    } else {
+                        f.whole = 0;
+                        // contact-rectangle centres (centre2D, D:space.py:371) reuse px/py (hull no longer needed)
+#pragma unroll 1
+                        for (int s = 0; s < k; s++) {
+                            px[s] = (rect[s][0] + rect[s][2]) * 0.5;  // (x1 + x2) / 2, exact
+                            py[s] = (rect[s][1] + rect[s][3]) * 0.5;
+                        }
+                        if (k == 2) {
+                            double lx = px[0] - px[1], ly = py[0] - py[1];
+                            const double len = dsqrt(fma(ly, ly, lx * lx));
+                            const double len2 = len * len;
+                            lx = ddiv(lx, len2); ly = ddiv(ly, len2);
+                            sup_m[base + 0] = f.st.m * fabs(dot2(f.st.cx - px[1], f.st.cy - py[1], lx, ly));
+                            sup_m[base + 1] = f.st.m * fabs(dot2(f.st.cx - px[0], f.st.cy - py[0], lx, ly));
+                        } else {
+                            double lR[KSUP_SMALL * KSUP_SMALL], lV[KSUP_SMALL * KSUP_SMALL], ly_[KSUP_SMALL], lrow[KSUP_SMALL], lx_[KSUP_SMALL];
+                            LsWork w;
+                            w.R = small ? lR : big->R; w.V = small ? lV : big->V; w.y = small ? ly_ : big->y;
+                            w.row = small ? lrow : big->row; w.x = small ? lx_ : big->x; w.ld = small ? KSUP_SMALL : KSUP_MAX;
+                            lstsq_ratios(w, k, px, py, f.st.cx, f.st.cy);
+#pragma unroll 1
+                            for (int s = 0; s < k; s++) sup_m[base + s] = f.st.m * w.x[s];
                         }
                     }
-                    for (int t = 0; t < k; t++) w.row[t] = 1;
-                    ls_add_row(w, k, 1.0);
-                    rows++;
-                    ls_solve(w, k, rows);
-                    for (int s = 0; s < k; s++) sup_m[base + s] = f.st.m * w.x[s];
-                    if (!small) { __threadfence_block(); atomicExch(lock, 0); }
+                }
+                if (real) {
+                    // persist the loads: up_edges[self] = Stack(...) for every support, in support order
+#pragma unroll 1
+                    for (int s = 0; s < k; s++) {
+                        Stack4 e;
+                        e.cx = f.st.cx; e.cy = f.st.cy; e.cz = f.st.cz;
+                        if (!f.whole) { e.cx = px[s]; e.cy = py[s]; }
+                        e.m = sup_m[base + s];
+                        int pos = -1;
+#pragma unroll 1
+                        for (int q = 0; q < pool.n; q++)
+                            if (pool.upper[q] == f.node && pool.lower[q] == sup_id[base + s]) { pos = q; break; }
+                        if (pos < 0) {
+                            if (pool.n >= EDGE_MAX) { flags |= PCT_FLAG_EDGE_OVERFLOW; ok = false; break; }
+                            pos = pool.n++;
+                            pool.upper[pos] = f.node;
+                            pool.lower[pos] = sup_id[base + s];
+                        }
+                        pool.st[pos] = e;
+                    }
                 }
             }
-            if (REAL) {
-                // persist the loads: up_edges[self] = Stack(...) for every support, in support order
-                for (int s = 0; s < k; s++) {
-                    Stack4 e;
-                    if (f.whole) { e.cx = f.st.cx; e.cy = f.st.cy; e.cz = f.st.cz; }
-                    else {
-                        double x1, y1, x2, y2;
-                        g.support_rect(cur, sup_id[base + s], x1, y1, x2, y2);
-                        e.cx = (x1 + x2) / 2; e.cy = (y1 + y2) / 2; e.cz = f.st.cz;
-                    }
-                    e.m = sup_m[base + s];
-                    int pos = -1;
-                    for (int q = 0; q < pool.n; q++)
-                        if (pool.upper[q] == f.node && pool.lower[q] == sup_id[base + s]) { pos = q; break; }
-                    if (pos < 0) {
-                        if (pool.n >= EDGE_MAX) { flags |= 16; return STAB_FALSE; }
-                        pos = pool.n++;
-                        pool.upper[pos] = f.node;
-                        pool.lower[pos] = sup_id[base + s];
-                    }
-                    pool.st[pos] = e;
-                }
-            }
-            continue;  // fall into CHILD phase on the next iteration
+            if (!small) { __threadfence_block(); atomicExch(lock, 0); }
+            if (!ok) return 0;
+            continue;  // CHILD phase next iteration
         }
         // ---------------- CHILD: recurse into support f.i ----------------
         if (f.i == f.k) { depth--; continue; }  // all supports passed -> True
-        if (depth + 1 >= STAB_DEPTH) { flags |= 32; return STAB_FALSE; }
+        if (depth + 1 >= STAB_DEPTH) { flags |= PCT_FLAG_SUPPORT_OVERFLOW; return 0; }
         const int s = f.i++;
         const int sid = sup_id[f.base + s];
-        StabNode sb;
+        Node sb;
         g.node_box(sid, sb);
         // calculate_new_com (D:space.py:51-71)
-        double ccx = (sb.lx + sb.dx / 2) * sb.mass, ccy = (sb.ly + sb.dy / 2) * sb.mass, ccz = (sb.lz + sb.dz / 2) * sb.mass;
-        double mm = sb.mass;
+        double ccx, ccy, ccz, mm = sb.mass;
+        g.centre(sb, ccx, ccy, ccz);
+        ccx *= mm; ccy *= mm; ccz *= mm;
+#pragma unroll 1
         for (int q = 0; q < pool.n; q++) {
             if (pool.lower[q] != sid) continue;
-            if (!REAL && pool.upper[q] == f.node) continue;  // `involved` path member: its real load is replaced by the virtual one
-            Stack4 e = pool.st[q];
+            if (!real && pool.upper[q] == f.node) continue;  // `involved` path member: its real load is replaced by the virtual one
+            const Stack4 e = pool.st[q];
             ccx += e.cx * e.m; ccy += e.cy * e.m; ccz += e.cz * e.m;
             mm += e.m;
         }
-        if (!REAL) {
-            double vm = sup_m[f.base + s];
-            if (f.whole != 2 || vm != 0.0) {  // zero-mass loads add +0.0: skipped (exact)
-                double vx, vy;
-                if (f.whole) { vx = f.st.cx; vy = f.st.cy; }
-                else {
-                    // centre2D of this support's contact rectangle with the parent
-                    StabNode par;
-                    if (f.node != NODE_NEW) g.node_box(f.node, par);
-                    else par = root;
-                    double x1, y1, x2, y2;
-                    g.support_rect(par, sid, x1, y1, x2, y2);
-                    vx = (x1 + x2) / 2; vy = (y1 + y2) / 2;
+        if (!real) {
+            const double vm = sup_m[f.base + s];
+            if (f.whole != 2 || vm != 0.0) {  // zero-mass loads of the direct-edge case add +0.0: skipped (exact)
+                double vx = f.st.cx, vy = f.st.cy;
+                if (!f.whole) {  // centre2D of this support's contact rectangle with the parent
+                    double r[4];
+                    g.support(cur, sid, r);
+                    vx = (r[0] + r[2]) * 0.5; vy = (r[1] + r[3]) * 0.5;
                 }
                 ccx += vx * vm; ccy += vy * vm; ccz += f.st.cz * vm;
                 mm += vm;
             }
         }
-        ccx /= mm; ccy /= mm; ccz /= mm;
         StabFrame &c = fr[depth + 1];
-        c.st = Stack4{ccx, ccy, ccz, mm};
+        c.st.cx = ddiv(ccx, mm); c.st.cy = ddiv(ccy, mm); c.st.cz = ddiv(ccz, mm); c.st.m = mm;
         c.node = (uint8_t)sid;
         c.base = (uint8_t)(f.base + f.k);
         c.k = 0xFF; c.i = 0; c.whole = 1;
         depth++;
     }
-    return STAB_TRUE;
+    return 1;
 }
 
 }  // namespace pct
