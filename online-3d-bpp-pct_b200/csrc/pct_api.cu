@@ -154,8 +154,9 @@ static int launch(pct_handle h, int mode, const void *actions, int action_f64, c
     p.actions = actions; p.action_f64 = action_f64; p.leaf_idx = leaf_idx;
     p.obs = obs; p.obs_f64 = h->cfg.obs_dtype == PCT_F64;
     p.reward = rew; p.done = done; p.info = info; p.mode = mode;
+    p.dbg = (long long *)h->dbg;
     CK(h, launch_discrete(p, st));
-    h->launches++;
+    h->launches += discrete_kernels_per_step();
     return PCT_OK;
 }
 
@@ -266,5 +267,7 @@ int64_t pct_state_bytes_per_env(pct_handle h) {
     return (int64_t)(sizeof(DEnvHot) + sizeof(DEnvCold));
 }
 int64_t pct_kernel_launches(pct_handle h) { return h ? h->launches : 0; }
+/* debug: device buffer of n_envs x 8 int64 phase timers (library built with -DPCT_PHASE_TIMERS) */
+void pct_debug_set_timer_buffer(pct_handle h, void *d_buf) { if (h) h->dbg = d_buf; }
 
 }  // extern "C"

@@ -68,18 +68,23 @@ struct GeomD {
 // Candidate keys are canonical integers: xs | ys << B | zs << 2B | rot << 3B  (rot = first rotation index with
 // the same oriented dims).  B = 4 bits when every container side is <= 16 (16-bit table slots), else 8 bits
 // (32-bit slots).
-template <typename SlotT>
+// The CPython-set emulation walks table sizes 8 -> 32 -> 128 -> 512 -> 2048, alternating between two buffers:
+// A holds the 8 / 128 / 2048 stages, B the 32 / 512 stages.  BIGSM = true keeps the 2048 stage in shared memory
+// (setting 2: 6 orientations, hundreds of candidates per step); BIGSM = false (settings 1/3: <= 306 candidates in
+// practice) keeps A at 128 slots and spills the rare 2048 stage to the env's cold record in HBM, which lets 28
+// warps (= 4096 envs / 148 SMs) be resident per SM.
+template <typename SlotT, bool BIGSM>
 struct Lay {
+    static constexpr int A_SLOTS = BIGSM ? TAB_A : 128;
     static constexpr int HOT = 0;
     static constexpr int TAB_A_OFF = sizeof(DEnvHot);
-    static constexpr int TAB_B_OFF = TAB_A_OFF + TAB_A * sizeof(SlotT);
+    static constexpr int TAB_B_OFF = TAB_A_OFF + A_SLOTS * sizeof(SlotT);
     static constexpr int LEAF = TAB_B_OFF + TAB_B * sizeof(SlotT);  // NL_MAX x 6 x i16
     static constexpr int MISC = LEAF + NL_MAX * 12;                 // mbarrier (8) + lock (4) + pad (4) + RotTab (32)
     static constexpr int PER_WARP = MISC + 48;
     static constexpr int BITS = sizeof(SlotT) == 2 ? 4 : 8;
-    static constexpr SlotT EMPTY = (SlotT)~(SlotT)0;
     static_assert(TAB_A_OFF % 16 == 0 && PER_WARP % 16 == 0, "alignment");
-    static_assert(E_MAX * 12 <= TAB_A * sizeof(SlotT), "EMS temp aliases table A");
+    static_assert(E_MAX * 12 <= MISC - TAB_A_OFF, "EMS temp aliases tables + leaf buffer");
 };
 
 struct RotTab {   // per env/item: oriented dims of the R rotations (D:space.py:540-562), validity, canonical index
@@ -203,12 +208,13 @@ __device__ __noinline__ int genems_warp(int16_t (*ems)[6], const int n0, int16_t
         if (i < n) {
 #pragma unroll
             for (int t = 0; t < 6; t++) a[t] = tmp[i][t];
-            keep = true;
-#pragma unroll 1
+            int hit = 0;
+#pragma unroll 4
             for (int j = 0; j < n; j++) {
                 const int16_t *b = tmp[j];
-                if (j != i && a[0] >= b[0] && a[1] >= b[1] && a[2] >= b[2] && a[3] <= b[3] && a[4] <= b[4] && a[5] <= b[5]) { keep = false; break; }
+                hit |= (int)(j != i && a[0] >= b[0] && a[1] >= b[1] && a[2] >= b[2] && a[3] <= b[3] && a[4] <= b[4] && a[5] <= b[5]);
             }
+            keep = !hit;
         }
         const uint32_t bm = __ballot_sync(FULL, keep);
         if (keep) {
@@ -231,24 +237,30 @@ __device__ __forceinline__ void table_insert_clean(SlotT *tab, uint32_t mask, ui
 #pragma unroll 1
     for (;;) {
         const int probes = (i + 9 <= mask) ? 9 : 0;
-#pragma unroll 1
-        for (int j = 0; j <= probes; j++)
-            if (tab[i + j] == Lay<SlotT>::EMPTY) {
-                if (lane == 0) tab[i + j] = key;
-                __syncwarp();
-                return;
-            }
+        // lanes 0..probes inspect slots i..i+probes in one shared-memory access
+        const bool empty = lane <= probes && tab[i + lane] == (SlotT)~(SlotT)0;
+        const uint32_t em = __ballot_sync(FULL, empty);
+        if (em) {
+            if (lane == 0) tab[i + __ffs(em) - 1] = key;
+            __syncwarp();
+            return;
+        }
         perturb >>= 5;
         i = (uint32_t)((uint64_t)i * 5 + 1 + perturb) & mask;
     }
 }
 
-// returns the candidate count; the ordered keys end up at the start of `out`
+// returns the candidate count; the ordered keys end up at the start of `out`.
+// Inserting a key that is already in the set is a no-op, so only FIRST occurrences have to go through the
+// order-defining serial insertion: every lane first looks its key up in the current table (read-only, the
+// lookup of a present key follows exactly the probe sequence that placed it), duplicates inside the 32-wide
+// chunk are collapsed onto their lowest lane with __match_any_sync, and the surviving new keys are inserted
+// in lane (= reference insertion) order by the whole warp with set_insert_clean semantics.
 template <typename SlotT>
-__device__ __noinline__ int build_candidates(const int16_t (*ems)[6], int n_ems, const RotTab *rt, int R, SlotT *tabA, SlotT *tabB, SlotT *&out,
-                                             int lane, int &flags) {
-    constexpr int BITS = Lay<SlotT>::BITS;
-    constexpr SlotT EMPTY = Lay<SlotT>::EMPTY;
+__device__ __noinline__ int build_candidates(const int16_t (*ems)[6], int n_ems, const RotTab *rt, int R, SlotT *tabA, SlotT *tabB, SlotT *tabBig,
+                                             SlotT *&out, int lane, int &flags) {
+    constexpr int BITS = sizeof(SlotT) == 2 ? 4 : 8;
+    constexpr SlotT EMPTY = (SlotT)~(SlotT)0;
     SlotT *tab = tabA;
     uint32_t mask = 7;
     int fill = 0;
@@ -261,7 +273,7 @@ __device__ __noinline__ int build_candidates(const int16_t (*ems)[6], int n_ems,
         const int r = base + lane;
         bool valid = false;
         uint64_t hash = 0;
-        uint32_t key = 0;
+        uint32_t key = 0xFFFFFFFFu;
         if (r < raw) {
             const int q = r & 3, er = r >> 2;
             const int rot = er % R, ei = er / R;
@@ -277,40 +289,37 @@ __device__ __noinline__ int build_candidates(const int16_t (*ems)[6], int n_ems,
                 }
             }
         }
+        // first occurrence inside the chunk
+        const uint32_t same = __match_any_sync(FULL, key);
+        if (valid && (same & ((1u << lane) - 1))) valid = false;
+        // already in the set?  (set_add_entry probe sequence, read-only)
+        if (valid) {
+            uint64_t perturb = hash;
+            uint32_t i = (uint32_t)hash & mask;
+            bool open = true;
+            while (open) {
+                const int probes = (i + 9 <= mask) ? 9 : 0;
+                for (int j = 0; j <= probes; j++) {
+                    const SlotT e = tab[i + j];
+                    if (e == EMPTY) { open = false; break; }
+                    if (e == (SlotT)key) { open = false; valid = false; break; }
+                }
+                perturb >>= 5;
+                i = (uint32_t)((uint64_t)i * 5 + 1 + perturb) & mask;
+            }
+        }
         uint32_t vm = __ballot_sync(FULL, valid);
 #pragma unroll 1
         while (vm) {
             const int k = __ffs(vm) - 1;
             vm &= vm - 1;
-            const uint64_t h = __shfl_sync(FULL, hash, k);
-            const SlotT ky = (SlotT)__shfl_sync(FULL, key, k);
-            // set_add_entry (setobject.c), uniform across the warp
-            uint64_t perturb = h;
-            uint32_t i = (uint32_t)h & mask;
-            int state = 0;  // 1 inserted, 2 already present
-#pragma unroll 1
-            while (!state) {
-                const int probes = (i + 9 <= mask) ? 9 : 0;
-#pragma unroll 1
-                for (int j = 0; j <= probes; j++) {
-                    const SlotT e = tab[i + j];
-                    if (e == EMPTY) {
-                        if (lane == 0) tab[i + j] = ky;
-                        state = 1;
-                        break;
-                    }
-                    if (e == ky) { state = 2; break; }
-                }
-                perturb >>= 5;
-                i = (uint32_t)((uint64_t)i * 5 + 1 + perturb) & mask;
-            }
-            __syncwarp();
-            if (state == 1 && (uint32_t)(++fill) * 5 >= mask * 3) {
+            table_insert_clean<SlotT>(tab, mask, __shfl_sync(FULL, hash, k), (SlotT)__shfl_sync(FULL, key, k), lane);
+            if ((uint32_t)(++fill) * 5 >= mask * 3) {
                 // set_table_resize(used * 4): smallest power of two > 4 * used, re-insert in slot order
                 uint32_t newsize = 8;
                 while (newsize <= (uint32_t)fill * 4) newsize <<= 1;
                 if (newsize > TAB_A) { flags |= PCT_FLAG_CAND_OVERFLOW; stop = true; break; }
-                SlotT *nt = (tab == tabA) ? tabB : tabA;
+                SlotT *nt = newsize == TAB_A ? tabBig : ((tab == tabA) ? tabB : tabA);
                 for (uint32_t t = lane; t < newsize; t += 32) nt[t] = EMPTY;
                 __syncwarp();
 #pragma unroll 1
@@ -380,7 +389,7 @@ __device__ __noinline__ void reset_space(DEnvHot *hot, const DParams &p, int e, 
 
 template <typename OT>
 __device__ __noinline__ void write_obs(const DParams &p, int e, const DEnvHot *hot, const DEnvCold *cold, const int16_t (*leaf)[6], int n_leaf,
-                                       int lane) {
+                                       int tid, int nthreads) {
     OT *obs = (OT *)p.obs + (size_t)e * (size_t)((p.nb + p.nl + 1) * 9);
     const int n_box = hot->h.n_box;
     const int total = (p.nb + p.nl + 1) * 9;
@@ -388,38 +397,44 @@ __device__ __noinline__ void write_obs(const DParams &p, int e, const DEnvHot *h
     if (s1 < s0) { int t = s0; s0 = s1; s1 = t; }
     if (s2 < s1) { int t = s1; s1 = s2; s2 = t; }
     if (s1 < s0) { int t = s0; s0 = s1; s1 = t; }
-#pragma unroll 1
-    for (int f = lane; f < total; f += 32) {
-        const int row = f / 9, col = f - row * 9;
-        double v = 0;
+    const OT den = (OT)hot->h.next_den;
+    const bool s3 = p.setting == 3;
+    // flat index f = nthreads*it + tid; (row, col) advance by (nthreads / 9, nthreads % 9) per iteration
+    int row = tid / 9, col = tid - row * 9;
+    const int dr = nthreads / 9, dc = nthreads - dr * 9;
+#pragma unroll 4
+    for (int f = tid; f < total; f += nthreads) {
+        OT v = 0;
         if (row < p.nb) {
             if (row < n_box) {
-                if (col < 6) v = hot->box[row][col];
-                else if (col == 6) v = p.setting == 3 ? cold->density[row] : 1.0;
+                if (col < 6) v = (OT)hot->box[row][col];
+                else if (col == 6) v = s3 ? (OT)cold->density[row] : (OT)1;
                 else if (col == 8) v = 1;
             } else if (row == 0 && col == 8) v = 1;  // D:space.py:294-295
         } else if (row < p.nb + p.nl) {
             const int k = row - p.nb;
             if (k < n_leaf) {
-                if (col < 5) v = leaf[k][col];
-                else if (col == 5) v = p.H;  // D:bin3D.py:128 — bin height, not ze
+                if (col < 5) v = (OT)leaf[k][col];
+                else if (col == 5) v = (OT)p.H;  // D:bin3D.py:128 — bin height, not ze
                 else if (col == 8) v = 1;
             }
         } else {
-            if (col == 0) v = hot->h.next_den;
-            else if (col == 3) v = s0;
-            else if (col == 4) v = s1;
-            else if (col == 5) v = s2;
+            if (col == 0) v = den;
+            else if (col == 3) v = (OT)s0;
+            else if (col == 4) v = (OT)s1;
+            else if (col == 5) v = (OT)s2;
             else if (col == 8) v = 1;
         }
-        obs[f] = (OT)v;
+        obs[f] = v;
+        row += dr; col += dc;
+        if (col >= 9) { col -= 9; row++; }
     }
 }
 
 // resting height of a footprint: max top over the placed boxes it overlaps (== np.max(plain[lx:lx+x, ly:ly+y]))
 __device__ __forceinline__ int rest_height(const int16_t (*box)[6], int first, int n, int stride, int lx, int ly, int hx, int hy) {
     int mh = 0;
-#pragma unroll 1
+#pragma unroll 4
     for (int t = first; t < n; t += stride) {
         const int16_t *b = box[t];
         if (lx < b[3] && hx > b[0] && ly < b[4] && hy > b[1]) mh = max(mh, (int)b[5]);
@@ -427,28 +442,35 @@ __device__ __forceinline__ int rest_height(const int16_t (*box)[6], int first, i
     return mh;
 }
 
-// ---- the kernel -------------------------------------------------------------------------------------------
-template <typename OT, bool STAB, typename SlotT>
-__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) pct_discrete_kernel(const DParams p) {
-    typedef Lay<SlotT> LY;
+// ======================================================================================================
+// The step is a pipeline of three kernels (plus the optional synthetic-policy kernel).  A monolithic
+// one-warp-per-env kernel was measured first (profiles/r1_monolithic_*.txt): it was instruction-fetch bound
+// (each warp streamed ~80 KB of SASS once per step, warps of an SM sat in different phases) and its duration
+// was the latency of the slowest env.  Splitting by phase keeps every kernel's code small and hot in the
+// instruction cache and lets the heavy phase run one THREAD per candidate leaf.
+//   K1 apply      warp / env    action decode, real placement (+ load-propagating stability), EMS update,
+//                               reward / done / info, auto-reset, next item
+//   K2 candidates warp / env    EMSPoint in CPython-set order -> ordered candidate list in HBM
+//   K3 feas_emit  block / env   thread per candidate: bounds, resting height, virtual stability;
+//                               ordered compaction into the leaf slots; observation write
+// ======================================================================================================
+constexpr int K1_SM_PER_WARP = sizeof(DEnvHot) + E_MAX * 12 + 16;  // record + EMS temp + mbarrier/lock
+static_assert(K1_SM_PER_WARP % 16 == 0, "alignment");
+
+template <bool STAB>
+__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) pct_apply_kernel(const DParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int e = blockIdx.x * WARPS_PER_BLOCK + warp;
     if (e >= p.n_envs) return;
-    unsigned char *sm = smem_raw + (size_t)warp * LY::PER_WARP;
-    DEnvHot *hot = (DEnvHot *)(sm + LY::HOT);
-    SlotT *tabA = (SlotT *)(sm + LY::TAB_A_OFF), *tabB = (SlotT *)(sm + LY::TAB_B_OFF);
-    int16_t (*ems_tmp)[6] = (int16_t (*)[6])(sm + LY::TAB_A_OFF);
-    int16_t (*leaf)[6] = (int16_t (*)[6])(sm + LY::LEAF);
-    uint64_t *mbar = (uint64_t *)(sm + LY::MISC);
-    int *lock = (int *)(sm + LY::MISC + 8);
-    RotTab *rt = (RotTab *)(sm + LY::MISC + 16);
-    static_assert(sizeof(RotTab) <= 32, "RotTab slot");
+    unsigned char *sm = smem_raw + (size_t)warp * K1_SM_PER_WARP;
+    DEnvHot *hot = (DEnvHot *)sm;
+    int16_t (*ems_tmp)[6] = (int16_t (*)[6])(sm + sizeof(DEnvHot));
+    uint64_t *mbar = (uint64_t *)(sm + sizeof(DEnvHot) + E_MAX * 12);
+    int *lock = (int *)(mbar + 1);
     DEnvHot *ghot = p.hot + e;
     DEnvCold *cold = p.cold + e;
-    EdgePool pool{cold->e_upper, cold->e_lower, cold->e_st, 0};
     DHdr &h = hot->h;
-
     if (lane == 0) *lock = 0;
     float reward = 0.f;
     int done = 0;
@@ -533,8 +555,8 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) pct_discrete_kernel(cons
                     int fl = 0;
                     GeomD g{hot->box, n_box0, p.setting == 3 ? cold->density : nullptr};
                     NodeD root{lx, ly, max_h, x, y, z, (double)(x * y * z) * next_den0};
-                    pool.n = h.n_edge;
-                    res = stability_check<GeomD>(g, root, pool, &cold->big, lock, true, n_box0, fl);
+                    EdgePool pool{cold->e_upper, cold->e_lower, cold->e_st, h.n_edge};
+                    res = stability_check<true, GeomD>(g, root, pool, &cold->big, lock, n_box0, fl);
                     h.n_edge = pool.n;
                     h.flags |= fl;
                 }
@@ -586,66 +608,6 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) pct_discrete_kernel(cons
             reset_space(hot, p, e, lane);
         }
     }
-
-    // ---------------- cur_observation (D:bin3D.py:70-93) + get_possible_position (:100-136) ----------------
-    {
-        const int nb3[3] = {h.next_box[0], h.next_box[1], h.next_box[2]};
-        const int R = p.setting == 2 ? 6 : 2;
-        if (lane == 0) make_rot_tab(nb3, R, *rt);
-        __syncwarp();
-        SlotT *cand = nullptr;
-        int fl = 0;
-        const int n_cand = build_candidates<SlotT>(hot->ems, h.n_ems, rt, R, tabA, tabB, cand, lane, fl);
-        int n_leaf = 0;
-        const int n_box = h.n_box;
-        const double den = h.next_den;
-        GeomD g{hot->box, n_box, p.setting == 3 ? cold->density : nullptr};
-        pool.n = h.n_edge;
-        __syncwarp();
-#pragma unroll 1
-        for (int base = 0; base < n_cand && n_leaf < p.nl; base += 32) {
-            const int c = base + lane;
-            bool feas = false;
-            int xs = 0, ys = 0, zs = 0, rot = 0, sx = 0, sy = 0, sz = 0;
-            if (c < n_cand) {
-                key_unpack<LY::BITS>(cand[c], xs, ys, zs, rot);
-                sx = rt->d[rot][0]; sy = rt->d[rot][1]; sz = rt->d[rot][2];
-                // drop_box_virtual (D:space.py:393-433) + check_box (:436-454)
-                const int mh = rest_height(hot->box, 0, n_box, 1, xs, ys, xs + sx, ys + sy);
-                if (xs + sx > p.W || ys + sy > p.L) feas = false;
-                else if (mh + sz > p.H) feas = false;
-                else if (!STAB || mh == 0) feas = true;
-                else {
-                    NodeD root{xs, ys, mh, sx, sy, sz, (double)(sx * sy * sz) * den};
-                    feas = stability_check<GeomD>(g, root, pool, &cold->big, lock, false, 0, fl) != 0;
-                }
-            }
-            const uint32_t fm = __ballot_sync(FULL, feas);
-            if (feas) {
-                const int k = n_leaf + __popc(fm & ((1u << lane) - 1));
-                if (k < p.nl) {
-                    leaf[k][0] = (int16_t)xs; leaf[k][1] = (int16_t)ys; leaf[k][2] = (int16_t)zs;
-                    leaf[k][3] = (int16_t)(xs + sx); leaf[k][4] = (int16_t)(ys + sy); leaf[k][5] = (int16_t)(zs + sz);
-                }
-            }
-            n_leaf += __popc(fm);
-        }
-        if (n_leaf > p.nl) n_leaf = p.nl;
-        fl = __reduce_or_sync(FULL, fl);
-        __syncwarp();
-        if (lane == 0) {
-            h.n_leaf = n_leaf;
-            h.n_cand = n_cand;
-            h.flags |= fl;
-        }
-        info.n_leaf = n_leaf;
-        info.n_cand = n_cand;
-        info.n_ems = h.n_ems;
-        // persist the emitted leaves for the leaf-index action path
-        for (int t = lane; t < n_leaf * 6; t += 32) ((int16_t *)cold->leaf)[t] = ((int16_t *)leaf)[t];
-        __syncwarp();
-        write_obs<OT>(p, e, hot, cold, leaf, n_leaf, lane);
-    }
     fence_proxy_async();
     __syncwarp();
     if (lane == 0) {
@@ -658,6 +620,147 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) pct_discrete_kernel(cons
     }
 }
 
+// ---- K2: candidate leaves -----------------------------------------------------------------------------------
+template <typename SlotT, bool BIGSM>
+__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) pct_candidates_kernel(const DParams p) {
+    typedef Lay<SlotT, BIGSM> LY;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int e = blockIdx.x * WARPS_PER_BLOCK + warp;
+    if (e >= p.n_envs) return;
+    unsigned char *sm = smem_raw + (size_t)warp * LY::PER_WARP;
+    DEnvHot *hot = (DEnvHot *)(sm + LY::HOT);
+    SlotT *tabA = (SlotT *)(sm + LY::TAB_A_OFF), *tabB = (SlotT *)(sm + LY::TAB_B_OFF);
+    uint64_t *mbar = (uint64_t *)(sm + LY::MISC);
+    RotTab *rt = (RotTab *)(sm + LY::MISC + 16);
+    static_assert(sizeof(RotTab) <= 32, "RotTab slot");
+    DEnvHot *ghot = p.hot + e;
+    DEnvCold *cold = p.cold + e;
+    if (lane == 0) {
+        mbar_init(mbar, 1);
+        fence_proxy_async();
+    }
+    __syncwarp();
+    if (lane == 0) {
+        mbar_expect_tx(mbar, (uint32_t)sizeof(DEnvHot));
+        tma_load_1d(hot, ghot, (uint32_t)sizeof(DEnvHot), mbar);
+    }
+    mbar_wait(mbar, 0);
+    __syncwarp();
+    const DHdr &h = hot->h;
+    const int nb3[3] = {h.next_box[0], h.next_box[1], h.next_box[2]};
+    const int R = p.setting == 2 ? 6 : 2;
+    if (lane == 0) make_rot_tab(nb3, R, *rt);
+    __syncwarp();
+    SlotT *cand = nullptr;
+    int fl = 0;
+    const int n_cand = build_candidates<SlotT>(hot->ems, h.n_ems, rt, R, tabA, tabB, BIGSM ? tabA : (SlotT *)cold->tab_big, cand, lane, fl);
+    SlotT *out = (SlotT *)cold->cand;
+    for (int t = lane; t < n_cand; t += 32) out[t] = cand[t];
+    if (lane == 0) {
+        ghot->h.n_cand = n_cand;
+        if (fl) ghot->h.flags = h.flags | fl;
+    }
+}
+
+// ---- K3: feasibility (thread per candidate) + leaf compaction + observation ------------------------------------
+constexpr int FEAS_WARPS = 2;
+constexpr int FEAS_THREADS = 32 * FEAS_WARPS;
+constexpr int K3_SMEM = sizeof(DEnvHot) + NL_MAX * 12 + 64;
+
+template <typename OT, bool STAB, typename SlotT>
+__global__ void __launch_bounds__(FEAS_THREADS) pct_feas_emit_kernel(const DParams p) {
+    constexpr int BITS = sizeof(SlotT) == 2 ? 4 : 8;
+    __shared__ __align__(16) unsigned char sm[K3_SMEM];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int e = blockIdx.x;
+    DEnvHot *hot = (DEnvHot *)sm;
+    int16_t (*leaf)[6] = (int16_t (*)[6])(sm + sizeof(DEnvHot));
+    uint64_t *mbar = (uint64_t *)(sm + sizeof(DEnvHot) + NL_MAX * 12);
+    int *lock = (int *)(mbar + 1);
+    uint32_t *wb = (uint32_t *)(mbar + 2);             // per-warp feasibility ballots of the current pass
+    RotTab *rt = (RotTab *)(sm + sizeof(DEnvHot) + NL_MAX * 12 + 32);
+    DEnvHot *ghot = p.hot + e;
+    DEnvCold *cold = p.cold + e;
+    if (tid == 0) {
+        *lock = 0;
+        mbar_init(mbar, 1);
+        fence_proxy_async();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(mbar, (uint32_t)sizeof(DEnvHot));
+        tma_load_1d(hot, ghot, (uint32_t)sizeof(DEnvHot), mbar);
+    }
+    mbar_wait(mbar, 0);
+    const DHdr &h = hot->h;
+    const int nb3[3] = {h.next_box[0], h.next_box[1], h.next_box[2]};
+    if (tid == 0) make_rot_tab(nb3, p.setting == 2 ? 6 : 2, *rt);
+    __syncthreads();
+    const int n_cand = h.n_cand, n_box = h.n_box;
+    const double den = h.next_den;
+    const SlotT *cand = (const SlotT *)cold->cand;
+    GeomD g{hot->box, n_box, p.setting == 3 ? cold->density : nullptr};
+    EdgePool pool{cold->e_upper, cold->e_lower, cold->e_st, h.n_edge};
+    int n_leaf = 0, fl = 0;
+    // ---------------- get_possible_position (D:bin3D.py:100-136): first `nl` feasible candidates in order ----------------
+#pragma unroll 1
+    for (int base = 0; base < n_cand && n_leaf < p.nl; base += FEAS_THREADS) {
+        const int c = base + tid;
+        bool feas = false;
+        int xs = 0, ys = 0, zs = 0, rot = 0, sx = 0, sy = 0, sz = 0;
+        if (c < n_cand) {
+            key_unpack<BITS>(cand[c], xs, ys, zs, rot);
+            sx = rt->d[rot][0]; sy = rt->d[rot][1]; sz = rt->d[rot][2];
+            // drop_box_virtual (D:space.py:393-433) + check_box (:436-454)
+            const int mh = rest_height(hot->box, 0, n_box, 1, xs, ys, xs + sx, ys + sy);
+            if (xs + sx > p.W || ys + sy > p.L) feas = false;
+            else if (mh + sz > p.H) feas = false;
+            else if (!STAB || mh == 0) feas = true;
+            else {
+                NodeD root{xs, ys, mh, sx, sy, sz, (double)(sx * sy * sz) * den};
+                feas = stability_check<false, GeomD>(g, root, pool, &cold->big, lock, 0, fl) != 0;
+            }
+        }
+        const uint32_t fm = __ballot_sync(FULL, feas);
+        if (lane == 0) wb[warp] = fm;
+        __syncthreads();
+        int before = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < FEAS_WARPS; w++) {
+            const int cnt = __popc(wb[w]);
+            if (w < warp) before += cnt;
+            total += cnt;
+        }
+        if (feas) {
+            const int k = n_leaf + before + __popc(fm & ((1u << lane) - 1));
+            if (k < p.nl) {
+                leaf[k][0] = (int16_t)xs; leaf[k][1] = (int16_t)ys; leaf[k][2] = (int16_t)zs;
+                leaf[k][3] = (int16_t)(xs + sx); leaf[k][4] = (int16_t)(ys + sy); leaf[k][5] = (int16_t)(zs + sz);
+            }
+        }
+        n_leaf += total;
+        __syncthreads();
+    }
+    if (n_leaf > p.nl) n_leaf = p.nl;
+    fl = __reduce_or_sync(FULL, fl);
+    if (fl && lane == 0) atomicOr(&ghot->h.flags, fl);
+    __syncthreads();
+    // persist the emitted leaves for the leaf-index action path; header / info
+    for (int t = tid; t < n_leaf * 6; t += FEAS_THREADS) ((int16_t *)cold->leaf)[t] = ((int16_t *)leaf)[t];
+    if (tid == 0) {
+        ghot->h.n_leaf = n_leaf;
+        if (p.info) {
+            p.info[e].n_leaf = n_leaf;
+            p.info[e].n_cand = n_cand;
+            p.info[e].n_ems = h.n_ems;
+            p.info[e].flags |= h.flags;
+        }
+    }
+    // ---------------- cur_observation (D:bin3D.py:70-93) ----------------
+    write_obs<OT>(p, e, hot, cold, leaf, n_leaf, tid, FEAS_THREADS);
+}
+
 // uniform-random valid-leaf policy: reads only the record headers
 __global__ void pct_policy_random_kernel(const DEnvHot *hot, int n_envs, int64_t env_id_base, uint64_t seed, int64_t t, int32_t *leaf_idx) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -667,17 +770,27 @@ __global__ void pct_policy_random_kernel(const DEnvHot *hot, int n_envs, int64_t
 }
 
 // ---- launchers ---------------------------------------------------------------------------------------------
+template <typename K>
+static cudaError_t set_smem(K kernel, size_t smem) {
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+
 template <typename OT, bool STAB, typename SlotT>
 static cudaError_t launch_t(const DParams &p, cudaStream_t st) {
+    constexpr bool BIGSM = !STAB;
     static bool attr_set = false;
-    const size_t smem = (size_t)Lay<SlotT>::PER_WARP * WARPS_PER_BLOCK;
+    const size_t smem1 = (size_t)K1_SM_PER_WARP * WARPS_PER_BLOCK;
+    const size_t smem2 = (size_t)Lay<SlotT, BIGSM>::PER_WARP * WARPS_PER_BLOCK;
     if (!attr_set) {
-        cudaError_t err = cudaFuncSetAttribute(pct_discrete_kernel<OT, STAB, SlotT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t err = set_smem(pct_apply_kernel<STAB>, smem1);
+        if (err == cudaSuccess) err = set_smem(pct_candidates_kernel<SlotT, BIGSM>, smem2);
         if (err != cudaSuccess) return err;
         attr_set = true;
     }
     const int blocks = (p.n_envs + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
-    pct_discrete_kernel<OT, STAB, SlotT><<<blocks, 32 * WARPS_PER_BLOCK, smem, st>>>(p);
+    pct_apply_kernel<STAB><<<blocks, 32 * WARPS_PER_BLOCK, smem1, st>>>(p);
+    pct_candidates_kernel<SlotT, BIGSM><<<blocks, 32 * WARPS_PER_BLOCK, smem2, st>>>(p);
+    pct_feas_emit_kernel<OT, STAB, SlotT><<<p.n_envs, FEAS_THREADS, 0, st>>>(p);
     return cudaGetLastError();
 }
 template <typename OT, bool STAB>
@@ -685,6 +798,9 @@ static cudaError_t launch_s(const DParams &p, cudaStream_t st) {
     if (p.W <= 16 && p.L <= 16 && p.H <= 16) return launch_t<OT, STAB, uint16_t>(p, st);
     return launch_t<OT, STAB, uint32_t>(p, st);
 }
+
+// number of kernels one reset / step enqueues (for pct_kernel_launches)
+int discrete_kernels_per_step() { return 3; }
 
 cudaError_t launch_discrete(const DParams &p, cudaStream_t st) {
     const bool stab = p.setting != 2;

@@ -26,5 +26,6 @@ struct pct_env_batch {
     uint8_t *d_done = nullptr;
     pct_step_info *d_info = nullptr;
     cudaStream_t own_stream = nullptr;
+    void *dbg = nullptr;
 };
 

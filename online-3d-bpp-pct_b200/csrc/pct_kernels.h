@@ -73,6 +73,8 @@ struct DEnvCold {
     double density[NB_MAX];   // per placed box (setting 3)
     uint8_t e_upper[EDGE_MAX], e_lower[EDGE_MAX];
     Stack4 e_st[EDGE_MAX];
+    uint32_t cand[1232];      // ordered candidate keys written by K2, read by K3 (<= 1228 distinct candidates)
+    uint32_t tab_big[TAB_A];  // 2048-slot stage of the set emulation when it does not live in shared memory
     BigScratch big;
 };
 
@@ -98,9 +100,10 @@ struct DParams {
     uint8_t *done;
     pct_step_info *info;
     int mode;  // 0 = reset all, 1 = step
+    long long *dbg;  // phase timers (only with -DPCT_PHASE_TIMERS)
 };
 
-size_t discrete_smem_bytes();
+int discrete_kernels_per_step();
 cudaError_t launch_discrete(const DParams &p, cudaStream_t st);
 cudaError_t launch_policy_random_discrete(const DEnvHot *hot, int n_envs, int64_t env_id_base, uint64_t seed, int64_t t, int32_t *leaf_idx,
                                           cudaStream_t st);

@@ -252,53 +252,120 @@ __device__ __noinline__ void lstsq_ratios(const LsWork &w, int k, const double *
 //   bool strictly_inside(cx, cy, const double r[4]) const         (direct-edge test)
 // ---------------------------------------------------------------------------------------------
 struct StabFrame {
-    Stack4 st;        // this node's (virtual) stack for this visit
+    Stack4 st;        // the node's stack for this visit
     uint8_t node;     // real box index, or NODE_NEW
     uint8_t base, k, i;
     uint8_t whole;    // 1: whole stack to the single support; 2: direct edge (others zero); 0: (c2d_i, st.cz) split
 };
 constexpr int NODE_NEW = 255;
 
-template <class G>
+// Single support (58 % of all visits): the "hull" of the 4 corners of one contact rectangle.
+// With P0=(x1,y1) P1=(x1,y2) P2=(x2,y1) P3=(x2,y2) perturbed by x += y*1e-6 (convex_hull.py:43) and
+// P0.x < P1.x < P2.x < P3.x (checked by the caller), ConvexHull's chain scans are fully determined:
+//   lower: [P0,P1] -> P2: slope(P0,P1) > 0 > slope(P1,P2) => pop P1 (then first==last => break), push P2;
+//          P3: slope(P0,P2) = 0 < slope(P2,P3) => keep                     => [P0,P2,P3] -> drop last
+//   upper: [P3,P2] -> P1: slope(P3,P2) > 0 > slope(P2,P1) => pop P2, push P1; P0: slope(P3,P1) = -0 < slope(P1,P0)
+//                                                                           => [P3,P1,P0] -> drop last
+// so the polygon is [P0,P2,P3,P1]; scale_down + point_in_polygen run on registers, same operation order as
+// hull_indices + pip_shrunk.
+__device__ __noinline__ bool pip_rect(double x1, double y1, double x2, double y2, double t1, double t2, double lat, double lon) {
+    // t1 = y1*1e-6, t2 = y2*1e-6 ; hull order P0,P2,P3,P1
+    const double hx[4] = {x1 + t1, x2 + t1, x2 + t2, x1 + t2};
+    const double hy[4] = {y1, y1, y2, y2};
+    const double sx = ((hx[0] + hx[1]) + hx[2]) + hx[3], sy = ((hy[0] + hy[1]) + hy[2]) + hy[3];
+    const double cx = ddiv(sx, 4.0), cy = ddiv(sy, 4.0);
+    double vx[4], vy[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        double d = hx[i] - cx;
+        vx[i] = hx[i] - d * 0.1;
+        d = hy[i] - cy;
+        vy[i] = hy[i] - d * 0.1;
+    }
+    bool odd = false;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int j = (i + 3) & 3;
+        const double a0 = vx[i] - lat, a1 = vy[i] - lon;
+        const double b0 = lat - vx[j], b1 = lon - vy[j];
+        const double m1 = a0 * b1, m2 = a1 * b0;
+        if (m1 - m2 == 0) return false;
+        if ((vy[i] < lon && vy[j] >= lon) || (vy[j] < lon && vy[i] >= lon)) {
+            const double t = ddiv(lon - vy[i], vy[j] - vy[i]);
+            const double u = t * (vx[j] - vx[i]);
+            if (vx[i] + u < lat) odd = !odd;
+        }
+    }
+    return odd;
+}
+
+// The DFS keeps the CURRENT node in registers; frames are pushed to the lane-local stack only for nodes with
+// >= 2 supports, and descending into the last (or only) support is a tail call (nothing is left to do in the
+// parent once its last child returns True).
+template <bool REAL, class G>
 __device__ __noinline__ int stability_check(const G &g, const typename G::Node &root, EdgePool &pool, BigScratch *big, int *lock,
-                                            const bool real, const int new_id, int &flags) {
+                                            const int new_id, int &flags) {
     typedef typename G::Node Node;
+    constexpr bool real = REAL;  // REAL: load-propagating update of a committed placement; else read-only feasibility check
     StabFrame fr[STAB_DEPTH];
     uint8_t sup_id[STAB_SUP_POOL];
     double sup_m[STAB_SUP_POOL];
-    // lane-local scratch for up to KSUP_SMALL supports
-    double lrect[KSUP_SMALL][4], lpx[4 * KSUP_SMALL], lpy[4 * KSUP_SMALL];
-    uint8_t lorder[4 * KSUP_SMALL], lhl[8 * KSUP_SMALL], lhu[4 * KSUP_SMALL + 4];
     const int root_id = real ? new_id : NODE_NEW;
-    int depth = 0;
-    g.centre(root, fr[0].st.cx, fr[0].st.cy, fr[0].st.cz);
-    fr[0].st.m = root.mass;
-    fr[0].node = (uint8_t)root_id;
-    fr[0].base = 0; fr[0].k = 0xFF; fr[0].i = 0; fr[0].whole = 1;
+    int depth = 0;            // number of pushed frames
+    int node = root_id, base = 0;
+    Stack4 st;
+    g.centre(root, st.cx, st.cy, st.cz);
+    st.m = root.mass;
 
 #pragma unroll 1
-    while (depth >= 0) {
-        StabFrame &f = fr[depth];
+    for (;;) {
+        // ================= ENTER(node, st) =================
         Node cur;
-        if (f.node != root_id) g.node_box(f.node, cur);
+        if (node != root_id) g.node_box(node, cur);
         else cur = root;
-        if (f.k == 0xFF) {
-            // ---------------- ENTER: supports, hull, PIP, load distribution ----------------
-            const int limit = (f.node == root_id) ? g.n_boxes() : (int)f.node;
-            const int base = f.base;
-            int k = 0;
-            double r[4];
+        const int limit = (node == root_id) ? g.n_boxes() : node;
+        int k = 0, sid0 = 0;
+        double r0[4], r[4];
 #pragma unroll 1
-            for (int t = 0; t < limit; t++) {
-                if (!g.support(cur, t, r)) continue;
-                if (base + k >= STAB_SUP_POOL || k >= KSUP_MAX) { flags |= PCT_FLAG_SUPPORT_OVERFLOW; return 0; }
-                sup_id[base + k] = (uint8_t)t;
-                if (k < KSUP_SMALL) { lrect[k][0] = r[0]; lrect[k][1] = r[1]; lrect[k][2] = r[2]; lrect[k][3] = r[3]; }
-                k++;
+        for (int t = 0; t < limit; t++) {
+            if (!g.support(cur, t, r)) continue;
+            if (base + k >= STAB_SUP_POOL || k >= KSUP_MAX) { flags |= PCT_FLAG_SUPPORT_OVERFLOW; return 0; }
+            if (k == 0) { sid0 = t; r0[0] = r[0]; r0[1] = r[1]; r0[2] = r[2]; r0[3] = r[3]; }
+            sup_id[base + k] = (uint8_t)t;
+            k++;
+        }
+        int child = -1;          // >= 0: tail-descend into this support with load (vx,vy,st.cz,vm)
+        double vx = st.cx, vy = st.cy, vm = st.m;
+        if (k == 1) {
+            const double t1 = r0[1] * 1e-6, t2 = r0[3] * 1e-6;
+            const bool fast = (r0[0] + t1 < r0[0] + t2) && (r0[0] + t2 < r0[2] + t1) && (r0[2] + t1 < r0[2] + t2);
+            bool ok;
+            if (fast) ok = pip_rect(r0[0], r0[1], r0[2], r0[3], t1, t2, st.cx, st.cy);
+            else {
+                double px[4] = {r0[0] + t1, r0[0] + t2, r0[2] + t1, r0[2] + t2}, py[4] = {r0[1], r0[3], r0[1], r0[3]};
+                uint8_t order[4], hl[8], hu[8];
+                const int m = hull_indices(px, py, 4, order, hl, hu);
+                ok = pip_shrunk(px, py, hl, m, st.cx, st.cy);
             }
-            f.k = (uint8_t)k;
-            f.i = 0;
-            if (k == 0) { depth--; continue; }  // return True
+            if (!ok) return 0;
+            if (real) {
+                int pos = -1;
+#pragma unroll 1
+                for (int q = 0; q < pool.n; q++)
+                    if (pool.upper[q] == node && pool.lower[q] == sid0) { pos = q; break; }
+                if (pos < 0) {
+                    if (pool.n >= EDGE_MAX) { flags |= PCT_FLAG_EDGE_OVERFLOW; return 0; }
+                    pos = pool.n++;
+                    pool.upper[pos] = (uint8_t)node;
+                    pool.lower[pos] = (uint8_t)sid0;
+                }
+                pool.st[pos] = st;
+            }
+            child = sid0;  // whole stack goes to the single support
+        } else if (k >= 2) {
+            // ---------- general case: hull over all contact-rectangle corners ----------
+            double lrect[KSUP_SMALL][4], lpx[4 * KSUP_SMALL], lpy[4 * KSUP_SMALL];
+            uint8_t lorder[4 * KSUP_SMALL], lhl[8 * KSUP_SMALL], lhu[4 * KSUP_SMALL + 4];
             const bool small = k <= KSUP_SMALL;
             double (*rect)[4] = lrect;
             double *px = lpx, *py = lpy;
@@ -307,9 +374,9 @@ __device__ __noinline__ int stability_check(const G &g, const typename G::Node &
                 while (atomicCAS(lock, 0, 1) != 0) { }
                 __threadfence_block();
                 rect = big->rect; px = big->px; py = big->py; order = big->order; hl = big->hl; hu = big->hu;
-#pragma unroll 1
-                for (int s = 0; s < k; s++) g.support(cur, sup_id[base + s], rect[s]);
             }
+#pragma unroll 1
+            for (int s = 0; s < k; s++) g.support(cur, sup_id[base + s], rect[s]);
             // combine_contact_points order: (x1,y1) (x1,y2) (x2,y1) (x2,y2); perturb x += y*1e-6 (convex_hull.py:43)
 #pragma unroll 1
             for (int s = 0; s < k; s++) {
@@ -321,62 +388,57 @@ __device__ __noinline__ int stability_check(const G &g, const typename G::Node &
                 px[4 * s + 3] = x2 + t2; py[4 * s + 3] = y2;
             }
             const int m = hull_indices(px, py, 4 * k, order, hl, hu);
-            bool ok = pip_shrunk(px, py, hl, m, f.st.cx, f.st.cy);
+            bool ok = pip_shrunk(px, py, hl, m, st.cx, st.cy);
+            int whole = 2;
             if (ok) {
                 // --- distribution ---
-                f.whole = 1;
-                if (k == 1) sup_m[base] = f.st.m;
-                else {
-                    int direct = -1;
+                int direct = -1;
 #pragma unroll 1
-                    for (int s = 0; s < k; s++)
-                        if (g.strictly_inside(f.st.cx, f.st.cy, rect[s])) { direct = s; break; }
-                    if (direct >= 0) {
+                for (int s = 0; s < k; s++)
+                    if (g.strictly_inside(st.cx, st.cy, rect[s])) { direct = s; break; }
+                if (direct >= 0) {
 #pragma unroll 1
-                        for (int s = 0; s < k; s++) sup_m[base + s] = (s == direct) ? f.st.m : 0.0;
-                        f.whole = 2;
+                    for (int s = 0; s < k; s++) sup_m[base + s] = (s == direct) ? st.m : 0.0;
+                } else {
+                    whole = 0;
+                    // contact-rectangle centres (centre2D, D:space.py:371) reuse px/py (hull no longer needed)
+#pragma unroll 1
+                    for (int s = 0; s < k; s++) {
+                        px[s] = (rect[s][0] + rect[s][2]) * 0.5;  // (x1 + x2) / 2, exact
+                        py[s] = (rect[s][1] + rect[s][3]) * 0.5;
+                    }
+                    if (k == 2) {
+                        double lx = px[0] - px[1], ly = py[0] - py[1];
+                        const double len = dsqrt(fma(ly, ly, lx * lx));
+                        const double len2 = len * len;
+                        lx = ddiv(lx, len2); ly = ddiv(ly, len2);
+                        sup_m[base + 0] = st.m * fabs(dot2(st.cx - px[1], st.cy - py[1], lx, ly));
+                        sup_m[base + 1] = st.m * fabs(dot2(st.cx - px[0], st.cy - py[0], lx, ly));
                     } else {
-                        f.whole = 0;
-                        // contact-rectangle centres (centre2D, D:space.py:371) reuse px/py (hull no longer needed)
+                        double lR[KSUP_SMALL * KSUP_SMALL], lV[KSUP_SMALL * KSUP_SMALL], ly_[KSUP_SMALL], lrow[KSUP_SMALL], lx_[KSUP_SMALL];
+                        LsWork w;
+                        w.R = small ? lR : big->R; w.V = small ? lV : big->V; w.y = small ? ly_ : big->y;
+                        w.row = small ? lrow : big->row; w.x = small ? lx_ : big->x; w.ld = small ? KSUP_SMALL : KSUP_MAX;
+                        lstsq_ratios(w, k, px, py, st.cx, st.cy);
 #pragma unroll 1
-                        for (int s = 0; s < k; s++) {
-                            px[s] = (rect[s][0] + rect[s][2]) * 0.5;  // (x1 + x2) / 2, exact
-                            py[s] = (rect[s][1] + rect[s][3]) * 0.5;
-                        }
-                        if (k == 2) {
-                            double lx = px[0] - px[1], ly = py[0] - py[1];
-                            const double len = dsqrt(fma(ly, ly, lx * lx));
-                            const double len2 = len * len;
-                            lx = ddiv(lx, len2); ly = ddiv(ly, len2);
-                            sup_m[base + 0] = f.st.m * fabs(dot2(f.st.cx - px[1], f.st.cy - py[1], lx, ly));
-                            sup_m[base + 1] = f.st.m * fabs(dot2(f.st.cx - px[0], f.st.cy - py[0], lx, ly));
-                        } else {
-                            double lR[KSUP_SMALL * KSUP_SMALL], lV[KSUP_SMALL * KSUP_SMALL], ly_[KSUP_SMALL], lrow[KSUP_SMALL], lx_[KSUP_SMALL];
-                            LsWork w;
-                            w.R = small ? lR : big->R; w.V = small ? lV : big->V; w.y = small ? ly_ : big->y;
-                            w.row = small ? lrow : big->row; w.x = small ? lx_ : big->x; w.ld = small ? KSUP_SMALL : KSUP_MAX;
-                            lstsq_ratios(w, k, px, py, f.st.cx, f.st.cy);
-#pragma unroll 1
-                            for (int s = 0; s < k; s++) sup_m[base + s] = f.st.m * w.x[s];
-                        }
+                        for (int s = 0; s < k; s++) sup_m[base + s] = st.m * w.x[s];
                     }
                 }
                 if (real) {
                     // persist the loads: up_edges[self] = Stack(...) for every support, in support order
 #pragma unroll 1
                     for (int s = 0; s < k; s++) {
-                        Stack4 e;
-                        e.cx = f.st.cx; e.cy = f.st.cy; e.cz = f.st.cz;
-                        if (!f.whole) { e.cx = px[s]; e.cy = py[s]; }
+                        Stack4 e = st;
+                        if (!whole) { e.cx = px[s]; e.cy = py[s]; }
                         e.m = sup_m[base + s];
                         int pos = -1;
 #pragma unroll 1
                         for (int q = 0; q < pool.n; q++)
-                            if (pool.upper[q] == f.node && pool.lower[q] == sup_id[base + s]) { pos = q; break; }
+                            if (pool.upper[q] == node && pool.lower[q] == sup_id[base + s]) { pos = q; break; }
                         if (pos < 0) {
                             if (pool.n >= EDGE_MAX) { flags |= PCT_FLAG_EDGE_OVERFLOW; ok = false; break; }
                             pos = pool.n++;
-                            pool.upper[pos] = f.node;
+                            pool.upper[pos] = (uint8_t)node;
                             pool.lower[pos] = sup_id[base + s];
                         }
                         pool.st[pos] = e;
@@ -385,48 +447,57 @@ __device__ __noinline__ int stability_check(const G &g, const typename G::Node &
             }
             if (!small) { __threadfence_block(); atomicExch(lock, 0); }
             if (!ok) return 0;
-            continue;  // CHILD phase next iteration
+            if (depth >= STAB_DEPTH) { flags |= PCT_FLAG_SUPPORT_OVERFLOW; return 0; }
+            StabFrame &f = fr[depth++];
+            f.st = st; f.node = (uint8_t)node; f.base = (uint8_t)base; f.k = (uint8_t)k; f.i = 0; f.whole = (uint8_t)whole;
         }
-        // ---------------- CHILD: recurse into support f.i ----------------
-        if (f.i == f.k) { depth--; continue; }  // all supports passed -> True
-        if (depth + 1 >= STAB_DEPTH) { flags |= PCT_FLAG_SUPPORT_OVERFLOW; return 0; }
-        const int s = f.i++;
-        const int sid = sup_id[f.base + s];
+        // ================= pick the next node to enter =================
+        int parent = node;
+        if (child < 0) {
+            // k == 0 (return True) or a frame was just pushed: continue with the top frame's next child
+            for (;;) {
+                if (depth == 0) return 1;
+                StabFrame &f = fr[depth - 1];
+                if (f.i == f.k) { depth--; continue; }  // all supports passed -> True
+                const int s = f.i++;
+                child = sup_id[f.base + s];
+                parent = f.node;
+                st = f.st;
+                vm = sup_m[f.base + s];
+                vx = st.cx; vy = st.cy;
+                if (!f.whole) {  // load sits at the centre of this support's contact rectangle with the parent
+                    Node par;
+                    if (parent != root_id) g.node_box(parent, par);
+                    else par = root;
+                    g.support(par, child, r);
+                    vx = (r[0] + r[2]) * 0.5; vy = (r[1] + r[3]) * 0.5;
+                }
+                base = f.base + f.k;
+                if (s == f.k - 1) { depth--; base = f.base; }  // tail call: the parent frame is finished
+                break;
+            }
+        }
+        // ---- calculate_new_com of `child` (D:space.py:51-71) under the load (vx, vy, st.cz, vm) of `parent` ----
         Node sb;
-        g.node_box(sid, sb);
-        // calculate_new_com (D:space.py:51-71)
+        g.node_box(child, sb);
         double ccx, ccy, ccz, mm = sb.mass;
         g.centre(sb, ccx, ccy, ccz);
         ccx *= mm; ccy *= mm; ccz *= mm;
 #pragma unroll 1
         for (int q = 0; q < pool.n; q++) {
-            if (pool.lower[q] != sid) continue;
-            if (!real && pool.upper[q] == f.node) continue;  // `involved` path member: its real load is replaced by the virtual one
+            if (pool.lower[q] != child) continue;
+            if (!real && pool.upper[q] == parent) continue;  // `involved` path member: its real load is replaced by the virtual one
             const Stack4 e = pool.st[q];
             ccx += e.cx * e.m; ccy += e.cy * e.m; ccz += e.cz * e.m;
             mm += e.m;
         }
-        if (!real) {
-            const double vm = sup_m[f.base + s];
-            if (f.whole != 2 || vm != 0.0) {  // zero-mass loads of the direct-edge case add +0.0: skipped (exact)
-                double vx = f.st.cx, vy = f.st.cy;
-                if (!f.whole) {  // centre2D of this support's contact rectangle with the parent
-                    double r[4];
-                    g.support(cur, sid, r);
-                    vx = (r[0] + r[2]) * 0.5; vy = (r[1] + r[3]) * 0.5;
-                }
-                ccx += vx * vm; ccy += vy * vm; ccz += f.st.cz * vm;
-                mm += vm;
-            }
+        if (!real && vm != 0.0) {  // zero-mass virtual loads add +0.0 to every sum: skipped (exact)
+            ccx += vx * vm; ccy += vy * vm; ccz += st.cz * vm;
+            mm += vm;
         }
-        StabFrame &c = fr[depth + 1];
-        c.st.cx = ddiv(ccx, mm); c.st.cy = ddiv(ccy, mm); c.st.cz = ddiv(ccz, mm); c.st.m = mm;
-        c.node = (uint8_t)sid;
-        c.base = (uint8_t)(f.base + f.k);
-        c.k = 0xFF; c.i = 0; c.whole = 1;
-        depth++;
+        st.cx = ddiv(ccx, mm); st.cy = ddiv(ccy, mm); st.cz = ddiv(ccz, mm); st.m = mm;
+        node = child;
     }
-    return 1;
 }
 
 }  // namespace pct
