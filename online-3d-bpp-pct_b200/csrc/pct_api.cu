@@ -76,6 +76,15 @@ int pct_create(const pct_config *cfg, int32_t n_envs, int32_t device, pct_handle
     h->item_mode = cfg->item_mode;
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
+    h->groups = n_envs >= 2048 ? 4 : 1;
+    if (const char *gv = getenv("PCT_B200_GROUPS")) h->groups = atoi(gv);
+    if (h->groups < 1) h->groups = 1;
+    if (h->groups > 8) h->groups = 8;
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
+    for (int gi = 1; gi < 8 && e == cudaSuccess; gi++) {
+        e = cudaStreamCreateWithFlags(&h->sub[gi], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_join[gi], cudaEventDisableTiming);
+    }
     if (e == cudaSuccess) {
         if (cfg->domain == PCT_DISCRETE) {
             e = cudaMalloc(&h->d_hot, sizeof(DEnvHot) * (size_t)n_envs);
@@ -103,6 +112,11 @@ void pct_destroy(pct_handle h) {
     cudaFree(h->d_hot); cudaFree(h->d_cold); cudaFree(h->d_item_set); cudaFree(h->d_stream);
     cudaFree(h->d_obs); cudaFree(h->d_act); cudaFree(h->d_idx); cudaFree(h->d_rew); cudaFree(h->d_done); cudaFree(h->d_info);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    for (int gi = 1; gi < 8; gi++) {
+        if (h->sub[gi]) cudaStreamDestroy(h->sub[gi]);
+        if (h->ev_join[gi]) cudaEventDestroy(h->ev_join[gi]);
+    }
     delete h;
 }
 
@@ -143,20 +157,37 @@ static int launch(pct_handle h, int mode, const void *actions, int action_f64, c
         if (rc == PCT_OK) h->launches++;
         return rc;
     }
+    // The batch is cut into `groups` contiguous env ranges, each enqueued on its own internal stream between a
+    // fork and a join event on the caller's stream: envs are independent, and a range whose kernels are waiting
+    // for a few heavy envs (deep stacking-stability recursions) no longer leaves the SMs idle.
+    const int G = h->groups;
+    if (G > 1) CK(h, cudaEventRecord(h->ev_fork, st));
+    for (int gi = 0; gi < G; gi++) {
+    const int off = (int)((int64_t)h->n_envs * gi / G), cnt = (int)((int64_t)h->n_envs * (gi + 1) / G) - off;
+    if (cnt <= 0) continue;
+    cudaStream_t gs = gi == 0 ? st : h->sub[gi];
+    if (gi > 0) CK(h, cudaStreamWaitEvent(gs, h->ev_fork, 0));
+    const size_t osz = h->cfg.obs_dtype == PCT_F64 ? 8 : 4, asz = action_f64 ? 8 : 4;
     DParams p{};
-    p.hot = h->d_hot; p.cold = h->d_cold; p.n_envs = h->n_envs;
+    p.hot = h->d_hot + off; p.cold = h->d_cold + off; p.n_envs = cnt;
     p.W = (int)h->cfg.container_size[0]; p.L = (int)h->cfg.container_size[1]; p.H = (int)h->cfg.container_size[2];
     p.nb = h->cfg.internal_node_holder; p.nl = h->cfg.leaf_node_holder; p.setting = h->cfg.setting;
     p.low_bound = h->cfg.size_minimum;
     p.item_mode = h->item_mode; p.item_set = h->d_item_set; p.n_items = h->n_items;
-    p.stream = h->d_stream; p.stream_len = h->stream_len;
-    p.seed = h->cfg.seed; p.env_id_base = h->cfg.env_id_base;
-    p.actions = actions; p.action_f64 = action_f64; p.leaf_idx = leaf_idx;
-    p.obs = obs; p.obs_f64 = h->cfg.obs_dtype == PCT_F64;
-    p.reward = rew; p.done = done; p.info = info; p.mode = mode;
+    p.stream = h->d_stream ? h->d_stream + (size_t)off * h->stream_len * 4 : nullptr; p.stream_len = h->stream_len;
+    p.seed = h->cfg.seed; p.env_id_base = h->cfg.env_id_base + off; p.env_id_base0 = h->cfg.env_id_base;
+    p.actions = actions ? (const char *)actions + (size_t)off * 9 * asz : nullptr; p.action_f64 = action_f64;
+    p.leaf_idx = leaf_idx ? leaf_idx + off : nullptr;
+    p.obs = (char *)obs + (size_t)off * h->obs_len * osz; p.obs_f64 = h->cfg.obs_dtype == PCT_F64;
+    p.reward = rew ? rew + off : nullptr; p.done = done ? done + off : nullptr; p.info = info ? info + off : nullptr; p.mode = mode;
     p.dbg = (long long *)h->dbg;
-    CK(h, launch_discrete(p, st));
+    CK(h, launch_discrete(p, gs));
     h->launches += discrete_kernels_per_step();
+    if (gi > 0) {
+        CK(h, cudaEventRecord(h->ev_join[gi], gs));
+        CK(h, cudaStreamWaitEvent(st, h->ev_join[gi], 0));
+    }
+    }
     return PCT_OK;
 }
 

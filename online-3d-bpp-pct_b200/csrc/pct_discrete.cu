@@ -77,7 +77,7 @@ template <typename SlotT, bool BIGSM>
 struct Lay {
     static constexpr int A_SLOTS = BIGSM ? TAB_A : 128;
     static constexpr int HOT = 0;
-    static constexpr int TAB_A_OFF = sizeof(DEnvHot);
+    static constexpr int TAB_A_OFF = HOT_PREFIX;
     static constexpr int TAB_B_OFF = TAB_A_OFF + A_SLOTS * sizeof(SlotT);
     static constexpr int LEAF = TAB_B_OFF + TAB_B * sizeof(SlotT);  // NL_MAX x 6 x i16
     static constexpr int MISC = LEAF + NL_MAX * 12;                 // mbarrier (8) + lock (4) + pad (4) + RotTab (32)
@@ -379,7 +379,7 @@ __device__ __noinline__ void draw_item(const DParams &p, int e, DHdr &h) {
 __device__ __noinline__ void reset_space(DEnvHot *hot, const DParams &p, int e, int lane) {
     if (lane == 0) {
         DHdr &h = hot->h;
-        h.n_box = 0; h.n_ems = 1; h.n_leaf = 0; h.flags = 0; h.n_edge = 0; h.vol_sum = 0; h.ep_len = 0; h.ep_reward = 0;
+        h.n_box = 0; h.n_ems = 1; h.n_leaf = 0; h.flags = 0; h.n_edge = 0; h.n_poly = 0; h.vol_sum = 0; h.ep_len = 0; h.ep_reward = 0;
         hot->ems[0][0] = 0; hot->ems[0][1] = 0; hot->ems[0][2] = 0;
         hot->ems[0][3] = (int16_t)p.W; hot->ems[0][4] = (int16_t)p.L; hot->ems[0][5] = (int16_t)p.H;
         draw_item(p, e, h);
@@ -454,11 +454,20 @@ __device__ __forceinline__ int rest_height(const int16_t (*box)[6], int first, i
 //   K3 feas_emit  block / env   thread per candidate: bounds, resting height, virtual stability;
 //                               ordered compaction into the leaf slots; observation write
 // ======================================================================================================
-constexpr int K1_SM_PER_WARP = sizeof(DEnvHot) + E_MAX * 12 + 16;  // record + EMS temp + mbarrier/lock
+#ifdef PCT_PHASE_TIMERS
+__device__ __forceinline__ long long gtime() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define KT_BEGIN() const long long kt0_ = gtime(); const long long kc0_ = clock64()
+#define KT_END(e, k) do { if (p.mode == 1 && p.dbg) { p.dbg[(size_t)(e) * 16 + (k) * 4 + 0] = kt0_; p.dbg[(size_t)(e) * 16 + (k) * 4 + 1] = gtime(); \
+        p.dbg[(size_t)(e) * 16 + (k) * 4 + 2] = clock64() - kc0_; } } while (0)
+#else
+#define KT_BEGIN()
+#define KT_END(e, k)
+#endif
+constexpr int K1_SM_PER_WARP = sizeof(DEnvHot) + E_MAX * 12 + 16 + EDGE_STAGE * 32 + POLY_STAGE * 16;  // record + EMS temp + mbarrier/lock + staged loads
 static_assert(K1_SM_PER_WARP % 16 == 0, "alignment");
 
 template <bool STAB>
-__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) pct_apply_kernel(const DParams p) {
+__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, 14) pct_apply_kernel(const DParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int e = blockIdx.x * WARPS_PER_BLOCK + warp;
@@ -468,9 +477,12 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) pct_apply_kernel(const D
     int16_t (*ems_tmp)[6] = (int16_t (*)[6])(sm + sizeof(DEnvHot));
     uint64_t *mbar = (uint64_t *)(sm + sizeof(DEnvHot) + E_MAX * 12);
     int *lock = (int *)(mbar + 1);
+    Stack4 *st_sm = (Stack4 *)(sm + sizeof(DEnvHot) + E_MAX * 12 + 16);
+    double *poly_sm = (double *)(st_sm + EDGE_STAGE);
     DEnvHot *ghot = p.hot + e;
     DEnvCold *cold = p.cold + e;
     DHdr &h = hot->h;
+    KT_BEGIN();
     if (lane == 0) *lock = 0;
     float reward = 0.f;
     int done = 0;
@@ -494,6 +506,17 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) pct_apply_kernel(const D
         }
         mbar_wait(mbar, 0);
         __syncwarp();
+        if (STAB && h.n_edge > 0) {  // stage the load edges and support polygons too (second phase of the same mbarrier)
+            const uint32_t bytes = (uint32_t)min(h.n_edge, EDGE_STAGE) * (uint32_t)sizeof(Stack4);
+            const uint32_t pbytes = (uint32_t)min(h.n_poly, POLY_STAGE) * 16u;
+            if (lane == 0) {
+                mbar_expect_tx(mbar, bytes + pbytes);
+                tma_load_1d(st_sm, cold->e_st, bytes, mbar);
+                if (pbytes) tma_load_1d(poly_sm, cold->poly, pbytes, mbar);
+            }
+            mbar_wait(mbar, 1);
+            __syncwarp();
+        }
 
         const int nb0 = h.next_box[0], nb1 = h.next_box[1], nb2 = h.next_box[2];
         const int n_box0 = h.n_box, n_leaf0 = h.n_leaf, flags0 = h.flags;
@@ -544,6 +567,12 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) pct_apply_kernel(const D
         const int maxax = max(p.W, p.L);
         bool ok = !bad && lx >= 0 && ly >= 0 && lx < maxax && ly < maxax && x > 0 && y > 0;
         int max_h = 0;
+        if (STAB && lane == 0) {  // CSR slot / incoming-list head of the box about to be placed
+            hot->e_off[n_box0] = (uint16_t)h.n_edge;
+            hot->poly_off[n_box0] = (uint16_t)h.n_poly;
+            hot->first_in[n_box0 < NB_MAX ? n_box0 : 0] = EDGE_NIL;
+        }
+        __syncwarp();
         if (ok) {
             // resting height: warp max-reduce over the placed boxes whose footprint overlaps
             max_h = __reduce_max_sync(FULL, rest_height(hot->box, lane, n_box0, 32, lx, ly, lx + x, ly + y));
@@ -555,9 +584,11 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) pct_apply_kernel(const D
                     int fl = 0;
                     GeomD g{hot->box, n_box0, p.setting == 3 ? cold->density : nullptr};
                     NodeD root{lx, ly, max_h, x, y, z, (double)(x * y * z) * next_den0};
-                    EdgePool pool{cold->e_upper, cold->e_lower, cold->e_st, h.n_edge};
+                    EdgePool pool{hot->e_lower, hot->e_next, hot->e_off, hot->first_in, hot->last_in, cold->e_st, st_sm, h.n_edge,
+                                  hot->poly_off, &cold->poly[0][0], poly_sm, h.n_poly};
                     res = stability_check<true, GeomD>(g, root, pool, &cold->big, lock, n_box0, fl);
                     h.n_edge = pool.n;
+                    h.n_poly = pool.n_poly;
                     h.flags |= fl;
                 }
                 __syncwarp();
@@ -579,6 +610,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) pct_apply_kernel(const D
                 if (p.setting == 3) cold->density[n_box0] = next_den0;
                 h.n_box = n_box0 + 1;
                 h.vol_sum += x * y * z;
+                if (STAB) { hot->e_off[n_box0 + 1] = (uint16_t)h.n_edge; hot->poly_off[n_box0 + 1] = (uint16_t)h.n_poly; }
             }
             const int n_ems0 = h.n_ems;
             __syncwarp();
@@ -616,7 +648,10 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) pct_apply_kernel(const D
         if (p.info) p.info[e] = info;
         // record back to HBM: smem -> global via TMA bulk store
         tma_store_1d(ghot, hot, (uint32_t)sizeof(DEnvHot));
+        if (STAB && p.mode == 1 && h.n_edge > 0) tma_store_1d(cold->e_st, st_sm, (uint32_t)min(h.n_edge, EDGE_STAGE) * (uint32_t)sizeof(Stack4));
+        if (STAB && p.mode == 1 && h.n_poly > 0) tma_store_1d(cold->poly, poly_sm, (uint32_t)min(h.n_poly, POLY_STAGE) * 16u);
         tma_store_commit_wait();
+        KT_END(p.env_id_base + e - p.env_id_base0, 0);
     }
 }
 
@@ -636,14 +671,15 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) pct_candidates_kernel(co
     static_assert(sizeof(RotTab) <= 32, "RotTab slot");
     DEnvHot *ghot = p.hot + e;
     DEnvCold *cold = p.cold + e;
+    KT_BEGIN();
     if (lane == 0) {
         mbar_init(mbar, 1);
         fence_proxy_async();
     }
     __syncwarp();
-    if (lane == 0) {
-        mbar_expect_tx(mbar, (uint32_t)sizeof(DEnvHot));
-        tma_load_1d(hot, ghot, (uint32_t)sizeof(DEnvHot), mbar);
+    if (lane == 0) {  // header + boxes + EMS list only
+        mbar_expect_tx(mbar, (uint32_t)HOT_PREFIX);
+        tma_load_1d(hot, ghot, (uint32_t)HOT_PREFIX, mbar);
     }
     mbar_wait(mbar, 0);
     __syncwarp();
@@ -660,16 +696,17 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) pct_candidates_kernel(co
     if (lane == 0) {
         ghot->h.n_cand = n_cand;
         if (fl) ghot->h.flags = h.flags | fl;
+        KT_END(p.env_id_base + e - p.env_id_base0, 1);
     }
 }
 
 // ---- K3: feasibility (thread per candidate) + leaf compaction + observation ------------------------------------
 constexpr int FEAS_WARPS = 2;
 constexpr int FEAS_THREADS = 32 * FEAS_WARPS;
-constexpr int K3_SMEM = sizeof(DEnvHot) + NL_MAX * 12 + 64;
+constexpr int K3_SMEM = sizeof(DEnvHot) + NL_MAX * 12 + 64 + EDGE_STAGE * 32 + POLY_STAGE * 16;
 
 template <typename OT, bool STAB, typename SlotT>
-__global__ void __launch_bounds__(FEAS_THREADS) pct_feas_emit_kernel(const DParams p) {
+__global__ void __launch_bounds__(FEAS_THREADS, 12) pct_feas_emit_kernel(const DParams p) {
     constexpr int BITS = sizeof(SlotT) == 2 ? 4 : 8;
     __shared__ __align__(16) unsigned char sm[K3_SMEM];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -680,8 +717,11 @@ __global__ void __launch_bounds__(FEAS_THREADS) pct_feas_emit_kernel(const DPara
     int *lock = (int *)(mbar + 1);
     uint32_t *wb = (uint32_t *)(mbar + 2);             // per-warp feasibility ballots of the current pass
     RotTab *rt = (RotTab *)(sm + sizeof(DEnvHot) + NL_MAX * 12 + 32);
+    Stack4 *st_sm = (Stack4 *)(sm + sizeof(DEnvHot) + NL_MAX * 12 + 64);
+    double *poly_sm = (double *)(st_sm + EDGE_STAGE);
     DEnvHot *ghot = p.hot + e;
     DEnvCold *cold = p.cold + e;
+    KT_BEGIN();
     if (tid == 0) {
         *lock = 0;
         mbar_init(mbar, 1);
@@ -693,7 +733,18 @@ __global__ void __launch_bounds__(FEAS_THREADS) pct_feas_emit_kernel(const DPara
         tma_load_1d(hot, ghot, (uint32_t)sizeof(DEnvHot), mbar);
     }
     mbar_wait(mbar, 0);
+    __syncthreads();  // every thread must have observed phase 0 before the barrier is re-armed
     const DHdr &h = hot->h;
+    if (STAB && h.n_edge > 0) {  // stage the load edges (second phase of the same mbarrier)
+        const uint32_t bytes = (uint32_t)min(h.n_edge, EDGE_STAGE) * (uint32_t)sizeof(Stack4);
+        const uint32_t pbytes = (uint32_t)min(h.n_poly, POLY_STAGE) * 16u;
+        if (tid == 0) {
+            mbar_expect_tx(mbar, bytes + pbytes);
+            tma_load_1d(st_sm, cold->e_st, bytes, mbar);
+            if (pbytes) tma_load_1d(poly_sm, cold->poly, pbytes, mbar);
+        }
+        mbar_wait(mbar, 1);
+    }
     const int nb3[3] = {h.next_box[0], h.next_box[1], h.next_box[2]};
     if (tid == 0) make_rot_tab(nb3, p.setting == 2 ? 6 : 2, *rt);
     __syncthreads();
@@ -701,7 +752,8 @@ __global__ void __launch_bounds__(FEAS_THREADS) pct_feas_emit_kernel(const DPara
     const double den = h.next_den;
     const SlotT *cand = (const SlotT *)cold->cand;
     GeomD g{hot->box, n_box, p.setting == 3 ? cold->density : nullptr};
-    EdgePool pool{cold->e_upper, cold->e_lower, cold->e_st, h.n_edge};
+    EdgePool pool{hot->e_lower, hot->e_next, hot->e_off, hot->first_in, hot->last_in, cold->e_st, st_sm, h.n_edge,
+                  hot->poly_off, &cold->poly[0][0], poly_sm, h.n_poly};
     int n_leaf = 0, fl = 0;
     // ---------------- get_possible_position (D:bin3D.py:100-136): first `nl` feasible candidates in order ----------------
 #pragma unroll 1
@@ -719,7 +771,22 @@ __global__ void __launch_bounds__(FEAS_THREADS) pct_feas_emit_kernel(const DPara
             else if (!STAB || mh == 0) feas = true;
             else {
                 NodeD root{xs, ys, mh, sx, sy, sz, (double)(sx * sy * sz) * den};
+#ifdef PCT_PHASE_TIMERS
+                const long long c0 = clock64();
+                int fl2 = 0;
+                long long prof[6];
+                feas = stability_check<false, GeomD>(g, root, pool, &cold->big, lock, 0, fl2, prof) != 0;
+                const long long dc = clock64() - c0;
+                fl |= fl2 & 0xFFFF;
+                if (p.mode == 1 && p.dbg) {
+                    unsigned long long packed = ((unsigned long long)dc << 24) | ((unsigned long long)((fl2 >> 16) & 0xFF) << 8) | (unsigned long long)((fl2 >> 24) & 0xFF);
+                    long long *slot = &p.dbg[(size_t)(p.env_id_base + e - p.env_id_base0) * 16];
+                    if (atomicMax((unsigned long long *)&slot[12], packed) < packed)
+                        { slot[3] = prof[0]; slot[7] = prof[1]; slot[11] = prof[2]; slot[13] = prof[3]; slot[14] = prof[4]; }
+                }
+#else
                 feas = stability_check<false, GeomD>(g, root, pool, &cold->big, lock, 0, fl) != 0;
+#endif
             }
         }
         const uint32_t fm = __ballot_sync(FULL, feas);
@@ -759,6 +826,7 @@ __global__ void __launch_bounds__(FEAS_THREADS) pct_feas_emit_kernel(const DPara
     }
     // ---------------- cur_observation (D:bin3D.py:70-93) ----------------
     write_obs<OT>(p, e, hot, cold, leaf, n_leaf, tid, FEAS_THREADS);
+    if (tid == 0) KT_END(p.env_id_base + e - p.env_id_base0, 2);
 }
 
 // uniform-random valid-leaf policy: reads only the record headers

@@ -27,5 +27,8 @@ struct pct_env_batch {
     pct_step_info *d_info = nullptr;
     cudaStream_t own_stream = nullptr;
     void *dbg = nullptr;
+    int groups = 1;               // env ranges stepped concurrently on internal streams
+    cudaStream_t sub[8] = {};
+    cudaEvent_t ev_fork = nullptr, ev_join[8] = {};
 };
 

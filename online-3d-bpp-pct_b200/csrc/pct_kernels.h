@@ -23,22 +23,42 @@ constexpr int KSUP_SMALL = 8;    // supports handled with lane-local scratch
 constexpr int KSUP_MAX = 32;     // supports handled with the per-env scratch in HBM (serialised by a lock)
 constexpr int STAB_DEPTH = 14;   // DFS depth (levels of boxes on top of each other)
 constexpr int STAB_SUP_POOL = 48;
-constexpr int EDGE_MAX = 256;
+constexpr int EDGE_MAX = 255;    // load edges per env; positions are uint8, 255 = NIL
+constexpr int EDGE_NIL = 255;
+constexpr int EDGE_STAGE = 64;
+constexpr int POLY_MAX = 256;     // stored support-polygon vertices per env (boxes with >= 2 supports)
+constexpr int POLY_STAGE = 96;    // vertices staged in shared memory   // loads staged in shared memory (serial DFS reads would otherwise be HBM-latency bound)
 
 struct Stack4 { double cx, cy, cz, m; };
 
-struct EdgePool {          // per-env, global memory
-    uint8_t *upper;        // [EDGE_MAX]
-    uint8_t *lower;        // [EDGE_MAX]
-    Stack4 *st;            // [EDGE_MAX]
+// Load-edge pool of one env.  Edges are appended when a box is placed (one per support, in support order), so the
+// pool is a CSR by upper box: the supports of placed box u are lower[off[u] .. off[u+1]).  The loads resting on a
+// box t (the reference's insertion-ordered `up_edges` dict of t) are the linked list first_in[t] -> next[..], which
+// is in pool (= placement) order.  Index arrays live in the staged record (shared memory), the loads in HBM.
+struct EdgePool {
+    uint8_t *lower;        // [EDGE_MAX] supporting box of edge e
+    uint8_t *next;         // [EDGE_MAX] next edge with the same lower box, EDGE_NIL at the end
+    uint16_t *off;         // [NB_MAX + 1] CSR offsets by upper box
+    uint8_t *first_in;     // [NB_MAX] first / last incoming edge of a box (EDGE_NIL if none)
+    uint8_t *last_in;
+    Stack4 *st;            // [EDGE_MAX] load centre xyz + mass (global memory)
+    Stack4 *st_sm;         // the first EDGE_STAGE loads, staged in shared memory by a TMA bulk copy
     int n;                 // current count (lane-local copy; the REAL path writes it back)
+    // support polygons (unshrunk hull vertices, x/y interleaved) of the placed boxes with >= 2 supports: the
+    // reference stores bottom_whole_contact_area per box at placement (D:space.py:378-379); CSR by box.
+    uint16_t *poly_off;    // [NB_MAX + 2]
+    double *poly;          // [POLY_MAX][2] global
+    double *poly_sm;       // first POLY_STAGE vertices staged in shared memory
+    int n_poly;
+    __device__ __forceinline__ Stack4 &load(int q) const { return q < EDGE_STAGE ? st_sm[q] : st[q]; }
+    __device__ __forceinline__ double *poly_at(int v) const { return v < POLY_STAGE ? poly_sm + 2 * v : poly + 2 * v; }
 };
 
 // per-env HBM scratch for the rare big cases (k > KSUP_SMALL)
 struct BigScratch {
     double rect[KSUP_MAX][4];
     double px[4 * KSUP_MAX], py[4 * KSUP_MAX];
-    uint8_t order[4 * KSUP_MAX], hl[8 * KSUP_MAX], hu[4 * KSUP_MAX + 4];
+    double hx[8 * KSUP_MAX], hy[8 * KSUP_MAX];
     double R[KSUP_MAX * KSUP_MAX], V[KSUP_MAX * KSUP_MAX], y[KSUP_MAX], row[KSUP_MAX], x[KSUP_MAX];
 };
 
@@ -56,23 +76,31 @@ struct alignas(16) DHdr {  // 64 bytes
     int32_t vol_sum;       // sum of packed volumes (get_ratio numerator)
     int32_t ep_len;
     int32_t n_cand;
-    int32_t pad_;
+    int32_t n_poly;        // vertices in the polygon pool
 };
 struct alignas(16) DEnvHot {
     DHdr h;
     int16_t box[NB_MAX][6];  // lx,ly,lz,hx,hy,hz  (placement order)
     int16_t ems[E_MAX][6];   // x1,y1,z1,x2,y2,z2  (reference list order)
+    // --- everything above is what the candidate kernel needs (HOT_PREFIX bytes) ---
+    uint16_t e_off[NB_MAX + 2];
+    uint8_t e_lower[EDGE_MAX + 1], e_next[EDGE_MAX + 1];
+    uint8_t first_in[NB_MAX], last_in[NB_MAX];
+    uint16_t poly_off[NB_MAX + 2];
+    uint8_t pad_[8];
 };
+constexpr int HOT_PREFIX = sizeof(DHdr) + NB_MAX * 12 + E_MAX * 12;
+static_assert(HOT_PREFIX % 16 == 0, "prefix is a TMA bulk copy");
 static_assert(sizeof(DHdr) == 72 || sizeof(DHdr) == 80 || sizeof(DHdr) == 64, "header size");
 static_assert(sizeof(DEnvHot) % 16 == 0, "TMA bulk copies move multiples of 16 bytes");
 
 // "Cold" record: touched only by the paths that need it (leaf-index actions, setting-3 densities, the
 // stability load edges, the rare >8-support scratch).  Lives in HBM / L2, never staged.
-struct DEnvCold {
+struct alignas(16) DEnvCold {
     int16_t leaf[NL_MAX][6];  // leaves emitted with the last observation (xs,ys,zs,xe,ye,ze)
     double density[NB_MAX];   // per placed box (setting 3)
-    uint8_t e_upper[EDGE_MAX], e_lower[EDGE_MAX];
-    Stack4 e_st[EDGE_MAX];
+    Stack4 e_st[EDGE_MAX + 1];
+    double poly[POLY_MAX][2];
     uint32_t cand[1232];      // ordered candidate keys written by K2, read by K3 (<= 1228 distinct candidates)
     uint32_t tab_big[TAB_A];  // 2048-slot stage of the set emulation when it does not live in shared memory
     BigScratch big;
@@ -91,6 +119,7 @@ struct DParams {
     int stream_len;
     uint64_t seed;
     int64_t env_id_base;
+    int64_t env_id_base0;  // env_id_base of env 0 of the handle (debug timers index by handle-local env)
     const void *actions;
     int action_f64;
     const int32_t *leaf_idx;

@@ -45,75 +45,102 @@ __device__ __forceinline__ int orient_of(double s1, double s2) {
     if (d == 0) return 0;
     return 1;
 }
+// Line2D(a,b).orientation(Line2D(b,c)) (convex_hull.py:4-32) with a division-saving pre-filter.
+// The verdict only depends on the ORDER of the two correctly rounded slopes.  Single-precision estimates of
+// both slopes (relative error < 1e-6) that differ by more than 1e-4 relative prove that the exact quotients
+// differ by far more than one rounding error, hence that the rounded doubles compare the same way; only
+// near-ties (collinear contact points) and vertical segments fall through to the exact FP64 divisions.
+__device__ __forceinline__ int orient3(double ax, double ay, double bx, double by, double cx, double cy) {
+    const double d1x = bx - ax, d1y = by - ay, d2x = cx - bx, d2y = cy - by;
+    if (d1x != 0 && d2x != 0) {
+        const float f1 = __fdividef((float)d1y, (float)d1x), f2 = __fdividef((float)d2y, (float)d2x);
+        const float gap = f2 - f1, tol = 1e-4f * (fabsf(f1) + fabsf(f2));
+        if (fabsf(gap) > tol && fabsf(f1) < 1e30f && fabsf(f2) < 1e30f) return gap > 0 ? -1 : 1;
+    }
+    return orient_of(slope_of(ax, ay, bx, by), slope_of(bx, by, cx, cy));
+}
 
 // ConvexHull (convex_hull.py:39-95) on n points already perturbed (x += y*1e-6).
-// Writes the hull as indices: lower chain (minus last) then upper chain (minus last) into `hl` (returns count).
-__device__ __noinline__ int hull_indices(const double *px, const double *py, int n, uint8_t *order, uint8_t *hl, uint8_t *hu) {
+// px/py are sorted IN PLACE (stable insertion sort by x, sorted(key=x[0]) :34-37); the hull (lower chain minus its
+// last point, then upper chain minus its last point, :89-92) is written as coordinates to hx/hy (capacity 2n).
+// The two topmost chain points live in registers, so the orientation test of the scan needs no reloads.
+__device__ __noinline__ int hull_coords(double *px, double *py, int n, double *hx, double *hy) {
 #pragma unroll 1
-    for (int i = 0; i < n; i++) {  // stable insertion sort by x (sorted(key=x[0]), :34-37)
-        const double kx = px[i];
+    for (int i = 1; i < n; i++) {
+        const double kx = px[i], ky = py[i];
         int j = i - 1;
 #pragma unroll 1
-        while (j >= 0 && px[order[j]] > kx) { order[j + 1] = order[j]; j--; }
-        order[j + 1] = (uint8_t)i;
+        while (j >= 0 && px[j] > kx) { px[j + 1] = px[j]; py[j + 1] = py[j]; j--; }
+        px[j + 1] = kx; py[j + 1] = ky;
     }
     int m = 0;
 #pragma unroll 1
     for (int pass = 0; pass < 2; pass++) {
-        uint8_t *H = pass == 0 ? hl : hu;
+        double *HX = hx + m, *HY = hy + m;  // this chain is built in place behind the previous one
         int nh = 0;
+        double tx = 0, ty = 0, ux = 0, uy = 0, fx = 0, fy = 0;  // top, second, first
 #pragma unroll 1
         for (int k = 0; k < n; k++) {
-            const int p = order[pass == 0 ? k : n - 1 - k];
+            const int p = pass == 0 ? k : n - 1 - k;
             const double qx = px[p], qy = py[p];
 #pragma unroll 1
             while (nh >= 2) {
-                const double s1 = slope_of(px[H[nh - 2]], py[H[nh - 2]], px[H[nh - 1]], py[H[nh - 1]]);
-                const double s2 = slope_of(px[H[nh - 1]], py[H[nh - 1]], qx, qy);
-                if (orient_of(s1, s2) == -1) break;
-                nh--;                                                                // pop
-                if (px[H[0]] == px[H[nh - 1]] && py[H[0]] == py[H[nh - 1]]) break;  // list equality :58-59
+                if (orient3(ux, uy, tx, ty, qx, qy) == -1) break;
+                nh--;  // pop
+                tx = ux; ty = uy;
+                if (nh >= 2) { ux = HX[nh - 2]; uy = HY[nh - 2]; }
+                if (fx == tx && fy == ty) break;  // lowerHull[0] == lowerHull[-1] (:58-59), list equality
             }
-            H[nh++] = (uint8_t)p;
+            HX[nh] = qx; HY[nh] = qy;
+            if (nh == 0) { fx = qx; fy = qy; }
+            ux = tx; uy = ty; tx = qx; ty = qy;
+            nh++;
         }
-        if (pass == 0) m = nh - 1;  // drop the last of each chain (:89-92)
-        else {
-#pragma unroll 1
-            for (int i = 0; i < nh - 1; i++) hl[m++] = hu[i];
-        }
+        m += nh - 1;  // drop the last point of the chain
     }
     return m;
 }
 
+// convex_hull.py:108 — is the edge's crossing with the horizontal ray strictly left of the point?
+//   coords[i][0] + (lon - coords[i][1]) / (coords[j][1] - coords[i][1]) * (coords[j][0] - coords[i][0]) < lat
+// Float estimate first (error < 1e-5 of the operand scale); the exact FP64 expression only near the threshold.
+__device__ __forceinline__ bool cross_left(double ix, double iy, double jx, double jy, double lat, double lon) {
+    const float xf = (float)ix + __fdividef((float)(lon - iy), (float)(jy - iy)) * (float)(jx - ix);
+    const float scale = fabsf((float)ix) + fabsf((float)(jx - ix)) + fabsf((float)lat);
+    const float gap = xf - (float)lat;
+    if (fabsf(gap) > 1e-4f * scale + 1e-30f) return gap < 0;
+    const double t = ddiv(lon - iy, jy - iy);
+    const double u = t * (jx - ix);
+    return ix + u < lat;
+}
+
 // scale_down (D:space.py:341-345) + point_in_polygen (convex_hull.py:97-112) fused: the shrunk polygon is
-// never stored, its vertices are produced on the fly from the hull indices.
-__device__ __noinline__ bool pip_shrunk(const double *px, const double *py, const uint8_t *hull, int m, double lat, double lon) {
+// never stored, its vertices are produced on the fly from the hull coordinates.
+__device__ __noinline__ bool pip_shrunk(const double *hx, const double *hy, int stride, int m, double lat, double lon) {
     double sx = 0, sy = 0;
 #pragma unroll 1
-    for (int i = 0; i < m; i++) { sx += px[hull[i]]; sy += py[hull[i]]; }
+    for (int i = 0; i < m; i++) { sx += hx[i * stride]; sy += hy[i * stride]; }
     const double cx = ddiv(sx, (double)m), cy = ddiv(sy, (double)m);
     double jx, jy;
     {
-        double v = px[hull[m - 1]], d = v - cx;
+        double v = hx[(m - 1) * stride], d = v - cx;
         jx = v - d * 0.1;
-        v = py[hull[m - 1]]; d = v - cy;
+        v = hy[(m - 1) * stride]; d = v - cy;
         jy = v - d * 0.1;
     }
     bool odd = false;
 #pragma unroll 1
     for (int i = 0; i < m; i++) {
-        double v = px[hull[i]], d = v - cx;
+        double v = hx[i * stride], d = v - cx;
         const double ix = v - d * 0.1;
-        v = py[hull[i]]; d = v - cy;
+        v = hy[i * stride]; d = v - cy;
         const double iy = v - d * 0.1;
         const double a0 = ix - lat, a1 = iy - lon;
         const double b0 = lat - jx, b1 = lon - jy;
         const double m1 = a0 * b1, m2 = a1 * b0;
         if (m1 - m2 == 0) return false;
         if ((iy < lon && jy >= lon) || (jy < lon && iy >= lon)) {
-            const double t = ddiv(lon - iy, jy - iy);
-            const double u = t * (jx - ix);
-            if (ix + u < lat) odd = !odd;
+            if (cross_left(ix, iy, jx, jy, lat, lon)) odd = !odd;
         }
         jx = ix; jy = iy;
     }
@@ -146,6 +173,21 @@ __device__ __noinline__ void ls_add_row(const LsWork &w, int k, double rhs) {
 __device__ __noinline__ void ls_solve(const LsWork &w, int k, int rows) {
     double *G = w.R, *V = w.V;
     const int ld = w.ld;
+    {   // full column rank and well conditioned (the usual case): the least-squares solution is R x = y
+        double rmin = fabs(G[0]), rmax = rmin;
+#pragma unroll 1
+        for (int i = 1; i < k; i++) { const double a = fabs(G[i * ld + i]); rmin = fmin(rmin, a); rmax = fmax(rmax, a); }
+        if (rmin * 1e4 > rmax) {
+#pragma unroll 1
+            for (int i = k - 1; i >= 0; i--) {
+                double acc = w.y[i];
+#pragma unroll 1
+                for (int j = i + 1; j < k; j++) acc -= G[i * ld + j] * w.x[j];
+                w.x[i] = ddiv(acc, G[i * ld + i]);
+            }
+            return;
+        }
+    }
 #pragma unroll 1
     for (int i = 0; i < k; i++)
 #pragma unroll 1
@@ -256,8 +298,21 @@ struct StabFrame {
     uint8_t node;     // real box index, or NODE_NEW
     uint8_t base, k, i;
     uint8_t whole;    // 1: whole stack to the single support; 2: direct edge (others zero); 0: (c2d_i, st.cz) split
+    uint8_t eoff;     // pool position of the node's first edge (placed boxes)
 };
 constexpr int NODE_NEW = 255;
+
+// append the edge (new box -> lower) to the pool and to lower's incoming list
+__device__ __forceinline__ bool pool_append(EdgePool &pool, int lower) {
+    if (pool.n >= EDGE_MAX) return false;
+    const int pos = pool.n++;
+    pool.lower[pos] = (uint8_t)lower;
+    pool.next[pos] = EDGE_NIL;
+    if (pool.first_in[lower] == EDGE_NIL) pool.first_in[lower] = (uint8_t)pos;
+    else pool.next[pool.last_in[lower]] = (uint8_t)pos;
+    pool.last_in[lower] = (uint8_t)pos;
+    return true;
+}
 
 // Single support (58 % of all visits): the "hull" of the 4 corners of one contact rectangle.
 // With P0=(x1,y1) P1=(x1,y2) P2=(x2,y1) P3=(x2,y2) perturbed by x += y*1e-6 (convex_hull.py:43) and
@@ -291,9 +346,7 @@ __device__ __noinline__ bool pip_rect(double x1, double y1, double x2, double y2
         const double m1 = a0 * b1, m2 = a1 * b0;
         if (m1 - m2 == 0) return false;
         if ((vy[i] < lon && vy[j] >= lon) || (vy[j] < lon && vy[i] >= lon)) {
-            const double t = ddiv(lon - vy[i], vy[j] - vy[i]);
-            const double u = t * (vx[j] - vx[i]);
-            if (vx[i] + u < lat) odd = !odd;
+            if (cross_left(vx[i], vy[i], vx[j], vy[j], lat, lon)) odd = !odd;
         }
     }
     return odd;
@@ -302,9 +355,12 @@ __device__ __noinline__ bool pip_rect(double x1, double y1, double x2, double y2
 // The DFS keeps the CURRENT node in registers; frames are pushed to the lane-local stack only for nodes with
 // >= 2 supports, and descending into the last (or only) support is a tail call (nothing is left to do in the
 // parent once its last child returns True).
+#ifdef PCT_PHASE_TIMERS
+__device__ long long *g_prof_dummy;
+#endif
 template <bool REAL, class G>
 __device__ __noinline__ int stability_check(const G &g, const typename G::Node &root, EdgePool &pool, BigScratch *big, int *lock,
-                                            const int new_id, int &flags) {
+                                            const int new_id, int &flags, long long *g_prof_out = nullptr) {
     typedef typename G::Node Node;
     constexpr bool real = REAL;  // REAL: load-propagating update of a committed placement; else read-only feasibility check
     StabFrame fr[STAB_DEPTH];
@@ -317,24 +373,50 @@ __device__ __noinline__ int stability_check(const G &g, const typename G::Node &
     g.centre(root, st.cx, st.cy, st.cz);
     st.m = root.mass;
 
+#ifdef PCT_PHASE_TIMERS
+    long long sec_[6] = {0, 0, 0, 0, 0, 0}, tq_ = clock64();
+#define SEC(i) do { long long n_ = clock64(); sec_[i] += n_ - tq_; tq_ = n_; } while (0)
+#define SEC_OUT() do { if (g_prof_out) for (int i_ = 0; i_ < 6; i_++) g_prof_out[i_] = sec_[i_]; } while (0)
+    flags += 1 << 16;  // debug: visits in bits 16..23, lstsq solves in bits 24..31 (masked off by the caller)
+#define DBG_VISIT() flags += 1 << 16
+#define DBG_LS() flags += 1 << 24
+#else
+#define DBG_VISIT()
+#define DBG_LS()
+#define SEC(i)
+#define SEC_OUT()
+#endif
 #pragma unroll 1
     for (;;) {
         // ================= ENTER(node, st) =================
         Node cur;
         if (node != root_id) g.node_box(node, cur);
         else cur = root;
-        const int limit = (node == root_id) ? g.n_boxes() : node;
         int k = 0, sid0 = 0;
         double r0[4], r[4];
+        const int eoff = (node == root_id) ? pool.n : (int)pool.off[node];  // pool position of this node's first edge
+        if (node == root_id) {
+            // the box being placed / tested: supports are found by scanning every placed box (D:space.py:360-376)
+            const int limit = g.n_boxes();
 #pragma unroll 1
-        for (int t = 0; t < limit; t++) {
-            if (!g.support(cur, t, r)) continue;
-            if (base + k >= STAB_SUP_POOL || k >= KSUP_MAX) { flags |= PCT_FLAG_SUPPORT_OVERFLOW; return 0; }
-            if (k == 0) { sid0 = t; r0[0] = r[0]; r0[1] = r[1]; r0[2] = r[2]; r0[3] = r[3]; }
-            sup_id[base + k] = (uint8_t)t;
-            k++;
+            for (int t = 0; t < limit; t++) {
+                if (!g.support(cur, t, r)) continue;
+                if (k >= STAB_SUP_POOL || k >= KSUP_MAX) { flags |= PCT_FLAG_SUPPORT_OVERFLOW; return 0; }
+                if (k == 0) { sid0 = t; r0[0] = r[0]; r0[1] = r[1]; r0[2] = r[2]; r0[3] = r[3]; }
+                sup_id[base + k] = (uint8_t)t;
+                k++;
+            }
+        } else {
+            // a placed box: its supports were recorded (in the same scan order) when it was placed
+            k = (int)pool.off[node + 1] - eoff;
+            if (base + k > STAB_SUP_POOL) { flags |= PCT_FLAG_SUPPORT_OVERFLOW; return 0; }
+#pragma unroll 1
+            for (int j = 0; j < k; j++) sup_id[base + j] = pool.lower[eoff + j];
+            if (k >= 1) { sid0 = sup_id[base]; g.support(cur, sid0, r0); }
         }
+        SEC(0);
         int child = -1;          // >= 0: tail-descend into this support with load (vx,vy,st.cz,vm)
+        int skip = EDGE_NIL;     // pool position of the real edge parent->child (replaced by the virtual load)
         double vx = st.cx, vy = st.cy, vm = st.m;
         if (k == 1) {
             const double t1 = r0[1] * 1e-6, t2 = r0[3] * 1e-6;
@@ -343,52 +425,58 @@ __device__ __noinline__ int stability_check(const G &g, const typename G::Node &
             if (fast) ok = pip_rect(r0[0], r0[1], r0[2], r0[3], t1, t2, st.cx, st.cy);
             else {
                 double px[4] = {r0[0] + t1, r0[0] + t2, r0[2] + t1, r0[2] + t2}, py[4] = {r0[1], r0[3], r0[1], r0[3]};
-                uint8_t order[4], hl[8], hu[8];
-                const int m = hull_indices(px, py, 4, order, hl, hu);
-                ok = pip_shrunk(px, py, hl, m, st.cx, st.cy);
+                double hx[8], hy[8];
+                const int m = hull_coords(px, py, 4, hx, hy);
+                ok = pip_shrunk(hx, hy, 1, m, st.cx, st.cy);
             }
-            if (!ok) return 0;
+            SEC(1);
+            if (!ok) { SEC_OUT(); return 0; }
             if (real) {
-                int pos = -1;
-#pragma unroll 1
-                for (int q = 0; q < pool.n; q++)
-                    if (pool.upper[q] == node && pool.lower[q] == sid0) { pos = q; break; }
-                if (pos < 0) {
-                    if (pool.n >= EDGE_MAX) { flags |= PCT_FLAG_EDGE_OVERFLOW; return 0; }
-                    pos = pool.n++;
-                    pool.upper[pos] = (uint8_t)node;
-                    pool.lower[pos] = (uint8_t)sid0;
-                }
-                pool.st[pos] = st;
+                if (node == root_id && !pool_append(pool, sid0)) { flags |= PCT_FLAG_EDGE_OVERFLOW; return 0; }
+                pool.load(eoff) = st;
             }
             child = sid0;  // whole stack goes to the single support
+            skip = (node == root_id) ? EDGE_NIL : eoff;
         } else if (k >= 2) {
             // ---------- general case: hull over all contact-rectangle corners ----------
-            double lrect[KSUP_SMALL][4], lpx[4 * KSUP_SMALL], lpy[4 * KSUP_SMALL];
-            uint8_t lorder[4 * KSUP_SMALL], lhl[8 * KSUP_SMALL], lhu[4 * KSUP_SMALL + 4];
+            double lrect[KSUP_SMALL][4], lpx[4 * KSUP_SMALL], lpy[4 * KSUP_SMALL], lhx[8 * KSUP_SMALL], lhy[8 * KSUP_SMALL];
             const bool small = k <= KSUP_SMALL;
             double (*rect)[4] = lrect;
-            double *px = lpx, *py = lpy;
-            uint8_t *order = lorder, *hl = lhl, *hu = lhu;
+            double *px = lpx, *py = lpy, *hx = lhx, *hy = lhy;
             if (!small) {  // rare: serialise the lanes of this env on the per-env HBM scratch
                 while (atomicCAS(lock, 0, 1) != 0) { }
                 __threadfence_block();
-                rect = big->rect; px = big->px; py = big->py; order = big->order; hl = big->hl; hu = big->hu;
+                rect = big->rect; px = big->px; py = big->py; hx = big->hx; hy = big->hy;
             }
 #pragma unroll 1
             for (int s = 0; s < k; s++) g.support(cur, sup_id[base + s], rect[s]);
-            // combine_contact_points order: (x1,y1) (x1,y2) (x2,y1) (x2,y2); perturb x += y*1e-6 (convex_hull.py:43)
+            bool ok;
+            const int pv = node == root_id ? 0 : (int)pool.poly_off[node], pm = node == root_id ? 0 : (int)pool.poly_off[node + 1] - pv;
+            if (pm > 0 && (pv + pm <= POLY_STAGE || pv >= POLY_STAGE)) {
+                // a placed box: its support polygon was stored when it was placed
+                const double *xy = pool.poly_at(pv);
+                ok = pip_shrunk(xy, xy + 1, 2, pm, st.cx, st.cy);
+            } else {
+                // combine_contact_points order: (x1,y1) (x1,y2) (x2,y1) (x2,y2); perturb x += y*1e-6 (convex_hull.py:43)
 #pragma unroll 1
-            for (int s = 0; s < k; s++) {
-                const double x1 = rect[s][0], y1 = rect[s][1], x2 = rect[s][2], y2 = rect[s][3];
-                const double t1 = y1 * 1e-6, t2 = y2 * 1e-6;
-                px[4 * s + 0] = x1 + t1; py[4 * s + 0] = y1;
-                px[4 * s + 1] = x1 + t2; py[4 * s + 1] = y2;
-                px[4 * s + 2] = x2 + t1; py[4 * s + 2] = y1;
-                px[4 * s + 3] = x2 + t2; py[4 * s + 3] = y2;
+                for (int s = 0; s < k; s++) {
+                    const double x1 = rect[s][0], y1 = rect[s][1], x2 = rect[s][2], y2 = rect[s][3];
+                    const double t1 = y1 * 1e-6, t2 = y2 * 1e-6;
+                    px[4 * s + 0] = x1 + t1; py[4 * s + 0] = y1;
+                    px[4 * s + 1] = x1 + t2; py[4 * s + 1] = y2;
+                    px[4 * s + 2] = x2 + t1; py[4 * s + 2] = y1;
+                    px[4 * s + 3] = x2 + t2; py[4 * s + 3] = y2;
+                }
+                const int m = hull_coords(px, py, 4 * k, hx, hy);
+                ok = pip_shrunk(hx, hy, 1, m, st.cx, st.cy);
+                if (real && ok && node == root_id && pool.n_poly + m <= POLY_MAX) {
+                    // the box being placed: remember its polygon (bottom_whole_contact_area, D:space.py:378-379)
+#pragma unroll 1
+                    for (int i = 0; i < m; i++) { double *v = pool.poly_at(pool.n_poly + i); v[0] = hx[i]; v[1] = hy[i]; }
+                    pool.n_poly += m;
+                }
             }
-            const int m = hull_indices(px, py, 4 * k, order, hl, hu);
-            bool ok = pip_shrunk(px, py, hl, m, st.cx, st.cy);
+            SEC(1);
             int whole = 2;
             if (ok) {
                 // --- distribution ---
@@ -419,11 +507,13 @@ __device__ __noinline__ int stability_check(const G &g, const typename G::Node &
                         LsWork w;
                         w.R = small ? lR : big->R; w.V = small ? lV : big->V; w.y = small ? ly_ : big->y;
                         w.row = small ? lrow : big->row; w.x = small ? lx_ : big->x; w.ld = small ? KSUP_SMALL : KSUP_MAX;
+                        DBG_LS();
                         lstsq_ratios(w, k, px, py, st.cx, st.cy);
 #pragma unroll 1
                         for (int s = 0; s < k; s++) sup_m[base + s] = st.m * w.x[s];
                     }
                 }
+                SEC(2);
                 if (real) {
                     // persist the loads: up_edges[self] = Stack(...) for every support, in support order
 #pragma unroll 1
@@ -431,37 +521,31 @@ __device__ __noinline__ int stability_check(const G &g, const typename G::Node &
                         Stack4 e = st;
                         if (!whole) { e.cx = px[s]; e.cy = py[s]; }
                         e.m = sup_m[base + s];
-                        int pos = -1;
-#pragma unroll 1
-                        for (int q = 0; q < pool.n; q++)
-                            if (pool.upper[q] == node && pool.lower[q] == sup_id[base + s]) { pos = q; break; }
-                        if (pos < 0) {
-                            if (pool.n >= EDGE_MAX) { flags |= PCT_FLAG_EDGE_OVERFLOW; ok = false; break; }
-                            pos = pool.n++;
-                            pool.upper[pos] = (uint8_t)node;
-                            pool.lower[pos] = sup_id[base + s];
-                        }
-                        pool.st[pos] = e;
+                        if (node == root_id && !pool_append(pool, sup_id[base + s])) { flags |= PCT_FLAG_EDGE_OVERFLOW; ok = false; break; }
+                        pool.load(eoff + s) = e;
                     }
                 }
             }
             if (!small) { __threadfence_block(); atomicExch(lock, 0); }
-            if (!ok) return 0;
+            SEC(3);
+            if (!ok) { SEC_OUT(); return 0; }
             if (depth >= STAB_DEPTH) { flags |= PCT_FLAG_SUPPORT_OVERFLOW; return 0; }
             StabFrame &f = fr[depth++];
             f.st = st; f.node = (uint8_t)node; f.base = (uint8_t)base; f.k = (uint8_t)k; f.i = 0; f.whole = (uint8_t)whole;
+            f.eoff = (uint8_t)eoff;
         }
         // ================= pick the next node to enter =================
         int parent = node;
         if (child < 0) {
             // k == 0 (return True) or a frame was just pushed: continue with the top frame's next child
             for (;;) {
-                if (depth == 0) return 1;
+                if (depth == 0) { SEC_OUT(); return 1; }
                 StabFrame &f = fr[depth - 1];
                 if (f.i == f.k) { depth--; continue; }  // all supports passed -> True
                 const int s = f.i++;
                 child = sup_id[f.base + s];
                 parent = f.node;
+                skip = (parent == root_id) ? EDGE_NIL : (int)f.eoff + s;
                 st = f.st;
                 vm = sup_m[f.base + s];
                 vx = st.cx; vy = st.cy;
@@ -484,10 +568,9 @@ __device__ __noinline__ int stability_check(const G &g, const typename G::Node &
         g.centre(sb, ccx, ccy, ccz);
         ccx *= mm; ccy *= mm; ccz *= mm;
 #pragma unroll 1
-        for (int q = 0; q < pool.n; q++) {
-            if (pool.lower[q] != child) continue;
-            if (!real && pool.upper[q] == parent) continue;  // `involved` path member: its real load is replaced by the virtual one
-            const Stack4 e = pool.st[q];
+        for (int q = pool.first_in[child]; q != EDGE_NIL; q = pool.next[q]) {
+            if (!real && q == skip) continue;  // `involved` path member: its real load is replaced by the virtual one
+            const Stack4 e = pool.load(q);
             ccx += e.cx * e.m; ccy += e.cy * e.m; ccz += e.cz * e.m;
             mm += e.m;
         }
@@ -497,6 +580,8 @@ __device__ __noinline__ int stability_check(const G &g, const typename G::Node &
         }
         st.cx = ddiv(ccx, mm); st.cy = ddiv(ccy, mm); st.cz = ddiv(ccz, mm); st.m = mm;
         node = child;
+        DBG_VISIT();
+        SEC(4);
     }
 }
 

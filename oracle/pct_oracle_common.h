@@ -164,6 +164,18 @@ static void po_ls_add_row(po_ls *s, double *row, double rhs) {
 static void po_ls_solve(po_ls *s, double *x) {
     int k = s->k;
     double (*G)[PO_MAX_SUP] = s->R;
+    {   /* full column rank and well conditioned (the usual case): least-squares solution of R x = y */
+        double rmin = fabs(G[0][0]), rmax = rmin;
+        for (int i = 1; i < k; i++) { double a = fabs(G[i][i]); rmin = fmin(rmin, a); rmax = fmax(rmax, a); }
+        if (rmin * 1e4 > rmax) {
+            for (int i = k - 1; i >= 0; i--) {
+                double acc = s->y[i];
+                for (int j = i + 1; j < k; j++) acc -= G[i][j] * x[j];
+                x[i] = acc / G[i][i];
+            }
+            return;
+        }
+    }
     static __thread double V[PO_MAX_SUP][PO_MAX_SUP];
     for (int i = 0; i < k; i++)
         for (int j = 0; j < k; j++) V[i][j] = (i == j) ? 1.0 : 0.0;
