@@ -73,6 +73,9 @@ typedef struct pct_config {
     uint64_t seed;                /* item generator seed (PCT_ITEMS_RANDOM)                       */
     int64_t env_id_base;          /* global index of env 0 of this handle (multi-GPU sharding:    */
                                   /*   per-env streams depend on the GLOBAL index only)           */
+    int32_t no_auto_reset;        /* 0: ShmemVecEnv worker semantics (finished envs are reset inside the step,   */
+                                  /*    wrapper/shmem_vec_env.py:141-142); 1: plain gym.Env semantics (the       */
+                                  /*    terminal observation is returned, the caller resets; D:bin3D.py:160-165) */
 } pct_config;
 
 /* Terminal-step info (the dict built at D:bin3D.py:163-164 plus what Monitor adds, wrapper/monitor.py:58-77) */
@@ -109,6 +112,9 @@ int pct_set_item_set(pct_handle h, const double *items_xyz, int32_t n_items);
 /* replaces box_creator (D:binCreator.py): host array (n_envs, len, 4) of (x,y,z,density) draws per env,
  * consumed one per reset and one per successful placement, cyclically. Switches the handle to PCT_ITEMS_STREAM. */
 int pct_set_item_stream(pct_handle h, const double *items_xyzd, int32_t len);
+/* LoadBoxCreator episodes (D:binCreator.py:41-72): the stream is a sequence of fixed-length trajectories and every
+ * reset jumps to the start of the next one (0 = plain continuous stream, the RandomBoxCreator discipline). */
+int pct_set_trajectory_length(pct_handle h, int32_t traj_len);
 
 /* VecEnv.reset()  (wrapper/shmem_vec_env.py:61-68 -> D:bin3D.py:61-67): resets every env, writes d_obs
  * (n_envs x obs_len elements of cfg.obs_dtype). */

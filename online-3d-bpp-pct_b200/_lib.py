@@ -19,7 +19,7 @@ class Config(C.Structure):
                 ("internal_node_holder", C.c_int32), ("leaf_node_holder", C.c_int32), ("obs_dtype", C.c_int32),
                 ("item_mode", C.c_int32), ("size_minimum", C.c_double), ("sample_from_distribution", C.c_int32),
                 ("sample_left_bound", C.c_double), ("sample_right_bound", C.c_double), ("seed", C.c_uint64),
-                ("env_id_base", C.c_int64)]
+                ("env_id_base", C.c_int64), ("no_auto_reset", C.c_int32)]
 
 
 class StepInfo(C.Structure):
@@ -33,7 +33,7 @@ class StateDump(C.Structure):
                 ("boxes", (C.c_double * 7) * 80), ("ems", (C.c_double * 6) * 256)]
 
 
-EXPORTS = ["pct_create", "pct_destroy", "pct_last_error", "pct_set_item_set", "pct_set_item_stream", "pct_reset", "pct_step",
+EXPORTS = ["pct_create", "pct_destroy", "pct_last_error", "pct_set_item_set", "pct_set_item_stream", "pct_set_trajectory_length", "pct_reset", "pct_step",
            "pct_step_host", "pct_reset_host", "pct_policy_random", "pct_get_state", "pct_obs_len", "pct_num_envs",
            "pct_state_bytes_per_env", "pct_kernel_launches", "pct_version"]
 
@@ -63,6 +63,7 @@ def lib():
     L.pct_last_error.restype = C.c_char_p
     L.pct_set_item_set.argtypes = [vp, C.POINTER(C.c_double), i32]
     L.pct_set_item_stream.argtypes = [vp, C.POINTER(C.c_double), i32]
+    L.pct_set_trajectory_length.argtypes = [vp, i32]
     L.pct_reset.argtypes = [vp, vp, vp]
     L.pct_step.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp, vp]
     L.pct_step_host.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp]

@@ -20,7 +20,7 @@ class PctBatch(object):
     def __init__(self, n_envs, setting, container_size=(10, 10, 10), item_set=None, internal_node_holder=80,
                  leaf_node_holder=50, continuous=False, obs_dtype=torch.float32, seed=0, env_id_base=0, device=0,
                  sample_from_distribution=False, sample_left_bound=None, sample_right_bound=None, item_stream=None,
-                 size_minimum=None):
+                 size_minimum=None, auto_reset=True):
         if not torch.cuda.is_available():
             raise PctError("pct_b200 needs a CUDA device (sm_100a kernels; there is no CPU fallback)")
         self.L = _lib.lib()
@@ -56,6 +56,7 @@ class PctBatch(object):
         cfg.size_minimum = float(size_minimum)
         cfg.seed = int(seed) & ((1 << 64) - 1)
         cfg.env_id_base = int(env_id_base)
+        cfg.no_auto_reset = 0 if auto_reset else 1
         self.cfg = cfg
         h = C.c_void_p()
         rc = self.L.pct_create(C.byref(cfg), self.n_envs, int(device), C.byref(h))
@@ -95,6 +96,9 @@ class PctBatch(object):
             a = np.concatenate([a, np.ones(a.shape[:2] + (1,))], axis=2)
         a = np.ascontiguousarray(a)
         self._check(self.L.pct_set_item_stream(self.h, a.ctypes.data_as(C.POINTER(C.c_double)), a.shape[1]), "pct_set_item_stream")
+
+    def set_trajectory_length(self, traj_len):
+        self._check(self.L.pct_set_trajectory_length(self.h, int(traj_len)), "pct_set_trajectory_length")
 
     # -- device-resident API -------------------------------------------------------------------------------
     def reset(self, out=None):

@@ -144,6 +144,12 @@ int pct_set_item_stream(pct_handle h, const double *items_xyzd, int32_t len) {
     return PCT_OK;
 }
 
+int pct_set_trajectory_length(pct_handle h, int32_t traj_len) {
+    if (!h || traj_len < 0) return PCT_ERR_INVALID;
+    h->traj_len = traj_len;
+    return PCT_OK;
+}
+
 static int launch(pct_handle h, int mode, const void *actions, int action_f64, const int32_t *leaf_idx, void *obs, float *rew, uint8_t *done,
                   pct_step_info *info, cudaStream_t st) {
     if (h->item_mode == PCT_ITEMS_RANDOM && !(h->cfg.domain == PCT_CONTINUOUS && h->cfg.sample_from_distribution) && !h->d_item_set) {
@@ -174,13 +180,14 @@ static int launch(pct_handle h, int mode, const void *actions, int action_f64, c
     p.nb = h->cfg.internal_node_holder; p.nl = h->cfg.leaf_node_holder; p.setting = h->cfg.setting;
     p.low_bound = h->cfg.size_minimum;
     p.item_mode = h->item_mode; p.item_set = h->d_item_set; p.n_items = h->n_items;
-    p.stream = h->d_stream ? h->d_stream + (size_t)off * h->stream_len * 4 : nullptr; p.stream_len = h->stream_len;
+    p.stream = h->d_stream ? h->d_stream + (size_t)off * h->stream_len * 4 : nullptr; p.stream_len = h->stream_len; p.traj_len = h->traj_len;
     p.seed = h->cfg.seed; p.env_id_base = h->cfg.env_id_base + off; p.env_id_base0 = h->cfg.env_id_base;
     p.actions = actions ? (const char *)actions + (size_t)off * 9 * asz : nullptr; p.action_f64 = action_f64;
     p.leaf_idx = leaf_idx ? leaf_idx + off : nullptr;
     p.obs = (char *)obs + (size_t)off * h->obs_len * osz; p.obs_f64 = h->cfg.obs_dtype == PCT_F64;
     p.reward = rew ? rew + off : nullptr; p.done = done ? done + off : nullptr; p.info = info ? info + off : nullptr; p.mode = mode;
     p.dbg = (long long *)h->dbg;
+    p.keep_draw = h->did_reset ? 1 : 0; p.no_auto_reset = h->cfg.no_auto_reset;
     CK(h, launch_discrete(p, gs));
     h->launches += discrete_kernels_per_step();
     if (gi > 0) {

@@ -382,6 +382,7 @@ __device__ __noinline__ void reset_space(DEnvHot *hot, const DParams &p, int e, 
         h.n_box = 0; h.n_ems = 1; h.n_leaf = 0; h.flags = 0; h.n_edge = 0; h.n_poly = 0; h.vol_sum = 0; h.ep_len = 0; h.ep_reward = 0;
         hot->ems[0][0] = 0; hot->ems[0][1] = 0; hot->ems[0][2] = 0;
         hot->ems[0][3] = (int16_t)p.W; hot->ems[0][4] = (int16_t)p.L; hot->ems[0][5] = (int16_t)p.H;
+        if (p.traj_len > 0 && h.draw_pos % p.traj_len) h.draw_pos += p.traj_len - h.draw_pos % p.traj_len;  // LoadBoxCreator.reset
         draw_item(p, e, h);
     }
     __syncwarp();
@@ -490,7 +491,10 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, 14) pct_apply_kernel(con
 
     if (p.mode == 0) {
         // ---------------- reset (D:bin3D.py:61-67, D:space.py:290-314) ----------------
+        const int64_t dp = p.keep_draw ? ghot->h.draw_pos : 0;  // box_creator.reset() does not rewind the item source
         for (int t = lane; t < (int)(sizeof(DEnvHot) / 4); t += 32) ((uint32_t *)hot)[t] = 0;
+        __syncwarp();
+        if (lane == 0) hot->h.draw_pos = dp;
         __syncwarp();
         reset_space(hot, p, e, lane);
     } else {
@@ -637,7 +641,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, 14) pct_apply_kernel(con
             info.ep_reward = (float)h.ep_reward;
             info.ep_len = h.ep_len + 1;
             __syncwarp();
-            reset_space(hot, p, e, lane);
+            if (!p.no_auto_reset) reset_space(hot, p, e, lane);
         }
     }
     fence_proxy_async();

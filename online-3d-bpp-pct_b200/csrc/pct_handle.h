@@ -18,6 +18,7 @@ struct pct_env_batch {
     int n_items = 0;
     double *d_stream = nullptr;
     int stream_len = 0;
+    int traj_len = 0;
     int item_mode = 0;
     // staging for the host-buffer entry points
     void *d_obs = nullptr, *d_act = nullptr;

@@ -117,6 +117,7 @@ struct DParams {
     int n_items;
     const double *stream;
     int stream_len;
+    int traj_len;  // > 0: resets jump to the next multiple of traj_len in the stream
     uint64_t seed;
     int64_t env_id_base;
     int64_t env_id_base0;  // env_id_base of env 0 of the handle (debug timers index by handle-local env)
@@ -129,6 +130,8 @@ struct DParams {
     uint8_t *done;
     pct_step_info *info;
     int mode;  // 0 = reset all, 1 = step
+    int keep_draw;      // mode 0: continue the item source instead of rewinding it (env.reset() after an episode)
+    int no_auto_reset;  // mode 1: leave a finished env untouched (gym.Env semantics)
     long long *dbg;  // phase timers (only with -DPCT_PHASE_TIMERS)
 };
 

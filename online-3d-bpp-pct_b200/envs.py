@@ -1,0 +1,172 @@
+"""Single-environment facades and factories with the reference's names and kwargs.
+
+    PackingDiscrete / PackingContinuous   <->  pct_envs/PctDiscrete0/bin3D.py:8-188, pct_envs/PctContinuous0/bin3D.py:8-207
+    make_vec_envs(args, log_dir, allow_early_resets)   <->  envs.py:75-116
+    registration_envs()                                 <->  tools.py:232-240
+
+The facades are a batch of ONE environment on the GPU in plain gym.Env mode (no auto-reset, float64
+observations as the reference returns them), so `evaluation_tools.evaluate` (evaluation_tools.py:7-52) and the
+heuristics' read-only attribute accesses work unchanged.  They exist for drop-in compatibility; throughput comes
+from PctVecEnv / PctBatch.
+"""
+import numpy as np
+import torch
+
+from .batch import PctBatch
+from .vec_env import PctVecEnv, _make_box
+
+
+class _SpaceView(object):
+    """The few `env.space.*` members external code reads (evaluation / heuristics): boxes, EMS, get_ratio()."""
+
+    def __init__(self, env):
+        self._env = env
+
+    @property
+    def boxes(self):
+        return [tuple(b) for b in self._env._state()["boxes"]]
+
+    @property
+    def EMS(self):
+        return [np.array(e) for e in self._env._state()["ems"]]
+
+    @property
+    def plain_size(self):
+        return np.array(self._env.bin_size)
+
+    def get_ratio(self):  # D:space.py:334-339
+        st = self._env._state()
+        b = st["boxes"]
+        vol = float(np.sum((b[:, 3] - b[:, 0]) * (b[:, 4] - b[:, 1]) * (b[:, 5] - b[:, 2]))) if len(b) else 0.0
+        return vol / float(np.prod(self._env.bin_size))
+
+
+class _PackingBase(object):
+    _continuous = False
+    metadata = {}
+    spec = None
+    action_space = None
+    reward_range = (-float("inf"), float("inf"))
+
+    def __init__(self, setting, container_size=(10, 10, 10), item_set=None, data_name=None, load_test_data=False,
+                 internal_node_holder=80, leaf_node_holder=50, next_holder=1, shuffle=False, LNES="EMS",
+                 sample_from_distribution=False, sample_left_bound=None, sample_right_bound=None, device=0, seed=0,
+                 item_stream=None, **kwags):
+        if next_holder != 1:
+            raise NotImplementedError("next_holder must be 1 (reference default)")
+        if LNES != "EMS" or shuffle:
+            raise NotImplementedError("pct_b200 builds LNES='EMS', shuffle=False")
+        self.internal_node_holder, self.leaf_node_holder, self.next_holder = internal_node_holder, leaf_node_holder, next_holder
+        self.bin_size = container_size
+        self.setting = setting
+        self.item_set = item_set
+        self.orientation = 6 if setting == 2 else 2
+        self.test = load_test_data
+        self.LNES = LNES
+        self.shuffle = shuffle
+        stream, traj_len = item_stream, 0
+        if load_test_data:
+            # LoadBoxCreator (binCreator.py:41-72): one trajectory per episode (reset() pre-increments the index, so
+            # trajectory 0 is never used), each followed by the [100,100,100] sentinel that ends the episode.
+            trajs = [np.array(t, dtype=np.float64) for t in torch.load(data_name)][1:]
+            traj_len = max(len(t) for t in trajs) + 1
+            seq = np.full((len(trajs), traj_len, 4), 100.0)
+            seq[:, :, 3] = 1.0
+            for i, t in enumerate(trajs):
+                seq[i, :len(t), :t.shape[1]] = t
+            stream = seq.reshape(1, -1, 4)
+        self._batch = PctBatch(1, setting, container_size=container_size, item_set=item_set, internal_node_holder=internal_node_holder,
+                               leaf_node_holder=leaf_node_holder, continuous=self._continuous, obs_dtype=torch.float64, seed=seed,
+                               device=device, sample_from_distribution=sample_from_distribution and self._continuous,
+                               sample_left_bound=sample_left_bound, sample_right_bound=sample_right_bound, item_stream=stream,
+                               auto_reset=False)
+        if traj_len:
+            self._batch.set_trajectory_length(traj_len)
+        self.observation_space = _make_box(0.0, float(container_size[2]), (self._batch.obs_len,))
+        self.space = _SpaceView(self)
+        self.SEED = seed
+
+    # ---- gym.Env API ----
+    def seed(self, seed=None):  # D:bin3D.py:47-54 (the item generator is counter-based: the seed is fixed at construction)
+        return [seed]
+
+    def reset(self):
+        return self._batch.reset().cpu().numpy()[0].copy()
+
+    def step(self, action):
+        a = np.asarray(action, dtype=np.float64).reshape(-1)
+        if len(a) == 3:  # (rot, lx, ly) triples of the heuristics (heuristic.py:127,221,289): expand to a leaf row
+            nb = self.next_box
+            x, y = (nb[1], nb[0]) if a[0] else (nb[0], nb[1])
+            a = np.array([a[1], a[2], 0, a[1] + x, a[2] + y, 0, 0, 0, 0], dtype=np.float64)
+        row = np.zeros(9)
+        row[:min(9, len(a))] = a[:9]
+        obs, rew, done, info = self._batch.step(actions=torch.from_numpy(row[None]).to(self._batch.device))
+        rec = PctBatch.decode_info(info)
+        d = bool(done.cpu().numpy()[0])
+        out = {"counter": int(rec["counter"][0])}
+        if d:
+            ratio = self.space.get_ratio()
+            out.update(ratio=ratio, reward=ratio * 10)
+        if rec["flags"][0]:
+            out["flags"] = int(rec["flags"][0])
+        return obs.cpu().numpy()[0].copy(), float(rew.cpu().numpy()[0]), d, out
+
+    def close(self):
+        self._batch.close()
+
+    @property
+    def unwrapped(self):
+        return self
+
+    # ---- attributes read by evaluation_tools.py:23 and heuristic.py ----
+    def _state(self):
+        return self._batch.state(0)
+
+    @property
+    def packed(self):
+        b = self._state()["boxes"]
+        conv = (lambda v: v) if self._continuous else int
+        return [[conv(r[3] - r[0]), conv(r[4] - r[1]), conv(r[5] - r[2]), conv(r[0]), conv(r[1]), conv(r[2]), 0] for r in b]
+
+    @property
+    def next_box(self):
+        nb = self._state()["next_box"]
+        return list(nb) if self._continuous else [int(v) for v in nb]
+
+    @property
+    def next_den(self):
+        return self._state()["next_den"]
+
+
+class PackingDiscrete(_PackingBase):
+    """Drop-in for pct_envs.PctDiscrete0.PackingDiscrete."""
+    _continuous = False
+
+
+class PackingContinuous(_PackingBase):
+    """Drop-in for pct_envs.PctContinuous0.PackingContinuous."""
+    _continuous = True
+
+
+def make_vec_envs(args, log_dir=None, allow_early_resets=True):
+    """envs.make_vec_envs (envs.py:75-116) on the GPU: `args` is the namespace of tools.get_args()."""
+    dev = getattr(args, "device", 0)
+    dev = 0 if isinstance(dev, str) else int(dev)
+    return PctVecEnv(args.num_processes, args.setting, container_size=args.container_size, item_set=args.item_size_set,
+                     internal_node_holder=args.internal_node_holder, leaf_node_holder=args.leaf_node_holder,
+                     continuous=getattr(args, "continuous", False) or str(getattr(args, "id", "")).startswith("PctContinuous"),
+                     device=dev, seed=args.seed, sample_from_distribution=getattr(args, "sample_from_distribution", False),
+                     sample_left_bound=getattr(args, "sample_left_bound", None), sample_right_bound=getattr(args, "sample_right_bound", None),
+                     LNES=getattr(args, "lnes", "EMS"), shuffle=False)
+
+
+def registration_envs():
+    """tools.registration_envs (tools.py:232-240): same ids, our entry points (no-op without gym)."""
+    try:
+        from gym.envs.registration import register
+    except Exception:
+        return False
+    register(id="PctDiscrete-v0", entry_point="pct_b200.envs:PackingDiscrete")
+    register(id="PctContinuous-v0", entry_point="pct_b200.envs:PackingContinuous")
+    return True

@@ -1,0 +1,115 @@
+"""GPU: the reference-facing host surface (PctVecEnv, PackingDiscrete facade) against the CPU oracle."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+from harness import ITEM_SET, OracleVec, make_stream, policy_pick  # noqa: E402
+from pct_oracle import OracleDiscrete  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("setting", [1, 2])
+def test_vec_env_matches_shmem_semantics(setting):
+    import pct_b200
+    n, seed = 24, 5
+    streams = np.stack([make_stream(seed, e, 300, setting) for e in range(n)])
+    orc = OracleVec(n, setting, streams)
+    env = pct_b200.PctVecEnv(n, setting, item_set=ITEM_SET, item_stream=streams)
+    assert env.num_envs == n and env.observation_space.shape == (1179,)
+    o_ref = orc.reset()
+    obs = env.reset()
+    assert obs.dtype == torch.float32 and obs.is_cuda and tuple(obs.shape) == (n, 1179)
+    for t in range(60):
+        assert np.array_equal(obs.cpu().numpy(), o_ref.astype(np.float32))
+        _, rows = orc.pick(o_ref, seed, t)
+        o_ref, r_ref, d_ref, i_ref = orc.step(rows)
+        # the trainer passes leaf rows as a float32 numpy array (train_tools.py:67)
+        obs, rew, done, infos = env.step(rows.astype(np.float32))
+        assert tuple(rew.shape) == (n, 1) and not rew.is_cuda and done.dtype == np.bool_
+        assert np.array_equal(done, d_ref)
+        assert np.array_equal(rew.numpy()[:, 0], r_ref.astype(np.float32))
+        for e in range(n):
+            assert infos[e]["counter"] == i_ref[e]["counter"]
+            if d_ref[e]:
+                assert abs(infos[e]["ratio"] - i_ref[e]["ratio"]) < 1e-6
+                assert abs(infos[e]["reward"] - i_ref[e]["reward"]) < 1e-5
+                assert set(infos[e]["episode"]) == {"r", "l", "t"}
+    env.close()
+
+
+@pytest.mark.parametrize("setting", [1, 3])
+def test_single_env_facade_gym_semantics(setting):
+    """No auto-reset: the terminal observation is the reference's cur_observation() after the failed placement,
+    reset() continues the item stream (box_creator.reset() does not rewind it)."""
+    import pct_b200
+    seed = 11
+    stream = make_stream(seed, 0, 400, setting)
+    orc = OracleDiscrete(setting, stream=stream)
+    env = pct_b200.PackingDiscrete(setting=setting, container_size=[10, 10, 10], item_set=ITEM_SET, item_stream=stream[None])
+    o_ref, o = orc.reset(), env.reset()
+    episodes = 0
+    for t in range(150):
+        assert o.dtype == np.float64 and np.array_equal(o, o_ref), "step %d" % t
+        _, row = policy_pick(o_ref, 80, 50, seed, 0, t)
+        o_ref, r_ref, d_ref, i_ref = orc.step(row)
+        o, r, d, info = env.step(row[:6] if t % 2 else row)  # 6-float rows as in evaluation_tools.py:24
+        assert (r, d) == (r_ref, d_ref)
+        assert info["counter"] == i_ref["counter"]
+        if d:
+            assert np.array_equal(o, o_ref), "terminal observation"
+            assert abs(info["ratio"] - i_ref["ratio"]) < 1e-12
+            assert env.packed == orc.packed
+            o_ref, o = orc.reset(), env.reset()
+            episodes += 1
+    assert episodes >= 3
+    env.close()
+
+
+def test_triple_actions_and_bad_action_flag():
+    import pct_b200
+    stream = np.array([[[2, 3, 4, 1.0]] * 8], dtype=np.float64)
+    env = pct_b200.PackingDiscrete(setting=2, container_size=[10, 10, 10], item_set=ITEM_SET, item_stream=stream)
+    orc = OracleDiscrete(2, stream=stream[0])
+    o, o_ref = env.reset(), orc.reset()
+    assert np.array_equal(o, o_ref)
+    o, r, d, info = env.step((0, 0, 0))          # heuristic-style (rot, lx, ly)
+    o_ref, r_ref, d_ref, _ = orc.step(np.array([0.0, 0.0, 0.0]))
+    assert np.array_equal(o, o_ref) and (r, d) == (r_ref, d_ref) and env.packed == orc.packed
+    o, r, d, info = env.step((1, 5, 5))          # rotated
+    o_ref, r_ref, d_ref, _ = orc.step(np.array([1.0, 5.0, 5.0]))
+    assert np.array_equal(o, o_ref) and env.packed == orc.packed
+    # a leaf row whose extents do not match the item: ValueError in the reference, flagged failure here
+    o, r, d, info = env.step(np.array([0, 0, 0, 7, 7, 10, 0, 0, 1.0]))
+    assert d and info.get("flags", 0) & 2
+    env.close()
+
+
+def test_trajectory_stream_mode():
+    """LoadBoxCreator discipline: every reset jumps to the next fixed-length trajectory."""
+    import pct_b200
+    L, n = 6, 3
+    items = np.ones((n, 4 * L, 4))
+    for e in range(n):
+        for k in range(4 * L):
+            items[e, k, :3] = [1 + (k // L) % 5, 1 + (e % 5), 2]
+    b = pct_b200.PctBatch(n, 2, item_set=ITEM_SET, item_stream=items, obs_dtype=torch.float64)
+    b.set_trajectory_length(L)
+    b.reset()
+    assert [b.state(e)["next_box"][0] for e in range(n)] == [1.0] * n and b.state(0)["draw_pos"] == 1
+    b.step(leaf_idx=torch.zeros(n, dtype=torch.int32, device="cuda"))
+    b.step(leaf_idx=torch.zeros(n, dtype=torch.int32, device="cuda"))
+    assert b.state(0)["draw_pos"] == 3
+    b.reset()   # env.reset() mid-trajectory -> start of trajectory 1
+    assert b.state(0)["draw_pos"] == L + 1 and b.state(0)["next_box"][0] == 2.0
+
+
+def test_create_errors_are_reported():
+    import pct_b200
+    with pytest.raises(pct_b200.PctError):
+        pct_b200.PctBatch(4, 7, item_set=ITEM_SET)
+    with pytest.raises(pct_b200.PctError):
+        pct_b200.PctBatch(4, 1, item_set=ITEM_SET, internal_node_holder=500)
+    b = pct_b200.PctBatch(4, 1, item_set=ITEM_SET)
+    with pytest.raises(pct_b200.PctError):
+        b.step(leaf_idx=torch.zeros(4, dtype=torch.int32, device="cuda"))  # step before reset

@@ -1,0 +1,39 @@
+"""CPU: the C oracle must reproduce the golden vectors recorded from the unmodified reference (tests/golden/*.npz,
+made by tests/golden/make_golden.py).  This is what pins the oracle when /root/reference is not mounted."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from pct_oracle import OracleDiscrete
+
+GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "discrete_s*.npz")))
+
+
+def test_golden_files_present():
+    assert len(GOLD) >= 6
+
+
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p) for p in GOLD])
+def test_oracle_replays_reference_trajectory(path):
+    g = np.load(path)
+    setting = int(g["setting"])
+    env = OracleDiscrete(setting, stream=g["stream"])
+    obs = g["obs"]
+    k = 0
+    o = env.reset()
+    assert np.array_equal(o, obs[k]); k += 1
+    for t in range(len(g["rows"])):
+        if t % 25 == 0:  # internals pinned at a few steps: EMS list and ordered candidate list of the reference
+            assert np.array_equal(env.ems(), g["ems_%d" % t]), "EMS list, step %d" % t
+            cand, _ = env.candidates()
+            assert np.array_equal(cand, g["cand_%d" % t].reshape(-1, 6)), "candidate order, step %d" % t
+        o, r, d, info = env.step(g["rows"][t])
+        assert np.array_equal(o, obs[k]), "observation after step %d (done=%s)" % (t, d); k += 1
+        assert r == g["reward"][t] and d == bool(g["done"][t]) and info["counter"] == g["counter"][t]
+        if d:
+            assert info["ratio"] == g["ratio"][t]
+            o = env.reset()
+            assert np.array_equal(o, obs[k]); k += 1
+    assert k == len(obs)

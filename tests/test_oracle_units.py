@@ -1,0 +1,101 @@
+"""CPU: the oracle's building blocks against CPython / numpy themselves (third-party arithmetic the reference leans on:
+set iteration order, tuple and float hashes, lstsq) and against the reference's convex_hull.py when it is mounted."""
+import ctypes as C
+import random
+
+import numpy as np
+import pytest
+
+import pct_oracle
+
+L = pct_oracle.lib()
+
+
+def test_set_order_matches_cpython():
+    rng = random.Random(5)
+    for trial in range(400):
+        n = rng.choice([1, 3, 7, 20, 60, 200, 700, 1300])
+        hi = rng.choice([3, 10, 11, 40])
+        keys = [tuple(rng.randrange(0, hi) for _ in range(6)) for _ in range(n)]
+        s = set()
+        for k in keys:
+            s.add(k)
+        want = list(s)
+        uniq, seen = [], set()
+        for k in keys:
+            if k not in seen:
+                seen.add(k); uniq.append(k)
+        arr = np.array(keys, dtype=np.int64)
+        order = np.zeros(len(keys) + 1, dtype=np.int32)
+        m = L.pcto_set_order6(arr.ctypes.data_as(C.POINTER(C.c_int64)), len(keys), order.ctypes.data_as(C.POINTER(C.c_int)))
+        got = [uniq[i] for i in order[:m]]
+        assert got == want, "trial %d n=%d" % (trial, n)
+
+
+def test_float_hash_matches_cpython():
+    rng = np.random.RandomState(1)
+    vals = list(rng.uniform(-3, 3, 2000)) + [0.0, 0.1, 0.5, 1.0, 0.123456, 1e-6, 123456.789, 2.0 ** 70, -0.3]
+    vals += [round(v, 3) for v in rng.uniform(0.1, 0.5, 500)] + [round(a + b, 6) for a, b in rng.uniform(0, 1, (300, 2))]
+    for v in vals:
+        assert L.pcto_hash_double(float(v)) == (hash(float(v)) & ((1 << 64) - 1)), v
+
+
+def test_lstsq_close_to_numpy():
+    rng = np.random.RandomState(2)
+    for k in (3, 4, 5, 8, 16):
+        for trial in range(40):
+            M = k * (k - 1) // 2 + 1
+            A = np.zeros((M, k))
+            c = 0
+            for i in range(k - 1):
+                for j in range(i + 1, k):
+                    if rng.rand() > 0.15:
+                        A[c, i] = 1; A[c, j] = -abs(rng.randn()) * rng.choice([1, 1, 1, -1])
+                    c += 1
+            A[-1] = 1
+            b = np.zeros(M); b[-1] = 1
+            x = np.zeros(k)
+            Ac = np.ascontiguousarray(A)
+            L.pcto_lstsq(Ac.ctypes.data_as(C.POINTER(C.c_double)), M, k, b.ctypes.data_as(C.POINTER(C.c_double)),
+                         x.ctypes.data_as(C.POINTER(C.c_double)))
+            want = np.linalg.lstsq(A, b[:, None], rcond=None)[0][:, 0]
+            assert np.allclose(x, want, rtol=1e-9, atol=1e-11), (k, trial)
+
+
+def test_lstsq_rank_deficient_minimum_norm():
+    A = np.zeros((4, 3)); A[-1] = 1          # all pair rows zero: x = 1/3 each
+    b = np.array([0, 0, 0, 1.0]); x = np.zeros(3)
+    L.pcto_lstsq(A.ctypes.data_as(C.POINTER(C.c_double)), 4, 3, b.ctypes.data_as(C.POINTER(C.c_double)), x.ctypes.data_as(C.POINTER(C.c_double)))
+    assert np.allclose(x, 1 / 3, atol=1e-14)
+    A = np.array([[1, -1e16, 0], [0, 0, 0], [0, 1, -2.0], [1, 1, 1]])  # huge ratio: truncated singular value like gelsd
+    want = np.linalg.lstsq(A, b[:, None], rcond=None)[0][:, 0]
+    L.pcto_lstsq(np.ascontiguousarray(A).ctypes.data_as(C.POINTER(C.c_double)), 4, 3, b.ctypes.data_as(C.POINTER(C.c_double)),
+                 x.ctypes.data_as(C.POINTER(C.c_double)))
+    assert np.allclose(x, want, rtol=1e-6, atol=1e-9)
+
+
+@pytest.mark.reference
+def test_hull_and_pip_match_reference_module():
+    import ref_shim
+    if not ref_shim.reference_available():
+        pytest.skip("reference not mounted")
+    D, _ = ref_shim.load_reference()
+    from pct_envs.PctDiscrete0.convex_hull import ConvexHull, point_in_polygen
+    from pct_envs.PctDiscrete0.space import Space
+    sp = Space(10, 10, 10, 1, 80)
+    rng = np.random.RandomState(3)
+    for trial in range(600):
+        k = rng.choice([1, 1, 2, 2, 3, 4, 6])
+        pts = []
+        for _ in range(k):
+            x1, y1 = rng.randint(0, 8, 2); x2, y2 = x1 + rng.randint(1, 4), y1 + rng.randint(1, 4)
+            pts += [[x1, y1], [x1, y2], [x2, y1], [x2, y2]]
+        want = np.array(sp.scale_down(ConvexHull([list(p) for p in pts])))
+        p = np.array(pts, dtype=np.float64)
+        out = np.zeros((2 * len(pts), 2))
+        m = L.pcto_hull_shrunk(p.ctypes.data_as(C.POINTER(C.c_double)), len(pts), out.ctypes.data_as(C.POINTER(C.c_double)))
+        assert m == len(want) and np.array_equal(out[:m], want), trial
+        for _ in range(6):
+            q = np.array([rng.randint(0, 20) / 2.0, rng.randint(0, 20) / 2.0]) if rng.rand() < 0.5 else rng.uniform(0, 10, 2)
+            got = L.pcto_pip(q[0], q[1], np.ascontiguousarray(want).ctypes.data_as(C.POINTER(C.c_double)), m)
+            assert bool(got) == bool(point_in_polygen(q, want.tolist()))
