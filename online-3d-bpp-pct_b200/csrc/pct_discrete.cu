@@ -186,7 +186,7 @@ __device__ __noinline__ int genems_warp(int16_t (*ems)[6], const int n0, int16_t
             else if (ch == 2) q4 = y1;
             else if (ch == 3) q1 = y2;
             else q2 = z2;
-            if (p < E_MAX) {
+            if (p < EMS_TMP_MAX) {
                 tmp[p][0] = (int16_t)q0; tmp[p][1] = (int16_t)q1; tmp[p][2] = (int16_t)q2;
                 tmp[p][3] = (int16_t)q3; tmp[p][4] = (int16_t)q4; tmp[p][5] = (int16_t)q5;
             } else overflow = true;
@@ -195,7 +195,7 @@ __device__ __noinline__ int genems_warp(int16_t (*ems)[6], const int n0, int16_t
         off += __shfl_sync(FULL, incl, 31);
     }
     if (__any_sync(FULL, overflow)) flags |= PCT_FLAG_EMS_OVERFLOW;
-    const int n = off < E_MAX ? off : E_MAX;
+    const int n = off < EMS_TMP_MAX ? off : EMS_TMP_MAX;  // intermediate list (survivors + children), before the inscribed-EMS purge
     __syncwarp();
     // EliminateInscribedEMS: drop i if some j != i contains it (non-strict; identical twins delete each other)
     int w = 0;
@@ -219,11 +219,14 @@ __device__ __noinline__ int genems_warp(int16_t (*ems)[6], const int n0, int16_t
         const uint32_t bm = __ballot_sync(FULL, keep);
         if (keep) {
             const int p = w + __popc(bm & ((1u << lane) - 1));
+            if (p < E_MAX) {
 #pragma unroll
-            for (int t = 0; t < 6; t++) ems[p][t] = a[t];
+                for (int t = 0; t < 6; t++) ems[p][t] = a[t];
+            }
         }
         w += __popc(bm);
     }
+    if (w > E_MAX) { flags |= PCT_FLAG_EMS_OVERFLOW; w = E_MAX; }
     __syncwarp();
     return w;
 }
@@ -464,7 +467,7 @@ __device__ __forceinline__ long long gtime() { long long t; asm volatile("mov.u6
 #define KT_BEGIN()
 #define KT_END(e, k)
 #endif
-constexpr int K1_SM_PER_WARP = sizeof(DEnvHot) + E_MAX * 12 + 16 + EDGE_STAGE * 32 + POLY_STAGE * 16;  // record + EMS temp + mbarrier/lock + staged loads
+constexpr int K1_SM_PER_WARP = sizeof(DEnvHot) + EMS_TMP_MAX * 12 + 16 + EDGE_STAGE * 32 + POLY_STAGE * 16;  // record + EMS temp + mbarrier/lock + staged loads
 static_assert(K1_SM_PER_WARP % 16 == 0, "alignment");
 
 template <bool STAB>
@@ -476,9 +479,9 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, 14) pct_apply_kernel(con
     unsigned char *sm = smem_raw + (size_t)warp * K1_SM_PER_WARP;
     DEnvHot *hot = (DEnvHot *)sm;
     int16_t (*ems_tmp)[6] = (int16_t (*)[6])(sm + sizeof(DEnvHot));
-    uint64_t *mbar = (uint64_t *)(sm + sizeof(DEnvHot) + E_MAX * 12);
+    uint64_t *mbar = (uint64_t *)(sm + sizeof(DEnvHot) + EMS_TMP_MAX * 12);
     int *lock = (int *)(mbar + 1);
-    Stack4 *st_sm = (Stack4 *)(sm + sizeof(DEnvHot) + E_MAX * 12 + 16);
+    Stack4 *st_sm = (Stack4 *)(sm + sizeof(DEnvHot) + EMS_TMP_MAX * 12 + 16);
     double *poly_sm = (double *)(st_sm + EDGE_STAGE);
     DEnvHot *ghot = p.hot + e;
     DEnvCold *cold = p.cold + e;

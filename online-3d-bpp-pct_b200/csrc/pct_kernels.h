@@ -8,6 +8,7 @@ namespace pct {
 
 constexpr int NB_MAX = 80;    // internal_node_holder capacity
 constexpr int NL_MAX = 64;    // leaf_node_holder capacity
+constexpr int EMS_TMP_MAX = 256;  // intermediate EMS list inside GENEMS (before EliminateInscribedEMS)
 constexpr int E_MAX = 128;    // EMS list capacity (reference: unbounded python list; max observed 51)
 constexpr int TAB_A = 2048;   // CPython-set emulation: largest table (<= 1228 distinct candidates)
 constexpr int TAB_B = 512;

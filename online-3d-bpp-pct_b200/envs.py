@@ -101,16 +101,18 @@ class _PackingBase(object):
             a = np.array([a[1], a[2], 0, a[1] + x, a[2] + y, 0, 0, 0, 0], dtype=np.float64)
         row = np.zeros(9)
         row[:min(9, len(a))] = a[:9]
+        nb = self.next_box  # reward in float64 like the reference: vol(item) / vol(bin) * 10 (D:bin3D.py:180-183)
         obs, rew, done, info = self._batch.step(actions=torch.from_numpy(row[None]).to(self._batch.device))
         rec = PctBatch.decode_info(info)
         d = bool(done.cpu().numpy()[0])
+        reward = 0.0 if d else (nb[0] * nb[1] * nb[2]) / (self.bin_size[0] * self.bin_size[1] * self.bin_size[2]) * 10
         out = {"counter": int(rec["counter"][0])}
         if d:
             ratio = self.space.get_ratio()
             out.update(ratio=ratio, reward=ratio * 10)
         if rec["flags"][0]:
             out["flags"] = int(rec["flags"][0])
-        return obs.cpu().numpy()[0].copy(), float(rew.cpu().numpy()[0]), d, out
+        return obs.cpu().numpy()[0].copy(), reward, d, out
 
     def close(self):
         self._batch.close()

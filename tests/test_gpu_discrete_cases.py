@@ -48,7 +48,7 @@ def test_other_holder_sizes():
 
 def test_big_candidate_sets_use_the_2048_slot_stage():
     # 16^3 bin, small items: hundreds of candidates per step, 16-bit keys; setting 1 exercises the HBM table stage
-    items = [(1, 1, 1), (1, 2, 1), (2, 1, 2), (1, 3, 2), (2, 2, 1)]
+    items = [(2, 2, 2), (3, 3, 2), (2, 3, 3), (4, 2, 2), (3, 4, 3)]  # EMS stays <= 128, > 306 distinct candidates occur
     m2 = _lockstep(2, 6, 70, (16, 16, 16), items, nb=80, nl=50)
     m1 = _lockstep(1, 6, 70, (16, 16, 16), items, nb=80, nl=50)
     assert m2 > 306 and m1 > 306, (m1, m2)  # > 306 distinct candidates forces the 2048-slot table
