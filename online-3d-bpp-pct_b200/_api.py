@@ -7,6 +7,8 @@ __all__ = ["PctBatch", "PctError", "build", "LIB_PATH"]
 try:  # host-side mirror of the reference's gym.Env / VecEnv surface
     from .vec_env import PctVecEnv
     from .envs import PackingDiscrete, PackingContinuous, make_vec_envs, registration_envs
-    __all__ += ["PctVecEnv", "PackingDiscrete", "PackingContinuous", "make_vec_envs", "registration_envs"]
+    from .distributed import shard_range, make_sharded_vec_env, gather_observations
+    __all__ += ["PctVecEnv", "PackingDiscrete", "PackingContinuous", "make_vec_envs", "registration_envs", "shard_range",
+                "make_sharded_vec_env", "gather_observations"]
 except ImportError:  # pragma: no cover - during bring-up
     pass
