@@ -1,11 +1,707 @@
-// Continuous PCT environment (pct_envs/PctContinuous0 in the reference) — placeholder until the kernels land.
+// Continuous PCT environment (pct_envs/PctContinuous0 in the reference, "C:" below): batched reset / step for sm_100a.
+//
+// Same three-kernel pipeline as the discrete domain (apply / candidates / feasibility+emit) and the same stability
+// routine (pct_stability.cuh) instantiated with a float64 geometry policy that carries the reference's 1e-6
+// tolerances and 6-decimal roundings.  This first version keeps the per-env record in HBM (no TMA staging): it is the
+// correctness path for BASELINE config 4; the discrete kernels are the tuned ones.
+//
+// Reference behaviour restated:
+//   PackingContinuous.step / reset / cur_observation / get_possible_position / LeafNode2Action   C:bin3D.py:69-207
+//   Space.interSect2D / drop_box / drop_box_virtual / check_box                                   C:space.py:305-439
+//   Space.interSectEMS3D / GENEMS / Difference / EliminateInscribedEMS / EMSPoint                 C:space.py:441-568
+// Parity contract (see oracle/pct_oracle_continuous.c): float64 leaf rows as actions; float32 rows are widened.
+#include "pct_common.cuh"
+#include "pct_stability.cuh"
 #include "pct_kernels.h"
 #include "pct_handle.h"
+
 namespace pct {
-int continuous_create(pct_env_batch *h) { h->err = "continuous domain is not built yet"; return PCT_ERR_INVALID; }
-void continuous_destroy(pct_env_batch *) {}
-int continuous_launch(pct_env_batch *h, int, const void *, int, const int32_t *, void *, float *, uint8_t *, pct_step_info *, cudaStream_t) { return PCT_ERR_INVALID; }
-int continuous_policy_random(pct_env_batch *, int32_t *, uint64_t, int64_t, cudaStream_t) { return PCT_ERR_INVALID; }
-int continuous_get_state(pct_env_batch *, int, pct_state_dump *) { return PCT_ERR_INVALID; }
-int64_t continuous_state_bytes() { return 0; }
+
+constexpr int CE_MAX = 256;     // EMS capacity (reference preallocates 1000, C:space.py:276)
+constexpr int CE_TMP = 512;     // intermediate list inside GENEMS
+constexpr int CC_TAB = 2048;    // set-emulation table (<= 1228 distinct candidates)
+
+struct CHdr {
+    int32_t n_box, n_ems, n_leaf, flags;
+    int64_t draw_pos;
+    double ep_reward;
+    double next_box[3];
+    double next_den;
+    double vol_sum;
+    int32_t ep_len, n_cand, n_edge, n_poly;
+};
+struct alignas(16) CEnv {
+    CHdr h;
+    double box[NB_MAX][6];      // lx,ly,lz,x,y,z
+    double den[NB_MAX];
+    double ems[CE_MAX][6];
+    double ems_tmp[CE_TMP][6];
+    uint16_t e_off[NB_MAX + 2], poly_off[NB_MAX + 2];
+    uint8_t e_lower[EDGE_MAX + 1], e_next[EDGE_MAX + 1], first_in[NB_MAX], last_in[NB_MAX];
+    Stack4 e_st[EDGE_MAX + 1];
+    double poly[POLY_MAX][2];
+    double leaf[NL_MAX][6];
+    uint16_t cand[1232];
+    BigScratch big;
+};
+
+struct CParams {
+    CEnv *env;
+    int n_envs;
+    double W, L, H, low_bound;
+    int nb, nl, setting;
+    int item_mode, sample_dist;
+    double sample_a, sample_b;
+    const double *item_set;
+    int n_items;
+    const double *stream;
+    int stream_len, traj_len;
+    uint64_t seed;
+    int64_t env_id_base;
+    const void *actions;
+    int action_f64;
+    const int32_t *leaf_idx;
+    void *obs;
+    int obs_f64;
+    float *reward;
+    uint8_t *done;
+    pct_step_info *info;
+    int mode, keep_draw, no_auto_reset;
+};
+
+__device__ __forceinline__ double around6(double v) { return ddiv(rint(v * 1e6), 1e6); }  // np.around(v, 6)
+
+// ---- geometry policy for the stability routine -------------------------------------------------------------
+struct NodeC { double lx, ly, lz, dx, dy, dz, mass; };
+struct GeomC {
+    typedef NodeC Node;
+    const double (*box)[6];
+    const double *den;
+    int n;
+    __device__ __forceinline__ int n_boxes() const { return n; }
+    __device__ __forceinline__ void node_box(int id, NodeC &o) const {
+        const double *b = box[id];
+        o.lx = b[0]; o.ly = b[1]; o.lz = b[2]; o.dx = b[3]; o.dy = b[4]; o.dz = b[5];
+        o.mass = b[3] * b[4] * b[5] * den[id];  // C:space.py:34
+    }
+    __device__ __forceinline__ void centre(const NodeC &o, double &cx, double &cy, double &cz) const {  // C:space.py:31
+        cx = o.lx + o.dx * 0.5; cy = o.ly + o.dy * 0.5; cz = o.lz + o.dz * 0.5;
+    }
+    // interSect2D + the support filter of drop_box (C:space.py:305-314, 350-359)
+    __device__ __noinline__ bool support(const NodeC &nd, int t, double r[4]) const {
+        const double *b = box[t];
+        if (!(fabs(b[2] + b[5] - nd.lz) < 1e-6)) return false;
+        const double i0 = around6(fmin(-nd.lx, -b[0])), i1 = around6(fmin(-nd.ly, -b[1]));
+        const double i2 = around6(fmin(nd.lx + nd.dx, b[0] + b[3])), i3 = around6(fmin(nd.ly + nd.dy, b[1] + b[4]));
+        if (!((i0 + i2 > 0) && (i1 + i3 > 0))) return false;
+        r[0] = -i0; r[1] = -i1; r[2] = i2; r[3] = i3;
+        return true;
+    }
+    __device__ __forceinline__ bool strictly_inside(double cx, double cy, const double r[4]) const {  // C:space.py:85-86
+        return cx - r[0] > 1e-6 && r[2] - cx > 1e-6 && cy - r[1] > 1e-6 && r[3] - cy > 1e-6;
+    }
+};
+
+// resting height: max top over the boxes whose rounded footprint intersection is positive (interSect2D)
+__device__ __forceinline__ double rest_height_c(const double (*box)[6], int first, int n, int stride, double lx, double ly, double hx, double hy) {
+    double mh = 0;
+    bool any = false;
+    for (int t = first; t < n; t += stride) {
+        const double *b = box[t];
+        const double i0 = around6(fmin(-lx, -b[0])), i1 = around6(fmin(-ly, -b[1]));
+        const double i2 = around6(fmin(hx, b[0] + b[3])), i3 = around6(fmin(hy, b[1] + b[4]));
+        if ((i0 + i2 > 0) && (i1 + i3 > 0)) {
+            const double top = b[2] + b[5];
+            if (!any || top > mh) mh = top;
+            any = true;
+        }
+    }
+    return any ? mh : -1.0;  // -1: no overlap (the reference returns 0 then)
 }
+
+__device__ __forceinline__ bool rot_dims_c(const double nb[3], int rot, double &sx, double &sy, double &sz) {  // C:space.py:537-559
+    switch (rot) {
+    case 0: sx = nb[0]; sy = nb[1]; sz = nb[2]; return true;
+    case 1: sx = nb[1]; sy = nb[0]; sz = nb[2]; return !(fabs(sx - sy) < 1e-6);
+    case 2: sx = nb[0]; sy = nb[2]; sz = nb[1]; return !(fabs(sx - sy) < 1e-6 && fabs(sy - sz) < 1e-6);
+    case 3: sx = nb[1]; sy = nb[2]; sz = nb[0]; return !(fabs(sx - sy) < 1e-6 && fabs(sy - sz) < 1e-6);
+    case 4: sx = nb[2]; sy = nb[0]; sz = nb[1]; return !(fabs(sx - sy) < 1e-6);
+    default: sx = nb[2]; sy = nb[1]; sz = nb[0]; return !(fabs(sx - sy) < 1e-6);
+    }
+}
+// candidate code = ems_idx << 5 | rot << 2 | corner  ->  the 6-tuple the reference adds to its set (C:space.py:563-566)
+__device__ __forceinline__ void cand_tuple(uint16_t code, const double (*ems)[6], const double nb[3], double t[6]) {
+    const double *m = ems[code >> 5];
+    double sx, sy, sz;
+    rot_dims_c(nb, (code >> 2) & 7, sx, sy, sz);
+    const int q = code & 3;
+    if (q & 1) { t[0] = m[3] - sx; t[3] = m[3]; } else { t[0] = m[0]; t[3] = m[0] + sx; }
+    if (q & 2) { t[1] = m[4] - sy; t[4] = m[4]; } else { t[1] = m[1]; t[4] = m[1] + sy; }
+    t[2] = m[2]; t[5] = m[2] + sz;
+}
+__device__ __noinline__ uint64_t cand_hash_c(const double t[6]) {
+    uint64_t l[6];
+#pragma unroll 1
+    for (int i = 0; i < 6; i++) l[i] = hash_double(t[i]);
+    return tuple_hash6(l);
+}
+
+__device__ __noinline__ void draw_item_c(const CParams &p, int e, CHdr &h) {
+    const uint64_t gid = (uint64_t)(p.env_id_base + e), d = (uint64_t)h.draw_pos;
+    if (p.item_mode == 0 && p.sample_dist) {  // C:bin3D.py:103-112
+        auto u01 = [&](uint64_t salt) { return (double)(rnd_u64(p.seed ^ salt, gid, d) >> 11) * (1.0 / 9007199254740992.0); };
+        auto r3 = [&](double v) { return ddiv(rint(v * 1000.0), 1000.0); };
+        h.next_box[0] = r3(p.sample_a + (p.sample_b - p.sample_a) * u01(0x11));
+        h.next_box[1] = r3(p.sample_a + (p.sample_b - p.sample_a) * u01(0x22));
+        if (p.setting == 2) h.next_box[2] = r3(p.sample_a + (p.sample_b - p.sample_a) * u01(0x33));
+        else {
+            const double ch[5] = {0.1, 0.2, 0.3, 0.4, 0.5};
+            h.next_box[2] = ch[rnd_u64(p.seed ^ 0x44, gid, d) % 5];
+        }
+        h.next_den = p.setting == 3 ? rnd_density(p.seed, gid, d) : 1.0;
+    } else {
+        const double *it = p.item_mode == 0 ? p.item_set + (rnd_u64(p.seed, gid, d) % (uint64_t)p.n_items) * 3
+                                            : p.stream + ((size_t)e * p.stream_len + (size_t)(d % (uint64_t)p.stream_len)) * 4;
+        h.next_box[0] = it[0]; h.next_box[1] = it[1]; h.next_box[2] = it[2];
+        h.next_den = p.setting == 3 ? (p.item_mode == 0 ? rnd_density(p.seed, gid, d) : it[3]) : 1.0;
+    }
+    h.draw_pos++;
+}
+
+__device__ __noinline__ void reset_space_c(CEnv *ev, const CParams &p, int e, int lane) {
+    if (lane == 0) {
+        CHdr &h = ev->h;
+        h.n_box = 0; h.n_ems = 1; h.n_leaf = 0; h.flags = 0; h.n_edge = 0; h.n_poly = 0; h.vol_sum = 0; h.ep_len = 0; h.ep_reward = 0;
+        ev->ems[0][0] = 0; ev->ems[0][1] = 0; ev->ems[0][2] = 0; ev->ems[0][3] = p.W; ev->ems[0][4] = p.L; ev->ems[0][5] = p.H;
+        if (p.traj_len > 0 && h.draw_pos % p.traj_len) h.draw_pos += p.traj_len - h.draw_pos % p.traj_len;
+        draw_item_c(p, e, h);
+    }
+    __syncwarp();
+}
+
+// GENEMS (C:space.py:441-528): same ballot / scan compaction as the discrete kernel, float64 with rounded intersections
+__device__ __noinline__ int genems_warp_c(CEnv *ev, const int n0, const double loc[6], double lb, int lane, int &flags) {
+    double (*ems)[6] = ev->ems, (*tmp)[6] = ev->ems_tmp;
+    const int nch = (n0 + 31) >> 5;
+    const double itn[6] = {-loc[0], -loc[1], -loc[2], loc[3], loc[4], loc[5]};
+    int off = 0;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; pass++) {
+#pragma unroll 1
+        for (int c = 0; c < nch; c++) {
+            const int i = c * 32 + lane;
+            bool inter = false;
+            double it[6], m[6];
+            if (i < n0) {
+#pragma unroll
+                for (int t = 0; t < 6; t++) m[t] = ems[i][t];
+#pragma unroll
+                for (int t = 0; t < 6; t++) it[t] = around6(fmin(itn[t], t < 3 ? -m[t] : m[t]));
+                inter = (it[0] + it[3] > 0) && (it[1] + it[4] > 0) && (it[2] + it[5] > 0);
+            }
+            if (pass == 0) {  // survivors keep their order
+                const bool keep = i < n0 && !inter;
+                const uint32_t bm = __ballot_sync(FULL, keep);
+                if (keep) {
+                    const int p = off + __popc(bm & ((1u << lane) - 1));
+#pragma unroll
+                    for (int t = 0; t < 6; t++) tmp[p][t] = m[t];
+                }
+                off += __popc(bm);
+            } else {  // children: left, right, front, back, top (Difference, :490-502)
+                uint32_t cm = 0;
+                const double x3 = -it[0], y3 = -it[1], x4 = it[3], y4 = it[4], z4 = it[5];
+                if (inter) {
+                    const bool ux = m[3] - m[0] + 1e-6 >= lb, uy = m[4] - m[1] + 1e-6 >= lb, uz = m[5] - m[2] + 1e-6 >= lb;
+                    if (x3 - m[0] + 1e-6 >= lb && uy && uz) cm |= 1;
+                    if (m[3] - x4 + 1e-6 >= lb && uy && uz) cm |= 2;
+                    if (ux && y3 - m[1] + 1e-6 >= lb && uz) cm |= 4;
+                    if (ux && m[4] - y4 + 1e-6 >= lb && uz) cm |= 8;
+                    if (ux && uy && m[5] - z4 + 1e-6 >= lb) cm |= 16;
+                }
+                const int cnt = __popc(cm);
+                const int incl = warp_incl_scan(cnt, lane);
+                int p = off + incl - cnt;
+#pragma unroll 1
+                for (int ch = 0; ch < 5 && cm; ch++) {
+                    if (!(cm & (1u << ch))) continue;
+                    double q[6] = {m[0], m[1], m[2], m[3], m[4], m[5]};
+                    if (ch == 0) q[3] = x3; else if (ch == 1) q[0] = x4; else if (ch == 2) q[4] = y3; else if (ch == 3) q[1] = y4; else q[2] = z4;
+                    if (p < CE_TMP) {
+#pragma unroll
+                        for (int t = 0; t < 6; t++) tmp[p][t] = q[t];
+                    } else flags |= PCT_FLAG_EMS_OVERFLOW;
+                    p++;
+                }
+                off += __shfl_sync(FULL, incl, 31);
+            }
+        }
+    }
+    flags = __reduce_or_sync(FULL, flags);
+    const int n = off < CE_TMP ? off : CE_TMP;
+    __syncwarp();
+    int w = 0;
+    const int nch2 = (n + 31) >> 5;
+#pragma unroll 1
+    for (int c = 0; c < nch2; c++) {
+        const int i = c * 32 + lane;
+        bool keep = false;
+        double a[6];
+        if (i < n) {
+#pragma unroll
+            for (int t = 0; t < 6; t++) a[t] = tmp[i][t];
+            int hit = 0;
+#pragma unroll 2
+            for (int j = 0; j < n; j++) {
+                const double *b = tmp[j];
+                hit |= (int)(j != i && a[0] >= b[0] && a[1] >= b[1] && a[2] >= b[2] && a[3] <= b[3] && a[4] <= b[4] && a[5] <= b[5]);
+            }
+            keep = !hit;
+        }
+        const uint32_t bm = __ballot_sync(FULL, keep);
+        if (keep) {
+            const int p = w + __popc(bm & ((1u << lane) - 1));
+            if (p < CE_MAX) {
+#pragma unroll
+                for (int t = 0; t < 6; t++) ems[p][t] = a[t];
+            }
+        }
+        w += __popc(bm);
+    }
+    if (w > CE_MAX) { flags |= PCT_FLAG_EMS_OVERFLOW; w = CE_MAX; }
+    __syncwarp();
+    return w;
+}
+
+// ================= K1: apply =================
+template <bool STAB>
+__global__ void __launch_bounds__(64) pctc_apply_kernel(const CParams p) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int e = blockIdx.x * 2 + warp;
+    if (e >= p.n_envs) return;
+    __shared__ int lock_s[2];
+    int *lock = &lock_s[warp];
+    CEnv *ev = p.env + e;
+    CHdr &h = ev->h;
+    if (lane == 0) *lock = 0;
+    float reward = 0.f;
+    int done = 0;
+    pct_step_info info{};
+    if (p.mode == 0) {
+        const int64_t dp = p.keep_draw ? h.draw_pos : 0;
+        __syncwarp();
+        if (lane == 0) h.draw_pos = dp;
+        reset_space_c(ev, p, e, lane);
+    } else {
+        const double nb0 = h.next_box[0], nb1 = h.next_box[1], nb2 = h.next_box[2], den0 = h.next_den;
+        const int n_box0 = h.n_box, n_leaf0 = h.n_leaf, flags0 = h.flags, n_ems0 = h.n_ems;
+        __syncwarp();
+        // ---- LeafNode2Action (C:bin3D.py:151-167) ----
+        double lx = 0, ly = 0, x = nb0, y = nb1, z = nb2;
+        {
+            double a[6] = {0, 0, 0, 0, 0, 0}, s = 0;
+            bool zero = true;
+            if (p.leaf_idx) {
+                const int k = p.leaf_idx[e];
+                if (k >= 0 && k < n_leaf0) {
+                    zero = false;
+                    for (int t = 0; t < 6; t++) a[t] = ev->leaf[k][t];
+                }
+            } else {
+                for (int t = 0; t < 6; t++) {
+                    a[t] = p.action_f64 ? ((const double *)p.actions)[(size_t)e * 9 + t] : (double)((const float *)p.actions)[(size_t)e * 9 + t];
+                    s += a[t];
+                }
+                zero = (s == 0);
+            }
+            if (!zero) {
+                x = around6(a[3] - a[0]);
+                y = around6(a[4] - a[1]);
+                const double nb[3] = {nb0, nb1, nb2};
+                int rec[3] = {0, 1, 2}, n = 3;
+                for (int i = 0; i < n; i++)
+                    if (fabs(x - nb[rec[i]]) < 1e-6) { for (int u = i; u < n - 1; u++) rec[u] = rec[u + 1]; n--; break; }
+                for (int i = 0; i < n; i++)
+                    if (fabs(y - nb[rec[i]]) < 1e-6) { for (int u = i; u < n - 1; u++) rec[u] = rec[u + 1]; n--; break; }
+                z = nb[rec[0]];
+                lx = a[0]; ly = a[1];
+            }
+        }
+        lx = around6(lx); ly = around6(ly);  // C:bin3D.py:173
+        // ---- Space.drop_box (C:space.py:329-376) ----
+        bool ok = !(lx + x - 1e-6 > p.W || ly + y - 1e-6 > p.L) && !(lx + 1e-6 < 0 || ly + 1e-6 < 0);
+        double max_h = 0;
+        if (lane == 0) { ev->e_off[n_box0] = (uint16_t)h.n_edge; ev->poly_off[n_box0] = (uint16_t)h.n_poly; ev->first_in[n_box0 < NB_MAX ? n_box0 : 0] = EDGE_NIL; }
+        __syncwarp();
+        if (ok) {
+            double mh = rest_height_c(ev->box, lane, n_box0, 32, lx, ly, lx + x, ly + y);
+#pragma unroll
+            for (int d = 16; d; d >>= 1) mh = fmax(mh, __shfl_xor_sync(FULL, mh, d));
+            max_h = mh < 0 ? 0.0 : mh;
+            if (max_h + z - 1e-6 > p.H) ok = false;
+            else if (STAB && !(fabs(max_h) < 1e-6)) {
+                int res = 0;
+                if (lane == 0) {
+                    int fl = 0;
+                    GeomC g{ev->box, ev->den, n_box0};
+                    NodeC root{lx, ly, max_h, x, y, z, x * y * z * den0};
+                    EdgePool pool{ev->e_lower, ev->e_next, ev->e_off, ev->first_in, ev->last_in, ev->e_st, ev->e_st, h.n_edge,
+                                  ev->poly_off, &ev->poly[0][0], &ev->poly[0][0], h.n_poly};
+                    res = stability_check<true, GeomC>(g, root, pool, &ev->big, lock, n_box0, fl);
+                    h.n_edge = pool.n; h.n_poly = pool.n_poly;
+                    h.flags |= fl;
+                }
+                __syncwarp();
+                ok = __shfl_sync(FULL, res, 0) != 0;
+            }
+            if (ok && n_box0 >= p.nb) { ok = false; if (lane == 0) h.flags |= PCT_FLAG_BOX_OVERFLOW; }
+        }
+        __syncwarp();
+        const double binvol = p.W * p.L * p.H;
+        if (ok) {
+            if (lane == 0) {
+                double *b = ev->box[n_box0];
+                b[0] = lx; b[1] = ly; b[2] = max_h; b[3] = x; b[4] = y; b[5] = z;
+                ev->den[n_box0] = den0;
+                h.n_box = n_box0 + 1;
+                h.vol_sum += x * y * z;
+                ev->e_off[n_box0 + 1] = (uint16_t)h.n_edge; ev->poly_off[n_box0 + 1] = (uint16_t)h.n_poly;
+            }
+            __syncwarp();
+            int fl = 0;
+            const double loc[6] = {lx, ly, max_h, around6(lx + x), around6(ly + y), around6(max_h + z)};  // C:bin3D.py:191-194
+            const int n_ems = genems_warp_c(ev, n_ems0, loc, p.low_bound, lane, fl);
+            const double rw = (nb0 * nb1 * nb2) / binvol * 10;
+            reward = (float)rw;
+            info.counter = n_box0 + 1;
+            info.flags = flags0 | fl;
+            if (lane == 0) {
+                h.n_ems = n_ems; h.flags |= fl; h.ep_len++; h.ep_reward += rw;
+                draw_item_c(p, e, h);
+            }
+            __syncwarp();
+        } else {
+            done = 1;
+            info.counter = n_box0;
+            info.flags = h.flags;
+            info.ratio = (float)(h.vol_sum / binvol);
+            info.ep_reward = (float)h.ep_reward;
+            info.ep_len = h.ep_len + 1;
+            __syncwarp();
+            if (!p.no_auto_reset) reset_space_c(ev, p, e, lane);
+        }
+    }
+    if (lane == 0) {
+        if (p.reward) p.reward[e] = reward;
+        if (p.done) p.done[e] = (uint8_t)done;
+        if (p.info) p.info[e] = info;
+    }
+}
+
+// ================= K2: candidates in CPython-set order (C:space.py:531-568) =================
+__global__ void __launch_bounds__(32) pctc_candidates_kernel(const CParams p) {
+    __shared__ uint16_t tabA[CC_TAB], tabB[512];
+    const int lane = threadIdx.x, e = blockIdx.x;
+    CEnv *ev = p.env + e;
+    const CHdr &h = ev->h;
+    const double nb[3] = {h.next_box[0], h.next_box[1], h.next_box[2]};
+    const int R = p.setting == 2 ? 6 : 2, n_ems = h.n_ems;
+    constexpr uint16_t EMPTY = 0xFFFF;
+    uint16_t *tab = tabA;
+    uint32_t mask = 7;
+    int fill = 0, fl = 0;
+    if (lane < 8) tab[lane] = EMPTY;
+    __syncwarp();
+    const int raw = n_ems * R * 4;
+    bool stop = false;
+#pragma unroll 1
+    for (int base = 0; base < raw && !stop; base += 32) {
+        const int r = base + lane;
+        bool valid = false;
+        uint64_t hash = 0;
+        uint16_t code = 0;
+        double t6[6];
+        if (r < raw) {
+            const int q = r & 3, er = r >> 2, rot = er % R, ei = er / R;
+            double sx, sy, sz;
+            if (rot_dims_c(nb, rot, sx, sy, sz)) {
+                const double *m = ev->ems[ei];
+                if (m[3] - m[0] + 1e-6 >= sx && m[4] - m[1] + 1e-6 >= sy && m[5] - m[2] + 1e-6 >= sz) {
+                    valid = true;
+                    code = (uint16_t)((ei << 5) | (rot << 2) | q);
+                    cand_tuple(code, ev->ems, nb, t6);
+                    hash = cand_hash_c(t6);
+                }
+            }
+        }
+        // already present? (read-only probe; present keys sit on their own probe sequence)
+        if (valid) {
+            uint64_t perturb = hash;
+            uint32_t i = (uint32_t)hash & mask;
+            bool open = true;
+            while (open) {
+                const int probes = (i + 9 <= mask) ? 9 : 0;
+                for (int j = 0; j <= probes; j++) {
+                    const uint16_t s = tab[i + j];
+                    if (s == EMPTY) { open = false; break; }
+                    double u[6];
+                    cand_tuple(s, ev->ems, nb, u);
+                    if (u[0] == t6[0] && u[1] == t6[1] && u[2] == t6[2] && u[3] == t6[3] && u[4] == t6[4] && u[5] == t6[5]) { open = false; valid = false; break; }
+                }
+                perturb >>= 5;
+                i = (uint32_t)((uint64_t)i * 5 + 1 + perturb) & mask;
+            }
+        }
+        uint32_t vm = __ballot_sync(FULL, valid);
+#pragma unroll 1
+        while (vm) {
+            const int k = __ffs(vm) - 1;
+            vm &= vm - 1;
+            const uint64_t hk = __shfl_sync(FULL, hash, k);
+            const uint16_t ck = (uint16_t)__shfl_sync(FULL, (int)code, k);
+            double tk[6];
+#pragma unroll
+            for (int t = 0; t < 6; t++) tk[t] = __shfl_sync(FULL, t6[t], k);
+            // set_add_entry, uniform across the warp (earlier lanes of this chunk may have inserted the same tuple)
+            uint64_t perturb = hk;
+            uint32_t i = (uint32_t)hk & mask;
+            int state = 0;
+#pragma unroll 1
+            while (!state) {
+                const int probes = (i + 9 <= mask) ? 9 : 0;
+#pragma unroll 1
+                for (int j = 0; j <= probes; j++) {
+                    const uint16_t s = tab[i + j];
+                    if (s == EMPTY) { if (lane == 0) tab[i + j] = ck; state = 1; break; }
+                    double u[6];
+                    cand_tuple(s, ev->ems, nb, u);
+                    if (u[0] == tk[0] && u[1] == tk[1] && u[2] == tk[2] && u[3] == tk[3] && u[4] == tk[4] && u[5] == tk[5]) { state = 2; break; }
+                }
+                perturb >>= 5;
+                i = (uint32_t)((uint64_t)i * 5 + 1 + perturb) & mask;
+            }
+            __syncwarp();
+            if (state == 1 && (uint32_t)(++fill) * 5 >= mask * 3) {
+                uint32_t newsize = 8;
+                while (newsize <= (uint32_t)fill * 4) newsize <<= 1;
+                if (newsize > CC_TAB) { fl |= PCT_FLAG_CAND_OVERFLOW; stop = true; break; }
+                uint16_t *nt = (tab == tabA) ? tabB : tabA;
+                for (uint32_t t = lane; t < newsize; t += 32) nt[t] = EMPTY;
+                __syncwarp();
+#pragma unroll 1
+                for (uint32_t b2 = 0; b2 <= mask; b2 += 32) {
+                    const uint32_t s = b2 + lane;
+                    const uint16_t c2 = s <= mask ? tab[s] : EMPTY;
+                    uint64_t eh = 0;
+                    if (c2 != EMPTY) { double u[6]; cand_tuple(c2, ev->ems, nb, u); eh = cand_hash_c(u); }
+                    uint32_t em = __ballot_sync(FULL, c2 != EMPTY);
+#pragma unroll 1
+                    while (em) {
+                        const int kk = __ffs(em) - 1;
+                        em &= em - 1;
+                        const uint64_t hh = __shfl_sync(FULL, eh, kk);
+                        const uint16_t cc = (uint16_t)__shfl_sync(FULL, (int)c2, kk);
+                        uint64_t pt = hh;
+                        uint32_t ii = (uint32_t)hh & (newsize - 1);
+                        bool placed = false;
+#pragma unroll 1
+                        while (!placed) {  // set_insert_clean
+                            const int pr = (ii + 9 <= newsize - 1) ? 9 : 0;
+                            for (int j = 0; j <= pr; j++)
+                                if (nt[ii + j] == EMPTY) { if (lane == 0) nt[ii + j] = cc; placed = true; break; }
+                            pt >>= 5;
+                            ii = (uint32_t)((uint64_t)ii * 5 + 1 + pt) & (newsize - 1);
+                        }
+                        __syncwarp();
+                    }
+                }
+                tab = nt;
+                mask = newsize - 1;
+            }
+        }
+    }
+    __syncwarp();
+    int cnt = 0;
+#pragma unroll 1
+    for (uint32_t b2 = 0; b2 <= mask; b2 += 32) {
+        const uint32_t s = b2 + lane;
+        const uint16_t c2 = s <= mask ? tab[s] : EMPTY;
+        const uint32_t em = __ballot_sync(FULL, c2 != EMPTY);
+        if (c2 != EMPTY) ev->cand[cnt + __popc(em & ((1u << lane) - 1))] = c2;
+        cnt += __popc(em);
+    }
+    if (lane == 0) {
+        ev->h.n_cand = cnt;
+        if (fl) ev->h.flags |= fl;
+    }
+}
+
+// ================= K3: feasibility per candidate + leaf compaction + observation =================
+template <typename OT>
+__device__ __noinline__ void write_obs_c(const CParams &p, int e, const CEnv *ev, const double (*leaf)[6], int n_leaf, int tid, int nthreads) {
+    OT *obs = (OT *)p.obs + (size_t)e * (size_t)((p.nb + p.nl + 1) * 9);
+    const int n_box = ev->h.n_box, total = (p.nb + p.nl + 1) * 9;
+    double s0 = ev->h.next_box[0], s1 = ev->h.next_box[1], s2 = ev->h.next_box[2];
+    if (s1 < s0) { double t = s0; s0 = s1; s1 = t; }
+    if (s2 < s1) { double t = s1; s1 = s2; s2 = t; }
+    if (s1 < s0) { double t = s0; s0 = s1; s1 = t; }
+#pragma unroll 1
+    for (int f = tid; f < total; f += nthreads) {
+        const int row = f / 9, col = f - row * 9;
+        double v = 0;
+        if (row < p.nb) {
+            if (row < n_box) {  // C:space.py:372-373  [lx,ly,lz,lx+x,ly+y,lz+z,0,0,1]
+                const double *b = ev->box[row];
+                if (col < 3) v = b[col];
+                else if (col < 6) v = b[col - 3] + b[col];
+                else if (col == 8) v = 1;
+            } else if (row == 0 && col == 8) v = 1;
+        } else if (row < p.nb + p.nl) {
+            const int k = row - p.nb;
+            if (k < n_leaf) {
+                if (col < 5) v = leaf[k][col];
+                else if (col == 5) v = p.H;
+                else if (col == 8) v = 1;
+            }
+        } else {
+            if (col == 0) v = ev->h.next_den;
+            else if (col == 3) v = s0;
+            else if (col == 4) v = s1;
+            else if (col == 5) v = s2;
+            else if (col == 8) v = 1;
+        }
+        obs[f] = (OT)v;
+    }
+}
+
+template <typename OT, bool STAB>
+__global__ void __launch_bounds__(64) pctc_feas_emit_kernel(const CParams p) {
+    __shared__ double leaf[NL_MAX][6];
+    __shared__ uint32_t wb[2];
+    __shared__ int lock;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, e = blockIdx.x;
+    CEnv *ev = p.env + e;
+    const CHdr &h = ev->h;
+    if (tid == 0) lock = 0;
+    __syncthreads();
+    const double nb[3] = {h.next_box[0], h.next_box[1], h.next_box[2]};
+    const int n_cand = h.n_cand, n_box = h.n_box;
+    const double den = h.next_den;
+    GeomC g{ev->box, ev->den, n_box};
+    EdgePool pool{ev->e_lower, ev->e_next, ev->e_off, ev->first_in, ev->last_in, ev->e_st, ev->e_st, h.n_edge,
+                  ev->poly_off, &ev->poly[0][0], &ev->poly[0][0], h.n_poly};
+    int n_leaf = 0, fl = 0;
+#pragma unroll 1
+    for (int base = 0; base < n_cand && n_leaf < p.nl; base += 64) {
+        const int c = base + tid;
+        bool feas = false;
+        double t6[6] = {0, 0, 0, 0, 0, 0};
+        if (c < n_cand) {
+            cand_tuple(ev->cand[c], ev->ems, nb, t6);
+            // get_possible_position: x = xe - xs ... (C:bin3D.py:134-137); drop_box_virtual (C:space.py:380-425)
+            const double x = t6[3] - t6[0], y = t6[4] - t6[1], z = t6[5] - t6[2], lx = t6[0], ly = t6[1];
+            bool chk = !(lx + x - 1e-6 > p.W || ly + y - 1e-6 > p.L) && !(lx + 1e-6 < 0 || ly + 1e-6 < 0);
+            double mh = rest_height_c(ev->box, 0, n_box, 1, lx, ly, lx + x, ly + y);
+            if (mh < 0) mh = 0.0;
+            if (mh + z - 1e-6 > p.H) chk = false;
+            if (!chk) feas = false;
+            else if (!STAB || fabs(mh) < 1e-6) feas = true;
+            else {
+                NodeC root{lx, ly, mh, x, y, z, x * y * z * den};
+                feas = stability_check<false, GeomC>(g, root, pool, &ev->big, &lock, 0, fl) != 0;
+            }
+        }
+        const uint32_t fm = __ballot_sync(FULL, feas);
+        if (lane == 0) wb[warp] = fm;
+        __syncthreads();
+        const int before = warp == 1 ? __popc(wb[0]) : 0, total = __popc(wb[0]) + __popc(wb[1]);
+        if (feas) {
+            const int k = n_leaf + before + __popc(fm & ((1u << lane) - 1));
+            if (k < p.nl)
+                for (int t = 0; t < 6; t++) leaf[k][t] = t6[t];
+        }
+        n_leaf += total;
+        __syncthreads();
+    }
+    if (n_leaf > p.nl) n_leaf = p.nl;
+    fl = __reduce_or_sync(FULL, fl);
+    if (fl && lane == 0) atomicOr(&ev->h.flags, fl);
+    __syncthreads();
+    for (int t = tid; t < n_leaf * 6; t += 64) ((double *)ev->leaf)[t] = ((double *)leaf)[t];
+    if (tid == 0) {
+        ev->h.n_leaf = n_leaf;
+        if (p.info) {
+            p.info[e].n_leaf = n_leaf; p.info[e].n_cand = n_cand; p.info[e].n_ems = h.n_ems; p.info[e].flags |= h.flags;
+        }
+    }
+    write_obs_c<OT>(p, e, ev, leaf, n_leaf, tid, 64);
+}
+
+__global__ void pctc_policy_random_kernel(const CEnv *env, int n_envs, int64_t env_id_base, uint64_t seed, int64_t t, int32_t *leaf_idx) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_envs) return;
+    const int n = env[e].h.n_leaf;
+    leaf_idx[e] = n > 0 ? (int32_t)(rnd_u64(seed, (uint64_t)(env_id_base + e), (uint64_t)t) % (uint64_t)n) : 0;
+}
+
+// ================= host side =================
+int continuous_create(pct_env_batch *h) {
+    cudaError_t e = cudaMalloc(&h->c_state, sizeof(CEnv) * (size_t)h->n_envs);
+    if (e == cudaSuccess) e = cudaMemset(h->c_state, 0, sizeof(CEnv) * (size_t)h->n_envs);
+    if (e != cudaSuccess) { h->err = std::string("continuous_create: ") + cudaGetErrorString(e); return PCT_ERR_CUDA; }
+    return PCT_OK;
+}
+void continuous_destroy(pct_env_batch *h) { cudaFree(h->c_state); h->c_state = nullptr; }
+int64_t continuous_state_bytes() { return (int64_t)sizeof(CEnv); }
+
+int continuous_launch(pct_env_batch *h, int mode, const void *actions, int action_f64, const int32_t *leaf_idx, void *obs, float *rew,
+                      uint8_t *done, pct_step_info *info, cudaStream_t st) {
+    CParams p{};
+    p.env = (CEnv *)h->c_state; p.n_envs = h->n_envs;
+    p.W = h->cfg.container_size[0]; p.L = h->cfg.container_size[1]; p.H = h->cfg.container_size[2];
+    p.low_bound = h->cfg.size_minimum;
+    p.nb = h->cfg.internal_node_holder; p.nl = h->cfg.leaf_node_holder; p.setting = h->cfg.setting;
+    p.item_mode = h->item_mode; p.sample_dist = h->cfg.sample_from_distribution;
+    p.sample_a = h->cfg.sample_left_bound; p.sample_b = h->cfg.sample_right_bound;
+    p.item_set = h->d_item_set; p.n_items = h->n_items; p.stream = h->d_stream; p.stream_len = h->stream_len; p.traj_len = h->traj_len;
+    p.seed = h->cfg.seed; p.env_id_base = h->cfg.env_id_base;
+    p.actions = actions; p.action_f64 = action_f64; p.leaf_idx = leaf_idx;
+    p.obs = obs; p.obs_f64 = h->cfg.obs_dtype == PCT_F64; p.reward = rew; p.done = done; p.info = info;
+    p.mode = mode; p.keep_draw = h->did_reset ? 1 : 0; p.no_auto_reset = h->cfg.no_auto_reset;
+    const bool stab = p.setting != 2;
+    const int b2 = (p.n_envs + 1) / 2;
+    if (stab) pctc_apply_kernel<true><<<b2, 64, 0, st>>>(p); else pctc_apply_kernel<false><<<b2, 64, 0, st>>>(p);
+    pctc_candidates_kernel<<<p.n_envs, 32, 0, st>>>(p);
+    if (p.obs_f64) { if (stab) pctc_feas_emit_kernel<double, true><<<p.n_envs, 64, 0, st>>>(p); else pctc_feas_emit_kernel<double, false><<<p.n_envs, 64, 0, st>>>(p); }
+    else { if (stab) pctc_feas_emit_kernel<float, true><<<p.n_envs, 64, 0, st>>>(p); else pctc_feas_emit_kernel<float, false><<<p.n_envs, 64, 0, st>>>(p); }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { h->err = std::string("continuous launch: ") + cudaGetErrorString(e); return PCT_ERR_CUDA; }
+    h->launches += 2;  // the caller counts one
+    return PCT_OK;
+}
+
+int continuous_policy_random(pct_env_batch *h, int32_t *leaf_idx, uint64_t seed, int64_t t, cudaStream_t st) {
+    pctc_policy_random_kernel<<<(h->n_envs + 127) / 128, 128, 0, st>>>((const CEnv *)h->c_state, h->n_envs, h->cfg.env_id_base, seed, t, leaf_idx);
+    return cudaGetLastError() == cudaSuccess ? PCT_OK : PCT_ERR_CUDA;
+}
+
+int continuous_get_state(pct_env_batch *h, int env, pct_state_dump *out) {
+    CEnv *tmp = (CEnv *)malloc(sizeof(CEnv));
+    if (cudaMemcpy(tmp, (CEnv *)h->c_state + env, sizeof(CEnv), cudaMemcpyDeviceToHost) != cudaSuccess) { free(tmp); return PCT_ERR_CUDA; }
+    memset(out, 0, sizeof(*out));
+    out->n_boxes = tmp->h.n_box; out->n_ems = tmp->h.n_ems; out->n_leaf = tmp->h.n_leaf; out->flags = tmp->h.flags;
+    out->draw_pos = tmp->h.draw_pos; out->next_den = tmp->h.next_den;
+    for (int i = 0; i < 3; i++) out->next_box[i] = tmp->h.next_box[i];
+    for (int i = 0; i < tmp->h.n_box && i < 80; i++) {
+        const double *b = tmp->box[i];
+        out->boxes[i][0] = b[0]; out->boxes[i][1] = b[1]; out->boxes[i][2] = b[2];
+        out->boxes[i][3] = b[0] + b[3]; out->boxes[i][4] = b[1] + b[4]; out->boxes[i][5] = b[2] + b[5];
+        out->boxes[i][6] = tmp->den[i];
+    }
+    for (int i = 0; i < tmp->h.n_ems && i < 256; i++)
+        for (int t = 0; t < 6; t++) out->ems[i][t] = tmp->ems[i][t];
+    free(tmp);
+    return PCT_OK;
+}
+
+}  // namespace pct

@@ -30,8 +30,8 @@
 
 namespace pct {
 
-__device__ __noinline__ double ddiv(double a, double b) { return a / b; }
-__device__ __noinline__ double dsqrt(double a) { return sqrt(a); }
+static __device__ __noinline__ double ddiv(double a, double b) { return a / b; }
+static __device__ __noinline__ double dsqrt(double a) { return sqrt(a); }
 __device__ __forceinline__ double dot2(double u0, double u1, double v0, double v1) { return fma(u1, v1, u0 * v0); }
 
 __device__ __forceinline__ double slope_of(double ax, double ay, double bx, double by) {
@@ -64,7 +64,7 @@ __device__ __forceinline__ int orient3(double ax, double ay, double bx, double b
 // px/py are sorted IN PLACE (stable insertion sort by x, sorted(key=x[0]) :34-37); the hull (lower chain minus its
 // last point, then upper chain minus its last point, :89-92) is written as coordinates to hx/hy (capacity 2n).
 // The two topmost chain points live in registers, so the orientation test of the scan needs no reloads.
-__device__ __noinline__ int hull_coords(double *px, double *py, int n, double *hx, double *hy) {
+static __device__ __noinline__ int hull_coords(double *px, double *py, int n, double *hx, double *hy) {
 #pragma unroll 1
     for (int i = 1; i < n; i++) {
         const double kx = px[i], ky = py[i];
@@ -116,7 +116,7 @@ __device__ __forceinline__ bool cross_left(double ix, double iy, double jx, doub
 
 // scale_down (D:space.py:341-345) + point_in_polygen (convex_hull.py:97-112) fused: the shrunk polygon is
 // never stored, its vertices are produced on the fly from the hull coordinates.
-__device__ __noinline__ bool pip_shrunk(const double *hx, const double *hy, int stride, int m, double lat, double lon) {
+static __device__ __noinline__ bool pip_shrunk(const double *hx, const double *hy, int stride, int m, double lat, double lon) {
     double sx = 0, sy = 0;
 #pragma unroll 1
     for (int i = 0; i < m; i++) { sx += hx[i * stride]; sy += hy[i * stride]; }
@@ -151,7 +151,7 @@ __device__ __noinline__ bool pip_shrunk(const double *hx, const double *hy, int 
 // identical operation order to oracle/pct_oracle_common.h po_ls_*).  ld = leading dimension of R and V.
 struct LsWork { double *R, *V, *y, *row, *x; int ld; };
 
-__device__ __noinline__ void ls_add_row(const LsWork &w, int k, double rhs) {
+static __device__ __noinline__ void ls_add_row(const LsWork &w, int k, double rhs) {
 #pragma unroll 1
     for (int i = 0; i < k; i++) {
         const double b = w.row[i];
@@ -170,7 +170,7 @@ __device__ __noinline__ void ls_add_row(const LsWork &w, int k, double rhs) {
         rhs = c * rhs - sn * yi;
     }
 }
-__device__ __noinline__ void ls_solve(const LsWork &w, int k, int rows) {
+static __device__ __noinline__ void ls_solve(const LsWork &w, int k, int rows) {
     double *G = w.R, *V = w.V;
     const int ld = w.ld;
     {   // full column rank and well conditioned (the usual case): the least-squares solution is R x = y
@@ -253,7 +253,7 @@ __device__ __noinline__ void ls_solve(const LsWork &w, int k, int rows) {
 
 // lstsq load split for k >= 3 supports without a direct edge (D:space.py:134-152 / 231-250):
 // c2x/c2y = contact-rectangle centres, (cx,cy) = stack COM; writes the k assignment ratios to w.x
-__device__ __noinline__ void lstsq_ratios(const LsWork &w, int k, const double *c2x, const double *c2y, double cx, double cy) {
+static __device__ __noinline__ void lstsq_ratios(const LsWork &w, int k, const double *c2x, const double *c2y, double cx, double cy) {
 #pragma unroll 1
     for (int i = 0; i < k; i++) {
         w.y[i] = 0;
@@ -323,7 +323,7 @@ __device__ __forceinline__ bool pool_append(EdgePool &pool, int lower) {
 //                                                                           => [P3,P1,P0] -> drop last
 // so the polygon is [P0,P2,P3,P1]; scale_down + point_in_polygen run on registers, same operation order as
 // hull_indices + pip_shrunk.
-__device__ __noinline__ bool pip_rect(double x1, double y1, double x2, double y2, double t1, double t2, double lat, double lon) {
+static __device__ __noinline__ bool pip_rect(double x1, double y1, double x2, double y2, double t1, double t2, double lat, double lon) {
     // t1 = y1*1e-6, t2 = y2*1e-6 ; hull order P0,P2,P3,P1
     const double hx[4] = {x1 + t1, x2 + t1, x2 + t2, x1 + t2};
     const double hy[4] = {y1, y1, y2, y2};
@@ -359,7 +359,7 @@ __device__ __noinline__ bool pip_rect(double x1, double y1, double x2, double y2
 __device__ long long *g_prof_dummy;
 #endif
 template <bool REAL, class G>
-__device__ __noinline__ int stability_check(const G &g, const typename G::Node &root, EdgePool &pool, BigScratch *big, int *lock,
+static __device__ __noinline__ int stability_check(const G &g, const typename G::Node &root, EdgePool &pool, BigScratch *big, int *lock,
                                             const int new_id, int &flags, long long *g_prof_out = nullptr) {
     typedef typename G::Node Node;
     constexpr bool real = REAL;  // REAL: load-propagating update of a committed placement; else read-only feasibility check

@@ -202,3 +202,93 @@ class OracleBatch(object):
             self.close()
         except Exception:
             pass
+
+
+class OracleContinuous(object):
+    """Single continuous env (pct_envs/PctContinuous0/bin3D.py:8-207), float64 actions, injected item stream."""
+
+    def __init__(self, setting, container_size=(1.0, 1.0, 1.0), internal_node_holder=80, leaf_node_holder=50,
+                 size_minimum=0.1, stream=None):
+        L = lib()
+        dp = C.POINTER(C.c_double)
+        L.pctc_create.restype = C.c_void_p
+        L.pctc_create.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, C.c_double]
+        L.pctc_destroy.argtypes = [C.c_void_p]
+        L.pctc_set_stream.argtypes = [C.c_void_p, dp, C.c_int]
+        L.pctc_obs_len.argtypes = [C.c_void_p]
+        L.pctc_reset.argtypes = [C.c_void_p, dp]
+        L.pctc_step.argtypes = [C.c_void_p, dp, C.c_int, dp, dp, C.POINTER(C.c_int), dp]
+        L.pctc_get_ems.argtypes = [C.c_void_p, dp, C.c_int]
+        L.pctc_get_candidates.argtypes = [C.c_void_p, dp, C.POINTER(C.c_int), C.c_int]
+        L.pctc_get_packed.argtypes = [C.c_void_p, dp, C.c_int]
+        L.pctc_n_lstsq.argtypes = [C.c_void_p]
+        self.L = L
+        self.h = L.pctc_create(setting, float(container_size[0]), float(container_size[1]), float(container_size[2]),
+                               internal_node_holder, leaf_node_holder, float(size_minimum))
+        self.nb, self.nl = internal_node_holder, leaf_node_holder
+        self.obs_len = L.pctc_obs_len(self.h)
+        if stream is not None:
+            self.set_stream(stream)
+
+    def set_stream(self, stream):
+        s = np.ascontiguousarray(stream, dtype=np.float64)
+        if s.shape[1] == 3:
+            s = np.concatenate([s, np.ones((len(s), 1))], axis=1)
+        self._stream = np.ascontiguousarray(s)
+        self.L.pctc_set_stream(self.h, _dp(self._stream), len(self._stream))
+
+    def reset(self):
+        obs = np.zeros(self.obs_len)
+        self.L.pctc_reset(self.h, _dp(obs))
+        return obs
+
+    def step(self, action):
+        a = np.ascontiguousarray(action, dtype=np.float64)
+        obs = np.zeros(self.obs_len)
+        rew, done, info = C.c_double(), C.c_int(), np.zeros(3)
+        err = self.L.pctc_step(self.h, _dp(a), len(a), _dp(obs), C.byref(rew), C.byref(done), _dp(info))
+        d = {"counter": int(info[0])}
+        if done.value:
+            d.update(ratio=float(info[1]), reward=float(info[2]))
+        if err:
+            d["error"] = err
+        return obs, rew.value, bool(done.value), d
+
+    def ems(self):
+        buf = np.zeros((1000, 6))
+        n = self.L.pctc_get_ems(self.h, _dp(buf), 1000)
+        return buf[:n].copy()
+
+    def candidates(self):
+        buf = np.zeros((8192, 6))
+        feas = np.zeros(8192, dtype=np.int32)
+        n = self.L.pctc_get_candidates(self.h, _dp(buf), _ip(feas), 8192)
+        return buf[:n].copy(), feas[:n].copy()
+
+    @property
+    def packed(self):
+        buf = np.zeros((128, 7))
+        n = self.L.pctc_get_packed(self.h, _dp(buf), 128)
+        return buf[:n].tolist()
+
+    @property
+    def n_lstsq(self):
+        return self.L.pctc_n_lstsq(self.h)
+
+    def __del__(self):
+        try:
+            self.L.pctc_destroy(self.h)
+        except Exception:
+            pass
+
+
+def make_continuous_stream(seed, env, n, setting):
+    """Per-env draw sequence with the distribution of C:bin3D.py:103-115 (values rounded to 3 decimals)."""
+    s = np.zeros((n, 4))
+    u = lambda salt, d: ((rnd_u64(seed ^ salt, env, d) >> 11) / float(1 << 53))
+    for d in range(n):
+        s[d, 0] = round(0.1 + 0.4 * u(0x11, d), 3)
+        s[d, 1] = round(0.1 + 0.4 * u(0x22, d), 3)
+        s[d, 2] = round(0.1 + 0.4 * u(0x33, d), 3) if setting == 2 else [0.1, 0.2, 0.3, 0.4, 0.5][rnd_u64(seed ^ 0x44, env, d) % 5]
+        s[d, 3] = max((rnd_u64(seed ^ 0xABCDEF, env, d) >> 11), 1) / float(1 << 53) if setting == 3 else 1.0
+    return s

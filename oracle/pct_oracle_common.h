@@ -336,6 +336,43 @@ static void po_pyset_add(po_pyset *s, const uint64_t key[6]) {
         i = (i * 5 + 1 + perturb) & s->mask;
     }
 }
+/* hash lanes and equality payload given separately (float tuples: lanes = float hashes, payload = value bits) */
+static void po_pyset_add_kv(po_pyset *s, const uint64_t lanes[6], const uint64_t key[6]) {
+    uint64_t hash = po_tuple_hash6(lanes);
+    uint64_t perturb = hash, i = hash & s->mask;
+    for (;;) {
+        int probes = (i + 9 <= s->mask) ? 9 : 0;
+        for (int j = 0; j <= probes; j++) {
+            int32_t e = s->table[i + j];
+            if (e < 0) {
+                if (s->n == s->cap) {
+                    s->cap *= 2;
+                    s->keys = realloc(s->keys, sizeof(uint64_t[6]) * s->cap);
+                    s->hashes = realloc(s->hashes, sizeof(uint64_t) * s->cap);
+                }
+                memcpy(s->keys[s->n], key, sizeof(uint64_t[6]));
+                s->hashes[s->n] = hash;
+                s->table[i + j] = s->n++;
+                s->fill++;
+                if ((uint64_t)s->fill * 5 < s->mask * 3) return;
+                /* set_table_resize(so, used*4): smallest power of two > used*4 (used <= 50000) */
+                uint64_t minused = (uint64_t)s->n * 4, newsize = 8;
+                while (newsize <= minused) newsize <<= 1;
+                int32_t *nt = malloc(sizeof(int32_t) * newsize);
+                for (uint64_t t = 0; t < newsize; t++) nt[t] = -1;
+                for (uint64_t t = 0; t <= s->mask; t++)
+                    if (s->table[t] >= 0) po_pyset_insert_clean(nt, newsize - 1, s->hashes[s->table[t]], s->table[t]);
+                free(s->table);
+                s->table = nt;
+                s->mask = newsize - 1;
+                return;
+            }
+            if (s->hashes[e] == hash && memcmp(s->keys[e], key, sizeof(uint64_t[6])) == 0) return;
+        }
+        perturb >>= 5;
+        i = (i * 5 + 1 + perturb) & s->mask;
+    }
+}
 /* iterate in slot order: writes key indices, returns count */
 static int po_pyset_order(const po_pyset *s, int *out) {
     int m = 0;

@@ -37,3 +37,25 @@ def test_oracle_replays_reference_trajectory(path):
             o = env.reset()
             assert np.array_equal(o, obs[k]); k += 1
     assert k == len(obs)
+
+
+GOLD_C = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "continuous_s*.npz")))
+
+
+@pytest.mark.parametrize("path", GOLD_C, ids=[os.path.basename(p) for p in GOLD_C])
+def test_continuous_oracle_replays_reference_trajectory(path):
+    from pct_oracle import OracleContinuous
+    g = np.load(path)
+    env = OracleContinuous(int(g["setting"]), stream=g["stream"])
+    obs, k = g["obs"], 0
+    o = env.reset()
+    assert np.array_equal(o, obs[k]); k += 1
+    for t in range(len(g["rows"])):
+        o, r, d, info = env.step(g["rows"][t])
+        assert np.array_equal(o, obs[k]), "observation after step %d (done=%s)" % (t, d); k += 1
+        assert r == g["reward"][t] and d == bool(g["done"][t]) and info["counter"] == g["counter"][t]
+        if d:
+            assert info["ratio"] == g["ratio"][t]
+            o = env.reset()
+            assert np.array_equal(o, obs[k]); k += 1
+    assert k == len(obs) and len(GOLD_C) == 3
