@@ -14,7 +14,7 @@ discrete, 10x10x10 bin, items {1..5}^3, 80 internal / 50 leaf holders, EMS schem
 `e2e`      : the same metric through the C-ABI host-buffer call (pct_step_host): actions come from pinned
              host memory, observation / reward / done / info are copied back to pinned host memory every
              step and the policy runs on the host from that observation.
-`roofline` : HBM roofline of the dominant kernel (pct_discrete_kernel), algorithmic bytes per launch
+`roofline` : HBM roofline of the dominant kernel (pct_feas_emit_kernel), algorithmic bytes per launch
               / its mean launch duration measured here with CUDA events.
 `cpu_baseline` / `--impl reference`: the CPU restatement of the reference env (oracle/, C, pthreads over
              envs like the reference's ShmemVecEnv workers) on this box's host cores.
@@ -46,10 +46,14 @@ def parse():
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between steps (diagnostic only)")
     ap.add_argument("--e2e-steps", type=int, default=200)
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--continuous", action="store_true", help="BASELINE config 4: PctContinuous, sample_from_distribution, bin 1x1x1")
     return ap.parse_args()
 
 
 def workload_name(a, n_gpus):
+    if a.continuous:
+        return "setting %d continuous (sample_from_distribution U(0.1,0.5)), bin 1x1x1, 80 internal / 50 leaf, EMS, %d envs/GPU x %d GPU" % (
+            a.setting, a.envs_per_gpu, n_gpus)
     return "setting %d discrete, bin 10x10x10, items 1-5, 80 internal / 50 leaf, EMS, %d envs/GPU x %d GPU" % (
         a.setting, a.envs_per_gpu, n_gpus)
 
@@ -169,7 +173,11 @@ def run_ours(a):
     n = a.envs_per_gpu
     K, W = a.steps, max(a.warmup, 3)
 
-    batch = pct_b200.PctBatch(n, a.setting, item_set=ITEM_SET, seed=ITEM_SEED, env_id_base=rank * n, device=local)
+    if a.continuous:
+        batch = pct_b200.PctBatch(n, a.setting, container_size=(1.0, 1.0, 1.0), continuous=True, sample_from_distribution=True,
+                                  seed=ITEM_SEED, env_id_base=rank * n, device=local)
+    else:
+        batch = pct_b200.PctBatch(n, a.setting, item_set=ITEM_SET, seed=ITEM_SEED, env_id_base=rank * n, device=local)
     launches0 = batch.kernel_launches
     flush = None if a.no_flush else torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 
@@ -192,6 +200,8 @@ def run_ours(a):
         time.sleep(0.3)
     barrier()
     l0 = batch.kernel_launches
+    if not a.continuous:
+        batch.profile(True)  # CUDA events around each of the three kernels of every step (pct_profile_enable)
     t_wall0 = time.perf_counter()
     for t in range(K):
         if flush is not None:
@@ -206,6 +216,9 @@ def run_ours(a):
     barrier()
     wall = time.perf_counter() - t_wall0
     launches = batch.kernel_launches - l0
+    kms, ksteps = (batch.profile_read() if not a.continuous else ({}, 0))
+    if not a.continuous:
+        batch.profile(False)
     clocks = sampler.finish() if sampler else None
     step_ms = sum(ev[t][0].elapsed_time(ev[t][2]) for t in range(K))
     kern_ms = sum(ev[t][1].elapsed_time(ev[t][2]) for t in range(K))
@@ -262,9 +275,19 @@ def run_ours(a):
 
     if rank == 0:
         peak, peak_src = measured_peak()
-        hot = 2576  # sizeof(DEnvHot)
-        b_env = 2 * hot + ol * 4 + 4 + 4 + 1 + 32 + 12 * mean_leaf + (34 * mean_boxes if a.setting != 2 else 0)
-        ach = b_env * n / (kern_ms / K * 1e-3) / 1e9
+        # algorithmic bytes per env-step.  Dominant kernel = pct_feas_emit_kernel (K3): it reads the
+        # hot record, the staged loads / polygons and the candidate list, writes the observation, the leaf list and info.
+        hot, prefix = 3584, 2576  # sizeof(DEnvHot), HOT_PREFIX
+        stab = a.setting != 2
+        edges = mean_boxes if stab else 0.0
+        b_k3 = hot + (32 * edges + 16 * 0.3 * edges if stab else 0) + 2 * mean_cand + ol * 4 + 12 * mean_leaf + 16
+        b_step = 2 * hot + prefix + 2 * 2 * mean_cand + b_k3 + (2 * 32 * edges if stab else 0) + 4 + 4 + 1 + 32
+        if ksteps:
+            k3_ms = kms["feas_emit"] / ksteps
+            ach = b_k3 * n / (k3_ms * 1e-3) / 1e9
+        else:
+            k3_ms = None
+            ach = b_step * n / (kern_ms / K * 1e-3) / 1e9
         traffic = ncu_traffic()
         line = {"metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": step_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -277,10 +300,12 @@ def run_ours(a):
                         "steps": Ke, "path": "pct_step_host (C ABI, pinned host buffers) + numpy policy on the host observation"},
                 "gpu_launches": int(launches), "kernel_ms_per_step": kern_ms / K, "wall_s_timed_loop": wall,
                 "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                             "traffic": traffic.get("dram_bytes_per_launch") if traffic else None, "kernel": "pct_discrete_kernel",
-                             "peak_source": peak_src, "algorithmic_bytes_per_env_step": b_env},
+                             "traffic": traffic.get("dram_bytes_per_launch") if traffic else None, "kernel": "pct_feas_emit_kernel",
+                             "peak_source": peak_src, "algorithmic_bytes_per_env_kernel": b_k3, "algorithmic_bytes_per_env_step": b_step,
+                             "kernel_ms": k3_ms, "all_kernels_ms": {k: v / ksteps for k, v in kms.items()} if ksteps else None,
+                             "step_fraction_of_peak": b_step * n / (kern_ms / K * 1e-3) / 1e9 / peak},
                 "clocks": clocks}
-        if world == 1 and not a.skip_cpu:
+        if world == 1 and not a.skip_cpu and not a.continuous:
             try:
                 rate, dt, cores = cpu_port_rate(a.setting, 2048, 20, 300)
                 line["cpu_baseline"] = {"value": rate, "unit": "env-steps/s", "cores": cores, "kind": "port",

@@ -146,6 +146,11 @@ int32_t pct_obs_len(pct_handle h);       /* (NB + NL + 1) * 9 */
 int32_t pct_num_envs(pct_handle h);
 int64_t pct_state_bytes_per_env(pct_handle h); /* HBM bytes of library-owned state per env (roofline accounting) */
 int64_t pct_kernel_launches(pct_handle h);     /* kernels launched by this handle so far */
+/* Per-kernel device timing for roofline accounting: while enabled, every pct_step records CUDA events around its three
+ * kernels on the launching stream; pct_profile_read synchronises and returns the summed milliseconds of
+ * {apply, candidates, feas_emit} and the number of steps recorded since pct_profile_enable(h, 1). */
+int pct_profile_enable(pct_handle h, int32_t on);
+int pct_profile_read(pct_handle h, double ms_out[3], int32_t *n_steps);
 const char *pct_version(void);
 
 #ifdef __cplusplus

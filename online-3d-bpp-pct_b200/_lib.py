@@ -35,7 +35,7 @@ class StateDump(C.Structure):
 
 EXPORTS = ["pct_create", "pct_destroy", "pct_last_error", "pct_set_item_set", "pct_set_item_stream", "pct_set_trajectory_length", "pct_reset", "pct_step",
            "pct_step_host", "pct_reset_host", "pct_policy_random", "pct_get_state", "pct_obs_len", "pct_num_envs",
-           "pct_state_bytes_per_env", "pct_kernel_launches", "pct_version"]
+           "pct_state_bytes_per_env", "pct_kernel_launches", "pct_version", "pct_profile_enable", "pct_profile_read"]
 
 
 def build(verbose=False):
@@ -77,5 +77,7 @@ def lib():
     L.pct_kernel_launches.argtypes = [vp]
     L.pct_kernel_launches.restype = i64
     L.pct_version.restype = C.c_char_p
+    L.pct_profile_enable.argtypes = [vp, i32]
+    L.pct_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i32)]
     _lib = L
     return L

@@ -163,6 +163,16 @@ class PctBatch(object):
         return dict(n_boxes=d.n_boxes, n_ems=d.n_ems, n_leaf=d.n_leaf, flags=d.flags, draw_pos=d.draw_pos,
                     next_box=list(d.next_box), next_den=d.next_den, boxes=boxes, ems=ems)
 
+    def profile(self, on=True):
+        self._check(self.L.pct_profile_enable(self.h, int(on)), "pct_profile_enable")
+
+    def profile_read(self):
+        """-> ({'apply': ms, 'candidates': ms, 'feas_emit': ms} summed over the recorded steps, n_steps)"""
+        ms = (C.c_double * 3)()
+        n = C.c_int32()
+        self._check(self.L.pct_profile_read(self.h, ms, C.byref(n)), "pct_profile_read")
+        return dict(apply=ms[0], candidates=ms[1], feas_emit=ms[2]), n.value
+
     @property
     def kernel_launches(self):
         return int(self.L.pct_kernel_launches(self.h))

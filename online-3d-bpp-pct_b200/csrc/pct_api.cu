@@ -76,7 +76,7 @@ int pct_create(const pct_config *cfg, int32_t n_envs, int32_t device, pct_handle
     h->item_mode = cfg->item_mode;
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
-    h->groups = n_envs >= 2048 ? 4 : 1;
+    h->groups = 1;  // PCT_B200_GROUPS > 1 splits the batch over internal streams (measured: no gain)
     if (const char *gv = getenv("PCT_B200_GROUPS")) h->groups = atoi(gv);
     if (h->groups < 1) h->groups = 1;
     if (h->groups > 8) h->groups = 8;
@@ -111,6 +111,7 @@ void pct_destroy(pct_handle h) {
     if (h->cfg.domain == PCT_CONTINUOUS) continuous_destroy(h);
     cudaFree(h->d_hot); cudaFree(h->d_cold); cudaFree(h->d_item_set); cudaFree(h->d_stream);
     cudaFree(h->d_obs); cudaFree(h->d_act); cudaFree(h->d_idx); cudaFree(h->d_rew); cudaFree(h->d_done); cudaFree(h->d_info);
+    for (cudaEvent_t ev : h->prof_ev) if (ev) cudaEventDestroy(ev);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     for (int gi = 1; gi < 8; gi++) {
@@ -188,7 +189,17 @@ static int launch(pct_handle h, int mode, const void *actions, int action_f64, c
     p.reward = rew ? rew + off : nullptr; p.done = done ? done + off : nullptr; p.info = info ? info + off : nullptr; p.mode = mode;
     p.dbg = (long long *)h->dbg;
     p.keep_draw = h->did_reset ? 1 : 0; p.no_auto_reset = h->cfg.no_auto_reset;
-    CK(h, launch_discrete(p, gs));
+    cudaEvent_t *prof = nullptr;
+    if (h->prof_on && mode == 1 && G == 1) {
+        if ((size_t)(h->prof_steps + 1) * 4 > h->prof_ev.size()) {
+            const size_t old = h->prof_ev.size();
+            h->prof_ev.resize(old + 4096, nullptr);
+            for (size_t i = old; i < h->prof_ev.size(); i++) CK(h, cudaEventCreate(&h->prof_ev[i]));
+        }
+        prof = &h->prof_ev[(size_t)h->prof_steps * 4];
+        h->prof_steps++;
+    }
+    CK(h, launch_discrete(p, gs, prof));
     h->launches += discrete_kernels_per_step();
     if (gi > 0) {
         CK(h, cudaEventRecord(h->ev_join[gi], gs));
@@ -305,6 +316,26 @@ int64_t pct_state_bytes_per_env(pct_handle h) {
     return (int64_t)(sizeof(DEnvHot) + sizeof(DEnvCold));
 }
 int64_t pct_kernel_launches(pct_handle h) { return h ? h->launches : 0; }
+int pct_profile_enable(pct_handle h, int32_t on) {
+    if (!h) return PCT_ERR_INVALID;
+    h->prof_on = on ? 1 : 0;
+    h->prof_steps = 0;
+    return PCT_OK;
+}
+int pct_profile_read(pct_handle h, double ms_out[3], int32_t *n_steps) {
+    if (!h || !ms_out || !n_steps) return PCT_ERR_INVALID;
+    CK(h, cudaSetDevice(h->device));
+    CK(h, cudaDeviceSynchronize());
+    ms_out[0] = ms_out[1] = ms_out[2] = 0;
+    for (int s = 0; s < h->prof_steps; s++)
+        for (int k = 0; k < 3; k++) {
+            float ms = 0;
+            CK(h, cudaEventElapsedTime(&ms, h->prof_ev[(size_t)s * 4 + k], h->prof_ev[(size_t)s * 4 + k + 1]));
+            ms_out[k] += ms;
+        }
+    *n_steps = h->prof_steps;
+    return PCT_OK;
+}
 /* debug: device buffer of n_envs x 8 int64 phase timers (library built with -DPCT_PHASE_TIMERS) */
 void pct_debug_set_timer_buffer(pct_handle h, void *d_buf) { if (h) h->dbg = d_buf; }
 

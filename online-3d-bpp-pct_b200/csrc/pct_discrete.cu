@@ -851,7 +851,7 @@ static cudaError_t set_smem(K kernel, size_t smem) {
 }
 
 template <typename OT, bool STAB, typename SlotT>
-static cudaError_t launch_t(const DParams &p, cudaStream_t st) {
+static cudaError_t launch_t(const DParams &p, cudaStream_t st, cudaEvent_t *prof) {
     constexpr bool BIGSM = !STAB;
     static bool attr_set = false;
     const size_t smem1 = (size_t)K1_SM_PER_WARP * WARPS_PER_BLOCK;
@@ -863,24 +863,28 @@ static cudaError_t launch_t(const DParams &p, cudaStream_t st) {
         attr_set = true;
     }
     const int blocks = (p.n_envs + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+    if (prof) cudaEventRecord(prof[0], st);
     pct_apply_kernel<STAB><<<blocks, 32 * WARPS_PER_BLOCK, smem1, st>>>(p);
+    if (prof) cudaEventRecord(prof[1], st);
     pct_candidates_kernel<SlotT, BIGSM><<<blocks, 32 * WARPS_PER_BLOCK, smem2, st>>>(p);
+    if (prof) cudaEventRecord(prof[2], st);
     pct_feas_emit_kernel<OT, STAB, SlotT><<<p.n_envs, FEAS_THREADS, 0, st>>>(p);
+    if (prof) cudaEventRecord(prof[3], st);
     return cudaGetLastError();
 }
 template <typename OT, bool STAB>
-static cudaError_t launch_s(const DParams &p, cudaStream_t st) {
-    if (p.W <= 16 && p.L <= 16 && p.H <= 16) return launch_t<OT, STAB, uint16_t>(p, st);
-    return launch_t<OT, STAB, uint32_t>(p, st);
+static cudaError_t launch_s(const DParams &p, cudaStream_t st, cudaEvent_t *prof) {
+    if (p.W <= 16 && p.L <= 16 && p.H <= 16) return launch_t<OT, STAB, uint16_t>(p, st, prof);
+    return launch_t<OT, STAB, uint32_t>(p, st, prof);
 }
 
 // number of kernels one reset / step enqueues (for pct_kernel_launches)
 int discrete_kernels_per_step() { return 3; }
 
-cudaError_t launch_discrete(const DParams &p, cudaStream_t st) {
+cudaError_t launch_discrete(const DParams &p, cudaStream_t st, cudaEvent_t *prof) {
     const bool stab = p.setting != 2;
-    if (p.obs_f64) return stab ? launch_s<double, true>(p, st) : launch_s<double, false>(p, st);
-    return stab ? launch_s<float, true>(p, st) : launch_s<float, false>(p, st);
+    if (p.obs_f64) return stab ? launch_s<double, true>(p, st, prof) : launch_s<double, false>(p, st, prof);
+    return stab ? launch_s<float, true>(p, st, prof) : launch_s<float, false>(p, st, prof);
 }
 
 cudaError_t launch_policy_random_discrete(const DEnvHot *hot, int n_envs, int64_t env_id_base, uint64_t seed, int64_t t, int32_t *leaf_idx,

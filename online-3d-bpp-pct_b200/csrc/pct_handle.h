@@ -1,6 +1,7 @@
 // Internal: the object behind pct_handle.
 #pragma once
 #include <string>
+#include <vector>
 #include "pct_kernels.h"
 
 struct pct_env_batch {
@@ -28,6 +29,9 @@ struct pct_env_batch {
     pct_step_info *d_info = nullptr;
     cudaStream_t own_stream = nullptr;
     void *dbg = nullptr;
+    int prof_on = 0;
+    std::vector<cudaEvent_t> prof_ev;   // 4 events per recorded step
+    int prof_steps = 0;
     int groups = 1;               // env ranges stepped concurrently on internal streams
     cudaStream_t sub[8] = {};
     cudaEvent_t ev_fork = nullptr, ev_join[8] = {};
