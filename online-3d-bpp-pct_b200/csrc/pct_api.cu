@@ -91,6 +91,14 @@ int pct_create(const pct_config *cfg, int32_t n_envs, int32_t device, pct_handle
             if (e == cudaSuccess) e = cudaMalloc(&h->d_cold, sizeof(DEnvCold) * (size_t)n_envs);
             if (e == cudaSuccess) e = cudaMemset(h->d_hot, 0, sizeof(DEnvHot) * (size_t)n_envs);
             if (e == cudaSuccess) e = cudaMemset(h->d_cold, 0, sizeof(DEnvCold) * (size_t)n_envs);
+            if (e == cudaSuccess) e = cudaMalloc(&h->d_order, sizeof(int32_t) * 2 * (size_t)n_envs);
+            if (e == cudaSuccess) {
+                std::vector<int32_t> id(2 * (size_t)n_envs);
+                for (int i = 0; i < n_envs; i++) id[i] = id[n_envs + i] = i;
+                e = cudaMemcpy(h->d_order, id.data(), sizeof(int32_t) * id.size(), cudaMemcpyHostToDevice);
+            }
+            h->lpt = false;  // LPT block ordering measured: no gain (the heaviest env itself is the critical path); PCT_B200_LPT=1 enables it
+            if (const char *lv = getenv("PCT_B200_LPT")) h->lpt = atoi(lv) != 0;
         } else {
             int rc = continuous_create(h);
             if (rc != PCT_OK) { g_create_err = h->err; delete h; return rc; }
@@ -109,6 +117,7 @@ void pct_destroy(pct_handle h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->cfg.domain == PCT_CONTINUOUS) continuous_destroy(h);
+    cudaFree(h->d_order);
     cudaFree(h->d_hot); cudaFree(h->d_cold); cudaFree(h->d_item_set); cudaFree(h->d_stream);
     cudaFree(h->d_obs); cudaFree(h->d_act); cudaFree(h->d_idx); cudaFree(h->d_rew); cudaFree(h->d_done); cudaFree(h->d_info);
     for (cudaEvent_t ev : h->prof_ev) if (ev) cudaEventDestroy(ev);
@@ -188,6 +197,7 @@ static int launch(pct_handle h, int mode, const void *actions, int action_f64, c
     p.obs = (char *)obs + (size_t)off * h->obs_len * osz; p.obs_f64 = h->cfg.obs_dtype == PCT_F64;
     p.reward = rew ? rew + off : nullptr; p.done = done ? done + off : nullptr; p.info = info ? info + off : nullptr; p.mode = mode;
     p.dbg = (long long *)h->dbg;
+    p.order = (h->lpt && G == 1) ? h->d_order : nullptr;
     p.keep_draw = h->did_reset ? 1 : 0; p.no_auto_reset = h->cfg.no_auto_reset;
     cudaEvent_t *prof = nullptr;
     if (h->prof_on && mode == 1 && G == 1) {

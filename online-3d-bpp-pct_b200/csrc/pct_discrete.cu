@@ -474,8 +474,9 @@ template <bool STAB>
 __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, 14) pct_apply_kernel(const DParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int e = blockIdx.x * WARPS_PER_BLOCK + warp;
-    if (e >= p.n_envs) return;
+    const int slot = blockIdx.x * WARPS_PER_BLOCK + warp;
+    if (slot >= p.n_envs) return;
+    const int e = (p.order && p.mode == 1) ? p.order[slot] : slot;  // heaviest envs first (longest-processing-time-first)
     unsigned char *sm = smem_raw + (size_t)warp * K1_SM_PER_WARP;
     DEnvHot *hot = (DEnvHot *)sm;
     int16_t (*ems_tmp)[6] = (int16_t (*)[6])(sm + sizeof(DEnvHot));
@@ -717,7 +718,7 @@ __global__ void __launch_bounds__(FEAS_THREADS, 12) pct_feas_emit_kernel(const D
     constexpr int BITS = sizeof(SlotT) == 2 ? 4 : 8;
     __shared__ __align__(16) unsigned char sm[K3_SMEM];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int e = blockIdx.x;
+    const int e = p.order ? p.order[p.n_envs + blockIdx.x] : blockIdx.x;  // second half of `order`: K3's permutation
     DEnvHot *hot = (DEnvHot *)sm;
     int16_t (*leaf)[6] = (int16_t (*)[6])(sm + sizeof(DEnvHot));
     uint64_t *mbar = (uint64_t *)(sm + sizeof(DEnvHot) + NL_MAX * 12);
@@ -836,6 +837,34 @@ __global__ void __launch_bounds__(FEAS_THREADS, 12) pct_feas_emit_kernel(const D
     if (tid == 0) KT_END(p.env_id_base + e - p.env_id_base0, 2);
 }
 
+// Block scheduling order.  A launch lasts as long as its slowest block, and blocks are dispatched in index order, so the
+// envs with the most expected work should get the lowest block indices (LPT rule).  One 1024-thread block counting-sorts
+// the envs by a work estimate read from the record headers: which = 0 -> order[0..n) for the NEXT step's apply kernel
+// (boxes already placed drive the real stability DFS and the EMS update), which = 1 -> order[n..2n) for feas_emit
+// (candidates x stack depth).
+__global__ void __launch_bounds__(1024) pct_order_kernel(const DEnvHot *hot, int n_envs, int32_t *order, int which) {
+    __shared__ int hist[64], base[64];
+    const int tid = threadIdx.x;
+    if (tid < 64) hist[tid] = 0;
+    __syncthreads();
+    for (int e = tid; e < n_envs; e += 1024) {
+        const DHdr &h = hot[e].h;
+        const int key = which ? min(63, (h.n_cand * (4 + h.n_box)) >> 6) : min(63, h.n_box + (h.n_ems >> 1));
+        atomicAdd(&hist[63 - key], 1);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int s = 0;
+        for (int b = 0; b < 64; b++) { base[b] = s; s += hist[b]; }
+    }
+    __syncthreads();
+    for (int e = tid; e < n_envs; e += 1024) {
+        const DHdr &h = hot[e].h;
+        const int key = which ? min(63, (h.n_cand * (4 + h.n_box)) >> 6) : min(63, h.n_box + (h.n_ems >> 1));
+        order[which * n_envs + atomicAdd(&base[63 - key], 1)] = e;
+    }
+}
+
 // uniform-random valid-leaf policy: reads only the record headers
 __global__ void pct_policy_random_kernel(const DEnvHot *hot, int n_envs, int64_t env_id_base, uint64_t seed, int64_t t, int32_t *leaf_idx) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -867,8 +896,10 @@ static cudaError_t launch_t(const DParams &p, cudaStream_t st, cudaEvent_t *prof
     pct_apply_kernel<STAB><<<blocks, 32 * WARPS_PER_BLOCK, smem1, st>>>(p);
     if (prof) cudaEventRecord(prof[1], st);
     pct_candidates_kernel<SlotT, BIGSM><<<blocks, 32 * WARPS_PER_BLOCK, smem2, st>>>(p);
+    if (p.order) pct_order_kernel<<<1, 1024, 0, st>>>(p.hot, p.n_envs, p.order, 1);
     if (prof) cudaEventRecord(prof[2], st);
     pct_feas_emit_kernel<OT, STAB, SlotT><<<p.n_envs, FEAS_THREADS, 0, st>>>(p);
+    if (p.order) pct_order_kernel<<<1, 1024, 0, st>>>(p.hot, p.n_envs, p.order, 0);
     if (prof) cudaEventRecord(prof[3], st);
     return cudaGetLastError();
 }

@@ -29,6 +29,8 @@ struct pct_env_batch {
     pct_step_info *d_info = nullptr;
     cudaStream_t own_stream = nullptr;
     void *dbg = nullptr;
+    int32_t *d_order = nullptr;   // block -> env permutations (LPT scheduling)
+    bool lpt = false;
     int prof_on = 0;
     std::vector<cudaEvent_t> prof_ev;   // 4 events per recorded step
     int prof_steps = 0;

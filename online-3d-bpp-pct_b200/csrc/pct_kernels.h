@@ -134,6 +134,7 @@ struct DParams {
     int keep_draw;      // mode 0: continue the item source instead of rewinding it (env.reset() after an episode)
     int no_auto_reset;  // mode 1: leave a finished env untouched (gym.Env semantics)
     long long *dbg;  // phase timers (only with -DPCT_PHASE_TIMERS)
+    int32_t *order;  // [2 * n_envs] block -> env permutations (apply, feas_emit), nullptr = identity
 };
 
 int discrete_kernels_per_step();

@@ -51,7 +51,7 @@ class _PackingBase(object):
     def __init__(self, setting, container_size=(10, 10, 10), item_set=None, data_name=None, load_test_data=False,
                  internal_node_holder=80, leaf_node_holder=50, next_holder=1, shuffle=False, LNES="EMS",
                  sample_from_distribution=False, sample_left_bound=None, sample_right_bound=None, device=0, seed=0,
-                 item_stream=None, **kwags):
+                 item_stream=None, size_minimum=None, **kwags):
         if next_holder != 1:
             raise NotImplementedError("next_holder must be 1 (reference default)")
         if LNES != "EMS" or shuffle:
@@ -79,7 +79,7 @@ class _PackingBase(object):
                                leaf_node_holder=leaf_node_holder, continuous=self._continuous, obs_dtype=torch.float64, seed=seed,
                                device=device, sample_from_distribution=sample_from_distribution and self._continuous,
                                sample_left_bound=sample_left_bound, sample_right_bound=sample_right_bound, item_stream=stream,
-                               auto_reset=False)
+                               size_minimum=size_minimum, auto_reset=False)
         if traj_len:
             self._batch.set_trajectory_length(traj_len)
         self.observation_space = _make_box(0.0, float(container_size[2]), (self._batch.obs_len,))
@@ -105,7 +105,7 @@ class _PackingBase(object):
         obs, rew, done, info = self._batch.step(actions=torch.from_numpy(row[None]).to(self._batch.device))
         rec = PctBatch.decode_info(info)
         d = bool(done.cpu().numpy()[0])
-        reward = 0.0 if d else (nb[0] * nb[1] * nb[2]) / (self.bin_size[0] * self.bin_size[1] * self.bin_size[2]) * 10
+        reward = 0.0 if d else (nb[0] * nb[1] * nb[2]) / (self.bin_size[0] * self.bin_size[1] * self.bin_size[2]) * 10  # C:bin3D.py:199-202 too
         out = {"counter": int(rec["counter"][0])}
         if d:
             ratio = self.space.get_ratio()

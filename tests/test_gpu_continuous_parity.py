@@ -72,3 +72,28 @@ def test_continuous_random_items_run():
     assert nxt.min() > 0.0999 and nxt.max() < 0.5001
     assert not b.decode_info(info)["flags"].any()
     assert np.allclose(nxt * 1000, np.round(nxt * 1000), atol=1e-3)
+
+
+@pytest.mark.parametrize("setting", [1, 2])
+def test_continuous_single_env_facade(setting):
+    """PackingContinuous drop-in: float64 observations incl. the terminal one, reset() continues the stream, `packed`."""
+    import pct_b200
+    seed = 8
+    stream = make_continuous_stream(seed, 0, 300, setting)
+    orc = OracleContinuous(setting, stream=stream)
+    env = pct_b200.PackingContinuous(setting=setting, container_size=[1, 1, 1], item_set=None, sample_from_distribution=False,
+                                     item_stream=stream[None], size_minimum=0.1)
+    o_ref, o = orc.reset(), env.reset()
+    episodes = 0
+    for t in range(90):
+        assert np.array_equal(o, o_ref), t
+        _, row = policy_pick(o_ref, 80, 50, seed, 0, t)
+        o_ref, r_ref, d_ref, i_ref = orc.step(row)
+        o, r, d, info = env.step(row)
+        assert d == d_ref and abs(r - r_ref) < 1e-12 and info["counter"] == i_ref["counter"]
+        if d:
+            assert np.array_equal(o, o_ref), "terminal observation"
+            assert np.allclose(np.array(env.packed)[:, :6], np.array(orc.packed)[:, :6], rtol=0, atol=1e-12)
+            o_ref, o = orc.reset(), env.reset()
+            episodes += 1
+    assert episodes >= 2
