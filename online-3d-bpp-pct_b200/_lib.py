@@ -6,7 +6,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpct_b200.so")
+LIB_PATH = os.environ.get("PCT_B200_LIB", os.path.join(_HERE, "libpct_b200.so"))  # env override: tuning experiments only
 
 PCT_DISCRETE, PCT_CONTINUOUS = 0, 1
 PCT_F32, PCT_F64 = 0, 1

@@ -467,11 +467,17 @@ __device__ __forceinline__ long long gtime() { long long t; asm volatile("mov.u6
 #define KT_BEGIN()
 #define KT_END(e, k)
 #endif
+#ifndef K1_MINB
+#define K1_MINB 6   // sweep (r1): 168 regs / 6 blocks per SM beats 72 regs / 14 blocks — spills cost more than occupancy gives
+#endif
+#ifndef K3_MINB
+#define K3_MINB 8   // sweep (r1): 128 regs / 8 blocks per SM
+#endif
 constexpr int K1_SM_PER_WARP = sizeof(DEnvHot) + EMS_TMP_MAX * 12 + 16 + EDGE_STAGE * 32 + POLY_STAGE * 16;  // record + EMS temp + mbarrier/lock + staged loads
 static_assert(K1_SM_PER_WARP % 16 == 0, "alignment");
 
 template <bool STAB>
-__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, 14) pct_apply_kernel(const DParams p) {
+__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, K1_MINB) pct_apply_kernel(const DParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int slot = blockIdx.x * WARPS_PER_BLOCK + warp;
@@ -714,7 +720,7 @@ constexpr int FEAS_THREADS = 32 * FEAS_WARPS;
 constexpr int K3_SMEM = sizeof(DEnvHot) + NL_MAX * 12 + 64 + EDGE_STAGE * 32 + POLY_STAGE * 16;
 
 template <typename OT, bool STAB, typename SlotT>
-__global__ void __launch_bounds__(FEAS_THREADS, 12) pct_feas_emit_kernel(const DParams p) {
+__global__ void __launch_bounds__(FEAS_THREADS, K3_MINB) pct_feas_emit_kernel(const DParams p) {
     constexpr int BITS = sizeof(SlotT) == 2 ? 4 : 8;
     __shared__ __align__(16) unsigned char sm[K3_SMEM];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
