@@ -323,32 +323,41 @@ __device__ __forceinline__ bool pool_append(EdgePool &pool, int lower) {
 //                                                                           => [P3,P1,P0] -> drop last
 // so the polygon is [P0,P2,P3,P1]; scale_down + point_in_polygen run on registers, same operation order as
 // hull_indices + pip_shrunk.
+// one polygon edge (j -> i) of point_in_polygen: returns 2 when the point is collinear with the edge's line (-> False),
+// else 1 / 0 for "the ray crossing toggles" / "does not toggle"
+__device__ __forceinline__ int pip_edge(double ix, double iy, double jx, double jy, double lat, double lon) {
+    const double a0 = ix - lat, a1 = iy - lon;
+    const double b0 = lat - jx, b1 = lon - jy;
+    const double m1 = a0 * b1, m2 = a1 * b0;
+    if (m1 - m2 == 0) return 2;
+    if ((iy < lon && jy >= lon) || (jy < lon && iy >= lon)) return cross_left(ix, iy, jx, jy, lat, lon) ? 1 : 0;
+    return 0;
+}
 static __device__ __noinline__ bool pip_rect(double x1, double y1, double x2, double y2, double t1, double t2, double lat, double lon) {
-    // t1 = y1*1e-6, t2 = y2*1e-6 ; hull order P0,P2,P3,P1
-    const double hx[4] = {x1 + t1, x2 + t1, x2 + t2, x1 + t2};
-    const double hy[4] = {y1, y1, y2, y2};
-    const double sx = ((hx[0] + hx[1]) + hx[2]) + hx[3], sy = ((hy[0] + hy[1]) + hy[2]) + hy[3];
-    const double cx = ddiv(sx, 4.0), cy = ddiv(sy, 4.0);
-    double vx[4], vy[4];
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        double d = hx[i] - cx;
-        vx[i] = hx[i] - d * 0.1;
-        d = hy[i] - cy;
-        vy[i] = hy[i] - d * 0.1;
-    }
-    bool odd = false;
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        const int j = (i + 3) & 3;
-        const double a0 = vx[i] - lat, a1 = vy[i] - lon;
-        const double b0 = lat - vx[j], b1 = lon - vy[j];
-        const double m1 = a0 * b1, m2 = a1 * b0;
-        if (m1 - m2 == 0) return false;
-        if ((vy[i] < lon && vy[j] >= lon) || (vy[j] < lon && vy[i] >= lon)) {
-            if (cross_left(vx[i], vy[i], vx[j], vy[j], lat, lon)) odd = !odd;
-        }
-    }
+    // t1 = y1*1e-6, t2 = y2*1e-6 ; hull order P0,P2,P3,P1 = (x1+t1,y1) (x2+t1,y1) (x2+t2,y2) (x1+t2,y2)
+    const double h0 = x1 + t1, h1 = x2 + t1, h2 = x2 + t2, h3 = x1 + t2;
+    const double sx = ((h0 + h1) + h2) + h3, sy = ((y1 + y1) + y2) + y2;
+    const double cx = sx * 0.25, cy = sy * 0.25;  // mean of 4 (exact power-of-two division)
+    double d;
+    d = h0 - cx; const double v0x = h0 - d * 0.1;
+    d = h1 - cx; const double v1x = h1 - d * 0.1;
+    d = h2 - cx; const double v2x = h2 - d * 0.1;
+    d = h3 - cx; const double v3x = h3 - d * 0.1;
+    d = y1 - cy; const double vlo = y1 - d * 0.1;  // y of P0, P2
+    d = y2 - cy; const double vhi = y2 - d * 0.1;  // y of P3, P1
+    // edges in polygon order, j = previous vertex: (P1->P0) (P0->P2) (P2->P3) (P3->P1)
+    int r = pip_edge(v0x, vlo, v3x, vhi, lat, lon);
+    if (r == 2) return false;
+    bool odd = r == 1;
+    r = pip_edge(v1x, vlo, v0x, vlo, lat, lon);
+    if (r == 2) return false;
+    odd ^= (r == 1);
+    r = pip_edge(v2x, vhi, v1x, vlo, lat, lon);
+    if (r == 2) return false;
+    odd ^= (r == 1);
+    r = pip_edge(v3x, vhi, v2x, vhi, lat, lon);
+    if (r == 2) return false;
+    odd ^= (r == 1);
     return odd;
 }
 
