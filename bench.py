@@ -250,12 +250,15 @@ def run_ours(a):
             return z ^ (z >> np.uint64(31))
 
     def host_policy(t):
-        nvalid = (obs_h.reshape(n, -1, 9)[:, batch.nb:batch.nb + batch.nl, 8] == 1).sum(1).astype(np.uint64)
+        # uniform choice among the valid leaves, on the HOST from the step's returned records: the number of valid leaf rows
+        # is pct_step_info.n_leaf (== the count of 1s in column 8 of the leaf rows of the returned observation)
+        nvalid = info_h[:, 5].astype(np.uint64)
         with np.errstate(over="ignore"):
             r = sm64(sm64(np.uint64(POLICY_SEED) ^ (gid * GOLD)) + np.uint64(t))
         idx_h[:] = np.where(nvalid > 0, r % np.maximum(nvalid, np.uint64(1)), 0).astype(np.int32)
 
     batch.reset_host(obs_h)
+    info_h[:, 5] = (obs_h.reshape(n, -1, 9)[:, batch.nb:batch.nb + batch.nl, 8] == 1).sum(1)  # first step: count from the observation
     for t in range(We):
         host_policy(t)
         batch.step_host(obs_h, rew_h, done_h, info_h, leaf_idx=idx_h)
@@ -297,7 +300,7 @@ def run_ours(a):
                            "flushed between steps (256 MiB memset outside the timed interval)",
                            "mean_boxes": mean_boxes, "mean_valid_leaves": mean_leaf, "mean_candidates": mean_cand},
                 "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                        "steps": Ke, "path": "pct_step_host (C ABI, pinned host buffers) + numpy policy on the host observation"},
+                        "steps": Ke, "path": "pct_step_host (C ABI, pinned host buffers, 4 pipelined env ranges) + numpy policy on the host from the returned step records"},
                 "gpu_launches": int(launches), "kernel_ms_per_step": kern_ms / K, "wall_s_timed_loop": wall,
                 "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                              "traffic": traffic.get("dram_bytes_per_launch") if traffic else None, "kernel": "pct_feas_emit_kernel",

@@ -78,6 +78,10 @@ int pct_create(const pct_config *cfg, int32_t n_envs, int32_t device, pct_handle
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
     h->groups = 1;  // PCT_B200_GROUPS > 1 splits the batch over internal streams (measured: no gain)
     if (const char *gv = getenv("PCT_B200_GROUPS")) h->groups = atoi(gv);
+    h->host_groups = 4;
+    if (const char *gv = getenv("PCT_B200_HOST_GROUPS")) h->host_groups = atoi(gv);
+    if (h->host_groups < 1) h->host_groups = 1;
+    if (h->host_groups > 8) h->host_groups = 8;
     if (h->groups < 1) h->groups = 1;
     if (h->groups > 8) h->groups = 8;
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
@@ -160,29 +164,9 @@ int pct_set_trajectory_length(pct_handle h, int32_t traj_len) {
     return PCT_OK;
 }
 
-static int launch(pct_handle h, int mode, const void *actions, int action_f64, const int32_t *leaf_idx, void *obs, float *rew, uint8_t *done,
-                  pct_step_info *info, cudaStream_t st) {
-    if (h->item_mode == PCT_ITEMS_RANDOM && !(h->cfg.domain == PCT_CONTINUOUS && h->cfg.sample_from_distribution) && !h->d_item_set) {
-        h->err = "no item source: call pct_set_item_set or pct_set_item_stream first";
-        return PCT_ERR_STATE;
-    }
-    if (h->item_mode == PCT_ITEMS_STREAM && !h->d_stream) { h->err = "item stream not set"; return PCT_ERR_STATE; }
-    CK(h, cudaSetDevice(h->device));
-    if (h->cfg.domain == PCT_CONTINUOUS) {
-        int rc = continuous_launch(h, mode, actions, action_f64, leaf_idx, obs, rew, done, info, st);
-        if (rc == PCT_OK) h->launches++;
-        return rc;
-    }
-    // The batch is cut into `groups` contiguous env ranges, each enqueued on its own internal stream between a
-    // fork and a join event on the caller's stream: envs are independent, and a range whose kernels are waiting
-    // for a few heavy envs (deep stacking-stability recursions) no longer leaves the SMs idle.
-    const int G = h->groups;
-    if (G > 1) CK(h, cudaEventRecord(h->ev_fork, st));
-    for (int gi = 0; gi < G; gi++) {
-    const int off = (int)((int64_t)h->n_envs * gi / G), cnt = (int)((int64_t)h->n_envs * (gi + 1) / G) - off;
-    if (cnt <= 0) continue;
-    cudaStream_t gs = gi == 0 ? st : h->sub[gi];
-    if (gi > 0) CK(h, cudaStreamWaitEvent(gs, h->ev_fork, 0));
+// enqueue reset / step of the env range [off, off + cnt) on stream `gs`; all buffer pointers are BASE pointers
+static int launch_range(pct_handle h, int mode, int off, int cnt, const void *actions, int action_f64, const int32_t *leaf_idx, void *obs,
+                        float *rew, uint8_t *done, pct_step_info *info, cudaStream_t gs, bool whole_batch) {
     const size_t osz = h->cfg.obs_dtype == PCT_F64 ? 8 : 4, asz = action_f64 ? 8 : 4;
     DParams p{};
     p.hot = h->d_hot + off; p.cold = h->d_cold + off; p.n_envs = cnt;
@@ -197,10 +181,10 @@ static int launch(pct_handle h, int mode, const void *actions, int action_f64, c
     p.obs = (char *)obs + (size_t)off * h->obs_len * osz; p.obs_f64 = h->cfg.obs_dtype == PCT_F64;
     p.reward = rew ? rew + off : nullptr; p.done = done ? done + off : nullptr; p.info = info ? info + off : nullptr; p.mode = mode;
     p.dbg = (long long *)h->dbg;
-    p.order = (h->lpt && G == 1) ? h->d_order : nullptr;
+    p.order = (h->lpt && whole_batch) ? h->d_order : nullptr;
     p.keep_draw = h->did_reset ? 1 : 0; p.no_auto_reset = h->cfg.no_auto_reset;
     cudaEvent_t *prof = nullptr;
-    if (h->prof_on && mode == 1 && G == 1) {
+    if (h->prof_on && mode == 1 && whole_batch) {
         if ((size_t)(h->prof_steps + 1) * 4 > h->prof_ev.size()) {
             const size_t old = h->prof_ev.size();
             h->prof_ev.resize(old + 4096, nullptr);
@@ -211,10 +195,43 @@ static int launch(pct_handle h, int mode, const void *actions, int action_f64, c
     }
     CK(h, launch_discrete(p, gs, prof));
     h->launches += discrete_kernels_per_step();
-    if (gi > 0) {
-        CK(h, cudaEventRecord(h->ev_join[gi], gs));
-        CK(h, cudaStreamWaitEvent(st, h->ev_join[gi], 0));
+    return PCT_OK;
+}
+
+static int check_item_source(pct_handle h) {
+    if (h->item_mode == PCT_ITEMS_RANDOM && !(h->cfg.domain == PCT_CONTINUOUS && h->cfg.sample_from_distribution) && !h->d_item_set) {
+        h->err = "no item source: call pct_set_item_set or pct_set_item_stream first";
+        return PCT_ERR_STATE;
     }
+    if (h->item_mode == PCT_ITEMS_STREAM && !h->d_stream) { h->err = "item stream not set"; return PCT_ERR_STATE; }
+    return PCT_OK;
+}
+
+static int launch(pct_handle h, int mode, const void *actions, int action_f64, const int32_t *leaf_idx, void *obs, float *rew, uint8_t *done,
+                  pct_step_info *info, cudaStream_t st) {
+    int rc = check_item_source(h);
+    if (rc) return rc;
+    CK(h, cudaSetDevice(h->device));
+    if (h->cfg.domain == PCT_CONTINUOUS) {
+        rc = continuous_launch(h, mode, actions, action_f64, leaf_idx, obs, rew, done, info, st);
+        if (rc == PCT_OK) h->launches++;
+        return rc;
+    }
+    // PCT_B200_GROUPS > 1: the batch is cut into contiguous env ranges, each enqueued on its own internal stream between a
+    // fork and a join event on the caller's stream (measured: no gain for the device-resident path).
+    const int G = h->groups;
+    if (G > 1) CK(h, cudaEventRecord(h->ev_fork, st));
+    for (int gi = 0; gi < G; gi++) {
+        const int off = (int)((int64_t)h->n_envs * gi / G), cnt = (int)((int64_t)h->n_envs * (gi + 1) / G) - off;
+        if (cnt <= 0) continue;
+        cudaStream_t gs = gi == 0 ? st : h->sub[gi];
+        if (gi > 0) CK(h, cudaStreamWaitEvent(gs, h->ev_fork, 0));
+        rc = launch_range(h, mode, off, cnt, actions, action_f64, leaf_idx, obs, rew, done, info, gs, G == 1);
+        if (rc) return rc;
+        if (gi > 0) {
+            CK(h, cudaEventRecord(h->ev_join[gi], gs));
+            CK(h, cudaStreamWaitEvent(st, h->ev_join[gi], 0));
+        }
     }
     return PCT_OK;
 }
@@ -263,21 +280,31 @@ int pct_step_host(pct_handle h, const void *h_actions, int32_t action_f64, const
                   uint8_t *h_done, pct_step_info *h_info) {
     if (!h || !h_obs || !h_reward || !h_done) return PCT_ERR_INVALID;
     if ((h_actions == nullptr) == (h_leaf_idx == nullptr)) { h->err = "pct_step_host: pass exactly one of actions / leaf_idx"; return PCT_ERR_INVALID; }
+    if (!h->did_reset) { h->err = "pct_step_host before pct_reset"; return PCT_ERR_STATE; }
     CK(h, cudaSetDevice(h->device));
     int rc = ensure_staging(h);
     if (rc) return rc;
-    const size_t n = (size_t)h->n_envs;
-    cudaStream_t st = h->own_stream;
-    if (h_actions) CK(h, cudaMemcpyAsync(h->d_act, h_actions, n * 9 * (action_f64 ? 8 : 4), cudaMemcpyHostToDevice, st));
-    else CK(h, cudaMemcpyAsync(h->d_idx, h_leaf_idx, n * 4, cudaMemcpyHostToDevice, st));
-    rc = pct_step(h, h_actions ? h->d_act : nullptr, action_f64, h_actions ? nullptr : h->d_idx, h->d_obs, h->d_rew, h->d_done, h->d_info, st);
+    rc = check_item_source(h);
     if (rc) return rc;
-    const size_t ob = n * h->obs_len * (h->cfg.obs_dtype == PCT_F64 ? 8 : 4);
-    CK(h, cudaMemcpyAsync(h_obs, h->d_obs, ob, cudaMemcpyDeviceToHost, st));
-    CK(h, cudaMemcpyAsync(h_reward, h->d_rew, n * 4, cudaMemcpyDeviceToHost, st));
-    CK(h, cudaMemcpyAsync(h_done, h->d_done, n, cudaMemcpyDeviceToHost, st));
-    if (h_info) CK(h, cudaMemcpyAsync(h_info, h->d_info, n * sizeof(pct_step_info), cudaMemcpyDeviceToHost, st));
-    CK(h, cudaStreamSynchronize(st));
+    const size_t osz = h->cfg.obs_dtype == PCT_F64 ? 8 : 4, asz = action_f64 ? 8 : 4;
+    // Software pipeline over env ranges: range g's device->host copies overlap the kernels of range g+1 (envs are
+    // independent, so the ranges need no ordering between them).  Host buffers should be pinned.
+    const int G = (h->cfg.domain == PCT_DISCRETE && h->n_envs >= 1024) ? h->host_groups : 1;
+    for (int gi = 0; gi < G; gi++) {
+        const int off = (int)((int64_t)h->n_envs * gi / G), cnt = (int)((int64_t)h->n_envs * (gi + 1) / G) - off;
+        if (cnt <= 0) continue;
+        cudaStream_t st = gi == 0 ? h->own_stream : h->sub[gi];
+        if (h_actions) CK(h, cudaMemcpyAsync((char *)h->d_act + (size_t)off * 9 * asz, (const char *)h_actions + (size_t)off * 9 * asz, (size_t)cnt * 9 * asz, cudaMemcpyHostToDevice, st));
+        else CK(h, cudaMemcpyAsync(h->d_idx + off, h_leaf_idx + off, (size_t)cnt * 4, cudaMemcpyHostToDevice, st));
+        if (G == 1) rc = launch(h, 1, h_actions ? h->d_act : nullptr, action_f64, h_actions ? nullptr : h->d_idx, h->d_obs, h->d_rew, h->d_done, h->d_info, st);
+        else rc = launch_range(h, 1, off, cnt, h_actions ? h->d_act : nullptr, action_f64, h_actions ? nullptr : h->d_idx, h->d_obs, h->d_rew, h->d_done, h->d_info, st, false);
+        if (rc) return rc;
+        CK(h, cudaMemcpyAsync((char *)h_obs + (size_t)off * h->obs_len * osz, (char *)h->d_obs + (size_t)off * h->obs_len * osz, (size_t)cnt * h->obs_len * osz, cudaMemcpyDeviceToHost, st));
+        CK(h, cudaMemcpyAsync(h_reward + off, h->d_rew + off, (size_t)cnt * 4, cudaMemcpyDeviceToHost, st));
+        CK(h, cudaMemcpyAsync(h_done + off, h->d_done + off, (size_t)cnt, cudaMemcpyDeviceToHost, st));
+        if (h_info) CK(h, cudaMemcpyAsync(h_info + off, h->d_info + off, (size_t)cnt * sizeof(pct_step_info), cudaMemcpyDeviceToHost, st));
+    }
+    for (int gi = 0; gi < G; gi++) CK(h, cudaStreamSynchronize(gi == 0 ? h->own_stream : h->sub[gi]));
     return PCT_OK;
 }
 

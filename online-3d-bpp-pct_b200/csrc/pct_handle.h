@@ -34,6 +34,7 @@ struct pct_env_batch {
     int prof_on = 0;
     std::vector<cudaEvent_t> prof_ev;   // 4 events per recorded step
     int prof_steps = 0;
+    int host_groups = 4;          // env ranges pipelined by pct_step_host (kernels of one range overlap the D2H of another)
     int groups = 1;               // env ranges stepped concurrently on internal streams
     cudaStream_t sub[8] = {};
     cudaEvent_t ev_fork = nullptr, ev_join[8] = {};
