@@ -41,6 +41,7 @@ enum pct_status {
 
 enum pct_domain { PCT_DISCRETE = 0, PCT_CONTINUOUS = 1 };
 enum pct_obs_dtype { PCT_F32 = 0, PCT_F64 = 1 };
+enum pct_lnes { PCT_LNES_EMS = 0, PCT_LNES_EV = 1, PCT_LNES_EP = 2, PCT_LNES_CP = 3, PCT_LNES_FC = 4 };
 enum pct_item_mode {
     PCT_ITEMS_RANDOM = 0, /* uniform over item_set with the counter-based generator (RandomBoxCreator, */
                           /*   D:binCreator.py:24-39); continuous + sample_from_distribution: C:bin3D.py:103-115 */
@@ -76,6 +77,7 @@ typedef struct pct_config {
     int32_t no_auto_reset;        /* 0: ShmemVecEnv worker semantics (finished envs are reset inside the step,   */
                                   /*    wrapper/shmem_vec_env.py:141-142); 1: plain gym.Env semantics (the       */
                                   /*    terminal observation is returned, the caller resets; D:bin3D.py:160-165) */
+    int32_t lnes;                 /* leaf-node expansion scheme (D:bin3D.py:101-112): pct_lnes, 0 = EMS (reference default) */
 } pct_config;
 
 /* Terminal-step info (the dict built at D:bin3D.py:163-164 plus what Monitor adds, wrapper/monitor.py:58-77) */

@@ -58,6 +58,10 @@ int pct_create(const pct_config *cfg, int32_t n_envs, int32_t device, pct_handle
         g_create_err = "pct_create: holder sizes out of range (internal <= 80, leaf <= 64)";
         return PCT_ERR_INVALID;
     }
+    if (cfg->lnes < 0 || cfg->lnes > 4 || (cfg->lnes != 0 && cfg->domain != PCT_DISCRETE)) {
+        g_create_err = "pct_create: lnes must be 0 (EMS) .. 4 (FC); the continuous domain builds EMS only";
+        return PCT_ERR_INVALID;
+    }
     if (cfg->domain == PCT_DISCRETE) {
         for (int i = 0; i < 3; i++)
             if (cfg->container_size[i] < 1 || cfg->container_size[i] > 255 || cfg->container_size[i] != (int)cfg->container_size[i]) {
@@ -172,7 +176,7 @@ static int launch_range(pct_handle h, int mode, int off, int cnt, const void *ac
     p.hot = h->d_hot + off; p.cold = h->d_cold + off; p.n_envs = cnt;
     p.W = (int)h->cfg.container_size[0]; p.L = (int)h->cfg.container_size[1]; p.H = (int)h->cfg.container_size[2];
     p.nb = h->cfg.internal_node_holder; p.nl = h->cfg.leaf_node_holder; p.setting = h->cfg.setting;
-    p.low_bound = h->cfg.size_minimum;
+    p.low_bound = h->cfg.size_minimum; p.lnes = h->cfg.lnes;
     p.item_mode = h->item_mode; p.item_set = h->d_item_set; p.n_items = h->n_items;
     p.stream = h->d_stream ? h->d_stream + (size_t)off * h->stream_len * 4 : nullptr; p.stream_len = h->stream_len; p.traj_len = h->traj_len;
     p.seed = h->cfg.seed; p.env_id_base = h->cfg.env_id_base + off; p.env_id_base0 = h->cfg.env_id_base;

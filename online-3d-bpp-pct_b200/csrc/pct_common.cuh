@@ -42,6 +42,17 @@ __device__ __forceinline__ uint64_t tuple_hash6(const uint64_t lane[6]) {
     if (acc == ~0ull) return 1546275796ull;
     return acc;
 }
+__device__ __forceinline__ uint64_t tuple_hash_n(const uint64_t *lane, int n) {
+    uint64_t acc = XXP5;
+    for (int i = 0; i < n; i++) {
+        acc += lane[i] * XXP2;
+        acc = (acc << 31) | (acc >> 33);
+        acc *= XXP1;
+    }
+    acc += (uint64_t)n ^ (XXP5 ^ 3527539ull);
+    if (acc == ~0ull) return 1546275796ull;
+    return acc;
+}
 // _Py_HashDouble (Python/pyhash.c) for finite doubles: value mod (2^61 - 1) with sign, -1 -> -2
 __device__ __forceinline__ uint64_t hash_double(double v) {
     const uint64_t MOD = (1ull << 61) - 1;

@@ -64,6 +64,17 @@ struct GeomD {
     }
 };
 
+// resting height of a footprint: max top over the placed boxes it overlaps (== np.max(plain[lx:lx+x, ly:ly+y]))
+__device__ __forceinline__ int rest_height(const int16_t (*box)[6], int first, int n, int stride, int lx, int ly, int hx, int hy) {
+    int mh = 0;
+#pragma unroll 4
+    for (int t = first; t < n; t += stride) {
+        const int16_t *b = box[t];
+        if (lx < b[3] && hx > b[0] && ly < b[4] && hy > b[1]) mh = max(mh, (int)b[5]);
+    }
+    return mh;
+}
+
 // ---- shared-memory layout of one warp ------------------------------------------------------------------
 // Candidate keys are canonical integers: xs | ys << B | zs << 2B | rot << 3B  (rot = first rotation index with
 // the same oriented dims).  B = 4 bits when every container side is <= 16 (16-bit table slots), else 8 bits
@@ -265,7 +276,7 @@ struct SetStage {  // per-warp staging of (hash, key) pairs for the serial inser
 // instructions than a ballot-based warp-wide probe).  Resizes re-hash the old table in parallel, 32 slots at a time.
 template <typename SlotT>
 __device__ __noinline__ int build_candidates(const int16_t (*ems)[6], int n_ems, const RotTab *rt, int R, SlotT *tabA, SlotT *tabB, SlotT *tabBig,
-                                             SetStage *stg, SlotT *&out, int lane, int &flags) {
+                                             SetStage *stg, SlotT *&out, int lane, int &flags, const uint32_t *raw_keys = nullptr, int n_raw = 0) {
     constexpr int BITS = sizeof(SlotT) == 2 ? 4 : 8;
     constexpr SlotT EMPTY = (SlotT)~(SlotT)0;
     SlotT *tab = tabA;
@@ -273,7 +284,7 @@ __device__ __noinline__ int build_candidates(const int16_t (*ems)[6], int n_ems,
     int fill = 0;
     if (lane < 8) tab[lane] = EMPTY;
     __syncwarp();
-    const int raw = n_ems * R * 4;
+    const int raw = raw_keys ? n_raw : n_ems * R * 4;  // raw_keys: insertion sequence produced by an EV / EP / CP / FC generator
     bool stop = false;
 #pragma unroll 1
     for (int base = 0; base < raw && !stop; base += 32) {
@@ -281,7 +292,11 @@ __device__ __noinline__ int build_candidates(const int16_t (*ems)[6], int n_ems,
         bool valid = false;
         uint64_t hash = 0;
         uint32_t key = 0xFFFFFFFFu;
-        if (r < raw) {
+        if (r < raw && raw_keys) {
+            valid = true;
+            key = raw_keys[r];
+            hash = key_hash<BITS>(key, rt);
+        } else if (r < raw) {
             const int q = r & 3, er = r >> 2;
             const int rot = er % R, ei = er / R;
             if (rt->valid & (1 << rot)) {
@@ -396,6 +411,163 @@ __device__ __noinline__ int build_candidates(const int16_t (*ems)[6], int n_ems,
     return cnt;
 }
 
+// ---- the other leaf-node expansion schemes (D:bin3D.py:101-112): generators of the set-insertion sequence --------------
+constexpr int RAW_MAX = 2048;
+
+// FullCoord (D:space.py:573-610): every cell x valid rotation with lz = height of the cell, rot-major / lx / ly order
+template <int BITS>
+__device__ __noinline__ int gen_full_coord(const int16_t (*box)[6], int n_box, const RotTab *rt, int R, int W, int L, int H, uint32_t *raw,
+                                           int lane, int &flags) {
+    int n = 0;
+    const int cells = W * L;
+#pragma unroll 1
+    for (int rot = 0; rot < R; rot++) {
+        if (!(rt->valid & (1 << rot))) continue;
+        const int sx = rt->d[rot][0], sy = rt->d[rot][1], sz = rt->d[rot][2];
+#pragma unroll 1
+        for (int b = 0; b < cells; b += 32) {
+            const int c = b + lane, lx = c / L, ly = c - lx * L;
+            bool ok = false;
+            int lz = 0;
+            if (c < cells) {
+                lz = rest_height(box, 0, n_box, 1, lx, ly, lx + 1, ly + 1);
+                ok = lx + sx <= W && ly + sy <= L && lz + sz <= H;
+            }
+            const uint32_t m = __ballot_sync(FULL, ok);
+            if (ok) {
+                const int p = n + __popc(m & ((1u << lane) - 1));
+                if (p < RAW_MAX) raw[p] = key_pack<BITS>(lx, ly, lz, rt->canon[rot]);
+            }
+            n += __popc(m);
+        }
+    }
+    if (n > RAW_MAX) { flags |= PCT_FLAG_CAND_OVERFLOW; n = RAW_MAX; }
+    __syncwarp();
+    return n;
+}
+
+// EventPoint (D:space.py:613-693) as the reference actually behaves: GENEMS (which maintains EMS and ZMAP) only runs for
+// LNES == 'EMS' (D:bin3D.py:172-175), so ZMAP stays {0: x_up [0], y_left [0], x_bottom [W], y_right [L]} and the EMS list
+// stays [whole bin]: four bin-corner placements per rotation at z = 0 (oversized rotations produce nothing valid).
+template <int BITS>
+__device__ __noinline__ int gen_event_point(const RotTab *rt, int R, int W, int L, uint32_t *raw, int lane) {
+    int n = 0;
+    if (lane == 0) {
+        for (int rot = 0; rot < R; rot++) {
+            if (!(rt->valid & (1 << rot))) continue;
+            const int sx = rt->d[rot][0], sy = rt->d[rot][1], c = rt->canon[rot];
+            if (sx > W || sy > L) continue;
+            raw[n++] = key_pack<BITS>(0, 0, 0, c);
+            raw[n++] = key_pack<BITS>(0, L - sy, 0, c);
+            raw[n++] = key_pack<BITS>(W - sx, 0, 0, c);
+            raw[n++] = key_pack<BITS>(W - sx, L - sy, 0, c);
+        }
+    }
+    n = __shfl_sync(FULL, n, 0);
+    __syncwarp();
+    return n;
+}
+
+// ExtremePoint2D (ep = true, D:space.py:696-750 + PctTools.extreme2D :107-135) and CornerPoint (ep = false,
+// D:space.py:752-806 + PctTools.corners2D :137-159): per distinct top level k, the 2-D points of the boxes whose top is
+// above k; points new w.r.t. the previous level x rotations.  Small serial algorithms over <= 80 boxes: lane 0 runs them.
+// Returns -2 for the empty-bin special case (two hard-coded placements, a list, no set).
+template <int BITS>
+__device__ __noinline__ int gen_level_points(const int16_t (*box)[6], int n_box, const RotTab *rt, int R, int W, int L, int H, bool ep,
+                                             uint32_t *raw, int lane, int &flags) {
+    if (n_box == 0) return -2;
+    int n = 0;
+    if (lane == 0) {
+        int16_t tset[NB_MAX + 1];
+        int nt = 0;
+        tset[nt++] = 0;
+        for (int i = 0; i < n_box; i++) {
+            const int16_t t = box[i][5];
+            bool f = false;
+            for (int k = 0; k < nt; k++) f |= tset[k] == t;
+            if (!f) tset[nt++] = t;
+        }
+        for (int i = 1; i < nt; i++) { int16_t v = tset[i]; int j = i - 1; while (j >= 0 && tset[j] > v) { tset[j + 1] = tset[j]; j--; } tset[j + 1] = v; }
+        uint8_t ord[NB_MAX], em[NB_MAX];
+        int16_t cur[2 * NB_MAX + 2][2], last[2 * NB_MAX + 2][2];
+        int nlast = 0;
+        bool over = false;
+        for (int ti = 0; ti < nt; ti++) {
+            const int k = tset[ti];
+            int nr = 0, nc = 0;
+            for (int i = 0; i < n_box; i++)
+                if (box[i][5] > k) ord[nr++] = (uint8_t)i;  // IK in box order
+            if (nr == 0) { cur[0][0] = 0; cur[0][1] = 0; nc = 1; }
+            else if (!ep) {
+                // corners2D: stable sort by (y_end, x_end) descending, staircase of the items that extend x
+                for (int i = 1; i < nr; i++) {
+                    const uint8_t o = ord[i];
+                    int j = i - 1;
+                    while (j >= 0 && (box[ord[j]][4] < box[o][4] || (box[ord[j]][4] == box[o][4] && box[ord[j]][3] < box[o][3]))) { ord[j + 1] = ord[j]; j--; }
+                    ord[j + 1] = o;
+                }
+                int xrec = 0, m = 0;
+                for (int i = 0; i < nr; i++)
+                    if (box[ord[i]][3] > xrec) { em[m++] = ord[i]; xrec = box[ord[i]][3]; }
+                cur[nc][0] = 0; cur[nc][1] = box[ord[0]][4]; nc++;
+                for (int i = 1; i < m; i++) { cur[nc][0] = box[em[i - 1]][3]; cur[nc][1] = box[em[i]][4]; nc++; }
+                cur[nc][0] = box[em[m - 1]][3]; cur[nc][1] = 0; nc++;
+            } else {
+                // extreme2D: stable sort by (ly, x_end) ascending; the two `demo` walls use the reference's hard-coded 10
+                for (int i = 1; i < nr; i++) {
+                    const uint8_t o = ord[i];
+                    int j = i - 1;
+                    while (j >= 0 && (box[ord[j]][1] > box[o][1] || (box[ord[j]][1] == box[o][1] && box[ord[j]][3] > box[o][3]))) { ord[j + 1] = ord[j]; j--; }
+                    ord[j + 1] = o;
+                }
+                for (int i = 0; i < nr; i++) {
+                    const int16_t *ni = box[ord[i]];
+                    int maxb0 = -10, maxb2 = -10, e0x = 0, e0y = 0, e2x = 0, e2y = 0;
+                    bool has0 = false, has2 = false;
+                    for (int b = 0; b < 2 + i; b++) {
+                        int bx2, bx3;
+                        if (b == 0) { bx2 = 0; bx3 = 10; } else if (b == 1) { bx2 = 10; bx3 = 0; } else { bx2 = box[ord[b - 2]][3]; bx3 = box[ord[b - 2]][4]; }
+                        if (ni[0] >= bx2 && ni[4] < bx3 && bx2 > maxb0) { e0x = bx2; e0y = ni[4]; maxb0 = bx2; has0 = true; }
+                        if (ni[1] >= bx3 && ni[3] < bx2 && bx3 > maxb2) { e2x = ni[3]; e2y = bx3; maxb2 = bx3; has2 = true; }
+                    }
+                    int w = 0;  // deleteEps2D
+                    for (int q = 0; q < nc; q++)
+                        if (!(cur[q][0] >= ni[0] && cur[q][0] < ni[3] && cur[q][1] >= ni[1] && cur[q][1] < ni[4])) { cur[w][0] = cur[q][0]; cur[w][1] = cur[q][1]; w++; }
+                    nc = w;
+                    if (has0 && has2 && !(e0x == e2x && e0y == e2y)) {
+                        // list(set({(e0), (e2)})): CPython order of two int 2-tuples in an 8-slot table
+                        uint64_t l0[2] = {(uint64_t)e0x, (uint64_t)e0y}, l2[2] = {(uint64_t)e2x, (uint64_t)e2y};
+                        const uint64_t h0 = tuple_hash_n(l0, 2), h2 = tuple_hash_n(l2, 2);
+                        uint64_t s0 = h0 & 7, s2 = h2 & 7, pert = h2;
+                        while (s2 == s0) { pert >>= 5; s2 = (s2 * 5 + 1 + pert) & 7; }
+                        if (s0 < s2) { cur[nc][0] = e0x; cur[nc][1] = e0y; nc++; cur[nc][0] = e2x; cur[nc][1] = e2y; nc++; }
+                        else { cur[nc][0] = e2x; cur[nc][1] = e2y; nc++; cur[nc][0] = e0x; cur[nc][1] = e0y; nc++; }
+                    } else if (has0) { cur[nc][0] = e0x; cur[nc][1] = e0y; nc++; }
+                    else if (has2) { cur[nc][0] = e2x; cur[nc][1] = e2y; nc++; }
+                }
+            }
+            for (int q = 0; q < nc; q++) {
+                bool f = false;
+                for (int u = 0; u < nlast; u++) f |= last[u][0] == cur[q][0] && last[u][1] == cur[q][1];
+                if (f) continue;
+                for (int rot = 0; rot < R; rot++) {  // CI point x rotation -> insertion sequence of posVec
+                    if (!(rt->valid & (1 << rot))) continue;
+                    if (cur[q][0] + rt->d[rot][0] <= W && cur[q][1] + rt->d[rot][1] <= L && k + rt->d[rot][2] <= H) {
+                        if (n < RAW_MAX && cur[q][0] >= 0 && cur[q][1] >= 0) raw[n++] = key_pack<BITS>(cur[q][0], cur[q][1], k, rt->canon[rot]);
+                        else over = true;
+                    }
+                }
+            }
+            for (int q = 0; q < nc; q++) { last[q][0] = cur[q][0]; last[q][1] = cur[q][1]; }
+            nlast = nc;
+        }
+        if (over) flags |= PCT_FLAG_CAND_OVERFLOW;
+    }
+    n = __shfl_sync(FULL, n, 0);
+    __syncwarp();
+    return n;
+}
+
 // ---- item source ------------------------------------------------------------------------------------------
 __device__ __noinline__ void draw_item(const DParams &p, int e, DHdr &h) {
     const uint64_t gid = (uint64_t)(p.env_id_base + e);
@@ -469,17 +641,6 @@ __device__ __noinline__ void write_obs(const DParams &p, int e, const DEnvHot *h
         row += dr; col += dc;
         if (col >= 9) { col -= 9; row++; }
     }
-}
-
-// resting height of a footprint: max top over the placed boxes it overlaps (== np.max(plain[lx:lx+x, ly:ly+y]))
-__device__ __forceinline__ int rest_height(const int16_t (*box)[6], int first, int n, int stride, int lx, int ly, int hx, int hy) {
-    int mh = 0;
-#pragma unroll 4
-    for (int t = first; t < n; t += stride) {
-        const int16_t *b = box[t];
-        if (lx < b[3] && hx > b[0] && ly < b[4] && hy > b[1]) mh = max(mh, (int)b[5]);
-    }
-    return mh;
 }
 
 // ======================================================================================================
@@ -665,7 +826,8 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, K1_MINB) pct_apply_kerne
             const int n_ems0 = h.n_ems;
             __syncwarp();
             int fl = 0;
-            const int n_ems = genems_warp(hot->ems, n_ems0, ems_tmp, b, p.low_bound, lane, fl);
+            // GENEMS only runs for LNES == 'EMS' (D:bin3D.py:172-175)
+            const int n_ems = p.lnes == 0 ? genems_warp(hot->ems, n_ems0, ems_tmp, b, p.low_bound, lane, fl) : n_ems0;
             const double rw = (double)(nb0 * nb1 * nb2) / binvol * 10;  // D:bin3D.py:180-183
             reward = (float)rw;
             info.counter = n_box0 + 1;
@@ -740,10 +902,26 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) pct_candidates_kernel(co
     if (lane == 0) make_rot_tab(nb3, R, *rt);
     __syncwarp();
     SlotT *cand = nullptr;
-    int fl = 0;
-    const int n_cand = build_candidates<SlotT>(hot->ems, h.n_ems, rt, R, tabA, tabB, BIGSM ? tabA : (SlotT *)cold->tab_big, stg, cand, lane, fl);
+    int fl = 0, n_cand;
     SlotT *out = (SlotT *)cold->cand;
-    for (int t = lane; t < n_cand; t += 32) out[t] = cand[t];
+    constexpr int KB = sizeof(SlotT) == 2 ? 4 : 8;
+    if (p.lnes == 0) {
+        n_cand = build_candidates<SlotT>(hot->ems, h.n_ems, rt, R, tabA, tabB, BIGSM ? tabA : (SlotT *)cold->tab_big, stg, cand, lane, fl);
+    } else {
+        uint32_t *raw = cold->raw;
+        int n_raw;
+        if (p.lnes == 4) n_raw = gen_full_coord<KB>(hot->box, h.n_box, rt, R, p.W, p.L, p.H, raw, lane, fl);
+        else if (p.lnes == 1) n_raw = gen_event_point<KB>(rt, R, p.W, p.L, raw, lane);
+        else n_raw = gen_level_points<KB>(hot->box, h.n_box, rt, R, p.W, p.L, p.H, p.lnes == 2, raw, lane, fl);
+        if (n_raw == -2) {  // empty bin under EP / CP: the reference returns a 2-element LIST (D:space.py:700-701)
+            if (lane < 2) out[lane] = (SlotT)key_pack<KB>(0, 0, 0, rt->canon[lane]);
+            n_cand = 2;
+            cand = out;
+        } else
+            n_cand = build_candidates<SlotT>(hot->ems, h.n_ems, rt, R, tabA, tabB, BIGSM ? tabA : (SlotT *)cold->tab_big, stg, cand, lane, fl, raw, n_raw);
+    }
+    if (cand != out)
+        for (int t = lane; t < n_cand; t += 32) out[t] = cand[t];
     if (lane == 0) {
         ghot->h.n_cand = n_cand;
         if (fl) ghot->h.flags = h.flags | fl;

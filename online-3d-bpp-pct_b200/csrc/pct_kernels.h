@@ -103,6 +103,7 @@ struct alignas(16) DEnvCold {
     Stack4 e_st[EDGE_MAX + 1];
     double poly[POLY_MAX][2];
     uint32_t cand[1232];      // ordered candidate keys written by K2, read by K3 (<= 1228 distinct candidates)
+    uint32_t raw[2048];       // insertion sequence produced by the EV / EP / CP / FC generators
     uint32_t tab_big[TAB_A];  // 2048-slot stage of the set emulation when it does not live in shared memory
     BigScratch big;
 };
@@ -130,6 +131,7 @@ struct DParams {
     float *reward;
     uint8_t *done;
     pct_step_info *info;
+    int lnes;  // leaf-node expansion scheme: 0 EMS, 1 EV, 2 EP, 3 CP, 4 FC
     int mode;  // 0 = reset all, 1 = step
     int keep_draw;      // mode 0: continue the item source instead of rewinding it (env.reset() after an episode)
     int no_auto_reset;  // mode 1: leave a finished env untouched (gym.Env semantics)

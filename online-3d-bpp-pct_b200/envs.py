@@ -54,8 +54,8 @@ class _PackingBase(object):
                  item_stream=None, size_minimum=None, **kwags):
         if next_holder != 1:
             raise NotImplementedError("next_holder must be 1 (reference default)")
-        if LNES != "EMS" or shuffle:
-            raise NotImplementedError("pct_b200 builds LNES='EMS', shuffle=False")
+        if shuffle:
+            raise NotImplementedError("shuffle=True has no parity definition (global numpy RNG in the reference)")
         self.internal_node_holder, self.leaf_node_holder, self.next_holder = internal_node_holder, leaf_node_holder, next_holder
         self.bin_size = container_size
         self.setting = setting
@@ -79,7 +79,7 @@ class _PackingBase(object):
                                leaf_node_holder=leaf_node_holder, continuous=self._continuous, obs_dtype=torch.float64, seed=seed,
                                device=device, sample_from_distribution=sample_from_distribution and self._continuous,
                                sample_left_bound=sample_left_bound, sample_right_bound=sample_right_bound, item_stream=stream,
-                               size_minimum=size_minimum, auto_reset=False)
+                               size_minimum=size_minimum, auto_reset=False, LNES=LNES)
         if traj_len:
             self._batch.set_trajectory_length(traj_len)
         self.observation_space = _make_box(0.0, float(container_size[2]), (self._batch.obs_len,))

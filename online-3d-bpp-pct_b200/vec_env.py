@@ -43,15 +43,13 @@ class PctVecEnv(object):
     def __init__(self, num_envs, setting, container_size=(10, 10, 10), item_set=None, internal_node_holder=80,
                  leaf_node_holder=50, continuous=False, device=0, seed=0, env_id_base=0, sample_from_distribution=False,
                  sample_left_bound=None, sample_right_bound=None, item_stream=None, LNES="EMS", shuffle=False, **_ignored):
-        if LNES != "EMS":
-            raise NotImplementedError("pct_b200 builds the EMS leaf-node expansion scheme (reference default, --lnes EMS)")
         if shuffle:
             raise NotImplementedError("shuffle=True draws from the global numpy RNG in the reference and has no parity definition")
         self.batch = PctBatch(num_envs, setting, container_size=container_size, item_set=item_set,
                               internal_node_holder=internal_node_holder, leaf_node_holder=leaf_node_holder, continuous=continuous,
                               obs_dtype=torch.float32, seed=seed, env_id_base=env_id_base, device=device,
                               sample_from_distribution=sample_from_distribution, sample_left_bound=sample_left_bound,
-                              sample_right_bound=sample_right_bound, item_stream=item_stream)
+                              sample_right_bound=sample_right_bound, item_stream=item_stream, LNES=LNES)
         self.num_envs = int(num_envs)
         self.device = self.batch.device
         self.observation_space = _make_box(0.0, float(container_size[2]), (self.batch.obs_len,))

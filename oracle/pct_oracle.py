@@ -65,10 +65,12 @@ class OracleDiscrete(object):
     item stream (array (n,4): x, y, z, density)."""
 
     def __init__(self, setting, container_size=(10, 10, 10), internal_node_holder=80, leaf_node_holder=50,
-                 size_minimum=1, stream=None):
+                 size_minimum=1, stream=None, lnes="EMS"):
         self.L = lib()
         self.h = self.L.pcto_create(setting, *[int(c) for c in container_size], internal_node_holder,
                                     leaf_node_holder, float(size_minimum))
+        self.L.pcto_set_lnes.argtypes = [C.c_void_p, C.c_int]
+        self.L.pcto_set_lnes(self.h, {"EMS": 0, "EV": 1, "EP": 2, "CP": 3, "FC": 4}[lnes])
         self.nb, self.nl = internal_node_holder, leaf_node_holder
         self.obs_len = self.L.pcto_obs_len(self.h)
         self._stream = None

@@ -244,6 +244,18 @@ static inline uint64_t po_tuple_hash6(const uint64_t lane[6]) {
     if (acc == (uint64_t)-1) return 1546275796ULL;
     return acc;
 }
+/* tuplehash for an n-tuple of already hashed lanes (Objects/tupleobject.c) */
+static inline uint64_t po_tuple_hash_n(const uint64_t *lane, int n) {
+    uint64_t acc = PO_XXP5;
+    for (int i = 0; i < n; i++) {
+        acc += lane[i] * PO_XXP2;
+        acc = (acc << 31) | (acc >> 33);
+        acc *= PO_XXP1;
+    }
+    acc += (uint64_t)n ^ (PO_XXP5 ^ 3527539ULL);
+    if (acc == (uint64_t)-1) return 1546275796ULL;
+    return acc;
+}
 /* hash(int) for |v| < 2**61-1 */
 static inline uint64_t po_hash_int(int64_t v) { return v == -1 ? (uint64_t)-2 : (uint64_t)v; }
 /* _Py_HashDouble (Python/pyhash.c) for finite doubles */

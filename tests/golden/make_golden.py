@@ -19,17 +19,17 @@ from harness import ITEM_SET, make_stream, policy_pick  # noqa: E402
 from pct_oracle import make_continuous_stream  # noqa: E402
 
 
-def record(D, setting, seed, env_id, steps):
+def record(D, setting, seed, env_id, steps, lnes="EMS"):
     stream = make_stream(seed, env_id, steps + 64, setting)
     env = D.PackingDiscrete(setting=setting, container_size=[10, 10, 10], item_set=ITEM_SET, internal_node_holder=80,
-                            leaf_node_holder=50, shuffle=False, LNES="EMS")
+                            leaf_node_holder=50, shuffle=False, LNES=lnes)
     env.box_creator = ref_shim.make_stream_creator(D, [tuple(r) if setting == 3 else tuple(int(v) for v in r[:3]) for r in stream])
     env.test = True
     obs0 = env.reset()
     rows, obs, rew, done, counter, ratio, ems, cand = [], [obs0], [], [], [], [], {}, {}
     o = obs0
     for t in range(steps):
-        if t % 25 == 0:
+        if t % 25 == 0 and lnes == "EMS":
             ems[t] = np.array([list(map(int, e)) for e in env.space.EMS])
             cand[t] = np.array(env.space.EMSPoint(env.next_box, setting)).reshape(-1, 6)
         _, row = policy_pick(o, 80, 50, seed, env_id, t)
@@ -71,6 +71,12 @@ def record_continuous(Cm, setting, seed, env_id, steps):
 
 def main():
     D, Cm = ref_shim.load_reference()
+    for lnes in ("EV", "EP", "CP", "FC"):
+        for setting in (1, 2):
+            rec = record(D, setting, 31 + setting, 2, 160, lnes)
+            path = os.path.join(HERE, "discrete_%s_s%d.npz" % (lnes, setting))
+            np.savez_compressed(path, setting=setting, lnes=lnes, **rec)
+            print(path, os.path.getsize(path) // 1024, "KiB", "episodes", int(rec["done"].sum()))
     for setting in (1, 2, 3):
         rec = record_continuous(Cm, setting, 4242, 1, 200)
         path = os.path.join(HERE, "continuous_s%d_t0.npz" % setting)

@@ -97,3 +97,29 @@ def test_full_size_final_observations(setting, n):
     assert np.array_equal(nd.cpu().numpy(), nd_ref)
     assert np.array_equal(obs.cpu().numpy(), o_ref)
     assert np.allclose(rsum.cpu().numpy(), r_ref, rtol=0, atol=1e-4)  # GPU rewards are float32 (VecPyTorch contract)
+
+
+@pytest.mark.parametrize("lnes", ["FC", "EV", "CP", "EP"])
+@pytest.mark.parametrize("setting", [1, 2])
+def test_other_leaf_expansion_schemes(lnes, setting):
+    """EV (as degenerate as in the reference) / EP / CP / FC candidate generators (D:space.py:573-806) against the oracle."""
+    import pct_b200
+    from pct_oracle import policy_pick
+    n, steps, seed = 16, 70, 13
+    streams = np.stack([make_stream(seed, e, 300, setting) for e in range(n)])
+    orcs = [OracleDiscrete(setting, stream=streams[e], lnes=lnes) for e in range(n)]
+    gpu = pct_b200.PctBatch(n, setting, item_set=ITEM_SET, obs_dtype=torch.float64, item_stream=streams, LNES=lnes)
+    o_ref = np.stack([o.reset() for o in orcs])
+    o = gpu.reset().cpu().numpy()
+    for t in range(steps):
+        assert np.array_equal(o_ref, o), "%s setting %d step %d envs %s" % (lnes, setting, t, np.unique(np.argwhere(o_ref != o)[:, 0])[:5])
+        picks = [policy_pick(o_ref[e], 80, 50, seed, e, t) for e in range(n)]
+        rows = np.stack([p[1] for p in picks])
+        nxt = []
+        for e in range(n):
+            ob, r, d, info = orcs[e].step(rows[e])
+            nxt.append(orcs[e].reset() if d else ob)
+        o_ref = np.stack(nxt)
+        ob, r, d, info = gpu.step(actions=torch.from_numpy(rows).cuda())
+        o = ob.cpu().numpy()
+        assert not gpu.decode_info(info)["flags"].any()

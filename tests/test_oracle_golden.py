@@ -9,23 +9,25 @@ import pytest
 from pct_oracle import OracleDiscrete
 
 GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "discrete_s*.npz")))
+GOLD += sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "discrete_[ECF]*_s*.npz")))  # EV / EP / CP / FC schemes
 
 
 def test_golden_files_present():
-    assert len(GOLD) >= 6
+    assert len(GOLD) >= 14
 
 
 @pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p) for p in GOLD])
 def test_oracle_replays_reference_trajectory(path):
     g = np.load(path)
     setting = int(g["setting"])
-    env = OracleDiscrete(setting, stream=g["stream"])
+    lnes = str(g["lnes"]) if "lnes" in g.files else "EMS"
+    env = OracleDiscrete(setting, stream=g["stream"], lnes=lnes)
     obs = g["obs"]
     k = 0
     o = env.reset()
     assert np.array_equal(o, obs[k]); k += 1
     for t in range(len(g["rows"])):
-        if t % 25 == 0:  # internals pinned at a few steps: EMS list and ordered candidate list of the reference
+        if t % 25 == 0 and lnes == "EMS":  # internals pinned at a few steps: EMS list and ordered candidate list of the reference
             assert np.array_equal(env.ems(), g["ems_%d" % t]), "EMS list, step %d" % t
             cand, _ = env.candidates()
             assert np.array_equal(cand, g["cand_%d" % t].reshape(-1, 6)), "candidate order, step %d" % t
