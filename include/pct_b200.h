@@ -141,6 +141,9 @@ int pct_reset_host(pct_handle h, void *h_obs);
 /* Uniform-random choice among the valid leaf rows of each env (the synthetic policy of SURVEY.md §8(d)):
  * d_leaf_idx[e] = rnd(seed, env_id_base+e, t) % n_leaf[e]  (0 when there is no valid leaf). */
 int pct_policy_random(pct_handle h, int32_t *d_leaf_idx, uint64_t seed, int64_t t, void *stream);
+/* same, with the step counter read from device memory (*d_t) at execution time: lets a captured CUDA graph of
+ * policy -> step draw fresh actions on every replay (the caller increments *d_t inside the graph) */
+int pct_policy_random_dev(pct_handle h, int32_t *d_leaf_idx, uint64_t seed, const int64_t *d_t, void *stream);
 
 /* introspection */
 int pct_get_state(pct_handle h, int32_t env, pct_state_dump *out);

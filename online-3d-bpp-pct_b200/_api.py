@@ -8,7 +8,8 @@ try:  # host-side mirror of the reference's gym.Env / VecEnv surface
     from .vec_env import PctVecEnv
     from .envs import PackingDiscrete, PackingContinuous, make_vec_envs, registration_envs
     from .distributed import shard_range, make_sharded_vec_env, gather_observations
+    from .rollout import GraphedRollout
     __all__ += ["PctVecEnv", "PackingDiscrete", "PackingContinuous", "make_vec_envs", "registration_envs", "shard_range",
-                "make_sharded_vec_env", "gather_observations"]
+                "make_sharded_vec_env", "gather_observations", "GraphedRollout"]
 except ImportError:  # pragma: no cover - during bring-up
     pass

@@ -37,7 +37,7 @@ class StateDump(C.Structure):
 
 
 EXPORTS = ["pct_create", "pct_destroy", "pct_last_error", "pct_set_item_set", "pct_set_item_stream", "pct_set_trajectory_length", "pct_reset", "pct_step",
-           "pct_step_host", "pct_reset_host", "pct_policy_random", "pct_get_state", "pct_obs_len", "pct_num_envs",
+           "pct_step_host", "pct_reset_host", "pct_policy_random", "pct_policy_random_dev", "pct_get_state", "pct_obs_len", "pct_num_envs",
            "pct_state_bytes_per_env", "pct_kernel_launches", "pct_version", "pct_profile_enable", "pct_profile_read"]
 
 
@@ -72,6 +72,7 @@ def lib():
     L.pct_step_host.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp]
     L.pct_reset_host.argtypes = [vp, vp]
     L.pct_policy_random.argtypes = [vp, vp, u64, i64, vp]
+    L.pct_policy_random_dev.argtypes = [vp, vp, u64, vp, vp]
     L.pct_get_state.argtypes = [vp, i32, C.POINTER(StateDump)]
     L.pct_obs_len.argtypes = [vp]
     L.pct_num_envs.argtypes = [vp]

@@ -132,6 +132,13 @@ class PctBatch(object):
                     "pct_policy_random")
         return idx
 
+    def random_policy_dev(self, seed, t_dev, out=None):
+        """random_policy with the step counter read from a device int64 tensor at execution time (graph-capturable)"""
+        idx = self._idx if out is None else out
+        self._check(self.L.pct_policy_random_dev(self.h, C.c_void_p(idx.data_ptr()), int(seed) & ((1 << 64) - 1), C.c_void_p(t_dev.data_ptr()),
+                                                 self._stream()), "pct_policy_random_dev")
+        return idx
+
     # -- host-buffer API (what the reference's VecEnv exchanges over its pipes) --------------------------------
     def reset_host(self, obs_out):
         self._check(self.L.pct_reset_host(self.h, C.c_void_p(obs_out.ctypes.data)), "pct_reset_host")

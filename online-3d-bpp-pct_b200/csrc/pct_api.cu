@@ -326,6 +326,16 @@ int pct_policy_random(pct_handle h, int32_t *d_leaf_idx, uint64_t seed, int64_t 
     return PCT_OK;
 }
 
+int pct_policy_random_dev(pct_handle h, int32_t *d_leaf_idx, uint64_t seed, const int64_t *d_t, void *stream) {
+    if (!h || !d_leaf_idx || !d_t) return PCT_ERR_INVALID;
+    if (!h->did_reset) { h->err = "pct_policy_random_dev before pct_reset"; return PCT_ERR_STATE; }
+    if (h->cfg.domain != PCT_DISCRETE) { h->err = "pct_policy_random_dev: discrete domain only"; return PCT_ERR_INVALID; }
+    CK(h, cudaSetDevice(h->device));
+    CK(h, launch_policy_random_discrete(h->d_hot, h->n_envs, h->cfg.env_id_base, seed, 0, d_leaf_idx, (cudaStream_t)stream, d_t));
+    h->launches++;
+    return PCT_OK;
+}
+
 int pct_get_state(pct_handle h, int32_t env, pct_state_dump *out) {
     if (!h || !out || env < 0 || env >= h->n_envs) return PCT_ERR_INVALID;
     CK(h, cudaSetDevice(h->device));

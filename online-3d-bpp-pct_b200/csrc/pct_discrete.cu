@@ -1087,9 +1087,11 @@ __global__ void __launch_bounds__(1024) pct_order_kernel(const DEnvHot *hot, int
 }
 
 // uniform-random valid-leaf policy: reads only the record headers
-__global__ void pct_policy_random_kernel(const DEnvHot *hot, int n_envs, int64_t env_id_base, uint64_t seed, int64_t t, int32_t *leaf_idx) {
+__global__ void pct_policy_random_kernel(const DEnvHot *hot, int n_envs, int64_t env_id_base, uint64_t seed, int64_t t, const int64_t *t_dev,
+                                         int32_t *leaf_idx) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n_envs) return;
+    if (t_dev) t = *t_dev;
     const int n = hot[e].h.n_leaf;
     leaf_idx[e] = n > 0 ? (int32_t)(rnd_u64(seed, (uint64_t)(env_id_base + e), (uint64_t)t) % (uint64_t)n) : 0;
 }
@@ -1140,8 +1142,8 @@ cudaError_t launch_discrete(const DParams &p, cudaStream_t st, cudaEvent_t *prof
 }
 
 cudaError_t launch_policy_random_discrete(const DEnvHot *hot, int n_envs, int64_t env_id_base, uint64_t seed, int64_t t, int32_t *leaf_idx,
-                                          cudaStream_t st) {
-    pct_policy_random_kernel<<<(n_envs + 127) / 128, 128, 0, st>>>(hot, n_envs, env_id_base, seed, t, leaf_idx);
+                                          cudaStream_t st, const int64_t *t_dev) {
+    pct_policy_random_kernel<<<(n_envs + 127) / 128, 128, 0, st>>>(hot, n_envs, env_id_base, seed, t, t_dev, leaf_idx);
     return cudaGetLastError();
 }
 

@@ -142,6 +142,6 @@ struct DParams {
 int discrete_kernels_per_step();
 cudaError_t launch_discrete(const DParams &p, cudaStream_t st, cudaEvent_t *prof = nullptr);
 cudaError_t launch_policy_random_discrete(const DEnvHot *hot, int n_envs, int64_t env_id_base, uint64_t seed, int64_t t, int32_t *leaf_idx,
-                                          cudaStream_t st);
+                                          cudaStream_t st, const int64_t *t_dev = nullptr);
 
 }  // namespace pct
