@@ -220,7 +220,8 @@ def run_ours(a):
     if not a.continuous:
         batch.profile(False)
     clocks = sampler.finish() if sampler else None
-    step_ms = sum(ev[t][0].elapsed_time(ev[t][2]) for t in range(K))
+    per_step = sorted(ev[t][0].elapsed_time(ev[t][2]) for t in range(K))
+    step_ms = sum(per_step)
     kern_ms = sum(ev[t][1].elapsed_time(ev[t][2]) for t in range(K))
     tt = torch.tensor([step_ms, kern_ms], dtype=torch.float64, device=dev)
     if dist is not None:
@@ -301,7 +302,8 @@ def run_ours(a):
                            "mean_boxes": mean_boxes, "mean_valid_leaves": mean_leaf, "mean_candidates": mean_cand},
                 "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "steps": Ke, "path": "pct_step_host (C ABI, pinned host buffers, 4 pipelined env ranges) + numpy policy on the host from the returned step records"},
-                "gpu_launches": int(launches), "kernel_ms_per_step": kern_ms / K, "wall_s_timed_loop": wall,
+                "gpu_launches": int(launches), "kernel_ms_per_step": kern_ms / K,
+                "ms_per_step_p50": per_step[K // 2], "ms_per_step_p99": per_step[min(K - 1, int(K * 0.99))], "wall_s_timed_loop": wall,
                 "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                              "traffic": traffic.get("dram_bytes_per_launch") if traffic else None, "kernel": "pct_feas_emit_kernel",
                              "peak_source": peak_src, "algorithmic_bytes_per_env_kernel": b_k3, "algorithmic_bytes_per_env_step": b_step,
