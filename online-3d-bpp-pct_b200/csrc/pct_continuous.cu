@@ -472,7 +472,7 @@ __global__ void __launch_bounds__(32) pctc_candidates_kernel(const CParams p) {
 #pragma unroll 1
                 for (int j = 0; j <= probes; j++) {
                     const uint16_t s = tab[i + j];
-                    if (s == EMPTY) { if (lane == 0) tab[i + j] = ck; state = 1; break; }
+                    if (s == EMPTY) { __syncwarp(); if (lane == 0) tab[i + j] = ck; state = 1; break; }  // every lane has read the slot before lane 0 fills it
                     double u[6];
                     cand_tuple(s, ev->ems, nb, u);
                     if (u[0] == tk[0] && u[1] == tk[1] && u[2] == tk[2] && u[3] == tk[3] && u[4] == tk[4] && u[5] == tk[5]) { state = 2; break; }
@@ -508,7 +508,7 @@ __global__ void __launch_bounds__(32) pctc_candidates_kernel(const CParams p) {
                         while (!placed) {  // set_insert_clean
                             const int pr = (ii + 9 <= newsize - 1) ? 9 : 0;
                             for (int j = 0; j <= pr; j++)
-                                if (nt[ii + j] == EMPTY) { if (lane == 0) nt[ii + j] = cc; placed = true; break; }
+                                if (nt[ii + j] == EMPTY) { __syncwarp(); if (lane == 0) nt[ii + j] = cc; placed = true; break; }
                             pt >>= 5;
                             ii = (uint32_t)((uint64_t)ii * 5 + 1 + pt) & (newsize - 1);
                         }
