@@ -79,7 +79,14 @@ int pct_create(const pct_config *cfg, int32_t n_envs, int32_t device, pct_handle
     h->obs_len = (cfg->internal_node_holder + cfg->leaf_node_holder + 1) * 9;
     h->item_mode = cfg->item_mode;
     cudaError_t e = cudaSetDevice(device);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
+    // pct_step_host pipelines env ranges over these streams; earlier ranges get a higher priority so that their kernels
+    // finish (and their device->host copies start) while later ranges still compute.  PCT_B200_HOST_PRIO=0 disables.
+    int prio_least = 0, prio_greatest = 0;
+    bool use_prio = true;
+    if (const char *pv = getenv("PCT_B200_HOST_PRIO")) use_prio = atoi(pv) != 0;
+    if (e == cudaSuccess && use_prio) e = cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+    auto prio_of = [&](int gi) { int p = prio_greatest + gi; return p > prio_least ? prio_least : p; };
+    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&h->own_stream, cudaStreamNonBlocking, prio_of(0));
     h->groups = 1;  // PCT_B200_GROUPS > 1 splits the batch over internal streams (measured: no gain)
     if (const char *gv = getenv("PCT_B200_GROUPS")) h->groups = atoi(gv);
     h->host_groups = 4;
@@ -90,7 +97,7 @@ int pct_create(const pct_config *cfg, int32_t n_envs, int32_t device, pct_handle
     if (h->groups > 8) h->groups = 8;
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
     for (int gi = 1; gi < 8 && e == cudaSuccess; gi++) {
-        e = cudaStreamCreateWithFlags(&h->sub[gi], cudaStreamNonBlocking);
+        e = cudaStreamCreateWithPriority(&h->sub[gi], cudaStreamNonBlocking, prio_of(gi));
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_join[gi], cudaEventDisableTiming);
     }
     if (e == cudaSuccess) {

@@ -42,3 +42,35 @@ class OracleVec(object):
             k, row = policy_pick(obs[e], self.nb, self.nl, seed, env_id_base + e, t)
             idx.append(k); rows.append(row)
         return np.array(idx, dtype=np.int32), np.stack(rows)
+
+
+# ---- batched-evaluation parity helpers (evaluation_tools.py:7-52 restated as a plain loop) -------------------------------
+def eval_policy_np(obs, nb=80, nl=50):
+    """deterministic test policy: a fixed function of (#valid leaves, #valid internal rows)"""
+    o = obs.reshape(nb + nl + 1, 9)
+    nv, nbx = int((o[nb:nb + nl, 8] == 1).sum()), int((o[:nb, 8] == 1).sum())
+    return (7 * nv + 3 * nbx) % max(nv, 1)
+
+
+def eval_policy_torch(obs, batch):
+    import torch
+    o = obs.reshape(obs.shape[0], batch.nb + batch.nl + 1, 9)
+    nv, nbx = (o[:, batch.nb:batch.nb + batch.nl, 8] == 1).sum(1), (o[:, :batch.nb, 8] == 1).sum(1)
+    return ((7 * nv + 3 * nbx) % torch.clamp(nv, min=1)).to(torch.int32)
+
+
+def sequential_eval(make_env, episodes, nb=80, nl=50):
+    """the reference's evaluation loop on any single env with its call surface (reference env or oracle):
+    per episode -> (ratio, counter, packed)"""
+    out = []
+    for ep in range(episodes):
+        env, obs = make_env(ep)
+        while True:
+            k = eval_policy_np(obs, nb, nl)
+            row = obs.reshape(nb + nl + 1, 9)[nb + k].copy()
+            items = env.packed
+            obs, _, done, info = env.step(row)
+            if done:
+                out.append((float(info["ratio"]), int(info["counter"]), [list(p) for p in items]))
+                break
+    return out
