@@ -73,6 +73,7 @@ class OracleDiscrete(object):
         self.L.pcto_set_lnes(self.h, {"EMS": 0, "EV": 1, "EP": 2, "CP": 3, "FC": 4}[lnes])
         self.nb, self.nl = internal_node_holder, leaf_node_holder
         self.obs_len = self.L.pcto_obs_len(self.h)
+        self.container, self.setting = tuple(int(c) for c in container_size), int(setting)
         self._stream = None
         if stream is not None:
             self.set_stream(stream)
@@ -83,6 +84,9 @@ class OracleDiscrete(object):
             s = np.concatenate([s, np.ones((len(s), 1))], axis=1)
         self._stream = np.ascontiguousarray(s)
         self.L.pcto_set_stream(self.h, _dp(self._stream), len(self._stream))
+
+    def set_trajectory_length(self, n):
+        self.L.pcto_set_trajectory_length(self.h, int(n))
 
     def reset(self):
         obs = np.zeros(self.obs_len)
@@ -119,6 +123,33 @@ class OracleDiscrete(object):
         buf = np.zeros((256, 7), dtype=np.int32)
         n = self.L.pcto_get_packed(self.h, _ip(buf), 256)
         return buf[:n].tolist()
+
+    # -- what the heuristic baselines read from the env (heuristic.py): space.drop_box_virtual(returnH), space.plain, next_box/den
+    def drop_box_virtual(self, dims, lx, ly):
+        mh = C.c_int()
+        self.L.pcto_drop_box_virtual.argtypes = [C.c_void_p] + [C.c_int] * 5 + [C.c_double, C.POINTER(C.c_int)]
+        ok = self.L.pcto_drop_box_virtual(self.h, int(dims[0]), int(dims[1]), int(dims[2]), int(lx), int(ly), self.next_den, C.byref(mh))
+        return bool(ok), mh.value
+
+    def plain(self):
+        buf = np.zeros((self.container[0], self.container[1]), dtype=np.int32)
+        self.L.pcto_get_plain.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
+        self.L.pcto_get_plain(self.h, _ip(buf))
+        return buf
+
+    def _next(self):
+        out = np.zeros(4)
+        self.L.pcto_get_next.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        self.L.pcto_get_next(self.h, _dp(out))
+        return out
+
+    @property
+    def next_box(self):
+        return [int(v) for v in self._next()[:3]]
+
+    @property
+    def next_den(self):
+        return float(self._next()[3])
 
     @property
     def n_lstsq(self):
