@@ -42,6 +42,12 @@ enum pct_status {
 enum pct_domain { PCT_DISCRETE = 0, PCT_CONTINUOUS = 1 };
 enum pct_obs_dtype { PCT_F32 = 0, PCT_F64 = 1 };
 enum pct_lnes { PCT_LNES_EMS = 0, PCT_LNES_EV = 1, PCT_LNES_EP = 2, PCT_LNES_CP = 3, PCT_LNES_FC = 4 };
+/* heuristic baselines of the reference (heuristic.py): LASH :138-226, OnlineBPH :364-424, BR :500-577, MACS :11-131,
+ * DBL :431-493, heightmap_min :232-293, random :300-357 */
+enum pct_heuristic {
+    PCT_H_LSAH = 0, PCT_H_ONLINEBPH = 1, PCT_H_BR = 2, PCT_H_MACS = 3, /* placements taken from the EMS list   */
+    PCT_H_DBL = 4, PCT_H_HM = 5, PCT_H_RANDOM = 6                      /* placements taken from the (lx, ly) grid */
+};
 enum pct_item_mode {
     PCT_ITEMS_RANDOM = 0, /* uniform over item_set with the counter-based generator (RandomBoxCreator, */
                           /*   D:binCreator.py:24-39); continuous + sample_from_distribution: C:bin3D.py:103-115 */
@@ -144,6 +150,21 @@ int pct_policy_random(pct_handle h, int32_t *d_leaf_idx, uint64_t seed, int64_t 
 /* same, with the step counter read from device memory (*d_t) at execution time: lets a captured CUDA graph of
  * policy -> step draw fresh actions on every replay (the caller increments *d_t inside the graph) */
 int pct_policy_random_dev(pct_handle h, int32_t *d_leaf_idx, uint64_t seed, const int64_t *d_t, void *stream);
+
+/* Heuristic baselines, batched (discrete domain).  For every env: the placement the baseline `heuristic` (enum
+ * pct_heuristic) selects for the env's current item, written as an action row d_rows[e] = [lx, ly, 0, lx+x, ly+y, 0, 0, 0, 1]
+ * (float32, N x 9) that pct_step(d_actions = d_rows, action_f64 = 0) applies; where the baseline finds no feasible
+ * placement (the reference then ends the episode without stepping, e.g. heuristic.py:223-225) the row is
+ * [1,0,0,1,0,0,0,0,1], which no item matches, so pct_step ends the episode (PCT_FLAG_BAD_ACTION is set in its info).
+ * Replaces the per-env Python loops over Space.drop_box_virtual (D:space.py:393-433).  LSAH keeps its running footprint
+ * per env inside the handle.  PCT_H_RANDOM draws with rnd(seed, env_id_base+e, t).  PCT_H_BR needs pct_set_item_set;
+ * PCT_H_HM / PCT_H_MACS / PCT_H_RANDOM need container sides <= 32. */
+int pct_heuristic_actions(pct_handle h, int32_t heuristic, float *d_rows, uint64_t seed, int64_t t, void *stream);
+/* Space.drop_box_virtual(dims, (lx, ly), False, density, setting, returnH / returnMap) for ONE env (D:space.py:393-433): what
+ * the reference's heuristic.py calls on `env.space`; synchronous.  height_map: W*L int32 (row-major, after the virtual
+ * placement — Space.update_height_graph on a copy) or NULL. */
+int pct_query_placement(pct_handle h, int32_t env, const int32_t dims[3], int32_t lx, int32_t ly, double density,
+                        int32_t *feasible, int32_t *rest_height, int32_t *height_map);
 
 /* introspection */
 int pct_get_state(pct_handle h, int32_t env, pct_state_dump *out);

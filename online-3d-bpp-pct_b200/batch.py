@@ -139,6 +139,28 @@ class PctBatch(object):
                                                  self._stream()), "pct_policy_random_dev")
         return idx
 
+    # -- heuristic baselines (heuristic.py) ------------------------------------------------------------------
+    def heuristic_actions(self, name, seed=0, t=0, out=None):
+        """(N, 9) float32 CUDA tensor of action rows: the placement the baseline `name` (LSAH, OnlineBPH, BR, MACS, DBL, HM,
+        RANDOM) selects for every env's current item; feed to step(actions=...)."""
+        if out is None:
+            if getattr(self, "_hrows", None) is None:
+                self._hrows = torch.zeros((self.n_envs, 9), dtype=torch.float32, device=self.device)
+            out = self._hrows
+        self._check(self.L.pct_heuristic_actions(self.h, _lib.HEURISTIC_CODES[name], C.c_void_p(out.data_ptr()), int(seed) & ((1 << 64) - 1),
+                                                 int(t), self._stream()), "pct_heuristic_actions")
+        return out
+
+    def query_placement(self, env, dims, lx, ly, density=1.0, want_map=False):
+        """Space.drop_box_virtual for one env (D:space.py:393-433): -> (feasible, rest_height[, height map after])"""
+        d = (C.c_int32 * 3)(int(dims[0]), int(dims[1]), int(dims[2]))
+        feas, mh = C.c_int32(), C.c_int32()
+        W, L = int(self.container_size[0]), int(self.container_size[1])
+        hm = np.zeros((W, L), dtype=np.int32) if want_map else None
+        self._check(self.L.pct_query_placement(self.h, int(env), d, int(lx), int(ly), float(density), C.byref(feas), C.byref(mh),
+                                               hm.ctypes.data_as(C.POINTER(C.c_int32)) if want_map else None), "pct_query_placement")
+        return (bool(feas.value), mh.value, hm) if want_map else (bool(feas.value), mh.value)
+
     # -- host-buffer API (what the reference's VecEnv exchanges over its pipes) --------------------------------
     def reset_host(self, obs_out):
         self._check(self.L.pct_reset_host(self.h, C.c_void_p(obs_out.ctypes.data)), "pct_reset_host")

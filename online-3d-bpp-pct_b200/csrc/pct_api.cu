@@ -133,6 +133,7 @@ void pct_destroy(pct_handle h) {
     cudaSetDevice(h->device);
     if (h->cfg.domain == PCT_CONTINUOUS) continuous_destroy(h);
     cudaFree(h->d_order);
+    cudaFree(h->d_hstate); cudaFree(h->d_query);
     cudaFree(h->d_hot); cudaFree(h->d_cold); cudaFree(h->d_item_set); cudaFree(h->d_stream);
     cudaFree(h->d_obs); cudaFree(h->d_act); cudaFree(h->d_idx); cudaFree(h->d_rew); cudaFree(h->d_done); cudaFree(h->d_info);
     for (cudaEvent_t ev : h->prof_ev) if (ev) cudaEventDestroy(ev);
@@ -340,6 +341,66 @@ int pct_policy_random_dev(pct_handle h, int32_t *d_leaf_idx, uint64_t seed, cons
     CK(h, cudaSetDevice(h->device));
     CK(h, launch_policy_random_discrete(h->d_hot, h->n_envs, h->cfg.env_id_base, seed, 0, d_leaf_idx, (cudaStream_t)stream, d_t));
     h->launches++;
+    return PCT_OK;
+}
+
+// DParams of the whole batch for the read-only selection kernels (no action / observation buffers)
+static DParams state_params(pct_handle h) {
+    DParams p{};
+    p.hot = h->d_hot; p.cold = h->d_cold; p.n_envs = h->n_envs;
+    p.W = (int)h->cfg.container_size[0]; p.L = (int)h->cfg.container_size[1]; p.H = (int)h->cfg.container_size[2];
+    p.nb = h->cfg.internal_node_holder; p.nl = h->cfg.leaf_node_holder; p.setting = h->cfg.setting;
+    p.low_bound = h->cfg.size_minimum; p.lnes = h->cfg.lnes;
+    p.item_mode = h->item_mode; p.item_set = h->d_item_set; p.n_items = h->n_items;
+    p.seed = h->cfg.seed; p.env_id_base = h->cfg.env_id_base; p.env_id_base0 = h->cfg.env_id_base;
+    return p;
+}
+
+int pct_heuristic_actions(pct_handle h, int32_t heuristic, float *d_rows, uint64_t seed, int64_t t, void *stream) {
+    if (!h || !d_rows) return PCT_ERR_INVALID;
+    if (heuristic < PCT_H_LSAH || heuristic > PCT_H_RANDOM) { h->err = "pct_heuristic_actions: unknown heuristic"; return PCT_ERR_INVALID; }
+    if (h->cfg.domain != PCT_DISCRETE) { h->err = "pct_heuristic_actions: discrete domain only"; return PCT_ERR_INVALID; }
+    if (!h->did_reset) { h->err = "pct_heuristic_actions before pct_reset"; return PCT_ERR_STATE; }
+    CK(h, cudaSetDevice(h->device));
+    DParams p = state_params(h);
+    if (heuristic == PCT_H_BR && !h->d_item_set) { h->err = "PCT_H_BR scores an EMS by the item types that fit: call pct_set_item_set"; return PCT_ERR_STATE; }
+    if ((heuristic == PCT_H_HM || heuristic == PCT_H_MACS || heuristic == PCT_H_RANDOM) && (p.W > HEUR_SIDE_MAX || p.L > HEUR_SIDE_MAX)) {
+        h->err = "PCT_H_HM / PCT_H_MACS / PCT_H_RANDOM need container sides <= 32";
+        return PCT_ERR_INVALID;
+    }
+    if (!h->d_hstate) {
+        CK(h, cudaMalloc(&h->d_hstate, sizeof(int32_t) * 4 * (size_t)h->n_envs));
+        CK(h, cudaMemset(h->d_hstate, 0, sizeof(int32_t) * 4 * (size_t)h->n_envs));
+    }
+    HParams hp{};
+    hp.code = heuristic; hp.rows = d_rows; hp.hstate = h->d_hstate; hp.seed = seed; hp.t = t;
+    CK(h, launch_heuristic_discrete(p, hp, (cudaStream_t)stream));
+    h->launches++;
+    return PCT_OK;
+}
+
+int pct_query_placement(pct_handle h, int32_t env, const int32_t dims[3], int32_t lx, int32_t ly, double density, int32_t *feasible,
+                        int32_t *rest_height, int32_t *height_map) {
+    if (!h || !dims || !feasible || !rest_height || env < 0 || env >= h->n_envs) return PCT_ERR_INVALID;
+    if (h->cfg.domain != PCT_DISCRETE) { h->err = "pct_query_placement: discrete domain only"; return PCT_ERR_INVALID; }
+    if (!h->did_reset) { h->err = "pct_query_placement before pct_reset"; return PCT_ERR_STATE; }
+    CK(h, cudaSetDevice(h->device));
+    DParams p = state_params(h);
+    if (p.W > HEUR_SIDE_MAX || p.L > HEUR_SIDE_MAX) { h->err = "pct_query_placement needs container sides <= 32"; return PCT_ERR_INVALID; }
+    const size_t cells = (size_t)p.W * p.L;
+    if (!h->d_query) CK(h, cudaMalloc(&h->d_query, sizeof(int32_t) * (2 + HEUR_SIDE_MAX * HEUR_SIDE_MAX)));
+    HParams hp{};
+    hp.code = PCT_H_QUERY_; hp.q_env = env; hp.q_den = density; hp.q_out = h->d_query;
+    hp.q[0] = dims[0]; hp.q[1] = dims[1]; hp.q[2] = dims[2]; hp.q[3] = lx; hp.q[4] = ly;
+    CK(h, cudaDeviceSynchronize());
+    CK(h, launch_heuristic_discrete(p, hp, h->own_stream));
+    h->launches++;
+    std::vector<int32_t> out(2 + cells);
+    CK(h, cudaMemcpyAsync(out.data(), h->d_query, sizeof(int32_t) * out.size(), cudaMemcpyDeviceToHost, h->own_stream));
+    CK(h, cudaStreamSynchronize(h->own_stream));
+    *feasible = out[0];
+    *rest_height = out[1];
+    if (height_map) memcpy(height_map, out.data() + 2, sizeof(int32_t) * cells);
     return PCT_OK;
 }
 

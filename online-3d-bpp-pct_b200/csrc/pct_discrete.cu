@@ -1148,3 +1148,5 @@ cudaError_t launch_policy_random_discrete(const DEnvHot *hot, int n_envs, int64_
 }
 
 }  // namespace pct
+
+#include "pct_heuristics.cuh"

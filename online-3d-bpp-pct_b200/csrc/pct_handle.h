@@ -20,6 +20,8 @@ struct pct_env_batch {
     double *d_stream = nullptr;
     int stream_len = 0;
     int traj_len = 0;
+    int32_t *d_hstate = nullptr;  // (n_envs, 4) LSAH footprint state (pct_heuristic_actions)
+    int32_t *d_query = nullptr;   // 2 + W*L ints: result of pct_query_placement
     int item_mode = 0;
     // staging for the host-buffer entry points
     void *d_obs = nullptr, *d_act = nullptr;

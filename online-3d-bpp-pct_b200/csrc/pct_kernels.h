@@ -139,6 +139,21 @@ struct DParams {
     int32_t *order;  // [2 * n_envs] block -> env permutations (apply, feas_emit), nullptr = identity
 };
 
+// heuristic baselines (pct_heuristics.cuh)
+struct HParams {
+    int code;                // enum pct_heuristic; PCT_H_QUERY_ = single placement query
+    float *rows;             // (n_envs, 9) action rows
+    int32_t *hstate;         // (n_envs, 4) LSAH footprint of the packed items: maxX, maxY, minX, minY (heuristic.py:146-147)
+    uint64_t seed;           // RANDOM
+    int64_t t;
+    int q_env, q[5];         // query: handle-local env, oriented dims, lx, ly
+    double q_den;
+    int32_t *q_out;          // [feasible, rest height, W*L height map after the placement]
+};
+constexpr int PCT_H_QUERY_ = 7;
+constexpr int HEUR_SIDE_MAX = 32;  // height-map based codes (HM, MACS, RANDOM's bitmap, queries): W, L <= 32
+cudaError_t launch_heuristic_discrete(const DParams &p, const HParams &hp, cudaStream_t st);
+
 int discrete_kernels_per_step();
 cudaError_t launch_discrete(const DParams &p, cudaStream_t st, cudaEvent_t *prof = nullptr);
 cudaError_t launch_policy_random_discrete(const DEnvHot *hot, int n_envs, int64_t env_id_base, uint64_t seed, int64_t t, int32_t *leaf_idx,

@@ -34,6 +34,21 @@ class _SpaceView(object):
     def plain_size(self):
         return np.array(self._env.bin_size)
 
+    @property
+    def plain(self):  # the height map (D:space.py:316-326)
+        W, L = int(self._env.bin_size[0]), int(self._env.bin_size[1])
+        return self._env._batch.query_placement(0, (1, 1, 0), 0, 0, want_map=True)[2][:W, :L]
+
+    def drop_box_virtual(self, box_size, idx, flag, density, setting, returnH=False, returnMap=False):
+        """D:space.py:393-433 — what heuristic.py asks for every placement it considers"""
+        x, y, z = box_size if not flag else (box_size[1], box_size[0], box_size[2])
+        res = self._env._batch.query_placement(0, (x, y, z), idx[0], idx[1], density=density, want_map=returnMap and not returnH)
+        if returnH:
+            return res[0], res[1]
+        if returnMap:
+            return res[0], res[2]
+        return res[0]
+
     def get_ratio(self):  # D:space.py:334-339
         st = self._env._state()
         b = st["boxes"]
@@ -85,12 +100,14 @@ class _PackingBase(object):
         self.observation_space = _make_box(0.0, float(container_size[2]), (self._batch.obs_len,))
         self.space = _SpaceView(self)
         self.SEED = seed
+        self._next_box_override = None
 
     # ---- gym.Env API ----
     def seed(self, seed=None):  # D:bin3D.py:47-54 (the item generator is counter-based: the seed is fixed at construction)
         return [seed]
 
     def reset(self):
+        self._next_box_override = None
         return self._batch.reset().cpu().numpy()[0].copy()
 
     def step(self, action):
@@ -103,6 +120,7 @@ class _PackingBase(object):
         row[:min(9, len(a))] = a[:9]
         nb = self.next_box  # reward in float64 like the reference: vol(item) / vol(bin) * 10 (D:bin3D.py:180-183)
         obs, rew, done, info = self._batch.step(actions=torch.from_numpy(row[None]).to(self._batch.device))
+        self._next_box_override = None
         rec = PctBatch.decode_info(info)
         d = bool(done.cpu().numpy()[0])
         reward = 0.0 if d else (nb[0] * nb[1] * nb[2]) / (self.bin_size[0] * self.bin_size[1] * self.bin_size[2]) * 10  # C:bin3D.py:199-202 too
@@ -133,8 +151,14 @@ class _PackingBase(object):
 
     @property
     def next_box(self):
+        if self._next_box_override is not None:
+            return list(self._next_box_override)
         nb = self._state()["next_box"]
         return list(nb) if self._continuous else [int(v) for v in nb]
+
+    @next_box.setter
+    def next_box(self, dims):  # heuristic.py:120 etc.: `env.next_box = [x, y, z]` (the chosen orientation) before env.step([0, lx, ly])
+        self._next_box_override = list(dims)
 
     @property
     def next_den(self):
