@@ -61,7 +61,8 @@ enum pct_env_flags {
     PCT_FLAG_EMS_OVERFLOW = 4,      /* EMS list exceeded the fixed capacity                                */
     PCT_FLAG_CAND_OVERFLOW = 8,     /* candidate set exceeded the fixed capacity                           */
     PCT_FLAG_EDGE_OVERFLOW = 16,    /* support-edge pool exceeded the fixed capacity                       */
-    PCT_FLAG_SUPPORT_OVERFLOW = 32  /* more supports under one box than the stability routine handles      */
+    PCT_FLAG_SUPPORT_OVERFLOW = 32, /* more supports under one box than the stability routine handles      */
+    PCT_FLAG_SYNC_TIMEOUT = 64      /* internal: a kernel gave up waiting for the previous stage of this env */
 };
 
 /* Constructor arguments = the kwargs of PackingDiscrete / PackingContinuous.__init__

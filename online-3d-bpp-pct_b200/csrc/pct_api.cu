@@ -87,6 +87,7 @@ int pct_create(const pct_config *cfg, int32_t n_envs, int32_t device, pct_handle
     if (e == cudaSuccess && use_prio) e = cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
     auto prio_of = [&](int gi) { int p = prio_greatest + gi; return p > prio_least ? prio_least : p; };
     if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&h->own_stream, cudaStreamNonBlocking, prio_of(0));
+    if (const char *ov = getenv("PCT_B200_OVERLAP")) h->overlap = atoi(ov) != 0;
     h->groups = 1;  // PCT_B200_GROUPS > 1 splits the batch over internal streams (measured: no gain)
     if (const char *gv = getenv("PCT_B200_GROUPS")) h->groups = atoi(gv);
     h->host_groups = 4;
@@ -105,6 +106,8 @@ int pct_create(const pct_config *cfg, int32_t n_envs, int32_t device, pct_handle
             e = cudaMalloc(&h->d_hot, sizeof(DEnvHot) * (size_t)n_envs);
             if (e == cudaSuccess) e = cudaMalloc(&h->d_cold, sizeof(DEnvCold) * (size_t)n_envs);
             if (e == cudaSuccess) e = cudaMemset(h->d_hot, 0, sizeof(DEnvHot) * (size_t)n_envs);
+            if (e == cudaSuccess) e = cudaMalloc(&h->d_ready, sizeof(int32_t) * 2 * (size_t)n_envs);
+            if (e == cudaSuccess) e = cudaMemset(h->d_ready, 0, sizeof(int32_t) * 2 * (size_t)n_envs);
             if (e == cudaSuccess) e = cudaMemset(h->d_cold, 0, sizeof(DEnvCold) * (size_t)n_envs);
             if (e == cudaSuccess) e = cudaMalloc(&h->d_order, sizeof(int32_t) * 2 * (size_t)n_envs);
             if (e == cudaSuccess) {
@@ -134,6 +137,7 @@ void pct_destroy(pct_handle h) {
     if (h->cfg.domain == PCT_CONTINUOUS) continuous_destroy(h);
     cudaFree(h->d_order);
     cudaFree(h->d_hstate); cudaFree(h->d_query);
+    cudaFree(h->d_ready);
     cudaFree(h->d_hot); cudaFree(h->d_cold); cudaFree(h->d_item_set); cudaFree(h->d_stream);
     cudaFree(h->d_obs); cudaFree(h->d_act); cudaFree(h->d_idx); cudaFree(h->d_rew); cudaFree(h->d_done); cudaFree(h->d_info);
     for (cudaEvent_t ev : h->prof_ev) if (ev) cudaEventDestroy(ev);
@@ -195,6 +199,14 @@ static int launch_range(pct_handle h, int mode, int off, int cnt, const void *ac
     p.dbg = (long long *)h->dbg;
     p.order = (h->lpt && whole_batch) ? h->d_order : nullptr;
     p.keep_draw = h->did_reset ? 1 : 0; p.no_auto_reset = h->cfg.no_auto_reset;
+    // overlapped launch mode: not while a CUDA graph is being captured (the epoch would be frozen into the graph and a replay
+    // would find the flags of the previous replay already set), not under the per-kernel profiler, not with the LPT permutation
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(gs, &cap);
+    if (h->overlap && !h->prof_on && !p.order && cap == cudaStreamCaptureStatusNone) {
+        p.ready = h->d_ready + 2 * (size_t)off;
+        p.epoch = ++h->epoch;
+    }
     cudaEvent_t *prof = nullptr;
     if (h->prof_on && mode == 1 && whole_batch) {
         if ((size_t)(h->prof_steps + 1) * 4 > h->prof_ev.size()) {

@@ -114,6 +114,33 @@ __device__ __forceinline__ void tma_store_commit_wait() {
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
+__device__ __forceinline__ void tma_store_commit_wait_all() {  // completion of the WRITES (not only of the source reads)
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// ---- programmatic dependent launch + per-env hand-over flags -------------------------------------------------
+// The step is three kernels over the same envs; each lasts as long as its slowest env, so whole SMs idle in every tail.
+// With PDL the next kernel's blocks become resident as soon as every block of the previous one has STARTED; the data
+// dependency is per env, carried by a flag: the producer publishes `epoch` after its last write of env e, the consumer of
+// env e polls for it.  No block ever waits for a block that is not already resident, so the scheme cannot deadlock;
+// the poll is bounded anyway (a timeout is reported as a flag, never a hang).
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void env_publish(int32_t *flag, int32_t epoch) {
+    __threadfence();
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flag), "r"(epoch) : "memory");
+}
+__device__ __forceinline__ bool env_wait(const int32_t *flag, int32_t epoch) {
+    for (int it = 0; it < (1 << 22); it++) {
+        int32_t v;
+        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if (v == epoch) return true;
+        __nanosleep(it < 64 ? 32 : 256);
+    }
+    return false;
+}
+
 __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {

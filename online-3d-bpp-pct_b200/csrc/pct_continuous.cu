@@ -67,6 +67,8 @@ struct CParams {
     uint8_t *done;
     pct_step_info *info;
     int mode, keep_draw, no_auto_reset;
+    int32_t *ready;  // overlapped launch mode: per-env hand-over flags [2 * n_envs] (see pct_common.cuh), nullptr = off
+    int32_t epoch;
 };
 
 __device__ __forceinline__ double around6(double v) { return ddiv(rint(v * 1e6), 1e6); }  // np.around(v, 6)
@@ -283,6 +285,7 @@ __global__ void __launch_bounds__(64) pctc_apply_kernel(const CParams p) {
     int *lock = &lock_s[warp];
     CEnv *ev = p.env + e;
     CHdr &h = ev->h;
+    if (p.ready) pdl_launch_dependents();
     if (lane == 0) *lock = 0;
     float reward = 0.f;
     int done = 0;
@@ -391,10 +394,12 @@ __global__ void __launch_bounds__(64) pctc_apply_kernel(const CParams p) {
             if (!p.no_auto_reset) reset_space_c(ev, p, e, lane);
         }
     }
+    __syncwarp();
     if (lane == 0) {
         if (p.reward) p.reward[e] = reward;
         if (p.done) p.done[e] = (uint8_t)done;
         if (p.info) p.info[e] = info;
+        if (p.ready) env_publish(p.ready + e, p.epoch);
     }
 }
 
@@ -403,13 +408,19 @@ __global__ void __launch_bounds__(32) pctc_candidates_kernel(const CParams p) {
     __shared__ uint16_t tabA[CC_TAB], tabB[512];
     const int lane = threadIdx.x, e = blockIdx.x;
     CEnv *ev = p.env + e;
+    int fl = 0;
+    if (p.ready) {  // overlapped mode: wait for the apply kernel's hand-over of THIS env
+        pdl_launch_dependents();
+        if (lane == 0 && !env_wait(p.ready + e, p.epoch)) fl = PCT_FLAG_SYNC_TIMEOUT;
+        fl = __shfl_sync(FULL, fl, 0);
+    }
     const CHdr &h = ev->h;
     const double nb[3] = {h.next_box[0], h.next_box[1], h.next_box[2]};
     const int R = p.setting == 2 ? 6 : 2, n_ems = h.n_ems;
     constexpr uint16_t EMPTY = 0xFFFF;
     uint16_t *tab = tabA;
     uint32_t mask = 7;
-    int fill = 0, fl = 0;
+    int fill = 0;
     if (lane < 8) tab[lane] = EMPTY;
     __syncwarp();
     const int raw = n_ems * R * 4;
@@ -530,9 +541,11 @@ __global__ void __launch_bounds__(32) pctc_candidates_kernel(const CParams p) {
         if (c2 != EMPTY) ev->cand[cnt + __popc(em & ((1u << lane) - 1))] = c2;
         cnt += __popc(em);
     }
+    __syncwarp();
     if (lane == 0) {
         ev->h.n_cand = cnt;
         if (fl) ev->h.flags |= fl;
+        if (p.ready) env_publish(p.ready + p.n_envs + e, p.epoch);
     }
 }
 
@@ -582,7 +595,10 @@ __global__ void __launch_bounds__(64) pctc_feas_emit_kernel(const CParams p) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, e = blockIdx.x;
     CEnv *ev = p.env + e;
     const CHdr &h = ev->h;
-    if (tid == 0) lock = 0;
+    if (tid == 0) {
+        lock = 0;
+        if (p.ready && !env_wait(p.ready + p.n_envs + e, p.epoch)) atomicOr(&ev->h.flags, PCT_FLAG_SYNC_TIMEOUT);
+    }
     __syncthreads();
     const double nb[3] = {h.next_box[0], h.next_box[1], h.next_box[2]};
     const int n_cand = h.n_cand, n_box = h.n_box;
@@ -648,6 +664,8 @@ __global__ void pctc_policy_random_kernel(const CEnv *env, int n_envs, int64_t e
 int continuous_create(pct_env_batch *h) {
     cudaError_t e = cudaMalloc(&h->c_state, sizeof(CEnv) * (size_t)h->n_envs);
     if (e == cudaSuccess) e = cudaMemset(h->c_state, 0, sizeof(CEnv) * (size_t)h->n_envs);
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_ready, sizeof(int32_t) * 2 * (size_t)h->n_envs);
+    if (e == cudaSuccess) e = cudaMemset(h->d_ready, 0, sizeof(int32_t) * 2 * (size_t)h->n_envs);
     if (e != cudaSuccess) { h->err = std::string("continuous_create: ") + cudaGetErrorString(e); return PCT_ERR_CUDA; }
     return PCT_OK;
 }
@@ -668,12 +686,24 @@ int continuous_launch(pct_env_batch *h, int mode, const void *actions, int actio
     p.actions = actions; p.action_f64 = action_f64; p.leaf_idx = leaf_idx;
     p.obs = obs; p.obs_f64 = h->cfg.obs_dtype == PCT_F64; p.reward = rew; p.done = done; p.info = info;
     p.mode = mode; p.keep_draw = h->did_reset ? 1 : 0; p.no_auto_reset = h->cfg.no_auto_reset;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cap);
+    if (h->overlap && h->d_ready && cap == cudaStreamCaptureStatusNone) { p.ready = h->d_ready; p.epoch = ++h->epoch; }
     const bool stab = p.setting != 2;
     const int b2 = (p.n_envs + 1) / 2;
     if (stab) pctc_apply_kernel<true><<<b2, 64, 0, st>>>(p); else pctc_apply_kernel<false><<<b2, 64, 0, st>>>(p);
-    pctc_candidates_kernel<<<p.n_envs, 32, 0, st>>>(p);
-    if (p.obs_f64) { if (stab) pctc_feas_emit_kernel<double, true><<<p.n_envs, 64, 0, st>>>(p); else pctc_feas_emit_kernel<double, false><<<p.n_envs, 64, 0, st>>>(p); }
-    else { if (stab) pctc_feas_emit_kernel<float, true><<<p.n_envs, 64, 0, st>>>(p); else pctc_feas_emit_kernel<float, false><<<p.n_envs, 64, 0, st>>>(p); }
+    // candidates / feas_emit: with p.ready as programmatic dependent launches (their blocks become resident during the previous
+    // kernel's tail and wait per env on the hand-over flags), else plain back-to-back launches
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t cfg{};
+    cfg.stream = st; cfg.attrs = at; cfg.numAttrs = p.ready ? 1 : 0;
+    cfg.gridDim = dim3(p.n_envs); cfg.blockDim = dim3(32);
+    cudaLaunchKernelEx(&cfg, pctc_candidates_kernel, p);
+    cfg.blockDim = dim3(64);
+    if (p.obs_f64) { if (stab) cudaLaunchKernelEx(&cfg, pctc_feas_emit_kernel<double, true>, p); else cudaLaunchKernelEx(&cfg, pctc_feas_emit_kernel<double, false>, p); }
+    else { if (stab) cudaLaunchKernelEx(&cfg, pctc_feas_emit_kernel<float, true>, p); else cudaLaunchKernelEx(&cfg, pctc_feas_emit_kernel<float, false>, p); }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { h->err = std::string("continuous launch: ") + cudaGetErrorString(e); return PCT_ERR_CUDA; }
     h->launches += 2;  // the caller counts one

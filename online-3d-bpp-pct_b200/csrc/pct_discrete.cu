@@ -691,6 +691,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, K1_MINB) pct_apply_kerne
     DEnvCold *cold = p.cold + e;
     DHdr &h = hot->h;
     KT_BEGIN();
+    if (p.ready) pdl_launch_dependents();
     if (lane == 0) *lock = 0;
     float reward = 0.f;
     int done = 0;
@@ -862,7 +863,12 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, K1_MINB) pct_apply_kerne
         tma_store_1d(ghot, hot, (uint32_t)sizeof(DEnvHot));
         if (STAB && p.mode == 1 && h.n_edge > 0) tma_store_1d(cold->e_st, st_sm, (uint32_t)min(h.n_edge, EDGE_STAGE) * (uint32_t)sizeof(Stack4));
         if (STAB && p.mode == 1 && h.n_poly > 0) tma_store_1d(cold->poly, poly_sm, (uint32_t)min(h.n_poly, POLY_STAGE) * 16u);
-        tma_store_commit_wait();
+        if (p.ready) {  // overlapped mode: the record must be globally visible before the hand-over flag
+            tma_store_commit_wait_all();
+            fence_proxy_async_all();
+            env_publish(p.ready + e, p.epoch);
+        } else
+            tma_store_commit_wait();
         KT_END(p.env_id_base + e - p.env_id_base0, 0);
     }
 }
@@ -885,9 +891,15 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) pct_candidates_kernel(co
     DEnvHot *ghot = p.hot + e;
     DEnvCold *cold = p.cold + e;
     KT_BEGIN();
+    int sync_fl = 0;
+    if (p.ready) {  // overlapped mode: wait for the apply kernel's hand-over of THIS env
+        pdl_launch_dependents();
+        if (lane == 0 && !env_wait(p.ready + e, p.epoch)) sync_fl = PCT_FLAG_SYNC_TIMEOUT;
+        __syncwarp();
+    }
     if (lane == 0) {
         mbar_init(mbar, 1);
-        fence_proxy_async();
+        fence_proxy_async_all();
     }
     __syncwarp();
     if (lane == 0) {  // header + boxes + EMS list only
@@ -922,15 +934,21 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) pct_candidates_kernel(co
     }
     if (cand != out)
         for (int t = lane; t < n_cand; t += 32) out[t] = cand[t];
+    fl |= sync_fl;
+    __syncwarp();
     if (lane == 0) {
         ghot->h.n_cand = n_cand;
         if (fl) ghot->h.flags = h.flags | fl;
+        if (p.ready) env_publish(p.ready + p.n_envs + e, p.epoch);
         KT_END(p.env_id_base + e - p.env_id_base0, 1);
     }
 }
 
 // ---- K3: feasibility (thread per candidate) + leaf compaction + observation ------------------------------------
-constexpr int FEAS_WARPS = 2;
+#ifndef FEAS_WARPS_N
+#define FEAS_WARPS_N 2
+#endif
+constexpr int FEAS_WARPS = FEAS_WARPS_N;
 constexpr int FEAS_THREADS = 32 * FEAS_WARPS;
 constexpr int K3_SMEM = sizeof(DEnvHot) + NL_MAX * 12 + 64 + EDGE_STAGE * 32 + POLY_STAGE * 16;
 
@@ -958,6 +976,10 @@ __global__ void __launch_bounds__(FEAS_THREADS, K3_MINB) pct_feas_emit_kernel(co
     }
     __syncthreads();
     if (tid == 0) {
+        if (p.ready) {  // overlapped mode: wait for the candidates kernel's hand-over of THIS env
+            if (!env_wait(p.ready + p.n_envs + e, p.epoch)) atomicOr(&ghot->h.flags, PCT_FLAG_SYNC_TIMEOUT);
+            fence_proxy_async_all();
+        }
         mbar_expect_tx(mbar, (uint32_t)sizeof(DEnvHot));
         tma_load_1d(hot, ghot, (uint32_t)sizeof(DEnvHot), mbar);
     }
@@ -1117,6 +1139,20 @@ static cudaError_t launch_t(const DParams &p, cudaStream_t st, cudaEvent_t *prof
     const int blocks = (p.n_envs + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
     if (prof) cudaEventRecord(prof[0], st);
     pct_apply_kernel<STAB><<<blocks, 32 * WARPS_PER_BLOCK, smem1, st>>>(p);
+    if (p.ready) {
+        // overlapped mode (programmatic dependent launch): the candidates / feas_emit blocks become resident while the
+        // previous kernel's tail is still running and pick their env up through the per-env hand-over flags
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cudaLaunchConfig_t cfg{};
+        cfg.stream = st; cfg.attrs = at; cfg.numAttrs = 1;
+        cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(32 * WARPS_PER_BLOCK); cfg.dynamicSmemBytes = smem2;
+        cudaError_t err = cudaLaunchKernelEx(&cfg, pct_candidates_kernel<SlotT, BIGSM>, p);
+        if (err != cudaSuccess) return err;
+        cfg.gridDim = dim3(p.n_envs); cfg.blockDim = dim3(FEAS_THREADS); cfg.dynamicSmemBytes = 0;
+        return cudaLaunchKernelEx(&cfg, pct_feas_emit_kernel<OT, STAB, SlotT>, p);
+    }
     if (prof) cudaEventRecord(prof[1], st);
     pct_candidates_kernel<SlotT, BIGSM><<<blocks, 32 * WARPS_PER_BLOCK, smem2, st>>>(p);
     if (p.order) pct_order_kernel<<<1, 1024, 0, st>>>(p.hot, p.n_envs, p.order, 1);

@@ -20,6 +20,9 @@ struct pct_env_batch {
     double *d_stream = nullptr;
     int stream_len = 0;
     int traj_len = 0;
+    int32_t *d_ready = nullptr;   // [2 * n_envs] per-env hand-over flags of the overlapped launch mode
+    int32_t epoch = 0;
+    bool overlap = true;          // PCT_B200_OVERLAP=0: plain back-to-back kernels
     int32_t *d_hstate = nullptr;  // (n_envs, 4) LSAH footprint state (pct_heuristic_actions)
     int32_t *d_query = nullptr;   // 2 + W*L ints: result of pct_query_placement
     int item_mode = 0;

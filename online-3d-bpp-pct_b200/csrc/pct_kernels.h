@@ -137,6 +137,8 @@ struct DParams {
     int no_auto_reset;  // mode 1: leave a finished env untouched (gym.Env semantics)
     long long *dbg;  // phase timers (only with -DPCT_PHASE_TIMERS)
     int32_t *order;  // [2 * n_envs] block -> env permutations (apply, feas_emit), nullptr = identity
+    int32_t *ready;  // [2 * n_envs] per-env hand-over flags (apply -> candidates, candidates -> feas_emit); nullptr = kernels run back to back
+    int32_t epoch;   // value published in `ready` by this launch
 };
 
 // heuristic baselines (pct_heuristics.cuh)
