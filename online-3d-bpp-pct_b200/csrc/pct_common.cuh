@@ -132,11 +132,16 @@ __device__ __forceinline__ void env_publish(int32_t *flag, int32_t epoch) {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flag), "r"(epoch) : "memory");
 }
 __device__ __forceinline__ bool env_wait(const int32_t *flag, int32_t epoch) {
+    // poll with relaxed loads (served by L2, no L1 invalidation per iteration: the continuous kernels keep their working set in
+    // L1-cached global memory and share the SM with the pollers), then ONE acquire fence once the flag is seen
     for (int it = 0; it < (1 << 22); it++) {
         int32_t v;
-        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
-        if (v == epoch) return true;
-        __nanosleep(it < 64 ? 32 : 256);
+        asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if (v == epoch) {
+            asm volatile("fence.acq_rel.gpu;" ::: "memory");
+            return true;
+        }
+        __nanosleep(it < 64 ? 64 : 512);
     }
     return false;
 }

@@ -688,7 +688,7 @@ int continuous_launch(pct_env_batch *h, int mode, const void *actions, int actio
     p.mode = mode; p.keep_draw = h->did_reset ? 1 : 0; p.no_auto_reset = h->cfg.no_auto_reset;
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     cudaStreamIsCapturing(st, &cap);
-    if (h->overlap && h->d_ready && cap == cudaStreamCaptureStatusNone) { p.ready = h->d_ready; p.epoch = ++h->epoch; }
+    if (h->overlap_cont && h->d_ready && cap == cudaStreamCaptureStatusNone) { p.ready = h->d_ready; p.epoch = ++h->epoch; }
     const bool stab = p.setting != 2;
     const int b2 = (p.n_envs + 1) / 2;
     if (stab) pctc_apply_kernel<true><<<b2, 64, 0, st>>>(p); else pctc_apply_kernel<false><<<b2, 64, 0, st>>>(p);

@@ -879,8 +879,9 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) pct_candidates_kernel(co
     typedef Lay<SlotT, BIGSM> LY;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int e = blockIdx.x * WARPS_PER_BLOCK + warp;
-    if (e >= p.n_envs) return;
+    const int slot = blockIdx.x * WARPS_PER_BLOCK + warp;
+    if (slot >= p.n_envs) return;
+    const int e = (p.order && p.mode == 1) ? p.order[slot] : slot;
     unsigned char *sm = smem_raw + (size_t)warp * LY::PER_WARP;
     DEnvHot *hot = (DEnvHot *)(sm + LY::HOT);
     SlotT *tabA = (SlotT *)(sm + LY::TAB_A_OFF), *tabB = (SlotT *)(sm + LY::TAB_B_OFF);
@@ -957,7 +958,7 @@ __global__ void __launch_bounds__(FEAS_THREADS, K3_MINB) pct_feas_emit_kernel(co
     constexpr int BITS = sizeof(SlotT) == 2 ? 4 : 8;
     __shared__ __align__(16) unsigned char sm[K3_SMEM];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int e = p.order ? p.order[p.n_envs + blockIdx.x] : blockIdx.x;  // second half of `order`: K3's permutation
+    const int e = (p.order && p.mode == 1) ? p.order[blockIdx.x] : blockIdx.x;  // same heaviest-first permutation as K1 / K2
     DEnvHot *hot = (DEnvHot *)sm;
     int16_t (*leaf)[6] = (int16_t (*)[6])(sm + sizeof(DEnvHot));
     uint64_t *mbar = (uint64_t *)(sm + sizeof(DEnvHot) + NL_MAX * 12);
@@ -1151,11 +1152,12 @@ static cudaError_t launch_t(const DParams &p, cudaStream_t st, cudaEvent_t *prof
         cudaError_t err = cudaLaunchKernelEx(&cfg, pct_candidates_kernel<SlotT, BIGSM>, p);
         if (err != cudaSuccess) return err;
         cfg.gridDim = dim3(p.n_envs); cfg.blockDim = dim3(FEAS_THREADS); cfg.dynamicSmemBytes = 0;
-        return cudaLaunchKernelEx(&cfg, pct_feas_emit_kernel<OT, STAB, SlotT>, p);
+        err = cudaLaunchKernelEx(&cfg, pct_feas_emit_kernel<OT, STAB, SlotT>, p);
+        if (err == cudaSuccess && p.order) pct_order_kernel<<<1, 1024, 0, st>>>(p.hot, p.n_envs, p.order, 0);
+        return err != cudaSuccess ? err : cudaGetLastError();
     }
     if (prof) cudaEventRecord(prof[1], st);
     pct_candidates_kernel<SlotT, BIGSM><<<blocks, 32 * WARPS_PER_BLOCK, smem2, st>>>(p);
-    if (p.order) pct_order_kernel<<<1, 1024, 0, st>>>(p.hot, p.n_envs, p.order, 1);
     if (prof) cudaEventRecord(prof[2], st);
     pct_feas_emit_kernel<OT, STAB, SlotT><<<p.n_envs, FEAS_THREADS, 0, st>>>(p);
     if (p.order) pct_order_kernel<<<1, 1024, 0, st>>>(p.hot, p.n_envs, p.order, 0);

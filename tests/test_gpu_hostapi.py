@@ -115,15 +115,16 @@ def test_create_errors_are_reported():
         b.step(leaf_idx=torch.zeros(4, dtype=torch.int32, device="cuda"))  # step before reset
 
 
-@pytest.mark.parametrize("overlap", ["0", "1"])
+@pytest.mark.parametrize("overlap,lpt", [("1", "0"), ("1", "1"), ("0", "1")])
 @pytest.mark.parametrize("continuous", [False, True])
-def test_launch_modes_agree(overlap, continuous, monkeypatch):
-    """PCT_B200_OVERLAP=1 (default: programmatic dependent launch + per-env hand-over flags between the three kernels) and =0
-    (plain back-to-back kernels) must produce the same observation stream, also through the pipelined host call"""
+def test_launch_modes_agree(overlap, lpt, continuous, monkeypatch):
+    """PCT_B200_OVERLAP=1 (default: programmatic dependent launch + per-env hand-over flags between the three kernels), =0 (plain
+    back-to-back kernels) and the heaviest-env-first block order (PCT_B200_LPT) must all produce the same observation stream"""
     import pct_b200
     outs = []
-    for mode in ("0", overlap):
-        monkeypatch.setenv("PCT_B200_OVERLAP", mode)
+    for ov, lp in (("0", "0"), (overlap, lpt)):
+        monkeypatch.setenv("PCT_B200_OVERLAP", ov)
+        monkeypatch.setenv("PCT_B200_LPT", lp)
         kw = dict(container_size=(1.0, 1.0, 1.0), continuous=True, sample_from_distribution=True) if continuous else dict(item_set=ITEM_SET)
         b = pct_b200.PctBatch(1500, 1, seed=11, **kw)
         obs = b.reset().clone()
