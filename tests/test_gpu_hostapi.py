@@ -124,6 +124,7 @@ def test_launch_modes_agree(overlap, lpt, continuous, monkeypatch):
     outs = []
     for ov, lp in (("0", "0"), (overlap, lpt)):
         monkeypatch.setenv("PCT_B200_OVERLAP", ov)
+        monkeypatch.setenv("PCT_B200_OVERLAP_CONT", ov)  # the continuous domain keeps the overlapped mode opt-in (measured slower)
         monkeypatch.setenv("PCT_B200_LPT", lp)
         kw = dict(container_size=(1.0, 1.0, 1.0), continuous=True, sample_from_distribution=True) if continuous else dict(item_set=ITEM_SET)
         b = pct_b200.PctBatch(1500, 1, seed=11, **kw)
