@@ -255,11 +255,14 @@ class OracleContinuous(object):
         L.pctc_get_candidates.argtypes = [C.c_void_p, dp, C.POINTER(C.c_int), C.c_int]
         L.pctc_get_packed.argtypes = [C.c_void_p, dp, C.c_int]
         L.pctc_n_lstsq.argtypes = [C.c_void_p]
+        L.pctc_drop_box_virtual.argtypes = [C.c_void_p] + [C.c_double] * 6 + [dp]
+        L.pctc_get_next.argtypes = [C.c_void_p, dp]
         self.L = L
         self.h = L.pctc_create(setting, float(container_size[0]), float(container_size[1]), float(container_size[2]),
                                internal_node_holder, leaf_node_holder, float(size_minimum))
         self.nb, self.nl = internal_node_holder, leaf_node_holder
         self.obs_len = L.pctc_obs_len(self.h)
+        self.container, self.setting = tuple(float(c) for c in container_size), int(setting)
         if stream is not None:
             self.set_stream(stream)
 
@@ -303,6 +306,25 @@ class OracleContinuous(object):
         buf = np.zeros((128, 7))
         n = self.L.pctc_get_packed(self.h, _dp(buf), 128)
         return buf[:n].tolist()
+
+    # -- what the heuristic baselines read from the env (heuristic.py): space.drop_box_virtual(returnH), next_box / next_den
+    def drop_box_virtual(self, dims, lx, ly):
+        mh = C.c_double()
+        ok = self.L.pctc_drop_box_virtual(self.h, float(dims[0]), float(dims[1]), float(dims[2]), float(lx), float(ly), self.next_den, C.byref(mh))
+        return bool(ok), mh.value
+
+    def _next(self):
+        out = np.zeros(4)
+        self.L.pctc_get_next(self.h, _dp(out))
+        return out
+
+    @property
+    def next_box(self):
+        return [float(v) for v in self._next()[:3]]
+
+    @property
+    def next_den(self):
+        return float(self._next()[3])
 
     @property
     def n_lstsq(self):

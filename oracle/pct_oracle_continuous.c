@@ -534,3 +534,16 @@ int pctc_get_candidates(pctc_env *e, double *out6, int *feas, int cap) {
 }
 int pctc_get_packed(pctc_env *e, double *out7, int cap) { int n = e->n_packed < cap ? e->n_packed : cap; memcpy(out7, e->packed, sizeof(double[7]) * n); return e->n_packed; }
 int pctc_n_lstsq(pctc_env *e) { return e->n_lstsq; }
+
+/* What heuristic.py reads from a PackingContinuous env (heuristic.py:163-166,190-193,387-416,541-567):
+ * Space.drop_box_virtual(dims, (lx, ly), False, density, setting, returnH=True) (C:space.py:380-425; max_h is
+ * interSect2D's, :391) and env.next_box / env.next_den. */
+int pctc_drop_box_virtual(pctc_env *e, double x, double y, double z, double lx, double ly, double density, double *max_h) {
+    static __thread int idx[PC_MAX_BOXES];
+    static __thread double area[PC_MAX_BOXES][5];
+    int n;
+    double bi[5] = {-lx, -ly, lx + x, ly + y, 0};
+    *max_h = intersect2d(e, bi, idx, area, &n);
+    return drop_box_virtual(e, x, y, z, lx, ly, density);
+}
+void pctc_get_next(pctc_env *e, double *out4) { out4[0] = e->next_box[0]; out4[1] = e->next_box[1]; out4[2] = e->next_box[2]; out4[3] = e->next_den; }

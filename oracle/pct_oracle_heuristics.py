@@ -26,6 +26,14 @@ ROT = ((0, 1, 2), (1, 0, 2), (1, 2, 0), (2, 1, 0), (0, 2, 1), (2, 0, 1))
 BAD_ROW = np.array([1, 0, 0, 1, 0, 0, 0, 0, 1.0])  # "no placement": a non-zero leaf row of extent 0 cannot match any item -> the env ends the episode
 
 
+def bad_row(container, continuous):
+    """The continuous LeafNode2Action (C:bin3D.py:151-167) never raises: an unmatched row just picks next_box[0] as z, so the
+    "no placement" row there has to fail Space.drop_box's bounds test instead (lx = W + 1 > W, C:space.py:336)."""
+    if not continuous:
+        return BAD_ROW.copy()
+    return np.array([container[0] + 1.0, 0, 0, container[0] + 1.0, 0, 0, 0, 0, 1.0])
+
+
 def rot_dims(nb, rot):
     return [nb[ROT[rot][0]], nb[ROT[rot][1]], nb[ROT[rot][2]]]
 
@@ -141,9 +149,9 @@ def choose(name, view, state, item_set=None, seed=0, gid=0, t=0):
     return best
 
 
-def action_row(choice):
+def action_row(choice, container=None, continuous=False):
     if choice is None:
-        return BAD_ROW.copy()
+        return bad_row(container, continuous)
     d, lx, ly = choice
     return np.array([lx, ly, 0, lx + d[0], ly + d[1], 0, 0, 0, 1.0])
 
@@ -158,7 +166,12 @@ def note_placement(state, choice):
 
 
 def run_episodes(name, env, episodes, item_set=None, seed=0, gid=0):
-    """sequential baseline loop on one env (the shape of every function in heuristic.py): -> [(ratio, length, packed), ...]"""
+    """sequential baseline loop on one env (the shape of every function in heuristic.py): -> [(ratio, length, packed), ...]
+    Works on OracleDiscrete and — LSAH / OnlineBPH / BR only, like tools.py:217-218 — on OracleContinuous (float64 geometry:
+    every score below is written with the reference's operand order, so the float results are the reference's)."""
+    continuous = not isinstance(env.container[0], int)
+    if continuous and name not in ("LSAH", "OnlineBPH", "BR"):
+        raise ValueError("only LSAH, OnlineBPH, and BR allowed for continuous environment")  # tools.py:218
     out, t = [], 0
     env.reset()
     state = fresh_state(env.container)
@@ -166,7 +179,7 @@ def run_episodes(name, env, episodes, item_set=None, seed=0, gid=0):
         c = choose(name, env, state, item_set, seed, gid, t)
         t += 1
         items = env.packed
-        _, _, done, info = env.step(action_row(c))
+        _, _, done, info = env.step(action_row(c, env.container, continuous))
         if c is not None:
             note_placement(state, c)
         if done:

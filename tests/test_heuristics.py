@@ -7,8 +7,8 @@ import numpy as np
 import pytest
 
 import pct_oracle_heuristics as OH
-from harness import ITEM_SET
-from pct_oracle import OracleDiscrete
+from harness import CONT_ITEM_SET, ITEM_SET
+from pct_oracle import OracleContinuous, OracleDiscrete
 
 GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "heur_s*.npz")))
 RECORDED = ("LSAH", "OnlineBPH", "BR", "MACS", "DBL", "HM")
@@ -43,6 +43,37 @@ def test_restated_heuristics_replay_reference(path, name):
     env.set_trajectory_length(L)
     rec = OH.run_episodes(name, env, len(packed), item_set=ITEM_SET)
     assert [r[2] for r in rec] == packed
+
+
+# ---- continuous domain: LSAH / OnlineBPH / BR (tools.py:217-218) ---------------------------------------------------------
+GOLDEN_C = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "heur_cont_s*.npz")))
+CONT_NAMES = ("LSAH", "OnlineBPH", "BR")
+
+
+def golden_c(path, name):
+    g = np.load(path)
+    off = np.concatenate([[0], np.cumsum(g["len_" + name])])
+    return int(g["setting"]), g["stream"], [g["flat_" + name][off[i]:off[i + 1]].tolist() for i in range(len(off) - 1)]
+
+
+def test_golden_continuous_present():
+    assert len(GOLDEN_C) == 3
+
+
+@pytest.mark.parametrize("name", CONT_NAMES)
+@pytest.mark.parametrize("path", GOLDEN_C)
+def test_restated_heuristics_replay_reference_continuous(path, name):
+    """float64 packed lists [x, y, z, lx, ly, lz, 0] equal the unmodified heuristic.py on PackingContinuous, exactly"""
+    setting, stream, packed = golden_c(path, name)
+    env = OracleContinuous(setting, stream=stream)
+    rec = OH.run_episodes(name, env, len(packed), item_set=CONT_ITEM_SET)
+    assert [r[2] for r in rec] == packed
+
+
+def test_continuous_rejects_grid_heuristics():
+    env = OracleContinuous(1, stream=np.array([[0.2, 0.2, 0.2, 1.0]]))
+    with pytest.raises(ValueError):
+        OH.run_episodes("DBL", env, 1)
 
 
 # ---- GPU: the batched selection kernel ------------------------------------------------------------------------------------
