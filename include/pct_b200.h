@@ -161,6 +161,13 @@ int pct_policy_random_dev(pct_handle h, int32_t *d_leaf_idx, uint64_t seed, cons
  * per env inside the handle.  PCT_H_RANDOM draws with rnd(seed, env_id_base+e, t).  PCT_H_BR needs pct_set_item_set;
  * PCT_H_HM / PCT_H_MACS / PCT_H_RANDOM need container sides <= 32. */
 int pct_heuristic_actions(pct_handle h, int32_t heuristic, float *d_rows, uint64_t seed, int64_t t, void *stream);
+/* Same for the CONTINUOUS domain, where tools.py:217-218 allows PCT_H_LSAH, PCT_H_ONLINEBPH and PCT_H_BR only (heuristic.py
+ * LASH :138-226, OnlineBPH :364-424, BR :500-577 over pct_envs.PctContinuous0): float64 rows (N x 9) for
+ * pct_step(d_actions = d_rows, action_f64 = 1).  "No feasible placement" is the row [W+1,0,0,W+1,0,0,0,0,1]: the continuous
+ * LeafNode2Action (C:bin3D.py:151-167) never raises, Space.drop_box rejects the position (C:space.py:336) and the episode ends.
+ * Item sizes must carry <= 6 decimals (the reference's generators round to 3, C:bin3D.py:106-111), so that the
+ * round(xe - xs, 6) of LeafNode2Action returns the chosen orientation's sizes exactly. */
+int pct_heuristic_actions_f64(pct_handle h, int32_t heuristic, double *d_rows, void *stream);
 /* Space.drop_box_virtual(dims, (lx, ly), False, density, setting, returnH / returnMap) for ONE env (D:space.py:393-433): what
  * the reference's heuristic.py calls on `env.space`; synchronous.  height_map: W*L int32 (row-major, after the virtual
  * placement — Space.update_height_graph on a copy) or NULL. */

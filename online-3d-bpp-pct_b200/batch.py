@@ -142,7 +142,20 @@ class PctBatch(object):
     # -- heuristic baselines (heuristic.py) ------------------------------------------------------------------
     def heuristic_actions(self, name, seed=0, t=0, out=None):
         """(N, 9) float32 CUDA tensor of action rows: the placement the baseline `name` (LSAH, OnlineBPH, BR, MACS, DBL, HM,
-        RANDOM) selects for every env's current item; feed to step(actions=...)."""
+        RANDOM) selects for every env's current item; feed to step(actions=...).
+        Continuous domain: LSAH / OnlineBPH / BR (tools.py:217-218), float64 rows."""
+        if name not in _lib.HEURISTIC_CODES:
+            raise PctError("unknown heuristic %r" % (name,))
+        if self.continuous:
+            if out is None:
+                if getattr(self, "_hrows", None) is None:
+                    self._hrows = torch.zeros((self.n_envs, 9), dtype=torch.float64, device=self.device)
+                out = self._hrows
+            if out.dtype != torch.float64 or not out.is_contiguous() or out.shape != (self.n_envs, 9):
+                raise PctError("continuous heuristic rows must be a contiguous (n_envs, 9) float64 tensor")
+            self._check(self.L.pct_heuristic_actions_f64(self.h, _lib.HEURISTIC_CODES[name], C.c_void_p(out.data_ptr()), self._stream()),
+                        "pct_heuristic_actions_f64")
+            return out
         if out is None:
             if getattr(self, "_hrows", None) is None:
                 self._hrows = torch.zeros((self.n_envs, 9), dtype=torch.float32, device=self.device)

@@ -31,6 +31,7 @@ int continuous_launch(pct_env_batch *h, int mode, const void *actions, int actio
 int continuous_policy_random(pct_env_batch *h, int32_t *leaf_idx, uint64_t seed, int64_t t, cudaStream_t st);
 int continuous_get_state(pct_env_batch *h, int env, pct_state_dump *out);
 int64_t continuous_state_bytes();
+int continuous_heuristic(pct_env_batch *h, int code, double *rows, double *hstate, cudaStream_t st);
 }  // namespace pct
 
 extern "C" {
@@ -137,7 +138,7 @@ void pct_destroy(pct_handle h) {
     cudaSetDevice(h->device);
     if (h->cfg.domain == PCT_CONTINUOUS) continuous_destroy(h);
     cudaFree(h->d_order);
-    cudaFree(h->d_hstate); cudaFree(h->d_query);
+    cudaFree(h->d_hstate); cudaFree(h->d_hstate_c); cudaFree(h->d_query);
     cudaFree(h->d_ready);
     cudaFree(h->d_hot); cudaFree(h->d_cold); cudaFree(h->d_item_set); cudaFree(h->d_stream);
     cudaFree(h->d_obs); cudaFree(h->d_act); cudaFree(h->d_idx); cudaFree(h->d_rew); cudaFree(h->d_done); cudaFree(h->d_info);
@@ -388,6 +389,26 @@ int pct_heuristic_actions(pct_handle h, int32_t heuristic, float *d_rows, uint64
     HParams hp{};
     hp.code = heuristic; hp.rows = d_rows; hp.hstate = h->d_hstate; hp.seed = seed; hp.t = t;
     CK(h, launch_heuristic_discrete(p, hp, (cudaStream_t)stream));
+    h->launches++;
+    return PCT_OK;
+}
+
+int pct_heuristic_actions_f64(pct_handle h, int32_t heuristic, double *d_rows, void *stream) {
+    if (!h || !d_rows) return PCT_ERR_INVALID;
+    if (h->cfg.domain != PCT_CONTINUOUS) { h->err = "pct_heuristic_actions_f64: continuous domain only (discrete: pct_heuristic_actions)"; return PCT_ERR_INVALID; }
+    if (heuristic != PCT_H_LSAH && heuristic != PCT_H_ONLINEBPH && heuristic != PCT_H_BR) {  // tools.py:217-218
+        h->err = "only LSAH, OnlineBPH, and BR allowed for continuous environment";
+        return PCT_ERR_INVALID;
+    }
+    if (!h->did_reset) { h->err = "pct_heuristic_actions_f64 before pct_reset"; return PCT_ERR_STATE; }
+    if (heuristic == PCT_H_BR && !h->d_item_set) { h->err = "PCT_H_BR scores an EMS by the item types that fit: call pct_set_item_set"; return PCT_ERR_STATE; }
+    CK(h, cudaSetDevice(h->device));
+    if (!h->d_hstate_c) {
+        CK(h, cudaMalloc(&h->d_hstate_c, sizeof(double) * 4 * (size_t)h->n_envs));
+        CK(h, cudaMemset(h->d_hstate_c, 0, sizeof(double) * 4 * (size_t)h->n_envs));
+    }
+    int rc = continuous_heuristic(h, heuristic, d_rows, h->d_hstate_c, (cudaStream_t)stream);
+    if (rc != PCT_OK) return rc;
     h->launches++;
     return PCT_OK;
 }

@@ -735,3 +735,5 @@ int continuous_get_state(pct_env_batch *h, int env, pct_state_dump *out) {
 }
 
 }  // namespace pct
+
+#include "pct_heuristics_continuous.cuh"

@@ -152,6 +152,12 @@ struct HParams {
     double q_den;
     int32_t *q_out;          // [feasible, rest height, W*L height map after the placement]
 };
+// continuous domain (pct_heuristics_continuous.cuh): LSAH / OnlineBPH / BR, float64 rows and footprint state
+struct HParamsC {
+    int code;
+    double *rows;            // (n_envs, 9) float64 action rows
+    double *hstate;          // (n_envs, 4) LSAH footprint: maxX, maxY, minX, minY
+};
 constexpr int PCT_H_QUERY_ = 7;
 constexpr int HEUR_SIDE_MAX = 32;  // height-map based codes (HM, MACS, RANDOM's bitmap, queries): W, L <= 32
 cudaError_t launch_heuristic_discrete(const DParams &p, const HParams &hp, cudaStream_t st);

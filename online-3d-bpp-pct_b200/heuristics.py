@@ -16,18 +16,25 @@ from .batch import PctBatch
 from .evaluation import _streams, load_trajectories
 
 HEURISTICS = tuple(_lib.HEURISTIC_CODES)  # LSAH, OnlineBPH, BR, MACS, DBL, HM, RANDOM (tools.py:209)
+CONTINUOUS_HEURISTICS = ("LSAH", "OnlineBPH", "BR")  # tools.py:217-218
 
 
 def run_heuristic(name, setting, episodes, container_size=(10, 10, 10), item_set=None, data=None, n_envs=1024, seed=0, device=0,
-                  internal_node_holder=80, leaf_node_holder=50, max_steps=None, return_episodes=False):
+                  internal_node_holder=80, leaf_node_holder=50, max_steps=None, return_episodes=False, continuous=False,
+                  sample_from_distribution=False, sample_left_bound=None, sample_right_bound=None, item_stream=None):
     """Plays `episodes` episodes of baseline `name` spread over min(n_envs, episodes) envs of one GPU batch.
 
-    data=None: items are drawn on the fly from `item_set` (RandomBoxCreator); env e plays episodes e, e+N, ...
+    data=None: items are drawn on the fly from `item_set` (RandomBoxCreator) — or, continuous + sample_from_distribution, from
+    U(a, b) rounded to 3 decimals (C:bin3D.py:103-115); env e plays episodes e, e+N, ...
     data=path|list: the trajectory dataset of `--load-dataset` (LoadBoxCreator: episode k plays trajectory k+1).
+    item_stream: (n, len, 3|4) per-env draw sequences instead (tests).
+    continuous=True: PackingContinuous; only LSAH, OnlineBPH and BR (tools.py:217-218).
     -> (mean ratio, var ratio, mean length) like heuristic.py; with return_episodes also the per-episode arrays / packed lists.
     """
     if name not in _lib.HEURISTIC_CODES:
         raise ValueError("unknown heuristic %r (options: %s)" % (name, " ".join(HEURISTICS)))
+    if continuous and name not in CONTINUOUS_HEURISTICS:
+        raise ValueError("only LSAH, OnlineBPH, and BR allowed for continuous environment")  # tools.py:218
     episodes = int(episodes)
     n = max(1, min(int(n_envs), episodes))
     stream = traj_len = None
@@ -38,8 +45,14 @@ def run_heuristic(name, setting, episodes, container_size=(10, 10, 10), item_set
         stream, traj_len, quota = _streams(trajs, episodes, n)
     else:
         quota = np.array([(episodes - e + n - 1) // n for e in range(n)])
+        if item_stream is not None:
+            stream = np.asarray(item_stream, dtype=np.float64)[:n]
+    # continuous: float64 observations, so that the placed boxes read back below are the env's own float64 coordinates
+    odt = torch.float64 if continuous else torch.float32
     batch = PctBatch(n, setting, container_size=container_size, item_set=item_set, internal_node_holder=internal_node_holder,
-                     leaf_node_holder=leaf_node_holder, obs_dtype=torch.float32, seed=seed, device=device, item_stream=stream)
+                     leaf_node_holder=leaf_node_holder, obs_dtype=odt, seed=seed, device=device, item_stream=stream, continuous=continuous,
+                     sample_from_distribution=sample_from_distribution, sample_left_bound=sample_left_bound,
+                     sample_right_bound=sample_right_bound)
     if traj_len:
         batch.set_trajectory_length(traj_len)
     nb = batch.nb
@@ -47,7 +60,7 @@ def run_heuristic(name, setting, episodes, container_size=(10, 10, 10), item_set
     ratio, length, packed = np.zeros(episodes), np.zeros(episodes, dtype=np.int64), [None] * episodes
     played = np.zeros(n, dtype=np.int64)
     obs = batch.reset()
-    prev = torch.empty((n, nb * 9), dtype=torch.float32, device=obs.device) if return_episodes else None
+    prev = torch.empty((n, nb * 9), dtype=odt, device=obs.device) if return_episodes else None
     limit = int(max_steps) if max_steps else (int(quota.max()) + 1) * (internal_node_holder + 2)
     t = 0
     while not (played >= quota).all() and t < limit:
@@ -68,11 +81,15 @@ def run_heuristic(name, setting, episodes, container_size=(10, 10, 10), item_set
             length[ep] = c
             if boxes is None:
                 ratio[ep] = float(rec["ratio"][e])
-            else:  # Space.get_ratio in float64 from the placed boxes (D:space.py:334-339)
+            else:  # Space.get_ratio in float64 from the placed boxes (D:space.py:334-339 / C:space.py:316-321)
                 items, vol = [], 0.0
                 for r in boxes[k, :c]:
-                    x, y, z = int(r[3] - r[0]), int(r[4] - r[1]), int(r[5] - r[2])
-                    items.append([x, y, z, int(r[0]), int(r[1]), int(r[2]), 0])
+                    if continuous:  # rows are [lx, ly, lz, lx+x, ly+y, lz+z]; sizes carry <= 6 decimals, so rounding returns them exactly
+                        x, y, z = (float(np.round(r[3] - r[0], 6)), float(np.round(r[4] - r[1], 6)), float(np.round(r[5] - r[2], 6)))
+                        items.append([x, y, z, float(r[0]), float(r[1]), float(r[2]), 0])
+                    else:
+                        x, y, z = int(r[3] - r[0]), int(r[4] - r[1]), int(r[5] - r[2])
+                        items.append([x, y, z, int(r[0]), int(r[1]), int(r[2]), 0])
                     vol += x * y * z
                 packed[ep], ratio[ep] = items, vol / binvol
             played[e] += 1
@@ -88,17 +105,25 @@ def run_heuristic(name, setting, episodes, container_size=(10, 10, 10), item_set
 def main(argv=None):
     import argparse
     ap = argparse.ArgumentParser(description="Heuristic baseline arguments (tools.get_args_heuristic, tools.py:200-230)")
+    ap.add_argument("--continuous", action="store_true", help="Use continuous enviroment, otherwise the enviroment is discrete")
     ap.add_argument("--setting", type=int, default=2)
     ap.add_argument("--evaluation-episodes", type=int, default=10)
     ap.add_argument("--load-dataset", action="store_true")
     ap.add_argument("--dataset-path", type=str)
     ap.add_argument("--heuristic", type=str, default="LSAH", help="Options: LSAH DBL MACS OnlineBPH HM BR RANDOM")
+    ap.add_argument("--container-size", type=float, nargs=3, default=None, help="givenData.container_size: [10,10,10]; continuous: [1,1,1]")
     ap.add_argument("--num-envs", type=int, default=1024)
     ap.add_argument("--device", type=int, default=0)
     a = ap.parse_args(argv)
     item_set = [(i, j, k) for i in range(1, 6) for j in range(1, 6) for k in range(1, 6)]  # givenData.py:7-14
-    mean, var, length = run_heuristic(a.heuristic, a.setting, a.evaluation_episodes, item_set=item_set,
-                                      data=a.dataset_path if a.load_dataset else None, n_envs=a.num_envs, device=a.device)
+    cs = a.container_size or ([1.0, 1.0, 1.0] if a.continuous else [10, 10, 10])  # givenData.py:4-5
+    if not a.continuous:
+        cs = [int(c) for c in cs]
+    # heuristic.py:585-591 builds PackingContinuous with its defaults: sample_from_distribution=True, U(0.1, 0.5) (C:bin3D.py:14-16)
+    mean, var, length = run_heuristic(a.heuristic, a.setting, a.evaluation_episodes, container_size=cs, item_set=item_set,
+                                      data=a.dataset_path if a.load_dataset else None, n_envs=a.num_envs, device=a.device,
+                                      continuous=a.continuous, sample_from_distribution=a.continuous and not a.load_dataset,
+                                      sample_left_bound=0.1 if a.continuous else None, sample_right_bound=0.5 if a.continuous else None)
     print("The average space utilization:", mean)
     print("The variance of space utilization:", var)
     print("The average number of packed items:", length)
