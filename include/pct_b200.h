@@ -174,6 +174,11 @@ int pct_heuristic_actions_f64(pct_handle h, int32_t heuristic, double *d_rows, v
 int pct_query_placement(pct_handle h, int32_t env, const int32_t dims[3], int32_t lx, int32_t ly, double density,
                         int32_t *feasible, int32_t *rest_height, int32_t *height_map);
 
+/* Space.drop_box_virtual(dims, (lx, ly), False, density, setting, returnH=True) of the CONTINUOUS env (C:space.py:380-425) for
+ * ONE env; synchronous.  rest_height is interSect2D's max_h (C:space.py:391). */
+int pct_query_placement_f64(pct_handle h, int32_t env, const double dims[3], double lx, double ly, double density,
+                            int32_t *feasible, double *rest_height);
+
 /* introspection */
 int pct_get_state(pct_handle h, int32_t env, pct_state_dump *out);
 int32_t pct_obs_len(pct_handle h);       /* (NB + NL + 1) * 9 */

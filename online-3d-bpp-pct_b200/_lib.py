@@ -40,7 +40,7 @@ class StateDump(C.Structure):
 EXPORTS = ["pct_create", "pct_destroy", "pct_last_error", "pct_set_item_set", "pct_set_item_stream", "pct_set_trajectory_length", "pct_reset", "pct_step",
            "pct_step_host", "pct_reset_host", "pct_policy_random", "pct_policy_random_dev", "pct_get_state", "pct_obs_len", "pct_num_envs",
            "pct_state_bytes_per_env", "pct_kernel_launches", "pct_version", "pct_profile_enable", "pct_profile_read", "pct_heuristic_actions",
-           "pct_heuristic_actions_f64", "pct_query_placement"]
+           "pct_heuristic_actions_f64", "pct_query_placement", "pct_query_placement_f64"]
 
 
 def build(verbose=False):
@@ -88,5 +88,7 @@ def lib():
     L.pct_heuristic_actions.argtypes = [vp, i32, vp, u64, i64, vp]
     L.pct_heuristic_actions_f64.argtypes = [vp, i32, vp, vp]
     L.pct_query_placement.argtypes = [vp, i32, C.POINTER(i32), i32, i32, C.c_double, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
+    L.pct_query_placement_f64.argtypes = [vp, i32, C.POINTER(C.c_double), C.c_double, C.c_double, C.c_double, C.POINTER(i32),
+                                          C.POINTER(C.c_double)]
     _lib = L
     return L

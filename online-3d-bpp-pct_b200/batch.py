@@ -166,6 +166,11 @@ class PctBatch(object):
 
     def query_placement(self, env, dims, lx, ly, density=1.0, want_map=False):
         """Space.drop_box_virtual for one env (D:space.py:393-433): -> (feasible, rest_height[, height map after])"""
+        if self.continuous:  # C:space.py:380-425 has no returnMap
+            d, feas, mh = (C.c_double * 3)(float(dims[0]), float(dims[1]), float(dims[2])), C.c_int32(), C.c_double()
+            self._check(self.L.pct_query_placement_f64(self.h, int(env), d, float(lx), float(ly), float(density), C.byref(feas), C.byref(mh)),
+                        "pct_query_placement_f64")
+            return (bool(feas.value), mh.value, None) if want_map else (bool(feas.value), mh.value)
         d = (C.c_int32 * 3)(int(dims[0]), int(dims[1]), int(dims[2]))
         feas, mh = C.c_int32(), C.c_int32()
         W, L = int(self.container_size[0]), int(self.container_size[1])

@@ -32,6 +32,7 @@ int continuous_policy_random(pct_env_batch *h, int32_t *leaf_idx, uint64_t seed,
 int continuous_get_state(pct_env_batch *h, int env, pct_state_dump *out);
 int64_t continuous_state_bytes();
 int continuous_heuristic(pct_env_batch *h, int code, double *rows, double *hstate, cudaStream_t st);
+int continuous_query(pct_env_batch *h, int env, const double q[5], double density, double *d_out, cudaStream_t st);
 }  // namespace pct
 
 extern "C" {
@@ -138,7 +139,7 @@ void pct_destroy(pct_handle h) {
     cudaSetDevice(h->device);
     if (h->cfg.domain == PCT_CONTINUOUS) continuous_destroy(h);
     cudaFree(h->d_order);
-    cudaFree(h->d_hstate); cudaFree(h->d_hstate_c); cudaFree(h->d_query);
+    cudaFree(h->d_hstate); cudaFree(h->d_hstate_c); cudaFree(h->d_query_c); cudaFree(h->d_query);
     cudaFree(h->d_ready);
     cudaFree(h->d_hot); cudaFree(h->d_cold); cudaFree(h->d_item_set); cudaFree(h->d_stream);
     cudaFree(h->d_obs); cudaFree(h->d_act); cudaFree(h->d_idx); cudaFree(h->d_rew); cudaFree(h->d_done); cudaFree(h->d_info);
@@ -410,6 +411,26 @@ int pct_heuristic_actions_f64(pct_handle h, int32_t heuristic, double *d_rows, v
     int rc = continuous_heuristic(h, heuristic, d_rows, h->d_hstate_c, (cudaStream_t)stream);
     if (rc != PCT_OK) return rc;
     h->launches++;
+    return PCT_OK;
+}
+
+int pct_query_placement_f64(pct_handle h, int32_t env, const double dims[3], double lx, double ly, double density, int32_t *feasible,
+                            double *rest_height) {
+    if (!h || !dims || !feasible || !rest_height || env < 0 || env >= h->n_envs) return PCT_ERR_INVALID;
+    if (h->cfg.domain != PCT_CONTINUOUS) { h->err = "pct_query_placement_f64: continuous domain only (discrete: pct_query_placement)"; return PCT_ERR_INVALID; }
+    if (!h->did_reset) { h->err = "pct_query_placement_f64 before pct_reset"; return PCT_ERR_STATE; }
+    CK(h, cudaSetDevice(h->device));
+    if (!h->d_query_c) CK(h, cudaMalloc(&h->d_query_c, sizeof(double) * 2));
+    const double q[5] = {dims[0], dims[1], dims[2], lx, ly};
+    CK(h, cudaDeviceSynchronize());
+    int rc = continuous_query(h, env, q, density, h->d_query_c, h->own_stream);
+    if (rc != PCT_OK) return rc;
+    h->launches++;
+    double out[2];
+    CK(h, cudaMemcpyAsync(out, h->d_query_c, sizeof out, cudaMemcpyDeviceToHost, h->own_stream));
+    CK(h, cudaStreamSynchronize(h->own_stream));
+    *feasible = out[0] != 0.0;
+    *rest_height = out[1];
     return PCT_OK;
 }
 

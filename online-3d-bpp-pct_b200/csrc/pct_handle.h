@@ -26,6 +26,7 @@ struct pct_env_batch {
     bool overlap_cont = false;    // continuous domain: measured slower overlapped (5.35 M -> 3.97 M env-steps/s), off unless PCT_B200_OVERLAP_CONT=1
     int32_t *d_hstate = nullptr;  // (n_envs, 4) LSAH footprint state (pct_heuristic_actions)
     double *d_hstate_c = nullptr; // same for the continuous domain (pct_heuristic_actions_f64)
+    double *d_query_c = nullptr;  // 2 doubles: result of pct_query_placement_f64
     int32_t *d_query = nullptr;   // 2 + W*L ints: result of pct_query_placement
     int item_mode = 0;
     // staging for the host-buffer entry points

@@ -49,13 +49,14 @@ __global__ void __launch_bounds__(64) pctc_heuristic_kernel(const CParams p, con
     __shared__ int c_feas[64];
     __shared__ double c_score[64];
     __shared__ int lock, stop;
-    const int tid = threadIdx.x, lane = tid & 31, e = blockIdx.x, code = hp.code;
+    const int tid = threadIdx.x, lane = tid & 31, code = hp.code;
+    const int e = code == PCT_H_QUERY_ ? hp.q_env : blockIdx.x;
     CEnv *ev = p.env + e;
     const CHdr &h = ev->h;
     if (tid == 0) { lock = 0; stop = 0; }
     const double nb[3] = {h.next_box[0], h.next_box[1], h.next_box[2]};
     const int n_ems = h.n_ems, n_box = h.n_box, R = p.setting == 2 ? 6 : 2;
-    const double den = h.next_den;
+    const double den = code == PCT_H_QUERY_ ? hp.q_den : h.next_den;
     if (code == PCT_H_ONLINEBPH) {  // sorted(EMS, key=(z, y, x)) — stable (heuristic.py:383-384); all-zero rows are skipped (:395-396)
         for (int i = tid; i < n_ems; i += 64) {
             const double *a = ev->ems[i];
@@ -73,6 +74,25 @@ __global__ void __launch_bounds__(64) pctc_heuristic_kernel(const CParams p, con
     EdgePool pool{ev->e_lower, ev->e_next, ev->e_off, ev->first_in, ev->last_in, ev->e_st, ev->e_st, h.n_edge,
                   ev->poly_off, &ev->poly[0][0], &ev->poly[0][0], h.n_poly};
     int fl = 0;
+    if (code == PCT_H_QUERY_) {  // one Space.drop_box_virtual(..., returnH=True) call (C:space.py:380-425) for the single-env facade
+        if (tid == 0) {
+            const double sx = hp.q[0], sy = hp.q[1], sz = hp.q[2], lx = hp.q[3], ly = hp.q[4];
+            bool chk = !(lx + sx - 1e-6 > p.W || ly + sy - 1e-6 > p.L) && !(lx + 1e-6 < 0 || ly + 1e-6 < 0);
+            double mh = rest_height_c(ev->box, 0, n_box, 1, lx, ly, lx + sx, ly + sy);
+            if (mh < 0) mh = 0.0;
+            if (mh + sz - 1e-6 > p.H) chk = false;
+            int feas;
+            if (!chk) feas = 0;
+            else if (!STAB || fabs(mh) < 1e-6) feas = 1;
+            else {
+                NodeC root{lx, ly, mh, sx, sy, sz, sx * sy * sz * den};
+                feas = stability_check<false, GeomC>(g, root, pool, &ev->big, &lock, 0, fl) != 0;
+            }
+            hp.q_out[0] = (double)feas;
+            hp.q_out[1] = mh;
+        }
+        return;
+    }
     const int n_c = n_ems * R;
     // LSAH footprint state (heuristic.py:146-147, 217-220); a fresh episode (no box placed yet) starts from the empty footprint
     double maxX = 0, maxY = 0, minX = p.W, minY = p.L;
@@ -163,14 +183,32 @@ __global__ void __launch_bounds__(64) pctc_heuristic_kernel(const CParams p, con
     }
 }
 
-int continuous_heuristic(pct_env_batch *h, int code, double *rows, double *hstate, cudaStream_t st) {
+static CParams state_params_c(pct_env_batch *h) {
     CParams p{};
     p.env = (CEnv *)h->c_state; p.n_envs = h->n_envs;
     p.W = h->cfg.container_size[0]; p.L = h->cfg.container_size[1]; p.H = h->cfg.container_size[2];
     p.low_bound = h->cfg.size_minimum;
     p.nb = h->cfg.internal_node_holder; p.nl = h->cfg.leaf_node_holder; p.setting = h->cfg.setting;
     p.item_set = h->d_item_set; p.n_items = h->n_items;
-    HParamsC hp{code, rows, hstate};
+    return p;
+}
+
+int continuous_query(pct_env_batch *h, int env, const double q[5], double density, double *d_out, cudaStream_t st) {
+    const CParams p = state_params_c(h);
+    HParamsC hp{};
+    hp.code = PCT_H_QUERY_; hp.q_env = env; hp.q_den = density; hp.q_out = d_out;
+    for (int i = 0; i < 5; i++) hp.q[i] = q[i];
+    if (p.setting == 2) pctc_heuristic_kernel<false><<<1, 64, 0, st>>>(p, hp);
+    else pctc_heuristic_kernel<true><<<1, 64, 0, st>>>(p, hp);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { h->err = std::string("continuous query launch: ") + cudaGetErrorString(e); return PCT_ERR_CUDA; }
+    return PCT_OK;
+}
+
+int continuous_heuristic(pct_env_batch *h, int code, double *rows, double *hstate, cudaStream_t st) {
+    const CParams p = state_params_c(h);
+    HParamsC hp{};
+    hp.code = code; hp.rows = rows; hp.hstate = hstate;
     if (p.setting == 2) pctc_heuristic_kernel<false><<<p.n_envs, 64, 0, st>>>(p, hp);
     else pctc_heuristic_kernel<true><<<p.n_envs, 64, 0, st>>>(p, hp);
     cudaError_t e = cudaGetLastError();

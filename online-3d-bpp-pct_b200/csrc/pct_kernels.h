@@ -157,6 +157,9 @@ struct HParamsC {
     int code;
     double *rows;            // (n_envs, 9) float64 action rows
     double *hstate;          // (n_envs, 4) LSAH footprint: maxX, maxY, minX, minY
+    int q_env;               // PCT_H_QUERY_: handle-local env, oriented sizes + position, density, result [feasible, rest height]
+    double q[5], q_den;
+    double *q_out;
 };
 constexpr int PCT_H_QUERY_ = 7;
 constexpr int HEUR_SIDE_MAX = 32;  // height-map based codes (HM, MACS, RANDOM's bitmap, queries): W, L <= 32

@@ -67,3 +67,46 @@ def test_continuous_rejects_other_heuristics():
     with pytest.raises(pct_b200.PctError, match="pct_set_item_set"):
         b.heuristic_actions("BR")
     b.close()
+
+
+class _FacadeViewC(object):
+    """what heuristic.py touches on the env, routed to the drop-in PackingContinuous exactly the way heuristic.py calls it"""
+
+    def __init__(self, env):
+        self.env, self.container, self.setting = env, tuple(float(c) for c in env.bin_size), env.setting
+
+    def ems(self):
+        return [list(e) for e in self.env.space.EMS]
+
+    def drop_box_virtual(self, d, lx, ly):
+        return self.env.space.drop_box_virtual(list(d), (lx, ly), False, self.env.next_den, self.env.setting, returnH=True)
+
+    @property
+    def next_box(self):
+        return self.env.next_box
+
+
+@pytest.mark.parametrize("name", ["LSAH", "BR"])
+def test_single_env_facade_serves_the_reference_heuristic_loop_continuous(name):
+    """env.space.drop_box_virtual(returnH) / env.space.EMS / env.next_box = [...] / env.step([0, lx, ly]) on PackingContinuous"""
+    import pct_b200
+    setting, stream, packed = _golden(GOLDEN_C[0], name)
+    env = pct_b200.PackingContinuous(setting=setting, container_size=[1, 1, 1], item_set=CONT_ITEM_SET, sample_from_distribution=False,
+                                     item_stream=stream[None], size_minimum=0.1)
+    view = _FacadeViewC(env)
+    env.reset()
+    state, got = OH.fresh_state(view.container), []
+    while len(got) < 2:
+        c = OH.choose(name, view, state, CONT_ITEM_SET)
+        if c is None:
+            got.append(env.packed)
+            env.reset()
+            state = OH.fresh_state(view.container)
+            continue
+        env.next_box = c[0]
+        env.step([0, c[1], c[2]])
+        OH.note_placement(state, c)
+    for ep, ref in zip(got, packed[:2]):
+        assert len(ep) == len(ref)
+        assert np.allclose(np.array(ep), np.array(ref), rtol=0, atol=1e-12)  # `packed` of the facade derives sizes as hi - lo
+    env.close()
