@@ -1,9 +1,6 @@
 """GPU: batched heuristic baselines on the CONTINUOUS env (LSAH / OnlineBPH / BR, tools.py:217-218) — the selection kernel
 csrc/pct_heuristics_continuous.cuh behind pct_heuristic_actions_f64, against (a) records of the reference's unmodified
 heuristic.py on PackingContinuous (tests/golden/heur_cont_s*.npz) and (b) the CPU restatement on per-env item streams.
-
-HARDWARE STATUS: written after round 1's GPU budget was spent; not yet run on a B200.  The file name
-sorts it behind every hardware-verified test file, so `pytest -x` reaches it last.
 """
 import glob
 import os
