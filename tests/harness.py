@@ -17,6 +17,55 @@ def make_stream(seed, env, n, setting):
     return s
 
 
+# ---- non-default configurations (tests/golden/make_golden_cases.py records them from the reference; the GPU cases of
+# tests/test_gpu_discrete_cases.py use the same containers / item sets) ----------------------------------------------------
+def _case(setting, container, items, nb=80, nl=50, steps=90, lnes="EMS"):
+    return dict(setting=setting, container=tuple(container), items=[tuple(i) for i in items], nb=nb, nl=nl, steps=steps, lnes=lnes)
+
+
+_BIG = [(i, j, k) for i in (4, 6, 9) for j in (5, 8) for k in (3, 7, 10)]
+_SMALL = [(2, 2, 2), (3, 3, 2), (2, 3, 3), (4, 2, 2), (3, 4, 3)]
+CASES = {
+    "big_s1": _case(1, (20, 18, 24), _BIG), "big_s2": _case(2, (20, 18, 24), _BIG), "big_s3": _case(3, (20, 18, 24), _BIG),
+    "holders_s1": _case(1, (10, 10, 10), ITEM_SET, nb=60, nl=30), "holders_s2": _case(2, (10, 10, 10), ITEM_SET, nb=80, nl=64),
+    "dense16_s1": _case(1, (16, 16, 16), _SMALL, steps=70), "dense16_s2": _case(2, (16, 16, 16), _SMALL, steps=70),
+    "flat_s1": _case(1, (12, 7, 9), [(i, j, k) for i in (1, 2, 4) for j in (1, 3) for k in (2, 3)], nb=70, nl=40),
+    "cp_big_s1": _case(1, (14, 12, 10), ITEM_SET, steps=70, lnes="CP"), "ep_big_s2": _case(2, (14, 12, 10), ITEM_SET, steps=70, lnes="EP"),
+}
+
+
+def case_stream(c, seed, env, n):
+    """draw sequence (x, y, z, density) over the case's item set"""
+    s = np.zeros((n, 4))
+    for d in range(n):
+        s[d, :3] = c["items"][rnd_u64(seed, env, d) % len(c["items"])]
+        s[d, 3] = max((rnd_u64(seed ^ 0xABCDEF, env, d) >> 11), 1) / float(1 << 53) if c["setting"] == 3 else 1.0
+    return s
+
+
+def _ccase(setting, container, lo, hi, nb=80, nl=50, steps=110):
+    return dict(setting=setting, container=tuple(container), lo=lo, hi=hi, low=lo, nb=nb, nl=nl, steps=steps)
+
+
+# continuous: a non-unit container (bounds scale like tools.py:178-181: U(0.1, 0.5) x min side) and other holder sizes
+CONT_CASES = {"box2_s1": _ccase(1, (2.0, 1.5, 2.5), 0.15, 0.75), "box2_s2": _ccase(2, (2.0, 1.5, 2.5), 0.15, 0.75),
+              "box2_s3": _ccase(3, (2.0, 1.5, 2.5), 0.15, 0.75), "holders_s1": _ccase(1, (1.0, 1.0, 1.0), 0.1, 0.5, nb=60, nl=25)}
+
+
+def cont_case_stream(c, seed, env, n):
+    """x, y = round(U(lo, hi), 3); z likewise (setting 2) or one of five levels (C:bin3D.py:103-115 scaled to the container)"""
+    s = np.zeros((n, 4))
+    lo, hi = c["lo"], c["hi"]
+    u = lambda salt, d: ((rnd_u64(seed ^ salt, env, d) >> 11) / float(1 << 53))
+    levels = [round(lo * k, 3) for k in (1, 2, 3, 4, 5)]
+    for d in range(n):
+        s[d, 0] = round(lo + (hi - lo) * u(0x11, d), 3)
+        s[d, 1] = round(lo + (hi - lo) * u(0x22, d), 3)
+        s[d, 2] = round(lo + (hi - lo) * u(0x33, d), 3) if c["setting"] == 2 else levels[rnd_u64(seed ^ 0x44, env, d) % 5]
+        s[d, 3] = max((rnd_u64(seed ^ 0xABCDEF, env, d) >> 11), 1) / float(1 << 53) if c["setting"] == 3 else 1.0
+    return s
+
+
 class OracleVec(object):
     """N independent oracle envs with the ShmemVecEnv worker semantics (auto-reset on done,
     wrapper/shmem_vec_env.py:139-143) and the shared deterministic policy."""

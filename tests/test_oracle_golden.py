@@ -61,3 +61,48 @@ def test_continuous_oracle_replays_reference_trajectory(path):
             o = env.reset()
             assert np.array_equal(o, obs[k]); k += 1
     assert k == len(obs) and len(GOLD_C) == 3
+
+
+# ---- non-default configurations (tests/golden/make_golden_cases.py): other containers / item sets / holder sizes -----------
+from harness import CASES, CONT_CASES  # noqa: E402
+
+GOLD_CASES = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "case_*.npz")))
+GOLD_CCASES = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "ccase_*.npz")))
+
+
+def _replay(env, g):
+    obs, k = g["obs"], 0
+    o = env.reset()
+    assert np.array_equal(o, obs[k]); k += 1
+    for t in range(len(g["rows"])):
+        o, r, d, info = env.step(g["rows"][t])
+        assert np.array_equal(o, obs[k]), "observation after step %d (done=%s)" % (t, d); k += 1
+        assert r == g["reward"][t] and d == bool(g["done"][t]) and info["counter"] == g["counter"][t] and "error" not in info
+        if d:
+            assert info["ratio"] == g["ratio"][t]
+            o = env.reset()
+            assert np.array_equal(o, obs[k]); k += 1
+    assert k == len(obs)
+
+
+def test_case_files_present():
+    assert len(GOLD_CASES) == len(CASES) and len(GOLD_CCASES) == len(CONT_CASES)
+
+
+@pytest.mark.parametrize("path", GOLD_CASES, ids=[os.path.basename(p) for p in GOLD_CASES])
+def test_oracle_replays_reference_on_other_configurations(path):
+    g = np.load(path)
+    c = CASES[str(g["name"])]
+    env = OracleDiscrete(c["setting"], container_size=c["container"], internal_node_holder=c["nb"], leaf_node_holder=c["nl"],
+                         size_minimum=min(min(i) for i in c["items"]), stream=g["stream"], lnes=c["lnes"])
+    _replay(env, g)
+
+
+@pytest.mark.parametrize("path", GOLD_CCASES, ids=[os.path.basename(p) for p in GOLD_CCASES])
+def test_continuous_oracle_replays_reference_on_other_configurations(path):
+    from pct_oracle import OracleContinuous
+    g = np.load(path)
+    c = CONT_CASES[str(g["name"])]
+    env = OracleContinuous(c["setting"], container_size=c["container"], internal_node_holder=c["nb"], leaf_node_holder=c["nl"],
+                           size_minimum=c["low"], stream=g["stream"])
+    _replay(env, g)

@@ -30,3 +30,59 @@ def test_lockstep_with_reference(setting):
         assert (r1, d1) == (r2, d2) and i1 == i2
         if d1:
             o1, o2 = ref.reset(), orc.reset()
+
+
+# ---- other configurations, live (fresh seeds; the committed records of the same configurations are tests/golden/case_*.npz) ----
+import os  # noqa: E402
+import sys  # noqa: E402
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+from harness import CASES, CONT_CASES  # noqa: E402
+
+
+def _equal_records(a, b):
+    for k in ("obs", "reward", "done", "counter", "ratio"):
+        assert np.array_equal(a[k], b[k]), k
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_cases_lockstep_with_reference(name):
+    """the recorder of tests/golden/make_golden_cases.py on the reference vs the same loop on the oracle, new seed"""
+    import make_golden_cases as M
+    from harness import case_stream
+    D, _ = ref_shim.load_reference()
+    c = dict(CASES[name], steps=60)
+    ref = M.record_case(D, c, 8800, 4)
+
+    orc = OracleDiscrete(c["setting"], container_size=c["container"], internal_node_holder=c["nb"], leaf_node_holder=c["nl"],
+                         size_minimum=min(min(i) for i in c["items"]), stream=case_stream(c, 8800, 4, c["steps"] + 64), lnes=c["lnes"])
+    o = orc.reset()
+    obs, rew, done, counter, ratio = [o.copy()], [], [], [], []
+    for t in range(c["steps"]):
+        o, r, d, info = orc.step(ref["rows"][t])
+        obs.append(o.copy()); rew.append(r); done.append(d); counter.append(info["counter"]); ratio.append(info.get("ratio", -1.0))
+        if d:
+            o = orc.reset()
+            obs.append(o.copy())
+    _equal_records(ref, dict(obs=np.array(obs), reward=np.array(rew), done=np.array(done), counter=np.array(counter), ratio=np.array(ratio)))
+
+
+@pytest.mark.parametrize("name", sorted(CONT_CASES))
+def test_continuous_cases_lockstep_with_reference(name):
+    import make_golden_cases as M
+    from harness import cont_case_stream
+    from pct_oracle import OracleContinuous
+    _, Cm = ref_shim.load_reference()
+    c = dict(CONT_CASES[name], steps=70)
+    ref = M.record_cont_case(Cm, c, 8801, 5)
+    orc = OracleContinuous(c["setting"], container_size=c["container"], internal_node_holder=c["nb"], leaf_node_holder=c["nl"],
+                           size_minimum=c["low"], stream=cont_case_stream(c, 8801, 5, c["steps"] + 64))
+    o = orc.reset()
+    obs, rew, done, counter, ratio = [o.copy()], [], [], [], []
+    for t in range(c["steps"]):
+        o, r, d, info = orc.step(ref["rows"][t])
+        obs.append(o.copy()); rew.append(r); done.append(d); counter.append(info["counter"]); ratio.append(info.get("ratio", -1.0))
+        if d:
+            o = orc.reset()
+            obs.append(o.copy())
+    _equal_records(ref, dict(obs=np.array(obs), reward=np.array(rew), done=np.array(done), counter=np.array(counter), ratio=np.array(ratio)))
