@@ -121,6 +121,27 @@ __device__ __forceinline__ double rest_height_c(const double (*box)[6], int firs
     return any ? mh : -1.0;  // -1: no overlap (the reference returns 0 then)
 }
 
+// The same resting height from PRE-ROUNDED operands.  around6 is monotone non-decreasing (IEEE multiply by 1e6, rint and the
+// correctly rounded division by 1e6 all are), and a monotone f commutes with min: f(min(a, b)) == min(f(a), f(b)).  Hence
+//   around6(fmin(-lx, -b[0])) == fmin(around6(-lx), around6(-b[0]))        (bit for bit, for every input)
+// and the four roundings per (placement, box) pair of interSect2D become four per placement + four per box, the latter
+// computed once per launch into shared memory (rb[t] = {around6(-lx_t), around6(-ly_t), around6(hx_t), around6(hy_t), top_t}).
+// tests/test_oracle_units.py::test_around6_commutes_with_min checks the identity on the host.
+__device__ __forceinline__ double rest_height_pre(const double (*rb)[5], int n, double c0, double c1, double c2, double c3) {
+    double mh = 0;
+    bool any = false;
+    for (int t = 0; t < n; t++) {
+        const double *b = rb[t];
+        const double i0 = fmin(c0, b[0]), i1 = fmin(c1, b[1]), i2 = fmin(c2, b[2]), i3 = fmin(c3, b[3]);
+        if ((i0 + i2 > 0) && (i1 + i3 > 0)) {
+            const double top = b[4];
+            if (!any || top > mh) mh = top;
+            any = true;
+        }
+    }
+    return any ? mh : -1.0;
+}
+
 __device__ __forceinline__ bool rot_dims_c(const double nb[3], int rot, double &sx, double &sy, double &sz) {  // C:space.py:537-559
     switch (rot) {
     case 0: sx = nb[0]; sy = nb[1]; sz = nb[2]; return true;
@@ -587,9 +608,17 @@ __device__ __noinline__ void write_obs_c(const CParams &p, int e, const CEnv *ev
     }
 }
 
-template <typename OT, bool STAB>
+template <bool PRE>
+__device__ __forceinline__ double (*rb_store())[5] {  // the default instantiation owns no such array
+    if constexpr (PRE) { __shared__ double rb_s[NB_MAX][5]; return rb_s; }
+    else return nullptr;
+}
+
+// PRE: resting heights from pre-rounded box rectangles staged in shared memory (rest_height_pre; opt-in, PCT_B200_CONT_PRE=1)
+template <typename OT, bool STAB, bool PRE>
 __global__ void __launch_bounds__(64) pctc_feas_emit_kernel(const CParams p) {
     __shared__ double leaf[NL_MAX][6];
+    double (*rb)[5] = rb_store<PRE>();
     __shared__ uint32_t wb[2];
     __shared__ int lock;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, e = blockIdx.x;
@@ -607,6 +636,14 @@ __global__ void __launch_bounds__(64) pctc_feas_emit_kernel(const CParams p) {
     EdgePool pool{ev->e_lower, ev->e_next, ev->e_off, ev->first_in, ev->last_in, ev->e_st, ev->e_st, h.n_edge,
                   ev->poly_off, &ev->poly[0][0], &ev->poly[0][0], h.n_poly};
     int n_leaf = 0, fl = 0;
+    if (PRE) {
+        for (int t = tid; t < n_box; t += 64) {
+            const double *b = ev->box[t];
+            rb[t][0] = around6(-b[0]); rb[t][1] = around6(-b[1]); rb[t][2] = around6(b[0] + b[3]); rb[t][3] = around6(b[1] + b[4]);
+            rb[t][4] = b[2] + b[5];
+        }
+        __syncthreads();
+    }
 #pragma unroll 1
     for (int base = 0; base < n_cand && n_leaf < p.nl; base += 64) {
         const int c = base + tid;
@@ -617,7 +654,8 @@ __global__ void __launch_bounds__(64) pctc_feas_emit_kernel(const CParams p) {
             // get_possible_position: x = xe - xs ... (C:bin3D.py:134-137); drop_box_virtual (C:space.py:380-425)
             const double x = t6[3] - t6[0], y = t6[4] - t6[1], z = t6[5] - t6[2], lx = t6[0], ly = t6[1];
             bool chk = !(lx + x - 1e-6 > p.W || ly + y - 1e-6 > p.L) && !(lx + 1e-6 < 0 || ly + 1e-6 < 0);
-            double mh = rest_height_c(ev->box, 0, n_box, 1, lx, ly, lx + x, ly + y);
+            double mh = PRE ? rest_height_pre(rb, n_box, around6(-lx), around6(-ly), around6(lx + x), around6(ly + y))
+                            : rest_height_c(ev->box, 0, n_box, 1, lx, ly, lx + x, ly + y);
             if (mh < 0) mh = 0.0;
             if (mh + z - 1e-6 > p.H) chk = false;
             if (!chk) feas = false;
@@ -702,8 +740,13 @@ int continuous_launch(pct_env_batch *h, int mode, const void *actions, int actio
     cfg.gridDim = dim3(p.n_envs); cfg.blockDim = dim3(32);
     cudaLaunchKernelEx(&cfg, pctc_candidates_kernel, p);
     cfg.blockDim = dim3(64);
-    if (p.obs_f64) { if (stab) cudaLaunchKernelEx(&cfg, pctc_feas_emit_kernel<double, true>, p); else cudaLaunchKernelEx(&cfg, pctc_feas_emit_kernel<double, false>, p); }
-    else { if (stab) cudaLaunchKernelEx(&cfg, pctc_feas_emit_kernel<float, true>, p); else cudaLaunchKernelEx(&cfg, pctc_feas_emit_kernel<float, false>, p); }
+    if (h->cont_pre) {
+        if (p.obs_f64) { if (stab) cudaLaunchKernelEx(&cfg, pctc_feas_emit_kernel<double, true, true>, p); else cudaLaunchKernelEx(&cfg, pctc_feas_emit_kernel<double, false, true>, p); }
+        else { if (stab) cudaLaunchKernelEx(&cfg, pctc_feas_emit_kernel<float, true, true>, p); else cudaLaunchKernelEx(&cfg, pctc_feas_emit_kernel<float, false, true>, p); }
+    } else {
+        if (p.obs_f64) { if (stab) cudaLaunchKernelEx(&cfg, pctc_feas_emit_kernel<double, true, false>, p); else cudaLaunchKernelEx(&cfg, pctc_feas_emit_kernel<double, false, false>, p); }
+        else { if (stab) cudaLaunchKernelEx(&cfg, pctc_feas_emit_kernel<float, true, false>, p); else cudaLaunchKernelEx(&cfg, pctc_feas_emit_kernel<float, false, false>, p); }
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { h->err = std::string("continuous launch: ") + cudaGetErrorString(e); return PCT_ERR_CUDA; }
     h->launches += 2;  // the caller counts one

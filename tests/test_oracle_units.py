@@ -99,3 +99,20 @@ def test_hull_and_pip_match_reference_module():
             q = np.array([rng.randint(0, 20) / 2.0, rng.randint(0, 20) / 2.0]) if rng.rand() < 0.5 else rng.uniform(0, 10, 2)
             got = L.pcto_pip(q[0], q[1], np.ascontiguousarray(want).ctypes.data_as(C.POINTER(C.c_double)), m)
             assert bool(got) == bool(point_in_polygen(q, want.tolist()))
+
+
+def test_around6_commutes_with_min():
+    """The identity behind the opt-in pre-rounded resting-height loop of the continuous feasibility kernel
+    (csrc/pct_continuous.cu rest_height_pre): around6(v) = rint(v * 1e6) / 1e6 is monotone, hence
+    around6(min(a, b)) == min(around6(a), around6(b)) bit for bit — checked on random, nearly equal and half-way operands."""
+    rng = np.random.default_rng(5)
+    r6 = lambda v: np.rint(v * 1e6) / 1e6
+    a = rng.uniform(-3, 3, 400000)
+    pairs = [(a, rng.uniform(-3, 3, a.size)), (a, a + rng.uniform(-2e-6, 2e-6, a.size)), (a, np.nextafter(a, 9.0)), (a, np.nextafter(a, -9.0))]
+    k = rng.integers(-3000000, 3000000, a.size).astype(np.float64)
+    half = (k + 0.5) / 1e6  # operands around the rounding boundaries
+    pairs += [(half, np.nextafter(half, 9.0)), (half, np.nextafter(half, -9.0)), (half, half + rng.uniform(-1e-9, 1e-9, a.size)), (-half, half)]
+    for x, y in pairs:
+        lhs, rhs = r6(np.minimum(x, y)), np.minimum(r6(x), r6(y))
+        assert np.array_equal(lhs, rhs)
+        assert np.all(np.diff(r6(np.sort(x))) >= 0)  # monotone
