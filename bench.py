@@ -311,7 +311,9 @@ def run_ours(a):
                            "flushed between steps (256 MiB memset outside the timed interval)",
                            "mean_boxes": mean_boxes, "mean_valid_leaves": mean_leaf, "mean_candidates": mean_cand},
                 "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                        "steps": Ke, "path": "pct_step_host (C ABI, pinned host buffers, 4 pipelined env ranges) + numpy policy on the host from the returned step records"},
+                        "steps": Ke, "path": ("pct_step_host (C ABI, pinned host buffers, zero-copy: kernels write the observation into the mapped host buffer)"
+                                 if os.environ.get("PCT_B200_HOST_ZEROCOPY", "0") != "0" else
+                                 "pct_step_host (C ABI, pinned host buffers, 4 pipelined env ranges)") + " + numpy policy on the host from the returned step records"},
                 "gpu_launches": int(launches), "kernel_ms_per_step": kern_ms / K,
                 "ms_per_step_p50": per_step[K // 2], "ms_per_step_p99": per_step[min(K - 1, int(K * 0.99))], "wall_s_timed_loop": wall,
                 "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,

@@ -92,6 +92,7 @@ int pct_create(const pct_config *cfg, int32_t n_envs, int32_t device, pct_handle
     if (const char *ov = getenv("PCT_B200_OVERLAP")) h->overlap = atoi(ov) != 0;
     if (const char *ov = getenv("PCT_B200_OVERLAP_CONT")) h->overlap_cont = atoi(ov) != 0;
     if (const char *pv = getenv("PCT_B200_CONT_PRE")) h->cont_pre = atoi(pv) != 0;
+    if (const char *zv = getenv("PCT_B200_HOST_ZEROCOPY")) h->host_zero_copy = atoi(zv) != 0;
     h->groups = 1;  // PCT_B200_GROUPS > 1 splits the batch over internal streams (measured: no gain)
     if (const char *gv = getenv("PCT_B200_GROUPS")) h->groups = atoi(gv);
     h->host_groups = 4;
@@ -315,6 +316,28 @@ int pct_step_host(pct_handle h, const void *h_actions, int32_t action_f64, const
     rc = check_item_source(h);
     if (rc) return rc;
     const size_t osz = h->cfg.obs_dtype == PCT_F64 ? 8 : 4, asz = action_f64 ? 8 : 4;
+    if (h->host_zero_copy) {
+        // Zero-copy observation delivery (opt-in, PCT_B200_HOST_ZEROCOPY=1): when h_obs is pinned (mapped under UVA) the feasibility
+        // kernel writes every env's observation straight into it over PCIe as that env finishes — no staging copy after the kernels
+        // and no env-range pipeline; the whole batch runs as ONE launch sequence (overlapped mode, heaviest-env-first order).  The
+        // observation is write-only for the kernels.  Actions and the small reward / done / info records keep their staged copies
+        // (info is read back by the kernels).  Unpinned h_obs: the staged path below.
+        void *obs_alias = nullptr;
+        if (cudaHostGetDevicePointer(&obs_alias, h_obs, 0) == cudaSuccess && obs_alias) {
+            cudaStream_t st = h->own_stream;
+            const size_t n = (size_t)h->n_envs;
+            if (h_actions) CK(h, cudaMemcpyAsync(h->d_act, h_actions, n * 9 * asz, cudaMemcpyHostToDevice, st));
+            else CK(h, cudaMemcpyAsync(h->d_idx, h_leaf_idx, n * 4, cudaMemcpyHostToDevice, st));
+            rc = launch(h, 1, h_actions ? h->d_act : nullptr, action_f64, h_actions ? nullptr : h->d_idx, obs_alias, h->d_rew, h->d_done, h->d_info, st);
+            if (rc) return rc;
+            CK(h, cudaMemcpyAsync(h_reward, h->d_rew, n * 4, cudaMemcpyDeviceToHost, st));
+            CK(h, cudaMemcpyAsync(h_done, h->d_done, n, cudaMemcpyDeviceToHost, st));
+            if (h_info) CK(h, cudaMemcpyAsync(h_info, h->d_info, n * sizeof(pct_step_info), cudaMemcpyDeviceToHost, st));
+            CK(h, cudaStreamSynchronize(st));
+            return PCT_OK;
+        }
+        (void)cudaGetLastError();  // not a mapped host pointer
+    }
     // Software pipeline over env ranges: range g's device->host copies overlap the kernels of range g+1 (envs are
     // independent, so the ranges need no ordering between them).  Host buffers should be pinned.
     const int G = (h->cfg.domain == PCT_DISCRETE && h->n_envs >= 1024) ? h->host_groups : 1;
