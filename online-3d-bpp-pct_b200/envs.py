@@ -84,6 +84,9 @@ class _PackingBase(object):
             # LoadBoxCreator (binCreator.py:41-72): one trajectory per episode (reset() pre-increments the index, so
             # trajectory 0 is never used), each followed by the [100,100,100] sentinel that ends the episode.
             trajs = [np.array(t, dtype=np.float64) for t in torch.load(data_name)][1:]
+            if self._continuous:  # test mode rounds the item sizes to 3 decimals (C:bin3D.py:84-87)
+                from .evaluation import round3
+                trajs = round3(trajs)
             traj_len = max(len(t) for t in trajs) + 1
             seq = np.full((len(trajs), traj_len, 4), 100.0)
             seq[:, :, 3] = 1.0
@@ -146,8 +149,9 @@ class _PackingBase(object):
     @property
     def packed(self):
         b = self._state()["boxes"]
-        conv = (lambda v: v) if self._continuous else int
-        return [[conv(r[3] - r[0]), conv(r[4] - r[1]), conv(r[5] - r[2]), conv(r[0]), conv(r[1]), conv(r[2]), 0] for r in b]
+        if self._continuous:  # the state dump holds lo / hi corners; item sizes carry <= 6 decimals, so rounding the differences returns them
+            return [[float(np.round(r[3] - r[0], 6)), float(np.round(r[4] - r[1], 6)), float(np.round(r[5] - r[2], 6)), r[0], r[1], r[2], 0] for r in b]
+        return [[int(r[3] - r[0]), int(r[4] - r[1]), int(r[5] - r[2]), int(r[0]), int(r[1]), int(r[2]), 0] for r in b]
 
     @property
     def next_box(self):

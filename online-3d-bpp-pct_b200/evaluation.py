@@ -27,6 +27,19 @@ def load_trajectories(data):
     return [np.asarray(t, dtype=np.float64).reshape(len(t), -1) for t in data]
 
 
+def round3(trajs):
+    """PackingContinuous in test mode rounds every item size to 3 decimals with Python's round (C:bin3D.py:84-87); the density
+    column is left alone.  Applied on the host when the streams are built, so the kernels see what the reference env sees."""
+    out = []
+    for t in trajs:
+        t = np.array(t, dtype=np.float64)
+        for r in t:
+            for i in range(3):
+                r[i] = round(float(r[i]), 3)
+        out.append(t)
+    return out
+
+
 def first_leaf_policy(obs, batch):
     """Deterministic stand-in policy: the first leaf row (index 0), i.e. the first feasible candidate in reference order."""
     return torch.zeros((obs.shape[0],), dtype=torch.int32, device=obs.device)
@@ -63,6 +76,8 @@ def evaluate_batched(data, setting, policy=None, container_size=(10, 10, 10), it
     if not 0 < episodes <= len(trajs) - 1:
         raise ValueError("episodes must be in 1..len(dataset)-1 (the reference raises IndexError past the end)")
     n = max(1, min(int(n_envs), episodes))
+    if continuous:
+        trajs = round3(trajs)
     stream, traj_len, quota = _streams(trajs, episodes, n)
     policy = first_leaf_policy if policy is None else policy
     size_minimum = None
@@ -102,7 +117,10 @@ def evaluate_batched(data, setting, policy=None, container_size=(10, 10, 10), it
             c = int(counter[e])
             items, vol = [], 0.0
             for r in rows[k, :c]:
-                x, y, z = conv(r[3] - r[0]), conv(r[4] - r[1]), conv(r[5] - r[2])
+                if continuous:  # rows hold lo / hi corners; the sizes carry 3 decimals, so rounding the differences returns them exactly
+                    x, y, z = float(np.round(r[3] - r[0], 6)), float(np.round(r[4] - r[1], 6)), float(np.round(r[5] - r[2], 6))
+                else:
+                    x, y, z = conv(r[3] - r[0]), conv(r[4] - r[1]), conv(r[5] - r[2])
                 items.append([x, y, z, conv(r[0]), conv(r[1]), conv(r[2]), 0])  # D:bin3D.py:177-178
                 vol += x * y * z  # Space.get_ratio (D:space.py:334-339)
             packed[ep], ratio[ep], length[ep] = items, vol / binvol, c

@@ -88,3 +88,37 @@ def test_single_env_facade_replays_reference_evaluation(path, tmp_path):
     assert np.allclose([r[0] for r in rec], ratio[:8], rtol=0, atol=1e-15)
     assert [r[2] for r in rec] == packed[:8]
     env.close()
+
+
+# ---- continuous env (PackingContinuous in test mode: items rounded to 3 decimals, C:bin3D.py:84-87) ------------------------
+GOLDEN_C = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "eval_cont_s*.npz")))
+
+
+def _round3(t):
+    """what the continuous env does to a dataset item in test mode: Python round(v, 3) per size; the density column is untouched"""
+    out = np.array(t, dtype=np.float64)
+    for r in out:
+        for i in range(3):
+            r[i] = round(float(r[i]), 3)
+    return out
+
+
+def test_golden_continuous_present():
+    assert len(GOLDEN_C) == 3
+
+
+@pytest.mark.parametrize("path", GOLDEN_C)
+def test_oracle_replays_reference_evaluation_continuous(path):
+    from pct_oracle import OracleContinuous
+    setting, data, ratio, counter, packed = _golden(path)
+
+    def make_env(ep):
+        t = _round3(data[ep + 1])
+        s = np.concatenate([t if t.shape[1] == 4 else np.concatenate([t, np.ones((len(t), 1))], 1), [[100, 100, 100, 1.0]] * 2])
+        env = OracleContinuous(setting, stream=s)
+        return env, env.reset()
+
+    rec = sequential_eval(make_env, len(ratio))
+    assert [r[1] for r in rec] == counter.tolist()
+    assert [r[0] for r in rec] == ratio.tolist()
+    assert [r[2] for r in rec] == packed

@@ -73,3 +73,44 @@ def test_gpu_replays_reference_record_continuous(path):
                                      internal_node_holder=c["nb"], leaf_node_holder=c["nl"], item_stream=g["stream"][None], size_minimum=c["low"])
     _replay(env, g, False)  # the facade sums get_ratio with numpy, the reference with reduce(): last-bit differences allowed on the scalars
     env.close()
+
+
+# ---- dataset evaluation on the continuous env (records of the reference's own loop: tests/golden/eval_cont_s*.npz) ----------
+EVAL_C = sorted(glob.glob(os.path.join(G, "eval_cont_s*.npz")))
+
+
+def _eval_golden(path):
+    g = np.load(path)
+    off = np.concatenate([[0], np.cumsum(g["packed_len"])])
+    packed = [g["packed_flat"][off[i]:off[i + 1]].tolist() for i in range(len(g["ratio"]))]
+    return int(g["setting"]), g["data"], g["ratio"], g["counter"], packed
+
+
+@pytest.mark.parametrize("path", EVAL_C, ids=[os.path.basename(p) for p in EVAL_C])
+@pytest.mark.parametrize("n_envs", [1, 5])
+def test_batched_evaluation_matches_reference_continuous(path, n_envs):
+    from harness import eval_policy_torch
+    from pct_b200.evaluation import evaluate_batched
+    setting, data, ratio, counter, packed = _eval_golden(path)
+    out = evaluate_batched(list(data), setting, policy=eval_policy_torch, container_size=(1.0, 1.0, 1.0), continuous=True, sample_left_bound=0.1,
+                           n_envs=n_envs)
+    assert out["length"].tolist() == counter.tolist()
+    assert out["packed"] == packed
+    assert out["ratio"].tolist() == ratio.tolist()
+
+
+def test_single_env_facade_replays_reference_evaluation_continuous(tmp_path):
+    """the single-env loop of evaluation_tools.evaluate on the drop-in PackingContinuous(load_test_data=True)"""
+    import pct_b200
+    from harness import sequential_eval
+    setting, data, ratio, counter, packed = _eval_golden(EVAL_C[0])
+    ds = os.path.join(str(tmp_path), "set.pt")
+    torch.save([t.tolist() for t in data], ds)
+    env = pct_b200.PackingContinuous(setting=setting, container_size=[1, 1, 1], item_set=None, data_name=ds, load_test_data=True,
+                                     internal_node_holder=80, leaf_node_holder=50, shuffle=False, sample_from_distribution=True,
+                                     sample_left_bound=0.1, sample_right_bound=0.5)
+    rec = sequential_eval(lambda ep: (env, env.reset()), 5)
+    assert [r[1] for r in rec] == counter[:5].tolist()
+    assert [r[2] for r in rec] == packed[:5]
+    assert np.allclose([r[0] for r in rec], ratio[:5], rtol=0, atol=1e-12)
+    env.close()
