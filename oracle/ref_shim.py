@@ -149,3 +149,26 @@ def make_stream_creator(module, items):
             self.pos += 1
 
     return StreamCreator(items)
+
+
+def load_policy_module():
+    """The reference's policy network (model.DRL_GAT over attention_model.AttentionModel), unmodified except for the ONE in-memory
+    line Python >= 3.8 needs (SURVEY.md Appendix A.4: `super()` inside a NamedTuple body raises at class creation;
+    attention_model.py:25 becomes `return tuple.__getitem__(self, key)`).  No reference file is edited or copied."""
+    import importlib
+    load_reference()
+    if "attention_model" not in sys.modules:
+        path = os.path.join(REFERENCE_ROOT, "attention_model.py")
+        src = open(path).read().replace("return super(AttentionModelFixed, self).__getitem__(key)", "return tuple.__getitem__(self, key)")
+        mod = types.ModuleType("attention_model")
+        mod.__file__ = path
+        argv, sys.argv = sys.argv, sys.argv[:1]  # tools.py parses sys.argv in get_args(); importing it must not see pytest's flags
+        try:
+            sys.modules["attention_model"] = mod
+            exec(compile(src, path, "exec"), mod.__dict__)
+        except Exception:
+            sys.modules.pop("attention_model", None)
+            raise
+        finally:
+            sys.argv = argv
+    return importlib.import_module("model"), importlib.import_module("tools")
