@@ -93,6 +93,8 @@ int pct_create(const pct_config *cfg, int32_t n_envs, int32_t device, pct_handle
     if (const char *ov = getenv("PCT_B200_OVERLAP_CONT")) h->overlap_cont = atoi(ov) != 0;
     if (const char *pv = getenv("PCT_B200_CONT_PRE")) h->cont_pre = atoi(pv) != 0;
     if (const char *zv = getenv("PCT_B200_HOST_ZEROCOPY")) h->host_zero_copy = atoi(zv) != 0;
+    if (const char *dv = getenv("PCT_B200_OBS_DELTA")) h->obs_delta = atoi(dv) != 0;
+    if (h->obs_delta && e == cudaSuccess) e = cudaMalloc(&h->d_obs_prev, sizeof(int32_t) * 2 * (size_t)n_envs);
     h->groups = 1;  // PCT_B200_GROUPS > 1 splits the batch over internal streams (measured: no gain)
     if (const char *gv = getenv("PCT_B200_GROUPS")) h->groups = atoi(gv);
     h->host_groups = 4;
@@ -141,7 +143,7 @@ void pct_destroy(pct_handle h) {
     cudaSetDevice(h->device);
     if (h->cfg.domain == PCT_CONTINUOUS) continuous_destroy(h);
     cudaFree(h->d_order);
-    cudaFree(h->d_hstate); cudaFree(h->d_hstate_c); cudaFree(h->d_query_c); cudaFree(h->d_query);
+    cudaFree(h->d_hstate); cudaFree(h->d_hstate_c); cudaFree(h->d_query_c); cudaFree(h->d_query); cudaFree(h->d_obs_prev);
     cudaFree(h->d_ready);
     cudaFree(h->d_hot); cudaFree(h->d_cold); cudaFree(h->d_item_set); cudaFree(h->d_stream);
     cudaFree(h->d_obs); cudaFree(h->d_act); cudaFree(h->d_idx); cudaFree(h->d_rew); cudaFree(h->d_done); cudaFree(h->d_info);
@@ -186,6 +188,14 @@ int pct_set_trajectory_length(pct_handle h, int32_t traj_len) {
 }
 
 // enqueue reset / step of the env range [off, off + cnt) on stream `gs`; all buffer pointers are BASE pointers
+// Delta observation writes: called once per reset / step with the caller's observation buffer.  A buffer other than the one the
+// previous call wrote may hold anything, so its row counts are reset to "all rows" (by the launches of this step, on their streams).
+static void begin_obs(pct_handle h, const void *obs) {
+    if (!h->obs_delta) return;
+    h->fill_pending = obs != h->tracked_obs;
+    h->tracked_obs = obs;
+}
+
 static int launch_range(pct_handle h, int mode, int off, int cnt, const void *actions, int action_f64, const int32_t *leaf_idx, void *obs,
                         float *rew, uint8_t *done, pct_step_info *info, cudaStream_t gs, bool whole_batch) {
     const size_t osz = h->cfg.obs_dtype == PCT_F64 ? 8 : 4, asz = action_f64 ? 8 : 4;
@@ -211,6 +221,10 @@ static int launch_range(pct_handle h, int mode, int off, int cnt, const void *ac
     if (h->overlap && !h->prof_on && cap == cudaStreamCaptureStatusNone) {
         p.ready = h->d_ready + 2 * (size_t)off;
         p.epoch = ++h->epoch;
+    }
+    if (h->obs_delta && h->d_obs_prev) {
+        if (h->fill_pending) launch_fill_prev(h->d_obs_prev + 2 * (size_t)off, cnt, p.nb, p.nl, gs);
+        p.obs_prev = h->d_obs_prev + 2 * (size_t)off;
     }
     cudaEvent_t *prof = nullptr;
     if (h->prof_on && mode == 1 && whole_batch) {
@@ -241,6 +255,7 @@ static int launch(pct_handle h, int mode, const void *actions, int action_f64, c
     int rc = check_item_source(h);
     if (rc) return rc;
     CK(h, cudaSetDevice(h->device));
+    begin_obs(h, obs);
     if (h->cfg.domain == PCT_CONTINUOUS) {
         rc = continuous_launch(h, mode, actions, action_f64, leaf_idx, obs, rew, done, info, st);
         if (rc == PCT_OK) h->launches++;
@@ -262,6 +277,7 @@ static int launch(pct_handle h, int mode, const void *actions, int action_f64, c
             CK(h, cudaStreamWaitEvent(st, h->ev_join[gi], 0));
         }
     }
+    h->fill_pending = false;
     return PCT_OK;
 }
 
@@ -341,6 +357,7 @@ int pct_step_host(pct_handle h, const void *h_actions, int32_t action_f64, const
     // Software pipeline over env ranges: range g's device->host copies overlap the kernels of range g+1 (envs are
     // independent, so the ranges need no ordering between them).  Host buffers should be pinned.
     const int G = (h->cfg.domain == PCT_DISCRETE && h->n_envs >= 1024) ? h->host_groups : 1;
+    if (G > 1) begin_obs(h, h->d_obs);  // G == 1 goes through launch(), which does it
     for (int gi = 0; gi < G; gi++) {
         const int off = (int)((int64_t)h->n_envs * gi / G), cnt = (int)((int64_t)h->n_envs * (gi + 1) / G) - off;
         if (cnt <= 0) continue;
@@ -355,6 +372,7 @@ int pct_step_host(pct_handle h, const void *h_actions, int32_t action_f64, const
         CK(h, cudaMemcpyAsync(h_done + off, h->d_done + off, (size_t)cnt, cudaMemcpyDeviceToHost, st));
         if (h_info) CK(h, cudaMemcpyAsync(h_info + off, h->d_info + off, (size_t)cnt * sizeof(pct_step_info), cudaMemcpyDeviceToHost, st));
     }
+    h->fill_pending = false;
     for (int gi = 0; gi < G; gi++) CK(h, cudaStreamSynchronize(gi == 0 ? h->own_stream : h->sub[gi]));
     return PCT_OK;
 }

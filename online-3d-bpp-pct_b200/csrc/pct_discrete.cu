@@ -643,6 +643,59 @@ __device__ __noinline__ void write_obs(const DParams &p, int e, const DEnvHot *h
     }
 }
 
+// Delta variant (opt-in, PCT_B200_OBS_DELTA=1): the caller hands back the SAME observation buffer every step, and prev[0] / prev[1]
+// hold how many internal / leaf rows of it may be non-zero.  75 % of the (NB + NL + 1) x 9 observation is zero padding, so only the
+// rows below max(now, prev) and the next-item row are written (and prev is updated); every other row is zero already.  The written
+// values are the ones write_obs computes.  The host resets prev to {NB, NL} whenever the buffer changes.
+template <typename OT>
+__device__ __noinline__ void write_obs_delta(const DParams &p, int e, const DEnvHot *hot, const DEnvCold *cold, const int16_t (*leaf)[6], int n_leaf,
+                                             int tid, int nthreads) {
+    OT *obs = (OT *)p.obs + (size_t)e * (size_t)((p.nb + p.nl + 1) * 9);
+    int32_t *prev = p.obs_prev + 2 * (size_t)e;
+    const int n_box = hot->h.n_box;
+    const int pb = min(prev[0], p.nb), pl = min(prev[1], p.nl);
+    __syncthreads();  // every thread has read prev before thread 0 replaces it below
+    const int wb = max(max(n_box, pb), 1), wl = max(n_leaf, pl);  // row 0 always carries its valid flag (D:space.py:294-295)
+    int s0 = hot->h.next_box[0], s1 = hot->h.next_box[1], s2 = hot->h.next_box[2];
+    if (s1 < s0) { int t = s0; s0 = s1; s1 = t; }
+    if (s2 < s1) { int t = s1; s1 = s2; s2 = t; }
+    if (s1 < s0) { int t = s0; s0 = s1; s1 = t; }
+    const OT den = (OT)hot->h.next_den;
+    const bool s3 = p.setting == 3;
+    const int total = (wb + wl + 1) * 9;
+#pragma unroll 1
+    for (int f = tid; f < total; f += nthreads) {
+        const int r = f / 9, col = f - r * 9;
+        OT v = 0;
+        int row;
+        if (r < wb) {
+            row = r;
+            if (row < n_box) {
+                if (col < 6) v = (OT)hot->box[row][col];
+                else if (col == 6) v = s3 ? (OT)cold->density[row] : (OT)1;
+                else if (col == 8) v = 1;
+            } else if (row == 0 && col == 8) v = 1;
+        } else if (r < wb + wl) {
+            const int k = r - wb;
+            row = p.nb + k;
+            if (k < n_leaf) {
+                if (col < 5) v = (OT)leaf[k][col];
+                else if (col == 5) v = (OT)p.H;
+                else if (col == 8) v = 1;
+            }
+        } else {
+            row = p.nb + p.nl;
+            if (col == 0) v = den;
+            else if (col == 3) v = (OT)s0;
+            else if (col == 4) v = (OT)s1;
+            else if (col == 5) v = (OT)s2;
+            else if (col == 8) v = 1;
+        }
+        obs[row * 9 + col] = v;
+    }
+    if (tid == 0) { prev[0] = max(n_box, 1); prev[1] = n_leaf; }
+}
+
 // ======================================================================================================
 // The step is a pipeline of three kernels (plus the optional synthetic-policy kernel).  A monolithic
 // one-warp-per-env kernel was measured first (profiles/r1_monolithic_*.txt): it was instruction-fetch bound
@@ -953,7 +1006,7 @@ constexpr int FEAS_WARPS = FEAS_WARPS_N;
 constexpr int FEAS_THREADS = 32 * FEAS_WARPS;
 constexpr int K3_SMEM = sizeof(DEnvHot) + NL_MAX * 12 + 64 + EDGE_STAGE * 32 + POLY_STAGE * 16;
 
-template <typename OT, bool STAB, typename SlotT>
+template <typename OT, bool STAB, typename SlotT, bool DELTA = false>
 __global__ void __launch_bounds__(FEAS_THREADS, K3_MINB) pct_feas_emit_kernel(const DParams p) {
     constexpr int BITS = sizeof(SlotT) == 2 ? 4 : 8;
     __shared__ __align__(16) unsigned char sm[K3_SMEM];
@@ -1077,7 +1130,8 @@ __global__ void __launch_bounds__(FEAS_THREADS, K3_MINB) pct_feas_emit_kernel(co
         }
     }
     // ---------------- cur_observation (D:bin3D.py:70-93) ----------------
-    write_obs<OT>(p, e, hot, cold, leaf, n_leaf, tid, FEAS_THREADS);
+    if constexpr (DELTA) write_obs_delta<OT>(p, e, hot, cold, leaf, n_leaf, tid, FEAS_THREADS);
+    else write_obs<OT>(p, e, hot, cold, leaf, n_leaf, tid, FEAS_THREADS);
     if (tid == 0) KT_END(p.env_id_base + e - p.env_id_base0, 2);
 }
 
@@ -1119,6 +1173,14 @@ __global__ void pct_policy_random_kernel(const DEnvHot *hot, int n_envs, int64_t
     leaf_idx[e] = n > 0 ? (int32_t)(rnd_u64(seed, (uint64_t)(env_id_base + e), (uint64_t)t) % (uint64_t)n) : 0;
 }
 
+__global__ void pct_fill_prev_kernel(int32_t *prev, int n2, int nb, int nl) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n2) prev[i] = (i & 1) ? nl : nb;
+}
+void launch_fill_prev(int32_t *prev, int n_envs, int nb, int nl, cudaStream_t st) {
+    pct_fill_prev_kernel<<<(2 * n_envs + 255) / 256, 256, 0, st>>>(prev, 2 * n_envs, nb, nl);
+}
+
 // ---- launchers ---------------------------------------------------------------------------------------------
 template <typename K>
 static cudaError_t set_smem(K kernel, size_t smem) {
@@ -1152,14 +1214,16 @@ static cudaError_t launch_t(const DParams &p, cudaStream_t st, cudaEvent_t *prof
         cudaError_t err = cudaLaunchKernelEx(&cfg, pct_candidates_kernel<SlotT, BIGSM>, p);
         if (err != cudaSuccess) return err;
         cfg.gridDim = dim3(p.n_envs); cfg.blockDim = dim3(FEAS_THREADS); cfg.dynamicSmemBytes = 0;
-        err = cudaLaunchKernelEx(&cfg, pct_feas_emit_kernel<OT, STAB, SlotT>, p);
+        err = p.obs_prev ? cudaLaunchKernelEx(&cfg, pct_feas_emit_kernel<OT, STAB, SlotT, true>, p)
+                         : cudaLaunchKernelEx(&cfg, pct_feas_emit_kernel<OT, STAB, SlotT>, p);
         if (err == cudaSuccess && p.order) pct_order_kernel<<<1, 1024, 0, st>>>(p.hot, p.n_envs, p.order, 0);
         return err != cudaSuccess ? err : cudaGetLastError();
     }
     if (prof) cudaEventRecord(prof[1], st);
     pct_candidates_kernel<SlotT, BIGSM><<<blocks, 32 * WARPS_PER_BLOCK, smem2, st>>>(p);
     if (prof) cudaEventRecord(prof[2], st);
-    pct_feas_emit_kernel<OT, STAB, SlotT><<<p.n_envs, FEAS_THREADS, 0, st>>>(p);
+    if (p.obs_prev) pct_feas_emit_kernel<OT, STAB, SlotT, true><<<p.n_envs, FEAS_THREADS, 0, st>>>(p);
+    else pct_feas_emit_kernel<OT, STAB, SlotT><<<p.n_envs, FEAS_THREADS, 0, st>>>(p);
     if (p.order) pct_order_kernel<<<1, 1024, 0, st>>>(p.hot, p.n_envs, p.order, 0);
     if (prof) cudaEventRecord(prof[3], st);
     return cudaGetLastError();

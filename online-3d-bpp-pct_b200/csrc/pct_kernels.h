@@ -135,7 +135,14 @@ struct DParams {
     int mode;  // 0 = reset all, 1 = step
     int keep_draw;      // mode 0: continue the item source instead of rewinding it (env.reset() after an episode)
     int no_auto_reset;  // mode 1: leave a finished env untouched (gym.Env semantics)
-    long long *dbg;  // phase timers (only with -DPCT_PHASE_TIMERS)
+    // One pointer slot, two exclusive users (keeps sizeof(DParams), and with it the code of the default kernels, unchanged):
+    //   dbg      phase timers (only in -DPCT_PHASE_TIMERS builds)
+    //   obs_prev delta observation writes (opt-in, production builds): [2 * n_envs] rows of the caller's observation buffer that may be
+    //            non-zero (internal, leaf); nullptr = write the whole observation
+    union {
+        long long *dbg;
+        int32_t *obs_prev;
+    };
     int32_t *order;  // [2 * n_envs] block -> env permutations (apply, feas_emit), nullptr = identity
     int32_t *ready;  // [2 * n_envs] per-env hand-over flags (apply -> candidates, candidates -> feas_emit); nullptr = kernels run back to back
     int32_t epoch;   // value published in `ready` by this launch
@@ -164,6 +171,9 @@ struct HParamsC {
 constexpr int PCT_H_QUERY_ = 7;
 constexpr int HEUR_SIDE_MAX = 32;  // height-map based codes (HM, MACS, RANDOM's bitmap, queries): W, L <= 32
 cudaError_t launch_heuristic_discrete(const DParams &p, const HParams &hp, cudaStream_t st);
+
+// delta observation writes: prev[2i] = nb, prev[2i+1] = nl for n entries ("every row of the buffer may be non-zero")
+void launch_fill_prev(int32_t *prev, int n_envs, int nb, int nl, cudaStream_t st);
 
 int discrete_kernels_per_step();
 cudaError_t launch_discrete(const DParams &p, cudaStream_t st, cudaEvent_t *prof = nullptr);
