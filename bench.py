@@ -309,7 +309,8 @@ def run_ours(a):
                            "policy": "uniform over valid leaves (device kernel)", "launch_mode": os.environ.get("PCT_B200_OVERLAP", "1") != "0" and
                            "overlapped (PDL + per-env flags)" or "back-to-back kernels", "l2": "not flushed (diagnostic)" if a.no_flush else
                            "flushed between steps (256 MiB memset outside the timed interval)",
-                           "mean_boxes": mean_boxes, "mean_valid_leaves": mean_leaf, "mean_candidates": mean_cand},
+                           "mean_boxes": mean_boxes, "mean_valid_leaves": mean_leaf, "mean_candidates": mean_cand,
+                           "switches": {k: v for k, v in sorted(os.environ.items()) if k.startswith("PCT_B200_")}},
                 "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "steps": Ke, "path": ("pct_step_host (C ABI, pinned host buffers, zero-copy: kernels write the observation into the mapped host buffer)"
                                  if os.environ.get("PCT_B200_HOST_ZEROCOPY", "0") != "0" else
