@@ -193,7 +193,7 @@ def run_ours(a):
     torch.cuda.synchronize()
 
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
-    stats = torch.zeros((3,), dtype=torch.float64, device=dev)  # sums of counter, n_leaf, n_cand
+    stats = torch.zeros((4,), dtype=torch.float64, device=dev)  # sums of counter, n_leaf, n_cand, n_ems
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
@@ -210,7 +210,7 @@ def run_ours(a):
         _, _, _, info = batch.step(leaf_idx=idx)
         ev[t][2].record()
         if t % 16 == 0:
-            stats += torch.stack([info[:, 0].double().mean(), info[:, 5].double().mean(), info[:, 6].double().mean()])
+            stats += torch.stack([info[:, 0].double().mean(), info[:, 5].double().mean(), info[:, 6].double().mean(), info[:, 7].double().mean()])
     barrier()
     wall = time.perf_counter() - t_wall0
     launches = batch.kernel_launches - l0
@@ -237,7 +237,7 @@ def run_ours(a):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     step_ms, kern_ms = float(tt[0]), float(tt[1])
     nsamp = len(range(0, K, 16))
-    mean_boxes, mean_leaf, mean_cand = [float(x) / nsamp for x in stats.cpu()]
+    mean_boxes, mean_leaf, mean_cand, mean_ems = [float(x) / nsamp for x in stats.cpu()]
     value = world * n * K / (step_ms * 1e-3)
 
     # ---- e2e: host buffers through pct_step_host, host policy on the returned observation ----
@@ -309,7 +309,7 @@ def run_ours(a):
                            "policy": "uniform over valid leaves (device kernel)", "launch_mode": os.environ.get("PCT_B200_OVERLAP", "1") != "0" and
                            "overlapped (PDL + per-env flags)" or "back-to-back kernels", "l2": "not flushed (diagnostic)" if a.no_flush else
                            "flushed between steps (256 MiB memset outside the timed interval)",
-                           "mean_boxes": mean_boxes, "mean_valid_leaves": mean_leaf, "mean_candidates": mean_cand,
+                           "mean_boxes": mean_boxes, "mean_ems": mean_ems, "mean_valid_leaves": mean_leaf, "mean_candidates": mean_cand,
                            "switches": {k: v for k, v in sorted(os.environ.items()) if k.startswith("PCT_B200_")}},
                 "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "steps": Ke, "path": ("pct_step_host (C ABI, pinned host buffers, zero-copy: kernels write the observation into the mapped host buffer)"
