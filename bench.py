@@ -301,6 +301,10 @@ def run_ours(a):
         else:
             k3_ms = None
             ach = b_step * n / (kern_ms / K * 1e-3) / 1e9
+        # SURVEY.md 8(d) / BASELINE.md 3.5 figure for the WHOLE step, independent of this implementation's record layout:
+        # B_step = 5593 + 24 N + 48 E bytes (action, item, boxes, EMS before / after, height map, observation, reward / done)
+        b_survey = 5593.0 + 24.0 * mean_boxes + 48.0 * mean_ems
+        ach_survey = b_survey * n / (kern_ms / K * 1e-3) / 1e9  # per GPU: n envs of this rank over this rank's kernel time
         traffic = ncu_traffic()
         line = {"metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": step_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -324,7 +328,9 @@ def run_ours(a):
                              "kernel_timing": "second pass of %d steps right after the timed region with CUDA events between the three kernels; "
                                               "the events serialise the kernels, the timed region itself runs them overlapped (programmatic "
                                               "dependent launch + per-env hand-over flags), so ms_per_step < sum of these" % ksteps,
-                             "step_fraction_of_peak": b_step * n / (kern_ms / K * 1e-3) / 1e9 / peak},
+                             "step_fraction_of_peak": b_step * n / (kern_ms / K * 1e-3) / 1e9 / peak,
+                             "survey_formula": {"bytes_per_env_step": b_survey, "achieved": ach_survey, "frac": ach_survey / peak,
+                                                "note": "SURVEY 8(d): (5593 + 24 N + 48 E) B x env-steps/s of one GPU / peak, whole step"}},
                 "clocks": clocks}
         if world == 1 and not a.skip_cpu and not a.continuous:
             try:
