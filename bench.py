@@ -123,10 +123,13 @@ def ncu_traffic():
 
 
 # ------------------------------------------------------------------------------------------------------------
-def cpu_port_rate(setting, n_envs, warm, steps, threads=None):
+def cpu_port_rate(setting, n_envs, warm, steps, threads=None, continuous=False):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import pct_oracle  # the ONLY place bench.py touches oracle/: the CPU baseline / reference arm
-    b = pct_oracle.OracleBatch(n_envs, setting, ITEM_SET, ITEM_SEED, POLICY_SEED, threads=threads)
+    if continuous:  # BASELINE config 4: PackingContinuous, sample_from_distribution U(0.1, 0.5), unit container
+        b = pct_oracle.OracleBatchContinuous(n_envs, setting, ITEM_SEED, POLICY_SEED, threads=threads)
+    else:
+        b = pct_oracle.OracleBatch(n_envs, setting, ITEM_SET, ITEM_SEED, POLICY_SEED, threads=threads)
     if warm:
         b.run(warm)
     dt = b.run(steps)
@@ -142,9 +145,10 @@ def run_reference(a):
     n = a.envs_per_gpu * a.gpus  # whole-job workload of the GPU arm, stepped by all host threads
     # bounded sample: the CPU steps at most 8192 envs per vector step
     n_s = min(n, 8192)
-    rate, dt, cores = cpu_port_rate(a.setting, n_s, a.warmup, a.steps)
+    rate, dt, cores = cpu_port_rate(a.setting, n_s, a.warmup, a.steps, continuous=a.continuous)
     line = {"metric": METRIC, "value": rate, "unit": "env-steps/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
-            "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32+f64",
+            "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64" if a.continuous else "int32+f64",
             "data": "synthetic", "impl": "reference",
             "config": {"workload": workload_name(a, a.gpus), "note": "reference's CPU env path: C restatement (oracle/, kind=port; the "
                        "reference itself is pure Python and does not travel to the GPU box), pthreads over envs like ShmemVecEnv workers"},
@@ -332,9 +336,9 @@ def run_ours(a):
                              "survey_formula": {"bytes_per_env_step": b_survey, "achieved": ach_survey, "frac": ach_survey / peak,
                                                 "note": "SURVEY 8(d): (5593 + 24 N + 48 E) B x env-steps/s of one GPU / peak, whole step"}},
                 "clocks": clocks}
-        if world == 1 and not a.skip_cpu and not a.continuous:
+        if world == 1 and not a.skip_cpu:
             try:
-                rate, dt, cores = cpu_port_rate(a.setting, 2048, 20, 300)
+                rate, dt, cores = cpu_port_rate(a.setting, 2048, 20, 300, continuous=a.continuous)
                 line["cpu_baseline"] = {"value": rate, "unit": "env-steps/s", "cores": cores, "kind": "port",
                                         "sample": "2048 envs x 300 vector steps (+20 warm-up), same items / policy"}
             except Exception as ex:  # the oracle is test infrastructure; never fail the GPU number on it

@@ -237,6 +237,49 @@ class OracleBatch(object):
             pass
 
 
+class OracleBatchContinuous(object):
+    """N continuous oracle envs (sample_from_distribution items, C:bin3D.py:103-115) stepped by host threads with the synthetic
+    policy (oracle/pct_oracle_batch_continuous.c): BASELINE config 4 on the host cores."""
+
+    def __init__(self, n_envs, setting, item_seed, policy_seed, container_size=(1.0, 1.0, 1.0), nb=80, nl=50, lo=0.1, hi=0.5, gid_base=0,
+                 threads=None):
+        L = lib()
+        L.pctc_batch_create.restype = C.c_void_p
+        L.pctc_batch_create.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, C.c_double, C.c_double, C.c_uint64,
+                                        C.c_uint64, C.c_int64, C.c_int, C.c_int]
+        L.pctc_batch_run.restype = C.c_double
+        L.pctc_batch_run.argtypes = [C.c_void_p, C.c_int]
+        L.pctc_batch_get.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]
+        L.pctc_batch_destroy.argtypes = [C.c_void_p]
+        self.L = L
+        self.n, self.obs_len = n_envs, (nb + nl + 1) * 9
+        self.threads = threads or os.cpu_count() or 1
+        self.h = L.pctc_batch_create(setting, float(container_size[0]), float(container_size[1]), float(container_size[2]), nb, nl, float(lo),
+                                     float(hi), item_seed, policy_seed, gid_base, n_envs, self.threads)
+
+    def run(self, steps):
+        """returns elapsed seconds for `steps` vector steps"""
+        return self.L.pctc_batch_run(self.h, steps)
+
+    def get(self):
+        obs = np.zeros((self.n, self.obs_len))
+        rew = np.zeros(self.n)
+        nd = np.zeros(self.n, dtype=np.int32)
+        self.L.pctc_batch_get(self.h, _dp(obs), _dp(rew), _ip(nd))
+        return obs, rew, nd
+
+    def close(self):
+        if self.h:
+            self.L.pctc_batch_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class OracleContinuous(object):
     """Single continuous env (pct_envs/PctContinuous0/bin3D.py:8-207), float64 actions, injected item stream."""
 

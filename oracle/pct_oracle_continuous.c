@@ -49,6 +49,7 @@ typedef struct pctc_env {
     double (*ems)[6];
     double *box_vec;
     const double *stream; int stream_len, stream_pos; int have_item;
+    int use_rng; uint64_t rng_seed, rng_gid; double rng_lo, rng_hi; /* sample_from_distribution draws (C:bin3D.py:103-115), counter-based */
     double cur_item[4];
     double next_box[3];
     double next_den;
@@ -408,7 +409,24 @@ static int ems_point(pctc_env *e, const double nb[3], double (*out)[6], int cap)
     return n;
 }
 
+uint64_t pcto_rnd_u64(uint64_t seed, uint64_t a, uint64_t b);
+static double rng_u01(const pctc_env *e, uint64_t salt, uint64_t d) { return (double)(pcto_rnd_u64(e->rng_seed ^ salt, e->rng_gid, d) >> 11) * (1.0 / 9007199254740992.0); }
+static double round3(double v) { return rint(v * 1000.0) / 1000.0; }
 static void creator_generate(pctc_env *e) {
+    if (e->use_rng) { /* the same counter-based draws as the device generator (csrc/pct_continuous.cu draw_item_c) and make_continuous_stream */
+        const uint64_t d = (uint64_t)e->stream_pos;
+        const double lo = e->rng_lo, span = e->rng_hi - e->rng_lo;
+        e->cur_item[0] = round3(lo + span * rng_u01(e, 0x11, d));
+        e->cur_item[1] = round3(lo + span * rng_u01(e, 0x22, d));
+        if (e->setting == 2) e->cur_item[2] = round3(lo + span * rng_u01(e, 0x33, d));
+        else { static const double ch[5] = {0.1, 0.2, 0.3, 0.4, 0.5}; e->cur_item[2] = ch[pcto_rnd_u64(e->rng_seed ^ 0x44, e->rng_gid, d) % 5]; }
+        uint64_t r = pcto_rnd_u64(e->rng_seed ^ 0xABCDEFULL, e->rng_gid, d) >> 11;
+        if (r == 0) r = 1;
+        e->cur_item[3] = (double)r * (1.0 / 9007199254740992.0);
+        e->stream_pos++;
+        e->have_item = 1;
+        return;
+    }
     const double *it = &e->stream[4 * (e->stream_pos % e->stream_len)];
     e->stream_pos++;
     memcpy(e->cur_item, it, sizeof e->cur_item);
@@ -461,6 +479,9 @@ pctc_env *pctc_create(int setting, double W, double L, double H, int nb_holder, 
 }
 void pctc_destroy(pctc_env *e) { free(e->boxes); free(e->up_letter); free(e->ems); free(e->box_vec); free(e); }
 void pctc_set_stream(pctc_env *e, const double *items4, int n) { e->stream = items4; e->stream_len = n; e->stream_pos = 0; }
+void pctc_set_random_sample(pctc_env *e, uint64_t seed, uint64_t gid, double lo, double hi) {
+    e->use_rng = 1; e->rng_seed = seed; e->rng_gid = gid; e->rng_lo = lo; e->rng_hi = hi; e->stream_pos = 0;
+}
 int pctc_obs_len(pctc_env *e) { return (e->nb_holder + e->nl_holder + 1) * 9; }
 
 /* C:bin3D.py:69-75 + C:space.py:281-303 */

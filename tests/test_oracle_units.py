@@ -116,3 +116,27 @@ def test_around6_commutes_with_min():
         lhs, rhs = r6(np.minimum(x, y)), np.minimum(r6(x), r6(y))
         assert np.array_equal(lhs, rhs)
         assert np.all(np.diff(r6(np.sort(x))) >= 0)  # monotone
+
+
+@pytest.mark.parametrize("setting", [1, 2, 3])
+def test_threaded_continuous_batch_equals_single_env_oracle(setting):
+    """oracle/pct_oracle_batch_continuous.c (in-oracle sample_from_distribution draws, synthetic policy, auto-reset, pthreads) against the
+    Python-driven single-env oracle on make_continuous_stream: same final observations, reward sums and episode counts"""
+    from pct_oracle import OracleBatchContinuous, OracleContinuous, make_continuous_stream, policy_pick
+    n, steps, iseed, pseed = 6, 60, 1234, 4321
+    b = OracleBatchContinuous(n, setting, iseed, pseed, threads=3)
+    b.run(25)
+    b.run(steps - 25)  # the step counter of the policy continues across calls
+    obs, rew, nd = b.get()
+    for e in range(n):
+        env = OracleContinuous(setting, stream=make_continuous_stream(iseed, e, 400, setting))
+        o, rs, dn = env.reset(), 0.0, 0
+        for t in range(steps):
+            _, row = policy_pick(o, 80, 50, pseed, e, t)
+            o, r, d, _ = env.step(row)
+            rs += r
+            if d:
+                dn += 1
+                o = env.reset()
+        assert np.array_equal(o, obs[e]) and dn == nd[e] and abs(rs - rew[e]) < 1e-9, e
+    b.close()
