@@ -316,6 +316,10 @@ class OracleContinuous(object):
         self._stream = np.ascontiguousarray(s)
         self.L.pctc_set_stream(self.h, _dp(self._stream), len(self._stream))
 
+    def set_trajectory_length(self, n):
+        self.L.pctc_set_trajectory_length.argtypes = [C.c_void_p, C.c_int]
+        self.L.pctc_set_trajectory_length(self.h, int(n))
+
     def reset(self):
         obs = np.zeros(self.obs_len)
         self.L.pctc_reset(self.h, _dp(obs))

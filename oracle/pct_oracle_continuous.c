@@ -49,6 +49,7 @@ typedef struct pctc_env {
     double (*ems)[6];
     double *box_vec;
     const double *stream; int stream_len, stream_pos; int have_item;
+    int traj_len; /* > 0: LoadBoxCreator.reset discipline, every reset jumps to the next trajectory boundary (C:binCreator.py:51-62) */
     int use_rng; uint64_t rng_seed, rng_gid; double rng_lo, rng_hi; /* sample_from_distribution draws (C:bin3D.py:103-115), counter-based */
     double cur_item[4];
     double next_box[3];
@@ -485,8 +486,10 @@ void pctc_set_random_sample(pctc_env *e, uint64_t seed, uint64_t gid, double lo,
 int pctc_obs_len(pctc_env *e) { return (e->nb_holder + e->nl_holder + 1) * 9; }
 
 /* C:bin3D.py:69-75 + C:space.py:281-303 */
+void pctc_set_trajectory_length(pctc_env *e, int n) { e->traj_len = n; }
 void pctc_reset(pctc_env *e, double *obs) {
     e->have_item = 0;
+    if (e->traj_len > 0 && e->stream_pos % e->traj_len) e->stream_pos += e->traj_len - e->stream_pos % e->traj_len;
     e->n_packed = 0;
     memset(e->box_vec, 0, sizeof(double) * 9 * e->nb_holder);
     e->box_vec[8] = 1;
