@@ -97,3 +97,18 @@ def test_compat_runs_the_unmodified_evaluate(tmp_path):
         trajs = np.load(os.path.join(d, "trajs.npy"), allow_pickle=True)
         outs.append(([[list(map(float, p)) for p in ep] for ep in trajs], open(os.path.join(d, "result.txt")).read()))
     assert outs[0] == outs[1] and len(outs[0][0]) == 5 and outs[0][1].startswith("Evaluation using 5 episodes")
+    # env=None: compat builds the drop-in facade itself from `args` (evaluation.py:27-40); its batch is the oracle-backed stand-in here
+    import importlib
+    from fake_batch import FakeBatch
+    envs_mod = importlib.import_module("pct_b200.envs")
+    real = envs_mod.PctBatch
+    envs_mod.PctBatch = FakeBatch
+    try:
+        work = os.path.join(str(tmp_path), "facade")
+        os.makedirs(work)
+        with pytest.warns(UserWarning, match="shuffle"):
+            d = compat.reference_evaluate(ref_shim.REFERENCE_ROOT, args, policy=policy, custom="facade", work_dir=work)
+    finally:
+        envs_mod.PctBatch = real
+    trajs = np.load(os.path.join(d, "trajs.npy"), allow_pickle=True)
+    assert ([[list(map(float, p)) for p in ep] for ep in trajs], open(os.path.join(d, "result.txt")).read()) == outs[0]
