@@ -28,7 +28,9 @@ class _SpaceView(object):
 
     @property
     def EMS(self):
-        return [np.array(e) for e in self._env._state()["ems"]]
+        # integer rows in the discrete env (D:space.py:298: np.array([0, 0, 0, W, L, H])) — heuristic.py:50,115 slices arrays with them
+        ems = self._env._state()["ems"]
+        return [np.array(e) for e in ems] if self._env._continuous else [np.array(e).astype(np.int64) for e in ems]
 
     @property
     def plain_size(self):

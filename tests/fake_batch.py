@@ -83,6 +83,19 @@ class FakeBatch(object):
                 OH.note_placement(self._hstate[i], c)
         return torch.from_numpy(rows if self.continuous else rows.astype(np.float32))
 
+    def query_placement(self, env, dims, lx, ly, density=1.0, want_map=False):
+        """Space.drop_box_virtual(returnH / returnMap) for one env, like PctBatch.query_placement"""
+        e = self.envs[env]
+        if self.continuous:
+            ok, mh = e.drop_box_virtual(dims, lx, ly)
+            return (ok, mh, None) if want_map else (ok, mh)
+        ok, mh = e.drop_box_virtual(dims, lx, ly)
+        if not want_map:
+            return ok, mh
+        hm = e.plain().copy()
+        hm[int(lx):int(lx) + int(dims[0]), int(ly):int(ly) + int(dims[1])] = mh + int(dims[2])
+        return ok, mh, hm
+
     def state(self, env):
         e = self.envs[env]
         o = self._obs64[env].reshape(-1, 9)

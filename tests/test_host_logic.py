@@ -162,3 +162,70 @@ def test_vec_env_equals_reference_shmem_vecpytorch_monitor(fake, setting, tmp_pa
     finally:
         ref.close()
         ours.close()
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not ref_shim.reference_available(), reason="reference not mounted")
+@pytest.mark.parametrize("name,fn", [("LSAH", "LASH"), ("OnlineBPH", "OnlineBPH"), ("BR", "BR"), ("DBL", "DBL"), ("HM", "heightmap_min"), ("MACS", "MACS")])
+def test_unmodified_heuristic_functions_run_on_the_facade(fake, name, fn, tmp_path):
+    """heuristic.py's own LASH / OnlineBPH / BR / DBL / heightmap_min (unmodified) driving the drop-in PackingDiscrete: every attribute
+    they touch (space.EMS, space.boxes, space.get_ratio, space.drop_box_virtual(returnH / returnMap), next_box get + set, next_den,
+    orientation, bin_size, item_set, step([0, lx, ly]), reset) — episodes equal the records of the same functions on the reference env."""
+    import contextlib
+    import io
+    import sys
+    import pct_b200
+    ref_shim.load_reference()
+    argv, sys.argv = sys.argv, sys.argv[:1]
+    try:
+        H = importlib.import_module("heuristic")
+    finally:
+        sys.argv = argv
+    setting, data, packed = _heur_golden(os.path.join(G, "heur_s1.npz"), name, "data")
+    ds = os.path.join(str(tmp_path), "set.pt")
+    torch.save([t.tolist() for t in data], ds)
+
+    class Recording(pct_b200.PackingDiscrete):
+        def reset(self):
+            if getattr(self, "_played", False):
+                self.log.append([list(p) for p in self.packed])
+            self._played = True
+            return super().reset()
+
+    env = Recording(setting=setting, container_size=[10, 10, 10], item_set=ITEM_SET, data_name=ds, load_test_data=True)
+    env.log = []
+    episodes = 1 if name == "MACS" else 3
+    with contextlib.redirect_stdout(io.StringIO()):
+        getattr(H, fn)(env, episodes)
+    assert env.log[:episodes] == packed[:episodes]
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not ref_shim.reference_available(), reason="reference not mounted")
+@pytest.mark.parametrize("name,fn", [("LSAH", "LASH"), ("OnlineBPH", "OnlineBPH"), ("BR", "BR")])
+def test_unmodified_heuristic_functions_run_on_the_continuous_facade(fake, name, fn):
+    import contextlib
+    import io
+    import sys
+    import pct_b200
+    ref_shim.load_reference()
+    argv, sys.argv = sys.argv, sys.argv[:1]
+    try:
+        H = importlib.import_module("heuristic")
+    finally:
+        sys.argv = argv
+    setting, stream, packed = _heur_golden(os.path.join(G, "heur_cont_s1.npz"), name, "stream")
+
+    class Recording(pct_b200.PackingContinuous):
+        def reset(self):
+            if getattr(self, "_played", False):
+                self.log.append([list(map(float, p)) for p in self.packed])
+            self._played = True
+            return super().reset()
+
+    env = Recording(setting=setting, container_size=[1, 1, 1], item_set=CONT_ITEM_SET, sample_from_distribution=False, item_stream=stream[None],
+                    size_minimum=0.1)
+    env.log = []
+    with contextlib.redirect_stdout(io.StringIO()):
+        getattr(H, fn)(env, 3)
+    assert env.log[:3] == packed[:3]
