@@ -85,6 +85,12 @@ class OracleDiscrete(object):
         self._stream = np.ascontiguousarray(s)
         self.L.pcto_set_stream(self.h, _dp(self._stream), len(self._stream))
 
+    def set_random_items(self, item_set, seed, gid):
+        """RandomBoxCreator draws from the counter-based generator the device uses (item_set[rnd(seed, gid, d) % n], density for setting 3)"""
+        self._items = np.ascontiguousarray(np.array(item_set, dtype=np.float64).reshape(-1, 3))
+        self.L.pcto_set_random_items.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_int, C.c_uint64, C.c_uint64]
+        self.L.pcto_set_random_items(self.h, _dp(self._items), len(self._items), int(seed), int(gid))
+
     def set_trajectory_length(self, n):
         self.L.pcto_set_trajectory_length(self.h, int(n))
 
@@ -315,6 +321,11 @@ class OracleContinuous(object):
             s = np.concatenate([s, np.ones((len(s), 1))], axis=1)
         self._stream = np.ascontiguousarray(s)
         self.L.pctc_set_stream(self.h, _dp(self._stream), len(self._stream))
+
+    def set_random_sample(self, seed, gid, lo, hi):
+        """sample_from_distribution draws (C:bin3D.py:103-115) from the counter-based generator the device uses"""
+        self.L.pctc_set_random_sample.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_double, C.c_double]
+        self.L.pctc_set_random_sample(self.h, int(seed), int(gid), float(lo), float(hi))
 
     def set_trajectory_length(self, n):
         self.L.pctc_set_trajectory_length.argtypes = [C.c_void_p, C.c_int]

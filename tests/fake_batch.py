@@ -13,8 +13,6 @@ class FakeBatch(object):
     def __init__(self, n_envs, setting, container_size=(10, 10, 10), item_set=None, internal_node_holder=80, leaf_node_holder=50,
                  continuous=False, obs_dtype=torch.float32, seed=0, env_id_base=0, device=0, sample_from_distribution=False,
                  sample_left_bound=None, sample_right_bound=None, item_stream=None, size_minimum=None, auto_reset=True, LNES="EMS"):
-        if item_stream is None:
-            raise ValueError("FakeBatch needs explicit item streams (the device generators are not restated here)")
         self.n_envs, self.setting, self.continuous = int(n_envs), int(setting), bool(continuous)
         self.nb, self.nl = int(internal_node_holder), int(leaf_node_holder)
         self.obs_len = (self.nb + self.nl + 1) * 9
@@ -22,15 +20,31 @@ class FakeBatch(object):
         self.container_size, self.item_set = tuple(container_size), item_set
         if size_minimum is None:
             size_minimum = sample_left_bound if (continuous and sample_from_distribution) else (float(np.min(np.array(item_set))) if item_set is not None else 1.0)
-        stream = np.asarray(item_stream, dtype=np.float64)
-        assert stream.shape[0] == self.n_envs
-        self._streams = [np.ascontiguousarray(s) for s in stream]
+        if item_stream is not None:
+            stream = np.asarray(item_stream, dtype=np.float64)
+            assert stream.shape[0] == self.n_envs
+            self._streams = [np.ascontiguousarray(s) for s in stream]
+        else:  # the oracle's restatement of the device item generators, keyed by the global env index
+            self._streams = [None] * self.n_envs
+            if continuous and sample_from_distribution:
+                if sample_left_bound is None:  # PctBatch / tools.get_args :178-181
+                    sample_left_bound, sample_right_bound = 0.1 * min(container_size), 0.5 * min(container_size)
+                    if size_minimum is None or size_minimum == 1.0:
+                        size_minimum = sample_left_bound
         if continuous:
             self.envs = [OracleContinuous(setting, container_size=container_size, internal_node_holder=self.nb, leaf_node_holder=self.nl,
                                           size_minimum=size_minimum, stream=s) for s in self._streams]
         else:
             self.envs = [OracleDiscrete(setting, container_size=container_size, internal_node_holder=self.nb, leaf_node_holder=self.nl,
                                         size_minimum=size_minimum, stream=s, lnes=LNES) for s in self._streams]
+        if item_stream is None:
+            for i, e in enumerate(self.envs):
+                if continuous and sample_from_distribution:
+                    e.set_random_sample(seed, env_id_base + i, sample_left_bound, sample_right_bound)
+                elif continuous:
+                    raise ValueError("FakeBatch: continuous item_set mode needs an explicit stream")
+                else:
+                    e.set_random_items(item_set, seed, env_id_base + i)
         self._obs64 = np.zeros((self.n_envs, self.obs_len))
         self._hstate = [OH.fresh_state(self.envs[0].container) for _ in range(self.n_envs)]
         self._ep = np.zeros((self.n_envs, 2))  # reward sum, length of the running episode

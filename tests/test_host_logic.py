@@ -229,3 +229,32 @@ def test_unmodified_heuristic_functions_run_on_the_continuous_facade(fake, name,
     with contextlib.redirect_stdout(io.StringIO()):
         getattr(H, fn)(env, 3)
     assert env.log[:3] == packed[:3]
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not ref_shim.reference_available(), reason="reference not mounted")
+@pytest.mark.parametrize("argv,continuous", [(["--setting", "1", "--num-processes", "6", "--seed", "9"], False),
+                                              (["--setting", "2", "--continuous", "--sample-from-distribution", "--num-processes", "4"], True)])
+def test_make_vec_envs_takes_the_reference_args(fake, argv, continuous, monkeypatch):
+    """envs.make_vec_envs(args, log_dir, allow_early_resets) (envs.py:75-116) with the namespace tools.get_args() builds"""
+    import pct_b200
+    from pct_oracle import OracleBatch
+    compat = importlib.import_module("pct_b200.compat")
+    monkeypatch.setattr(importlib.import_module("pct_b200.vec_env"), "PctBatch", FakeBatch)
+    args = compat.reference_args(ref_shim.REFERENCE_ROOT, argv)
+    if continuous:
+        args.container_size = [1, 1, 1]  # givenData.py:5 (the commented alternative)
+        args.sample_left_bound, args.sample_right_bound = 0.1, 0.5
+    envs = pct_b200.make_vec_envs(args, "./logs/runinfo", True)
+    assert envs.num_envs == args.num_processes and envs.observation_space.shape == (1179,)
+    obs = envs.reset()
+    assert tuple(obs.shape) == (args.num_processes, 1179) and obs.dtype == torch.float32
+    for t in range(30):
+        leaf = obs.view(args.num_processes, 131, 9)[:, 80:130]
+        nvalid = (leaf[:, :, 8] == 1).sum(1)
+        rows = torch.stack([leaf[e, t % max(int(nvalid[e]), 1)] if nvalid[e] else torch.zeros(9) for e in range(args.num_processes)])
+        obs, rew, done, infos = envs.step(rows.numpy())
+        assert tuple(rew.shape) == (args.num_processes, 1) and len(infos) == args.num_processes
+    nxt = obs.view(args.num_processes, 131, 9)[:, 130, 3:6]
+    assert (nxt.min() >= 0.0999 and nxt.max() <= 0.5001) if continuous else (nxt.min() >= 1 and nxt.max() <= 5)
+    envs.close()
