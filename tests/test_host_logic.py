@@ -258,3 +258,83 @@ def test_make_vec_envs_takes_the_reference_args(fake, argv, continuous, monkeypa
     nxt = obs.view(args.num_processes, 131, 9)[:, 130, 3:6]
     assert (nxt.min() >= 0.0999 and nxt.max() <= 0.5001) if continuous else (nxt.min() >= 1 and nxt.max() <= 5)
     envs.close()
+
+
+class _Stop(Exception):
+    pass
+
+
+class _Counting(object):
+    """ends the reference's endless train loop after `limit` vector steps and logs what the trainer received"""
+
+    def __init__(self, venv, limit):
+        self.venv, self.limit, self.log = venv, limit, []
+
+    def __getattr__(self, name):
+        return getattr(self.venv, name)
+
+    def reset(self):
+        obs = self.venv.reset()
+        self.log.append(obs.clone())
+        return obs
+
+    def step(self, actions):
+        if len(self.log) > self.limit:
+            raise _Stop()
+        obs, rew, done, infos = self.venv.step(actions)
+        self.log.append(obs.clone())
+        return obs, rew, done, infos
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not ref_shim.reference_available(), reason="reference not mounted")
+@pytest.mark.parametrize("acktr", [True, False])
+def test_reference_trainer_runs_on_the_vector_surface(fake, acktr, tmp_path, monkeypatch):
+    """train_tools.train_n_steps (train_tools.py:32-150: rollouts through envs.step(leaf rows), PCTRolloutStorage, ACKTR / A2C updates) —
+    unmodified — on PctVecEnv and on the reference's own VecPyTorch(ShmemVecEnv(Monitor(env))) stack: same seeds, same item streams ->
+    the trainer sees the same observations step after step and ends with the same network parameters."""
+    from harness import make_stream
+    monkeypatch.setattr(importlib.import_module("pct_b200.vec_env"), "PctBatch", FakeBatch)
+    import pct_b200
+    compat = importlib.import_module("pct_b200.compat")
+    D, _ = ref_shim.load_reference()
+    model, _ = compat.load_policy_modules(ref_shim.REFERENCE_ROOT)
+    tt = importlib.import_module("train_tools")
+    renvs = importlib.import_module("envs")
+    ShmemVecEnv = importlib.import_module("wrapper.shmem_vec_env").ShmemVecEnv
+    Monitor = importlib.import_module("wrapper.monitor").Monitor
+    n, setting, limit = 4, 1, 16  # 3 updates of num_steps = 5, then one more step
+    args = compat.reference_args(ref_shim.REFERENCE_ROOT, ["--setting", str(setting), "--num-processes", str(n), "--no-cuda", "--seed", "3"])
+    args.use_acktr = acktr  # tools.py:121 `type=bool`: not settable to False from the command line
+    args.model_save_path = str(tmp_path)
+    streams = np.stack([make_stream(77, e, 400, setting) for e in range(n)])
+
+    def thunk(rank):
+        def _t():
+            env = D.PackingDiscrete(setting=setting, container_size=[10, 10, 10], item_set=ITEM_SET, internal_node_holder=80, leaf_node_holder=50,
+                                    shuffle=False, LNES="EMS")
+            env.box_creator = ref_shim.make_stream_creator(D, [tuple(int(v) for v in r[:3]) for r in streams[rank]])
+            env.test = True
+            return Monitor(env, os.path.join(str(tmp_path), str(rank)), allow_early_resets=True)
+        return _t
+
+    probe = D.PackingDiscrete(setting=setting, container_size=[10, 10, 10], item_set=ITEM_SET)
+    results = []
+    for which in ("reference", "ours"):
+        if which == "reference":
+            venv = renvs.VecPyTorch(ShmemVecEnv([thunk(r) for r in range(n)], [probe.observation_space, probe.action_space], context="fork"), "cpu")
+        else:
+            venv = pct_b200.PctVecEnv(n, setting, item_set=ITEM_SET, item_stream=streams)
+        counting = _Counting(venv, limit)
+        torch.manual_seed(11)
+        policy = model.DRL_GAT(args)
+        trainer = tt.train_tools(None, "t", policy, args)
+        try:
+            with pytest.raises(_Stop):
+                trainer.train_n_steps(counting, args, torch.device("cpu"))
+        finally:
+            venv.close()
+        results.append((torch.stack(counting.log), [p.detach().clone() for p in policy.parameters()], trainer.step_counter))
+    assert results[0][2] == results[1][2] == 4
+    assert torch.equal(results[0][0], results[1][0])
+    assert all(torch.equal(a, b) for a, b in zip(results[0][1], results[1][1]))
