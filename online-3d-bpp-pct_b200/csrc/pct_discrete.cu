@@ -524,22 +524,25 @@ __device__ __noinline__ int gen_level_points(const int16_t (*box)[6], int n_box,
                     const int16_t *ni = box[ord[i]];
                     int maxb0 = -10, maxb2 = -10, e0x = 0, e0y = 0, e2x = 0, e2y = 0;
                     bool has0 = false, has2 = false;
+                    bool first2 = false;  // newEps is a dict: .values() lists key 2 before key 0 when newEps[2] was assigned first (D:PctTools.py:121-127)
                     for (int b = 0; b < 2 + i; b++) {
                         int bx2, bx3;
                         if (b == 0) { bx2 = 0; bx3 = 10; } else if (b == 1) { bx2 = 10; bx3 = 0; } else { bx2 = box[ord[b - 2]][3]; bx3 = box[ord[b - 2]][4]; }
                         if (ni[0] >= bx2 && ni[4] < bx3 && bx2 > maxb0) { e0x = bx2; e0y = ni[4]; maxb0 = bx2; has0 = true; }
-                        if (ni[1] >= bx3 && ni[3] < bx2 && bx3 > maxb2) { e2x = ni[3]; e2y = bx3; maxb2 = bx3; has2 = true; }
+                        if (ni[1] >= bx3 && ni[3] < bx2 && bx3 > maxb2) { e2x = ni[3]; e2y = bx3; maxb2 = bx3; if (!has2 && !has0) first2 = true; has2 = true; }
                     }
                     int w = 0;  // deleteEps2D
                     for (int q = 0; q < nc; q++)
                         if (!(cur[q][0] >= ni[0] && cur[q][0] < ni[3] && cur[q][1] >= ni[1] && cur[q][1] < ni[4])) { cur[w][0] = cur[q][0]; cur[w][1] = cur[q][1]; w++; }
                     nc = w;
                     if (has0 && has2 && !(e0x == e2x && e0y == e2y)) {
-                        // list(set({(e0), (e2)})): CPython order of two int 2-tuples in an 8-slot table
+                        // list(set(newEps.values())): CPython order of two int 2-tuples in an 8-slot table; the values are inserted in the
+                        // dict's key order, the first takes its home slot, the second probes from its own (perturb path); iteration = slot order
                         uint64_t l0[2] = {(uint64_t)e0x, (uint64_t)e0y}, l2[2] = {(uint64_t)e2x, (uint64_t)e2y};
                         const uint64_t h0 = tuple_hash_n(l0, 2), h2 = tuple_hash_n(l2, 2);
-                        uint64_t s0 = h0 & 7, s2 = h2 & 7, pert = h2;
-                        while (s2 == s0) { pert >>= 5; s2 = (s2 * 5 + 1 + pert) & 7; }
+                        uint64_t s0 = h0 & 7, s2 = h2 & 7;
+                        if (first2) { uint64_t pert = h0; while (s0 == s2) { pert >>= 5; s0 = (s0 * 5 + 1 + pert) & 7; } }
+                        else { uint64_t pert = h2; while (s2 == s0) { pert >>= 5; s2 = (s2 * 5 + 1 + pert) & 7; } }
                         if (s0 < s2) { cur[nc][0] = e0x; cur[nc][1] = e0y; nc++; cur[nc][0] = e2x; cur[nc][1] = e2y; nc++; }
                         else { cur[nc][0] = e2x; cur[nc][1] = e2y; nc++; cur[nc][0] = e0x; cur[nc][1] = e0y; nc++; }
                     } else if (has0) { cur[nc][0] = e0x; cur[nc][1] = e0y; nc++; }

@@ -62,7 +62,7 @@ def record_cont_case(Cm, c, seed, env_id):
 def main():
     D, Cm = ref_shim.load_reference()
     for name, c in CASES.items():
-        rec = record_case(D, c, 517, 1)
+        rec = record_case(D, c, c.get("seed", 517), c.get("env", 1))
         path = os.path.join(HERE, "case_%s.npz" % name)
         np.savez_compressed(path, name=name, **rec)
         print(path, os.path.getsize(path) // 1024, "KiB", "episodes", int(rec["done"].sum()), flush=True)
