@@ -85,6 +85,11 @@ class OracleDiscrete(object):
         self._stream = np.ascontiguousarray(s)
         self.L.pcto_set_stream(self.h, _dp(self._stream), len(self._stream))
 
+    def set_alias_mode(self, on=True):
+        """read the up_edges values that ARE the upper box's own Stack object live, like the reference's Python objects"""
+        self.L.pcto_set_alias_mode.argtypes = [C.c_void_p, C.c_int]
+        self.L.pcto_set_alias_mode(self.h, int(on))
+
     def set_random_items(self, item_set, seed, gid):
         """RandomBoxCreator draws from the counter-based generator the device uses (item_set[rnd(seed, gid, d) % n], density for setting 3)"""
         self._items = np.ascontiguousarray(np.array(item_set, dtype=np.float64).reshape(-1, 3))
@@ -321,6 +326,10 @@ class OracleContinuous(object):
             s = np.concatenate([s, np.ones((len(s), 1))], axis=1)
         self._stream = np.ascontiguousarray(s)
         self.L.pctc_set_stream(self.h, _dp(self._stream), len(self._stream))
+
+    def set_alias_mode(self, on=True):
+        self.L.pctc_set_alias_mode.argtypes = [C.c_void_p, C.c_int]
+        self.L.pctc_set_alias_mode(self.h, int(on))
 
     def set_random_sample(self, seed, gid, lo, hi):
         """sample_from_distribution draws (C:bin3D.py:103-115) from the counter-based generator the device uses"""

@@ -12,7 +12,7 @@
 #include <stdio.h>
 
 typedef struct { double c[3]; double m; } Stack;
-typedef struct { int key; Stack s; } EdgeEnt;
+typedef struct { int key; Stack s; int alias; } EdgeEnt; /* alias: the value IS the upper box's live Stack object */
 
 typedef struct Box {
     int serial;
@@ -43,12 +43,14 @@ typedef struct pctc_env {
     int n_boxes;
     Box *boxes;
     Box *vbox;
+    Box *rbox;     /* the box a real drop_box is checking (not yet in boxes[0..n_boxes)) */
     int next_serial;
     double (*up_letter)[5]; /* C:space.py:273  [-lx,-ly,lx+x,ly+y,top] */
     int n_ems;
     double (*ems)[6];
     double *box_vec;
     const double *stream; int stream_len, stream_pos; int have_item;
+    int alias_mode; /* 1: up_edges values that are the upper box's own Stack object are read live (pctc_set_alias_mode) */
     int traj_len; /* > 0: LoadBoxCreator.reset discipline, every reset jumps to the next trajectory boundary (C:binCreator.py:51-62) */
     int use_rng; uint64_t rng_seed, rng_gid; double rng_lo, rng_hi; /* sample_from_distribution draws (C:bin3D.py:103-115), counter-based */
     double cur_item[4];
@@ -66,6 +68,7 @@ static double around6(double v) { return rint(v * 1e6) / 1e6; } /* np.around(v, 
 
 static Box *box_by_serial(pctc_env *e, int serial) {
     if (e->vbox && e->vbox->serial == serial) return e->vbox;
+    if (e->rbox && e->rbox->serial == serial) return e->rbox;
     for (int i = 0; i < e->n_boxes; i++)
         if (e->boxes[i].serial == serial) return &e->boxes[i];
     return NULL;
@@ -84,11 +87,11 @@ static void box_init(pctc_env *e, Box *b, double x, double y, double z, double l
     b->involved = 0;
 }
 
-static void dict_set(EdgeEnt *d, int *n, int key, const Stack *s, int *err) {
+static void dict_set(EdgeEnt *d, int *n, int key, const Stack *s, int alias, int *err) {
     for (int i = 0; i < *n; i++)
-        if (d[i].key == key) { d[i].s = *s; return; }
+        if (d[i].key == key) { d[i].s = *s; d[i].alias = alias; return; }
     if (*n >= PO_MAX_UP) { *err = 3; return; }
-    d[*n].key = key; d[*n].s = *s; (*n)++;
+    d[*n].key = key; d[*n].s = *s; d[*n].alias = alias; (*n)++;
 }
 static void dict_pop(EdgeEnt *d, int *n, int key) {
     for (int i = 0; i < *n; i++)
@@ -105,13 +108,15 @@ static void calculate_new_com(pctc_env *e, Box *b, int virt) {
     double m = b->mass;
     for (int i = 0; i < b->n_up; i++)
         if (!serial_involved(e, b->up[i].key)) {
-            const Stack *s = &b->up[i].s;
+            const Box *ub = (e->alias_mode && b->up[i].alias) ? box_by_serial(e, b->up[i].key) : NULL;
+            const Stack *s = ub ? &ub->thisStack : &b->up[i].s; /* a box that was never added (its real check failed) keeps its last value */
             c[0] += s->c[0] * s->m; c[1] += s->c[1] * s->m; c[2] += s->c[2] * s->m;
             m += s->m;
         }
     for (int i = 0; i < b->n_vup; i++)
         if (serial_involved(e, b->vup[i].key)) {
-            const Stack *s = &b->vup[i].s;
+            const Box *vb_ = (e->alias_mode && b->vup[i].alias) ? box_by_serial(e, b->vup[i].key) : NULL;
+            const Stack *s = vb_ ? &vb_->thisVStack : &b->vup[i].s;
             c[0] += s->c[0] * s->m; c[1] += s->c[1] * s->m; c[2] += s->c[2] * s->m;
             m += s->m;
         }
@@ -130,12 +135,15 @@ static int calculated_impact(pctc_env *e, Box *b, int virt, int first) {
         return 0;
     }
 #define SUP(i) (&e->boxes[b->be_box[i]])
-#define SET_EDGE(i, stk) do { Box *s_ = SUP(i); if (virt) dict_set(s_->vup, &s_->n_vup, b->serial, (stk), &e->error); \
-                              else dict_set(s_->up, &s_->n_up, b->serial, (stk), &e->error); \
+/* alias = 1: the reference stores the Stack OBJECT of the upper box (`up_edges[self] = self.thisStack`, space.py:82-83,98 / :179-180,195), whose
+ * fields calculate_new_com later rewrites in place — a support that recomputes its centre of mass before that box's own calculated_impact
+ * ran already sees the new load; alias = 0: a fresh Stack(...) object, i.e. a snapshot (:100,:121-122,:153 ...) */
+#define SET_EDGE(i, stk, alias_) do { Box *s_ = SUP(i); if (virt) dict_set(s_->vup, &s_->n_vup, b->serial, (stk), (alias_), &e->error); \
+                              else dict_set(s_->up, &s_->n_up, b->serial, (stk), (alias_), &e->error); \
                               calculate_new_com(e, s_, virt); } while (0)
     int k = b->n_be;
     if (k == 1) {
-        SET_EDGE(0, st);
+        SET_EDGE(0, st, 1);
         if (!calculated_impact(e, SUP(0), virt, 0)) { if (virt) b->involved = 0; return 0; }
     } else {
         int direct = -1;
@@ -145,12 +153,12 @@ static int calculated_impact(pctc_env *e, Box *b, int virt, int first) {
         }
         if (direct >= 0) {
             for (int i = 0; i < k; i++) {
-                if (i == direct) SET_EDGE(i, st);
+                if (i == direct) SET_EDGE(i, st, 1);
                 else {
                     Stack z; /* real: Stack(thisStack.centre, 0) :100 ; virtual: Stack(self.centre, 0) :197 */
                     memcpy(z.c, virt ? b->centre : st->c, sizeof z.c);
                     z.m = 0;
-                    SET_EDGE(i, &z);
+                    SET_EDGE(i, &z, 0);
                 }
             }
             for (int i = 0; i < k; i++)
@@ -166,8 +174,8 @@ static int calculated_impact(pctc_env *e, Box *b, int virt, int first) {
             double ratio1 = fabs(po_dot2(d0, line));
             Stack s0 = {{b->be_c2d[0][0], b->be_c2d[0][1], st->c[2]}, st->m * ratio0};
             Stack s1 = {{b->be_c2d[1][0], b->be_c2d[1][1], st->c[2]}, st->m * ratio1};
-            SET_EDGE(0, &s0);
-            SET_EDGE(1, &s1);
+            SET_EDGE(0, &s0, 0);
+            SET_EDGE(1, &s1, 0);
             if (!calculated_impact(e, SUP(0), virt, 0)) { if (virt) b->involved = 0; return 0; }
             if (!calculated_impact(e, SUP(1), virt, 0)) { if (virt) b->involved = 0; return 0; }
         } else {
@@ -195,7 +203,7 @@ static int calculated_impact(pctc_env *e, Box *b, int virt, int first) {
             po_ls_solve(&ls, ratio);
             for (int i = 0; i < k; i++) {
                 Stack s = {{b->be_c2d[i][0], b->be_c2d[i][1], st->c[2]}, st->m * ratio[i]};
-                SET_EDGE(i, &s);
+                SET_EDGE(i, &s, 0);
             }
             for (int i = 0; i < k; i++)
                 if (!calculated_impact(e, SUP(i), virt, 0)) { if (virt) b->involved = 0; return 0; }
@@ -294,7 +302,10 @@ static int drop_box(pctc_env *e, double x, double y, double z, double lx, double
     Box *b = &e->boxes[e->n_boxes];
     box_init(e, b, x, y, z, lx, ly, max_h, density);
     if (e->setting != 2) build_bottom(e, b, max_h, idx, area, n);
-    if (!check_box(e, max_h, b, 0)) return 0;
+    e->rbox = b;
+    const int stable = check_box(e, max_h, b, 0);
+    e->rbox = NULL;
+    if (!stable) return 0;
     if (e->n_boxes >= e->nb_holder) { e->error = 1; return 0; }
     memcpy(e->up_letter[e->n_boxes], bi, sizeof bi);
     double *r = &e->box_vec[e->n_boxes * 9];
@@ -470,6 +481,7 @@ static void cur_observation(pctc_env *e, double *obs) {
 
 pctc_env *pctc_create(int setting, double W, double L, double H, int nb_holder, int nl_holder, double low_bound) {
     pctc_env *e = calloc(1, sizeof(pctc_env));
+    { const char *am = getenv("PCT_ORACLE_ALIAS"); e->alias_mode = am && atoi(am) != 0; } /* default off: see pctc_set_alias_mode / DESIGN.md section 3 */
     e->setting = setting; e->W = W; e->L = L; e->H = H; e->height = H;
     e->nb_holder = nb_holder; e->nl_holder = nl_holder; e->low_bound = low_bound;
     e->boxes = calloc(PC_MAX_BOXES, sizeof(Box));
@@ -487,6 +499,7 @@ int pctc_obs_len(pctc_env *e) { return (e->nb_holder + e->nl_holder + 1) * 9; }
 
 /* C:bin3D.py:69-75 + C:space.py:281-303 */
 void pctc_set_trajectory_length(pctc_env *e, int n) { e->traj_len = n; }
+void pctc_set_alias_mode(pctc_env *e, int on) { e->alias_mode = on; }
 void pctc_reset(pctc_env *e, double *obs) {
     e->have_item = 0;
     if (e->traj_len > 0 && e->stream_pos % e->traj_len) e->stream_pos += e->traj_len - e->stream_pos % e->traj_len;
@@ -571,3 +584,14 @@ int pctc_drop_box_virtual(pctc_env *e, double x, double y, double z, double lx, 
     return drop_box_virtual(e, x, y, z, lx, ly, density);
 }
 void pctc_get_next(pctc_env *e, double *out4) { out4[0] = e->next_box[0]; out4[1] = e->next_box[1]; out4[2] = e->next_box[2]; out4[3] = e->next_den; }
+
+/* debug / soak triage: the persisted stack (centre xyz, mass) of placed box i and its up_edges entries (serial, centre xyz, mass) */
+int pctc_get_stack(pctc_env *e, int i, double *out4, double *up5, int cap) {
+    if (i < 0 || i >= e->n_boxes) return -1;
+    const Box *b = &e->boxes[i];
+    out4[0] = b->thisStack.c[0]; out4[1] = b->thisStack.c[1]; out4[2] = b->thisStack.c[2]; out4[3] = b->thisStack.m;
+    for (int k = 0; k < b->n_up && k < cap; k++) {
+        up5[5 * k] = b->up[k].key; up5[5 * k + 1] = b->up[k].s.c[0]; up5[5 * k + 2] = b->up[k].s.c[1]; up5[5 * k + 3] = b->up[k].s.c[2]; up5[5 * k + 4] = b->up[k].s.m;
+    }
+    return b->n_up;
+}

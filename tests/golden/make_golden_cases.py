@@ -67,7 +67,7 @@ def main():
         np.savez_compressed(path, name=name, **rec)
         print(path, os.path.getsize(path) // 1024, "KiB", "episodes", int(rec["done"].sum()), flush=True)
     for name, c in CONT_CASES.items():
-        rec = record_cont_case(Cm, c, 519, 2)
+        rec = record_cont_case(Cm, c, c.get("seed", 519), c.get("env", 2))
         path = os.path.join(HERE, "ccase_%s.npz" % name)
         np.savez_compressed(path, name=name, **rec)
         print(path, os.path.getsize(path) // 1024, "KiB", "episodes", int(rec["done"].sum()), flush=True)

@@ -16,12 +16,15 @@ import numpy as np
 import pytest
 
 torch = pytest.importorskip("torch")
-from harness import CASES, CONT_CASES, ITEM_SET  # noqa: E402
+from harness import CASES, CONT_CASES, ITEM_SET, KNOWN_DIVERGENT  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 G = os.path.join(os.path.dirname(__file__), "golden")
 DISCRETE = sorted(glob.glob(os.path.join(G, "discrete_*.npz"))) + sorted(glob.glob(os.path.join(G, "case_*.npz")))
 CONTINUOUS = sorted(glob.glob(os.path.join(G, "continuous_s*.npz"))) + sorted(glob.glob(os.path.join(G, "ccase_*.npz")))
+# the kernels hold snapshots of the loads (like the oracle's default mode); the record that needs the reference's object aliasing is the
+# documented divergence (tests/test_oracle_golden.py)
+CONTINUOUS = [p for p in CONTINUOUS if not any(os.path.basename(p) == "ccase_%s.npz" % n for n in KNOWN_DIVERGENT)]
 
 
 def _replay(env, g, exact_scalars):
@@ -44,7 +47,7 @@ def _replay(env, g, exact_scalars):
 
 
 def test_files_present():
-    assert len(DISCRETE) >= 14 + len(CASES) and len(CONTINUOUS) == 3 + len(CONT_CASES)
+    assert len(DISCRETE) >= 14 + len(CASES) and len(CONTINUOUS) == 3 + len(CONT_CASES) - len(KNOWN_DIVERGENT)
 
 
 @pytest.mark.parametrize("path", DISCRETE, ids=[os.path.basename(p) for p in DISCRETE])
