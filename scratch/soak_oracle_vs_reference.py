@@ -30,6 +30,14 @@ def replay(orc, rec, steps):
             assert np.array_equal(o, rec["obs"][k]), ("reset obs", t); k += 1
 
 
+def make_oracle(c, seed, env_id):
+    if "items" in c:
+        return OracleDiscrete(c["setting"], container_size=c["container"], internal_node_holder=c["nb"], leaf_node_holder=c["nl"],
+                              size_minimum=min(min(i) for i in c["items"]), stream=case_stream(c, seed, env_id, c["steps"] + 64), lnes=c["lnes"])
+    return OracleContinuous(c["setting"], container_size=c["container"], internal_node_holder=c["nb"], leaf_node_holder=c["nl"],
+                            size_minimum=c["low"], stream=cont_case_stream(c, seed, env_id, c["steps"] + 64))
+
+
 def main():
     minutes = float(sys.argv[1]) if len(sys.argv) > 1 else 5.0
     D, Cm = ref_shim.load_reference()
@@ -54,7 +62,17 @@ def main():
                     rec = M.record_cont_case(Cm, c, seed, n % 7)
                     orc = OracleContinuous(c["setting"], container_size=c["container"], internal_node_holder=c["nb"], leaf_node_holder=c["nl"],
                                            size_minimum=c["low"], stream=cont_case_stream(c, seed, n % 7, c["steps"] + 64))
-                replay(orc, rec, c["steps"])
+                try:
+                    replay(orc, rec, c["steps"])
+                except AssertionError as ex:  # classify: does the oracle's alias mode replay it?
+                    mk = make_oracle(c, seed, n % 7)
+                    mk.set_alias_mode(True)
+                    try:
+                        replay(mk, rec, c["steps"])
+                        kind = "object aliasing (alias mode replays it)"
+                    except AssertionError:
+                        kind = "NOT explained by alias mode (LAPACK tie or new)"
+                    print("MISMATCH", name, "seed", seed, "env", n % 7, ex.args, "->", kind, flush=True)
             except AssertionError as ex:
                 print("MISMATCH", name, "seed", seed, "env", n % 7, ex.args, flush=True)
             n += 1
