@@ -1,0 +1,106 @@
+"""CPU: the DEVICE stability routine (csrc/pct_stability.cuh: the explicit DFS, edge pool, hull / point-in-polygon / lstsq code the
+kernels compile) built for the HOST by g++ (tests/host_emul/stab_host.cpp, intrinsics shimmed, -ffp-contract=off) and driven through
+whole trajectories next to the CPU oracle: every real placement's verdict (stability_check<true>, with load persistence) and every
+virtual feasibility verdict of every candidate (stability_check<false>) must equal the oracle's — which is pinned on
+the reference.  This checks the kernels' SOURCE logic without a GPU; warp-level code, staging and SASS remain the GPU tests' business."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from harness import CASES, ITEM_SET, case_stream, make_stream, policy_pick
+from pct_oracle import OracleDiscrete
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = os.path.join(ROOT, "tests", "host_emul", "stab_host.cpp")
+OUT = os.path.join(ROOT, "tests", "host_emul", "_build", "libstab_host.so")
+CSRC = os.path.join(ROOT, "online-3d-bpp-pct_b200", "csrc")
+
+
+def _cuda_include():
+    for d in (os.environ.get("CUDA_HOME"), "/usr/local/cuda"):
+        if d and os.path.isfile(os.path.join(d, "include", "cuda_runtime.h")):
+            return os.path.join(d, "include")
+    return None
+
+
+@pytest.fixture(scope="module")
+def lib():
+    inc = _cuda_include()
+    if inc is None:
+        pytest.skip("CUDA headers not found")
+    deps = [SRC] + [os.path.join(CSRC, f) for f in ("pct_stability.cuh", "pct_geom.cuh", "pct_kernels.h")]
+    if not os.path.exists(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in deps):
+        os.makedirs(os.path.dirname(OUT), exist_ok=True)
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-w", "-I" + CSRC,
+                               "-I" + os.path.join(ROOT, "include"), "-I" + inc, "-o", OUT, SRC])
+    L = C.CDLL(OUT)
+    L.sh_create.restype = C.c_void_p
+    L.sh_create.argtypes = [C.c_int] * 4
+    for f in ("sh_destroy", "sh_reset"):
+        getattr(L, f).argtypes = [C.c_void_p]
+    L.sh_flags.argtypes = [C.c_void_p]
+    L.sh_virtual.argtypes = [C.c_void_p] + [C.c_int] * 5 + [C.c_double, C.POINTER(C.c_int)]
+    L.sh_place.argtypes = [C.c_void_p] + [C.c_int] * 5 + [C.c_double]
+    return L
+
+
+def _placement(row, next_box):
+    """LeafNode2Action (D:bin3D.py:139-150)"""
+    if np.sum(row[0:6]) == 0:
+        return tuple(next_box), 0, 0
+    x, y = int(row[3] - row[0]), int(row[4] - row[1])
+    z = list(next_box)
+    z.remove(x)
+    z.remove(y)
+    return (x, y, int(z[0])), int(row[0]), int(row[1])
+
+
+def _drive(L, env, setting, container, nb, nl, seed, env_id, steps):
+    h = L.sh_create(setting, *container)
+    L.sh_reset(h)
+    o = env.reset()
+    n_virtual = n_real = 0
+    for t in range(steps):
+        cand, feas = env.candidates()
+        den = env.next_den
+        for p, f in zip(cand, feas):
+            if f < 0:
+                continue  # beyond the leaf cap: the reference never evaluated it
+            mh = C.c_int()  # the item drops to the resting height of its footprint, whatever z the candidate tuple carries (the EMS's)
+            got = L.sh_virtual(h, int(p[3] - p[0]), int(p[4] - p[1]), int(p[5] - p[2]), int(p[0]), int(p[1]), den, C.byref(mh))
+            assert got == f, "step %d candidate %s: host build %d (rest %d), oracle %d" % (t, p.tolist(), got, mh.value, f)
+            n_virtual += 1
+        _, row = policy_pick(o, nb, nl, seed, env_id, t)
+        (x, y, z), lx, ly = _placement(row, env.next_box)
+        o, _, done, _ = env.step(row)
+        placed = L.sh_place(h, x, y, z, lx, ly, den)
+        assert placed == (not done), "step %d real placement: host build %d, oracle done=%s" % (t, placed, done)
+        n_real += 1
+        if done:
+            o = env.reset()
+            L.sh_reset(h)
+    assert L.sh_flags(h) == 0
+    L.sh_destroy(h)
+    return n_virtual, n_real
+
+
+@pytest.mark.parametrize("setting", [1, 3, 2])
+def test_device_stability_source_follows_the_oracle(lib, setting):
+    tot = 0
+    for env_id in range(6):
+        seed = 300 + setting
+        env = OracleDiscrete(setting, stream=make_stream(seed, env_id, 700, setting))
+        nv, nr = _drive(lib, env, setting, (10, 10, 10), 80, 50, seed, env_id, 350)
+        tot += nv
+    assert tot > 20000
+
+
+@pytest.mark.parametrize("name", ["big_s1", "dense16_s1", "flat_s1", "holders_s1"])
+def test_device_stability_source_on_other_configurations(lib, name):
+    c = CASES[name]
+    env = OracleDiscrete(c["setting"], container_size=c["container"], internal_node_holder=c["nb"], leaf_node_holder=c["nl"],
+                         size_minimum=min(min(i) for i in c["items"]), stream=case_stream(c, 91, 2, 600))
+    _drive(lib, env, c["setting"], c["container"], c["nb"], c["nl"], 91, 2, 300)
