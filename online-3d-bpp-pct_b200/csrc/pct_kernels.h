@@ -55,6 +55,15 @@ struct EdgePool {
     __device__ __forceinline__ double *poly_at(int v) const { return v < POLY_STAGE ? poly_sm + 2 * v : poly + 2 * v; }
 };
 
+// Extra state of the ALIAS variant of the stability routine (the reference's Python object aliasing): the
+// reference keeps every box's stack in an object (`thisStack`) that `calculate_new_com` rewrites in place at every SET_EDGE, and the
+// `up_edges` entries of a single support / of the direct support ARE that object.  Passed as the EdgePool& of stability_check<.., ALIAS = true>.
+struct EdgePoolA : EdgePool {
+    Stack4 *box_st;        // [NB_MAX + 1] thisStack of every placed box and of the box being placed
+    uint8_t *e_upper;      // [EDGE_MAX] upper box of edge q
+    uint32_t *e_alias;     // [(EDGE_MAX + 32) / 32] bit q: the entry is the upper box's own Stack object
+};
+
 // per-env HBM scratch for the rare big cases (k > KSUP_SMALL)
 struct BigScratch {
     double rect[KSUP_MAX][4];

@@ -361,17 +361,47 @@ static __device__ __noinline__ bool pip_rect(double x1, double y1, double x2, do
     return odd;
 }
 
+// ---- ALIAS variant helpers (opt-in; see EdgePoolA) ----------------------------------------------------------------------
+// calculate_new_com of a placed box under the reference's object semantics: entries that ARE the upper box's Stack object are read
+// through that box's current field, the others are the stored snapshots.  Same operation order as the lazy sum at the end of the DFS loop.
+template <class G>
+static __device__ __noinline__ void alias_recompute(const G &g, EdgePoolA &pa, int box) {
+    typename G::Node sb;
+    g.node_box(box, sb);
+    double cx, cy, cz, mm = sb.mass;
+    g.centre(sb, cx, cy, cz);
+    cx *= mm; cy *= mm; cz *= mm;
+#pragma unroll 1
+    for (int q = pa.first_in[box]; q != EDGE_NIL; q = pa.next[q]) {
+        const bool al = (pa.e_alias[q >> 5] >> (q & 31)) & 1u;
+        const Stack4 e = al ? pa.box_st[pa.e_upper[q]] : pa.load(q);
+        cx += e.cx * e.m; cy += e.cy * e.m; cz += e.cz * e.m;
+        mm += e.m;
+    }
+    Stack4 &d = pa.box_st[box];
+    d.cx = ddiv(cx, mm); d.cy = ddiv(cy, mm); d.cz = ddiv(cz, mm); d.m = mm;
+}
+// SET_EDGE bookkeeping of edge q (upper box `upper`, supporting box `lower`): kind of the entry, then the support's eager recompute
+template <class G>
+static __device__ __forceinline__ void alias_set_edge(const G &g, EdgePoolA &pa, int q, int upper, int lower, bool is_object) {
+    uint32_t &w = pa.e_alias[q >> 5];
+    w = is_object ? (w | (1u << (q & 31))) : (w & ~(1u << (q & 31)));
+    pa.e_upper[q] = (uint8_t)upper;
+    alias_recompute(g, pa, lower);
+}
+
 // The DFS keeps the CURRENT node in registers; frames are pushed to the lane-local stack only for nodes with
 // >= 2 supports, and descending into the last (or only) support is a tail call (nothing is left to do in the
 // parent once its last child returns True).
 #ifdef PCT_PHASE_TIMERS
 __device__ long long *g_prof_dummy;
 #endif
-template <bool REAL, class G>
+template <bool REAL, class G, bool ALIAS = false>
 static __device__ __noinline__ int stability_check(const G &g, const typename G::Node &root, EdgePool &pool, BigScratch *big, int *lock,
                                             const int new_id, int &flags, long long *g_prof_out = nullptr) {
     typedef typename G::Node Node;
     constexpr bool real = REAL;  // REAL: load-propagating update of a committed placement; else read-only feasibility check
+    constexpr bool alias = REAL && ALIAS;  // object semantics of the reference's load entries; `pool` is an EdgePoolA then
     StabFrame fr[STAB_DEPTH];
     uint8_t sup_id[STAB_SUP_POOL];
     double sup_m[STAB_SUP_POOL];
@@ -381,6 +411,7 @@ static __device__ __noinline__ int stability_check(const G &g, const typename G:
     Stack4 st;
     g.centre(root, st.cx, st.cy, st.cz);
     st.m = root.mass;
+    if constexpr (alias) static_cast<EdgePoolA &>(pool).box_st[new_id] = st;  // Box.__init__: thisStack = Stack(centre, mass)
 
 #ifdef PCT_PHASE_TIMERS
     long long sec_[6] = {0, 0, 0, 0, 0, 0}, tq_ = clock64();
@@ -443,6 +474,7 @@ static __device__ __noinline__ int stability_check(const G &g, const typename G:
             if (real) {
                 if (node == root_id && !pool_append(pool, sid0)) { flags |= PCT_FLAG_EDGE_OVERFLOW; return 0; }
                 pool.load(eoff) = st;
+                if constexpr (alias) alias_set_edge(g, static_cast<EdgePoolA &>(pool), eoff, node, sid0, true);  // up_edges[self] = self.thisStack
             }
             child = sid0;  // whole stack goes to the single support
             skip = (node == root_id) ? EDGE_NIL : eoff;
@@ -532,6 +564,8 @@ static __device__ __noinline__ int stability_check(const G &g, const typename G:
                         e.m = sup_m[base + s];
                         if (node == root_id && !pool_append(pool, sup_id[base + s])) { flags |= PCT_FLAG_EDGE_OVERFLOW; ok = false; break; }
                         pool.load(eoff + s) = e;
+                        // the direct support receives the object itself (space.py:98), every other entry is a fresh Stack(...)
+                        if constexpr (alias) alias_set_edge(g, static_cast<EdgePoolA &>(pool), eoff + s, node, sup_id[base + s], whole == 2 && s == direct);
                     }
                 }
             }
@@ -569,6 +603,12 @@ static __device__ __noinline__ int stability_check(const G &g, const typename G:
                 if (s == f.k - 1) { depth--; base = f.base; }  // tail call: the parent frame is finished
                 break;
             }
+        }
+        if constexpr (alias) {  // the support's stack was recomputed eagerly at its last SET_EDGE: calculated_impact reads the field
+            st = static_cast<EdgePoolA &>(pool).box_st[child];
+            node = child;
+            DBG_VISIT();
+            continue;
         }
         // ---- calculate_new_com of `child` (D:space.py:51-71) under the load (vx, vy, st.cz, vm) of `parent` ----
         Node sb;

@@ -25,6 +25,7 @@ def run(make, n_envs, steps, seed):
             total += 1
             if da != db or not np.array_equal(oa, ob):
                 div += 1
+                print("   diverges: env", e, "step", t, flush=True)
                 break  # count trajectories that diverge (first event)
             if da:
                 oa, ob = a.reset(), b.reset()

@@ -35,6 +35,11 @@ struct StabHost {
     double poly[POLY_MAX][2];
     BigScratch big;
     int lock;
+    // ALIAS variant (EdgePoolA): the reference's object semantics of the load entries
+    int alias;
+    Stack4 box_st[NB_MAX + 1];
+    uint8_t e_upper[EDGE_MAX + 1];
+    uint32_t e_alias[(EDGE_MAX + 32) / 32];
 };
 
 static EdgePool pool_of(StabHost *h) {
@@ -49,6 +54,7 @@ StabHost *sh_create(int setting, int W, int L, int H) {
     return h;
 }
 void sh_destroy(StabHost *h) { delete h; }
+void sh_set_alias(StabHost *h, int on) { h->alias = on; }
 void sh_reset(StabHost *h) { h->n_box = 0; h->n_edge = 0; h->n_poly = 0; h->flags = 0; h->lock = 0; }
 int sh_flags(StabHost *h) { return h->flags; }
 int sh_n_boxes(StabHost *h) { return h->n_box; }
@@ -82,9 +88,12 @@ int sh_place(StabHost *h, int x, int y, int z, int lx, int ly, double density) {
     if (h->setting != 2 && mh != 0) {
         GeomD g{h->box, n0, h->setting == 3 ? h->density : nullptr};
         NodeD root{lx, ly, mh, x, y, z, (double)(x * y * z) * density};
-        EdgePool pool = pool_of(h);
+        EdgePoolA pool;
+        static_cast<EdgePool &>(pool) = pool_of(h);
+        pool.box_st = h->box_st; pool.e_upper = h->e_upper; pool.e_alias = h->e_alias;
         int fl = 0;
-        const int res = stability_check<true, GeomD>(g, root, pool, &h->big, &h->lock, n0, fl);
+        const int res = h->alias ? stability_check<true, GeomD, true>(g, root, pool, &h->big, &h->lock, n0, fl)
+                                 : stability_check<true, GeomD>(g, root, pool, &h->big, &h->lock, n0, fl);
         h->n_edge = pool.n;
         h->n_poly = pool.n_poly;
         h->flags |= fl;

@@ -44,6 +44,7 @@ def lib():
     L.sh_flags.argtypes = [C.c_void_p]
     L.sh_virtual.argtypes = [C.c_void_p] + [C.c_int] * 5 + [C.c_double, C.POINTER(C.c_int)]
     L.sh_place.argtypes = [C.c_void_p] + [C.c_int] * 5 + [C.c_double]
+    L.sh_set_alias.argtypes = [C.c_void_p, C.c_int]
     return L
 
 
@@ -58,8 +59,9 @@ def _placement(row, next_box):
     return (x, y, int(z[0])), int(row[0]), int(row[1])
 
 
-def _drive(L, env, setting, container, nb, nl, seed, env_id, steps):
+def _drive(L, env, setting, container, nb, nl, seed, env_id, steps, alias=False):
     h = L.sh_create(setting, *container)
+    L.sh_set_alias(h, int(alias))
     L.sh_reset(h)
     o = env.reset()
     n_virtual = n_real = 0
@@ -104,3 +106,50 @@ def test_device_stability_source_on_other_configurations(lib, name):
     env = OracleDiscrete(c["setting"], container_size=c["container"], internal_node_holder=c["nb"], leaf_node_holder=c["nl"],
                          size_minimum=min(min(i) for i in c["items"]), stream=case_stream(c, 91, 2, 600))
     _drive(lib, env, c["setting"], c["container"], c["nb"], c["nl"], 91, 2, 300)
+
+
+# ---- the ALIAS variant (stability_check<true, G, ALIAS = true>: the reference's object semantics of the load entries, DESIGN.md
+# section 3 (b)) against the oracle's alias mode.  The trajectories below are the ones on which the two semantics part
+# (scratch/alias_rate.py: BASELINE item streams seed 1234, policy seed 4321): the snapshot build must follow the snapshot oracle and the
+# ALIAS build the alias oracle THROUGH the step where they part, and the two oracles must indeed part there. ----------------------------
+DIVERGING = [(1, 126, 39), (1, 835, 167), (3, 92, 103)]  # (setting, env id, step of the first difference)
+
+
+@pytest.mark.parametrize("setting,env_id,step", DIVERGING)
+@pytest.mark.parametrize("alias", [False, True], ids=["snapshot", "alias"])
+def test_alias_variant_follows_the_alias_oracle(lib, setting, env_id, step, alias):
+    env = OracleDiscrete(setting, stream=make_stream(1234, env_id, 600, setting))
+    env.set_alias_mode(alias)
+    _drive(lib, env, setting, (10, 10, 10), 80, 50, 4321, env_id, step + 25, alias=alias)
+
+
+@pytest.mark.parametrize("setting,env_id,step", DIVERGING)
+def test_the_two_semantics_part_on_these_trajectories(setting, env_id, step):
+    a, b = (OracleDiscrete(setting, stream=make_stream(1234, env_id, 600, setting)) for _ in range(2))
+    b.set_alias_mode(True)
+    oa, ob = a.reset(), b.reset()
+    for t in range(step + 1):
+        assert np.array_equal(oa, ob), t
+        _, row = policy_pick(oa, 80, 50, 4321, env_id, t)
+        oa, _, da, _ = a.step(row)
+        ob, _, db, _ = b.step(row)
+        if t < step and da:
+            oa, ob = a.reset(), b.reset()
+    assert da != db or not np.array_equal(oa, ob)
+
+
+@pytest.mark.parametrize("setting", [1, 3])
+def test_alias_variant_on_ordinary_trajectories(lib, setting):
+    for env_id in range(4):
+        env = OracleDiscrete(setting, stream=make_stream(300 + setting, env_id, 700, setting))
+        env.set_alias_mode(True)
+        _drive(lib, env, setting, (10, 10, 10), 80, 50, 300 + setting, env_id, 300, alias=True)
+
+
+def test_cross_check_is_sensitive(lib):
+    """the snapshot build does NOT follow the alias oracle on a diverging trajectory (so the agreement above means something)"""
+    setting, env_id, step = DIVERGING[0]
+    env = OracleDiscrete(setting, stream=make_stream(1234, env_id, 600, setting))
+    env.set_alias_mode(True)
+    with pytest.raises(AssertionError):
+        _drive(lib, env, setting, (10, 10, 10), 80, 50, 4321, env_id, step + 25, alias=False)
