@@ -94,7 +94,11 @@ int pct_create(const pct_config *cfg, int32_t n_envs, int32_t device, pct_handle
     if (const char *pv = getenv("PCT_B200_CONT_PRE")) h->cont_pre = atoi(pv) != 0;
     if (const char *zv = getenv("PCT_B200_HOST_ZEROCOPY")) h->host_zero_copy = atoi(zv) != 0;
     if (const char *dv = getenv("PCT_B200_OBS_DELTA")) h->obs_delta = atoi(dv) != 0;
-    if (h->obs_delta && e == cudaSuccess) e = cudaMalloc(&h->d_obs_prev, sizeof(int32_t) * 2 * (size_t)n_envs);
+    if (const char *av = getenv("PCT_B200_ALIAS")) h->alias_mode = atoi(av) != 0 && cfg->domain == PCT_DISCRETE;
+    if ((h->obs_delta || h->alias_mode) && e == cudaSuccess) {
+        e = cudaMalloc(&h->d_aux, sizeof(DEnvAux) * (size_t)n_envs);
+        if (e == cudaSuccess) e = cudaMemset(h->d_aux, 0, sizeof(DEnvAux) * (size_t)n_envs);
+    }
     h->groups = 1;  // PCT_B200_GROUPS > 1 splits the batch over internal streams (measured: no gain)
     if (const char *gv = getenv("PCT_B200_GROUPS")) h->groups = atoi(gv);
     h->host_groups = 4;
@@ -143,7 +147,7 @@ void pct_destroy(pct_handle h) {
     cudaSetDevice(h->device);
     if (h->cfg.domain == PCT_CONTINUOUS) continuous_destroy(h);
     cudaFree(h->d_order);
-    cudaFree(h->d_hstate); cudaFree(h->d_hstate_c); cudaFree(h->d_query_c); cudaFree(h->d_query); cudaFree(h->d_obs_prev);
+    cudaFree(h->d_hstate); cudaFree(h->d_hstate_c); cudaFree(h->d_query_c); cudaFree(h->d_query); cudaFree(h->d_aux);
     cudaFree(h->d_ready);
     cudaFree(h->d_hot); cudaFree(h->d_cold); cudaFree(h->d_item_set); cudaFree(h->d_stream);
     cudaFree(h->d_obs); cudaFree(h->d_act); cudaFree(h->d_idx); cudaFree(h->d_rew); cudaFree(h->d_done); cudaFree(h->d_info);
@@ -222,9 +226,10 @@ static int launch_range(pct_handle h, int mode, int off, int cnt, const void *ac
         p.ready = h->d_ready + 2 * (size_t)off;
         p.epoch = ++h->epoch;
     }
-    if (h->obs_delta && h->d_obs_prev) {
-        if (h->fill_pending) launch_fill_prev(h->d_obs_prev + 2 * (size_t)off, cnt, p.nb, p.nl, gs);
-        p.obs_prev = h->d_obs_prev + 2 * (size_t)off;
+    if (h->d_aux) {
+        if (h->obs_delta && h->fill_pending) launch_fill_prev(h->d_aux + off, cnt, p.nb, p.nl, gs);
+        p.aux = h->d_aux + off;
+        p.opt = (h->obs_delta ? PCT_OPT_DELTA : 0) | (h->alias_mode ? PCT_OPT_ALIAS : 0);
     }
     cudaEvent_t *prof = nullptr;
     if (h->prof_on && mode == 1 && whole_batch) {

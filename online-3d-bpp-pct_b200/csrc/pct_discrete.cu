@@ -611,7 +611,7 @@ template <typename OT>
 __device__ __noinline__ void write_obs_delta(const DParams &p, int e, const DEnvHot *hot, const DEnvCold *cold, const int16_t (*leaf)[6], int n_leaf,
                                              int tid, int nthreads) {
     OT *obs = (OT *)p.obs + (size_t)e * (size_t)((p.nb + p.nl + 1) * 9);
-    int32_t *prev = p.obs_prev + 2 * (size_t)e;
+    int32_t *prev = p.aux[e].obs_prev;
     const int n_box = hot->h.n_box;
     const int pb = min(prev[0], p.nb), pl = min(prev[1], p.nl);
     __syncthreads();  // every thread has read prev before thread 0 replaces it below
@@ -686,8 +686,8 @@ __device__ __forceinline__ long long gtime() { long long t; asm volatile("mov.u6
 constexpr int K1_SM_PER_WARP = sizeof(DEnvHot) + EMS_TMP_MAX * 12 + 16 + EDGE_STAGE * 32 + POLY_STAGE * 16;  // record + EMS temp + mbarrier/lock + staged loads
 static_assert(K1_SM_PER_WARP % 16 == 0, "alignment");
 
-template <bool STAB>
-__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, K1_MINB) pct_apply_kernel(const DParams p) {
+template <bool STAB, bool ALIAS = false>
+__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, K1_MINB) pct_apply_kernel(const DParams p) {  // ALIAS: see EdgePoolA (opt-in, PCT_B200_ALIAS=1)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int slot = blockIdx.x * WARPS_PER_BLOCK + warp;
@@ -809,11 +809,22 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, K1_MINB) pct_apply_kerne
                     int fl = 0;
                     GeomD g{hot->box, n_box0, p.setting == 3 ? cold->density : nullptr};
                     NodeD root{lx, ly, max_h, x, y, z, (double)(x * y * z) * next_den0};
+                    if constexpr (ALIAS) {  // the reference's object semantics of the load entries
+                        EdgePoolA pool;
+                        static_cast<EdgePool &>(pool) = EdgePool{hot->e_lower, hot->e_next, hot->e_off, hot->first_in, hot->last_in, cold->e_st, st_sm, h.n_edge,
+                                                                 hot->poly_off, &cold->poly[0][0], poly_sm, h.n_poly};
+                        DEnvAux *ax = p.aux + e;
+                        pool.box_st = ax->box_st; pool.e_upper = ax->e_upper; pool.e_alias = ax->e_alias;
+                        res = stability_check<true, GeomD, true>(g, root, pool, &cold->big, lock, n_box0, fl);
+                        h.n_edge = pool.n;
+                        h.n_poly = pool.n_poly;
+                    } else {
                     EdgePool pool{hot->e_lower, hot->e_next, hot->e_off, hot->first_in, hot->last_in, cold->e_st, st_sm, h.n_edge,
                                   hot->poly_off, &cold->poly[0][0], poly_sm, h.n_poly};
                     res = stability_check<true, GeomD>(g, root, pool, &cold->big, lock, n_box0, fl);
                     h.n_edge = pool.n;
                     h.n_poly = pool.n_poly;
+                    }
                     h.flags |= fl;
                 }
                 __syncwarp();
@@ -1133,12 +1144,12 @@ __global__ void pct_policy_random_kernel(const DEnvHot *hot, int n_envs, int64_t
     leaf_idx[e] = n > 0 ? (int32_t)(rnd_u64(seed, (uint64_t)(env_id_base + e), (uint64_t)t) % (uint64_t)n) : 0;
 }
 
-__global__ void pct_fill_prev_kernel(int32_t *prev, int n2, int nb, int nl) {
+__global__ void pct_fill_prev_kernel(DEnvAux *aux, int n, int nb, int nl) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n2) prev[i] = (i & 1) ? nl : nb;
+    if (i < n) { aux[i].obs_prev[0] = nb; aux[i].obs_prev[1] = nl; }
 }
-void launch_fill_prev(int32_t *prev, int n_envs, int nb, int nl, cudaStream_t st) {
-    pct_fill_prev_kernel<<<(2 * n_envs + 255) / 256, 256, 0, st>>>(prev, 2 * n_envs, nb, nl);
+void launch_fill_prev(DEnvAux *aux, int n_envs, int nb, int nl, cudaStream_t st) {
+    pct_fill_prev_kernel<<<(n_envs + 255) / 256, 256, 0, st>>>(aux, n_envs, nb, nl);
 }
 
 // ---- launchers ---------------------------------------------------------------------------------------------
@@ -1155,13 +1166,15 @@ static cudaError_t launch_t(const DParams &p, cudaStream_t st, cudaEvent_t *prof
     const size_t smem2 = (size_t)Lay<SlotT, BIGSM>::PER_WARP * WARPS_PER_BLOCK;
     if (!attr_set) {
         cudaError_t err = set_smem(pct_apply_kernel<STAB>, smem1);
+        if (err == cudaSuccess && STAB) err = set_smem(pct_apply_kernel<STAB, STAB>, smem1);  // the ALIAS variant (stability settings only)
         if (err == cudaSuccess) err = set_smem(pct_candidates_kernel<SlotT, BIGSM>, smem2);
         if (err != cudaSuccess) return err;
         attr_set = true;
     }
     const int blocks = (p.n_envs + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
     if (prof) cudaEventRecord(prof[0], st);
-    pct_apply_kernel<STAB><<<blocks, 32 * WARPS_PER_BLOCK, smem1, st>>>(p);
+    if (STAB && (p.opt & PCT_OPT_ALIAS)) pct_apply_kernel<STAB, STAB><<<blocks, 32 * WARPS_PER_BLOCK, smem1, st>>>(p);
+    else pct_apply_kernel<STAB><<<blocks, 32 * WARPS_PER_BLOCK, smem1, st>>>(p);
     if (p.ready) {
         // overlapped mode (programmatic dependent launch): the candidates / feas_emit blocks become resident while the
         // previous kernel's tail is still running and pick their env up through the per-env hand-over flags
@@ -1174,7 +1187,7 @@ static cudaError_t launch_t(const DParams &p, cudaStream_t st, cudaEvent_t *prof
         cudaError_t err = cudaLaunchKernelEx(&cfg, pct_candidates_kernel<SlotT, BIGSM>, p);
         if (err != cudaSuccess) return err;
         cfg.gridDim = dim3(p.n_envs); cfg.blockDim = dim3(FEAS_THREADS); cfg.dynamicSmemBytes = 0;
-        err = p.obs_prev ? cudaLaunchKernelEx(&cfg, pct_feas_emit_kernel<OT, STAB, SlotT, true>, p)
+        err = (p.opt & PCT_OPT_DELTA) ? cudaLaunchKernelEx(&cfg, pct_feas_emit_kernel<OT, STAB, SlotT, true>, p)
                          : cudaLaunchKernelEx(&cfg, pct_feas_emit_kernel<OT, STAB, SlotT>, p);
         if (err == cudaSuccess && p.order) pct_order_kernel<<<1, 1024, 0, st>>>(p.hot, p.n_envs, p.order, 0);
         return err != cudaSuccess ? err : cudaGetLastError();
@@ -1182,7 +1195,7 @@ static cudaError_t launch_t(const DParams &p, cudaStream_t st, cudaEvent_t *prof
     if (prof) cudaEventRecord(prof[1], st);
     pct_candidates_kernel<SlotT, BIGSM><<<blocks, 32 * WARPS_PER_BLOCK, smem2, st>>>(p);
     if (prof) cudaEventRecord(prof[2], st);
-    if (p.obs_prev) pct_feas_emit_kernel<OT, STAB, SlotT, true><<<p.n_envs, FEAS_THREADS, 0, st>>>(p);
+    if (p.opt & PCT_OPT_DELTA) pct_feas_emit_kernel<OT, STAB, SlotT, true><<<p.n_envs, FEAS_THREADS, 0, st>>>(p);
     else pct_feas_emit_kernel<OT, STAB, SlotT><<<p.n_envs, FEAS_THREADS, 0, st>>>(p);
     if (p.order) pct_order_kernel<<<1, 1024, 0, st>>>(p.hot, p.n_envs, p.order, 0);
     if (prof) cudaEventRecord(prof[3], st);

@@ -25,9 +25,12 @@ struct pct_env_batch {
     bool overlap = true;          // PCT_B200_OVERLAP=0: plain back-to-back kernels
     bool overlap_cont = false;    // continuous domain: measured slower overlapped (5.35 M -> 3.97 M env-steps/s), off unless PCT_B200_OVERLAP_CONT=1
     // delta observation writes (PCT_B200_OBS_DELTA=1; not yet measured): the feasibility kernel writes only the rows that can differ from what the
-    // SAME caller buffer already holds; d_obs_prev = per env the internal / leaf rows of the tracked buffer that may be non-zero
+    // SAME caller buffer already holds (DEnvAux::obs_prev = per env the internal / leaf rows of the tracked buffer that may be non-zero)
     bool obs_delta = false;
-    int32_t *d_obs_prev = nullptr;
+    // object semantics of the load entries in the real placement (PCT_B200_ALIAS=1, discrete domain; logic verified on
+    // the host build of the stability routine, not yet run on hardware): pct_apply_kernel<STAB, ALIAS = true>
+    bool alias_mode = false;
+    pct::DEnvAux *d_aux = nullptr;  // per-env state of the opt-in variants (allocated when one of them is on)
     const void *tracked_obs = nullptr;
     bool fill_pending = false;
     bool host_zero_copy = false;  // pct_step_host: kernels write the observation straight into the pinned host buffer (PCT_B200_HOST_ZEROCOPY=1; not yet measured)

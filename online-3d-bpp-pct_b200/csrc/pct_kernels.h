@@ -64,6 +64,16 @@ struct EdgePoolA : EdgePool {
     uint32_t *e_alias;     // [(EDGE_MAX + 32) / 32] bit q: the entry is the upper box's own Stack object
 };
 
+// Per-env state of the opt-in kernel variants (one allocation, reached through DParams::aux):
+//   PCT_OPT_ALIAS  K1: the three arrays of EdgePoolA
+//   PCT_OPT_DELTA  K3: obs_prev = how many internal / leaf rows of the caller's observation buffer may be non-zero
+struct DEnvAux {
+    Stack4 box_st[NB_MAX + 1];
+    uint8_t e_upper[EDGE_MAX + 1];
+    uint32_t e_alias[(EDGE_MAX + 32) / 32];
+    int32_t obs_prev[2];
+};
+
 // per-env HBM scratch for the rare big cases (k > KSUP_SMALL)
 struct BigScratch {
     double rect[KSUP_MAX][4];
@@ -146,16 +156,17 @@ struct DParams {
     int no_auto_reset;  // mode 1: leave a finished env untouched (gym.Env semantics)
     // One pointer slot, two exclusive users (keeps sizeof(DParams), and with it the code of the default kernels, unchanged):
     //   dbg      phase timers (only in -DPCT_PHASE_TIMERS builds)
-    //   obs_prev delta observation writes (opt-in, production builds): [2 * n_envs] rows of the caller's observation buffer that may be
-    //            non-zero (internal, leaf); nullptr = write the whole observation
+    //   aux      per-env state of the opt-in variants (production builds; nullptr unless `opt` is non-zero), see DEnvAux
     union {
         long long *dbg;
-        int32_t *obs_prev;
+        struct DEnvAux *aux;
     };
     int32_t *order;  // [2 * n_envs] block -> env permutations (apply, feas_emit), nullptr = identity
     int32_t *ready;  // [2 * n_envs] per-env hand-over flags (apply -> candidates, candidates -> feas_emit); nullptr = kernels run back to back
     int32_t epoch;   // value published in `ready` by this launch
+    int32_t opt;     // opt-in variants served by `aux`: PCT_OPT_DELTA (K3 delta observation writes), PCT_OPT_ALIAS (K1 object semantics of the loads)
 };
+constexpr int PCT_OPT_DELTA = 1, PCT_OPT_ALIAS = 2;
 
 // heuristic baselines (pct_heuristics.cuh)
 struct HParams {
@@ -181,8 +192,8 @@ constexpr int PCT_H_QUERY_ = 7;
 constexpr int HEUR_SIDE_MAX = 32;  // height-map based codes (HM, MACS, RANDOM's bitmap, queries): W, L <= 32
 cudaError_t launch_heuristic_discrete(const DParams &p, const HParams &hp, cudaStream_t st);
 
-// delta observation writes: prev[2i] = nb, prev[2i+1] = nl for n entries ("every row of the buffer may be non-zero")
-void launch_fill_prev(int32_t *prev, int n_envs, int nb, int nl, cudaStream_t st);
+// delta observation writes: aux[i].obs_prev = {nb, nl} for n envs ("every row of the buffer may be non-zero")
+void launch_fill_prev(DEnvAux *aux, int n_envs, int nb, int nl, cudaStream_t st);
 
 int discrete_kernels_per_step();
 cudaError_t launch_discrete(const DParams &p, cudaStream_t st, cudaEvent_t *prof = nullptr);

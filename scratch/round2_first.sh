@@ -5,7 +5,7 @@
 O=gpurun_out/r2_first; mkdir -p $O
 run() { name=$1; shift; echo "== $name: $*" | tee -a $O/summary.txt; ( timeout 240 "$@" ) > $O/$name.log 2>&1; echo "   rc=$?" | tee -a $O/summary.txt; tail -3 $O/$name.log | cut -c1-400 >> $O/summary.txt; }
 run tests_zz   python -m pytest tests/test_zz_gpu_golden_replay.py tests/test_zz_gpu_continuous_full_size.py -q --tb=short -m gpu
-run tests_zzz  python -m pytest tests/test_zzz_gpu_continuous_pre.py tests/test_zzz_gpu_host_zerocopy.py tests/test_zzz_gpu_obs_delta.py -q --tb=short -m gpu
+run tests_zzz  python -m pytest tests/test_zzz_gpu_continuous_pre.py tests/test_zzz_gpu_host_zerocopy.py tests/test_zzz_gpu_obs_delta.py tests/test_zzz_gpu_alias.py -q --tb=short -m gpu
 B="python bench.py --steps 400 --warmup 200 --e2e-steps 150 --skip-cpu"
 run bench_default            $B
 PCT_B200_HOST_ZEROCOPY=1 run bench_zerocopy          $B
