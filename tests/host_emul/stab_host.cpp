@@ -21,6 +21,7 @@ static inline double __longlong_as_double(long long v) { double d; memcpy(&d, &v
 #endif
 #include "pct_stability.cuh"
 #include "pct_geom.cuh"
+#include "pct_geom_continuous.cuh"
 
 using namespace pct;
 
@@ -105,6 +106,103 @@ int sh_place(StabHost *h, int x, int y, int z, int lx, int ly, double density) {
     h->n_box = n0 + 1;
     h->e_off[n0 + 1] = (uint16_t)h->n_edge;
     h->poly_off[n0 + 1] = (uint16_t)h->n_poly;
+    return 1;
+}
+}
+
+
+// ---- continuous domain (GeomC; what pctc_apply_kernel / pctc_feas_emit_kernel do around the routine, csrc/pct_continuous.cu) ----------
+struct StabHostC {
+    int setting;
+    double W, L, H;
+    int n_box, n_edge, n_poly, flags;
+    double box[NB_MAX][6];  // lx, ly, lz, x, y, z
+    double den[NB_MAX];
+    uint8_t e_lower[EDGE_MAX + 1], e_next[EDGE_MAX + 1], first_in[NB_MAX], last_in[NB_MAX];
+    uint16_t e_off[NB_MAX + 2], poly_off[NB_MAX + 2];
+    Stack4 e_st[EDGE_MAX + 1];
+    double poly[POLY_MAX][2];
+    BigScratch big;
+    int lock, alias;
+    Stack4 box_st[NB_MAX + 1];
+    uint8_t e_upper[EDGE_MAX + 1];
+    uint32_t e_alias[(EDGE_MAX + 32) / 32];
+};
+static EdgePool pool_of(StabHostC *h) {
+    return EdgePool{h->e_lower, h->e_next, h->e_off, h->first_in, h->last_in, h->e_st, h->e_st, h->n_edge, h->poly_off, &h->poly[0][0], &h->poly[0][0], h->n_poly};
+}
+
+extern "C" {
+StabHostC *shc_create(int setting, double W, double L, double H) {
+    StabHostC *h = new StabHostC();
+    memset(h, 0, sizeof *h);
+    h->setting = setting; h->W = W; h->L = L; h->H = H;
+    return h;
+}
+void shc_destroy(StabHostC *h) { delete h; }
+void shc_set_alias(StabHostC *h, int on) { h->alias = on; }
+void shc_reset(StabHostC *h) { h->n_box = 0; h->n_edge = 0; h->n_poly = 0; h->flags = 0; h->lock = 0; }
+int shc_flags(StabHostC *h) { return h->flags; }
+
+// pctc_feas_emit_kernel's feasibility of one candidate tuple (xs, ys, zs, xe, ye, ze)   (C:bin3D.py:134-137, C:space.py:380-425)
+int shc_virtual(StabHostC *h, const double t6[6], double density) {
+    const double x = t6[3] - t6[0], y = t6[4] - t6[1], z = t6[5] - t6[2], lx = t6[0], ly = t6[1];
+    bool chk = !(lx + x - 1e-6 > h->W || ly + y - 1e-6 > h->L) && !(lx + 1e-6 < 0 || ly + 1e-6 < 0);
+    double mh = rest_height_c(h->box, 0, h->n_box, 1, lx, ly, lx + x, ly + y);
+    if (mh < 0) mh = 0.0;
+    if (mh + z - 1e-6 > h->H) chk = false;
+    if (!chk) return 0;
+    if (h->setting == 2 || fabs(mh) < 1e-6) return 1;
+    GeomC g{h->box, h->den, h->n_box};
+    NodeC root{lx, ly, mh, x, y, z, x * y * z * density};
+    EdgePool pool = pool_of(h);
+    int fl = 0;
+    const int ok = stability_check<false, GeomC>(g, root, pool, &h->big, &h->lock, 0, fl) != 0;
+    h->flags |= fl;
+    return ok;
+}
+
+// pctc_apply_kernel on a 9-float leaf row: LeafNode2Action (C:bin3D.py:151-167) + Space.drop_box (C:space.py:329-376); 1 = placed
+int shc_place_row(StabHostC *h, const double a[6], const double nb[3], double density) {
+    double lx = 0, ly = 0, x = nb[0], y = nb[1], z = nb[2], s = 0;
+    for (int t = 0; t < 6; t++) s += a[t];
+    if (s != 0) {
+        x = around6(a[3] - a[0]);
+        y = around6(a[4] - a[1]);
+        int rec[3] = {0, 1, 2}, n = 3;
+        for (int i = 0; i < n; i++)
+            if (fabs(x - nb[rec[i]]) < 1e-6) { for (int u = i; u < n - 1; u++) rec[u] = rec[u + 1]; n--; break; }
+        for (int i = 0; i < n; i++)
+            if (fabs(y - nb[rec[i]]) < 1e-6) { for (int u = i; u < n - 1; u++) rec[u] = rec[u + 1]; n--; break; }
+        z = nb[rec[0]];
+        lx = a[0]; ly = a[1];
+    }
+    lx = around6(lx); ly = around6(ly);
+    const int n0 = h->n_box;
+    if (n0 >= NB_MAX) return 0;
+    bool ok = !(lx + x - 1e-6 > h->W || ly + y - 1e-6 > h->L) && !(lx + 1e-6 < 0 || ly + 1e-6 < 0);
+    h->e_off[n0] = (uint16_t)h->n_edge; h->poly_off[n0] = (uint16_t)h->n_poly; h->first_in[n0] = EDGE_NIL;
+    if (!ok) return 0;
+    double mh = rest_height_c(h->box, 0, n0, 1, lx, ly, lx + x, ly + y);
+    const double max_h = mh < 0 ? 0.0 : mh;
+    if (max_h + z - 1e-6 > h->H) return 0;
+    if (h->setting != 2 && !(fabs(max_h) < 1e-6)) {
+        GeomC g{h->box, h->den, n0};
+        NodeC root{lx, ly, max_h, x, y, z, x * y * z * density};
+        EdgePoolA pool;
+        static_cast<EdgePool &>(pool) = pool_of(h);
+        pool.box_st = h->box_st; pool.e_upper = h->e_upper; pool.e_alias = h->e_alias;
+        int fl = 0;
+        const int res = h->alias ? stability_check<true, GeomC, true>(g, root, pool, &h->big, &h->lock, n0, fl)
+                                 : stability_check<true, GeomC>(g, root, pool, &h->big, &h->lock, n0, fl);
+        h->n_edge = pool.n; h->n_poly = pool.n_poly; h->flags |= fl;
+        if (!res) return 0;
+    }
+    double *b = h->box[n0];
+    b[0] = lx; b[1] = ly; b[2] = max_h; b[3] = x; b[4] = y; b[5] = z;
+    h->den[n0] = density;
+    h->n_box = n0 + 1;
+    h->e_off[n0 + 1] = (uint16_t)h->n_edge; h->poly_off[n0 + 1] = (uint16_t)h->n_poly;
     return 1;
 }
 }

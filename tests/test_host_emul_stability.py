@@ -31,7 +31,7 @@ def lib():
     inc = _cuda_include()
     if inc is None:
         pytest.skip("CUDA headers not found")
-    deps = [SRC] + [os.path.join(CSRC, f) for f in ("pct_stability.cuh", "pct_geom.cuh", "pct_kernels.h")]
+    deps = [SRC] + [os.path.join(CSRC, f) for f in ("pct_stability.cuh", "pct_geom.cuh", "pct_geom_continuous.cuh", "pct_kernels.h")]
     if not os.path.exists(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in deps):
         os.makedirs(os.path.dirname(OUT), exist_ok=True)
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-w", "-I" + CSRC,
@@ -45,6 +45,14 @@ def lib():
     L.sh_virtual.argtypes = [C.c_void_p] + [C.c_int] * 5 + [C.c_double, C.POINTER(C.c_int)]
     L.sh_place.argtypes = [C.c_void_p] + [C.c_int] * 5 + [C.c_double]
     L.sh_set_alias.argtypes = [C.c_void_p, C.c_int]
+    dp = C.POINTER(C.c_double)
+    L.shc_create.restype = C.c_void_p
+    L.shc_create.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double]
+    for f in ("shc_destroy", "shc_reset", "shc_flags"):
+        getattr(L, f).argtypes = [C.c_void_p]
+    L.shc_set_alias.argtypes = [C.c_void_p, C.c_int]
+    L.shc_virtual.argtypes = [C.c_void_p, dp, C.c_double]
+    L.shc_place_row.argtypes = [C.c_void_p, dp, dp, C.c_double]
     return L
 
 
@@ -153,3 +161,67 @@ def test_cross_check_is_sensitive(lib):
     env.set_alias_mode(True)
     with pytest.raises(AssertionError):
         _drive(lib, env, setting, (10, 10, 10), 80, 50, 4321, env_id, step + 25, alias=False)
+
+
+# ---- continuous domain: GeomC + the float64 resting-height / rounding code, against the continuous oracle -------------------------------
+def _dpc(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _drive_c(L, env, setting, container, seed, env_id, steps, alias=False):
+    h = L.shc_create(setting, *container)
+    L.shc_set_alias(h, int(alias))
+    L.shc_reset(h)
+    o = env.reset()
+    n_virtual = 0
+    for t in range(steps):
+        cand, feas = env.candidates()
+        den = env.next_den
+        for p, f in zip(cand, feas):
+            if f < 0:
+                continue
+            got = L.shc_virtual(h, _dpc(np.ascontiguousarray(p, dtype=np.float64)), den)
+            assert got == f, "step %d candidate %s: host build %d, oracle %d" % (t, p.tolist(), got, f)
+            n_virtual += 1
+        _, row = policy_pick(o, 80, 50, seed, env_id, t)
+        nb = np.array(env.next_box, dtype=np.float64)
+        o, _, done, _ = env.step(row)
+        placed = L.shc_place_row(h, _dpc(np.ascontiguousarray(row[:6], dtype=np.float64)), _dpc(nb), den)
+        assert placed == (not done), "step %d real placement: host build %d, oracle done=%s" % (t, placed, done)
+        if done:
+            o = env.reset()
+            L.shc_reset(h)
+    assert L.shc_flags(h) == 0
+    L.shc_destroy(h)
+    return n_virtual
+
+
+@pytest.mark.parametrize("setting", [1, 3, 2])
+def test_device_stability_source_follows_the_continuous_oracle(lib, setting):
+    from pct_oracle import OracleContinuous, make_continuous_stream
+    tot = 0
+    for env_id in range(4):
+        env = OracleContinuous(setting, stream=make_continuous_stream(77 + setting, env_id, 600, setting))
+        tot += _drive_c(lib, env, setting, (1.0, 1.0, 1.0), 77 + setting, env_id, 250)
+    assert tot > 10000
+
+
+DIVERGING_C = [(1, 1, 169), (1, 548, 152), (1, 597, 103), (1, 638, 163), (3, 635, 215)]  # scratch/alias_rate.py, continuous streams
+
+
+@pytest.mark.parametrize("setting,env_id,step", DIVERGING_C)
+@pytest.mark.parametrize("alias", [False, True], ids=["snapshot", "alias"])
+def test_alias_variant_follows_the_alias_oracle_continuous(lib, setting, env_id, step, alias):
+    from pct_oracle import OracleContinuous, make_continuous_stream
+    env = OracleContinuous(setting, stream=make_continuous_stream(1234, env_id, 600, setting))
+    env.set_alias_mode(alias)
+    _drive_c(lib, env, setting, (1.0, 1.0, 1.0), 4321, env_id, step + 20, alias=alias)
+
+
+def test_cross_check_is_sensitive_continuous(lib):
+    from pct_oracle import OracleContinuous, make_continuous_stream
+    setting, env_id, step = DIVERGING_C[0]
+    env = OracleContinuous(setting, stream=make_continuous_stream(1234, env_id, 600, setting))
+    env.set_alias_mode(True)
+    with pytest.raises(AssertionError):
+        _drive_c(lib, env, setting, (1.0, 1.0, 1.0), 4321, env_id, step + 20, alias=False)
