@@ -94,7 +94,7 @@ int pct_create(const pct_config *cfg, int32_t n_envs, int32_t device, pct_handle
     if (const char *pv = getenv("PCT_B200_CONT_PRE")) h->cont_pre = atoi(pv) != 0;
     if (const char *zv = getenv("PCT_B200_HOST_ZEROCOPY")) h->host_zero_copy = atoi(zv) != 0;
     if (const char *dv = getenv("PCT_B200_OBS_DELTA")) h->obs_delta = atoi(dv) != 0;
-    if (const char *av = getenv("PCT_B200_ALIAS")) h->alias_mode = atoi(av) != 0 && cfg->domain == PCT_DISCRETE;
+    if (const char *av = getenv("PCT_B200_ALIAS")) h->alias_mode = atoi(av) != 0;
     if ((h->obs_delta || h->alias_mode) && e == cudaSuccess) {
         e = cudaMalloc(&h->d_aux, sizeof(DEnvAux) * (size_t)n_envs);
         if (e == cudaSuccess) e = cudaMemset(h->d_aux, 0, sizeof(DEnvAux) * (size_t)n_envs);

@@ -229,7 +229,12 @@ __device__ __noinline__ int genems_warp_c(CEnv *ev, const int n0, const double l
 }
 
 // ================= K1: apply =================
-template <bool STAB>
+// ALIAS variant (opt-in, PCT_B200_ALIAS=1): the reference's object semantics of the load entries (EdgePoolA).  CParams has no
+// free pointer slot (growing it would move the stack frames of the default kernels), so the per-env state is reached through this device
+// global, set on the launching stream right before the launch — one handle at a time while the switch is on.
+__device__ DEnvAux *g_pctc_alias_aux;
+
+template <bool STAB, bool ALIAS = false>
 __global__ void __launch_bounds__(64) pctc_apply_kernel(const CParams p) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int e = blockIdx.x * 2 + warp;
@@ -301,10 +306,20 @@ __global__ void __launch_bounds__(64) pctc_apply_kernel(const CParams p) {
                     int fl = 0;
                     GeomC g{ev->box, ev->den, n_box0};
                     NodeC root{lx, ly, max_h, x, y, z, x * y * z * den0};
+                    if constexpr (ALIAS) {
+                        EdgePoolA pool;
+                        static_cast<EdgePool &>(pool) = EdgePool{ev->e_lower, ev->e_next, ev->e_off, ev->first_in, ev->last_in, ev->e_st, ev->e_st, h.n_edge,
+                                                                 ev->poly_off, &ev->poly[0][0], &ev->poly[0][0], h.n_poly};
+                        DEnvAux *ax = g_pctc_alias_aux + e;
+                        pool.box_st = ax->box_st; pool.e_upper = ax->e_upper; pool.e_alias = ax->e_alias;
+                        res = stability_check<true, GeomC, true>(g, root, pool, &ev->big, lock, n_box0, fl);
+                        h.n_edge = pool.n; h.n_poly = pool.n_poly;
+                    } else {
                     EdgePool pool{ev->e_lower, ev->e_next, ev->e_off, ev->first_in, ev->last_in, ev->e_st, ev->e_st, h.n_edge,
                                   ev->poly_off, &ev->poly[0][0], &ev->poly[0][0], h.n_poly};
                     res = stability_check<true, GeomC>(g, root, pool, &ev->big, lock, n_box0, fl);
                     h.n_edge = pool.n; h.n_poly = pool.n_poly;
+                    }
                     h.flags |= fl;
                 }
                 __syncwarp();
@@ -661,7 +676,12 @@ int continuous_launch(pct_env_batch *h, int mode, const void *actions, int actio
     if (h->overlap_cont && h->d_ready && cap == cudaStreamCaptureStatusNone) { p.ready = h->d_ready; p.epoch = ++h->epoch; }
     const bool stab = p.setting != 2;
     const int b2 = (p.n_envs + 1) / 2;
-    if (stab) pctc_apply_kernel<true><<<b2, 64, 0, st>>>(p); else pctc_apply_kernel<false><<<b2, 64, 0, st>>>(p);
+    if (stab && h->alias_mode && h->d_aux) {
+        DEnvAux *aux = h->d_aux;
+        cudaMemcpyToSymbolAsync(g_pctc_alias_aux, &aux, sizeof aux, 0, cudaMemcpyHostToDevice, st);
+        pctc_apply_kernel<true, true><<<b2, 64, 0, st>>>(p);
+    } else if (stab) pctc_apply_kernel<true><<<b2, 64, 0, st>>>(p);
+    else pctc_apply_kernel<false><<<b2, 64, 0, st>>>(p);
     // candidates / feas_emit: with p.ready as programmatic dependent launches (their blocks become resident during the previous
     // kernel's tail and wait per env on the hand-over flags), else plain back-to-back launches
     cudaLaunchAttribute at[1];

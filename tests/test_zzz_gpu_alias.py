@@ -91,3 +91,31 @@ def test_alias_variant_on_a_batch(setting, monkeypatch):
         assert not gpu.decode_info(info)["flags"].any()
         o = obs.cpu().numpy()
     gpu.close()
+
+
+# ---- continuous domain (pctc_apply_kernel<true, ALIAS = true>) -------------------------------------------------------------------------
+DIVERGING_C = [(1, 1, 169), (1, 548, 152), (1, 597, 103), (1, 638, 163), (3, 635, 215)]  # scratch/alias_rate.py, sample_from_distribution streams
+
+
+@pytest.mark.parametrize("setting,env_id,step", DIVERGING_C)
+@pytest.mark.parametrize("alias", [True, False], ids=["alias", "snapshot"])
+def test_real_placement_semantics_on_the_parting_trajectories_continuous(setting, env_id, step, alias, monkeypatch):
+    import pct_b200
+    from pct_oracle import OracleContinuous, make_continuous_stream
+    monkeypatch.setenv("PCT_B200_ALIAS", "1" if alias else "0")
+    gpu = pct_b200.PctBatch(1, setting, container_size=(1.0, 1.0, 1.0), continuous=True, sample_from_distribution=True, seed=1234,
+                            env_id_base=env_id, obs_dtype=torch.float64)
+    orc = OracleContinuous(setting, stream=make_continuous_stream(1234, env_id, 600, setting))
+    orc.set_alias_mode(alias)
+    o_ref, o = orc.reset(), gpu.reset().cpu().numpy()[0]
+    for t in range(step + 25):
+        assert np.array_equal(o_ref, o), "step %d (alias=%s)" % (t, alias)
+        _, row = policy_pick(o_ref, 80, 50, 4321, env_id, t)
+        o_ref, _, d_ref, _ = orc.step(row)
+        if d_ref:
+            o_ref = orc.reset()
+        obs, _, d, info = gpu.step(leaf_idx=gpu.random_policy(4321, t))
+        assert bool(d.cpu().numpy()[0]) == d_ref, "done at step %d (alias=%s)" % (t, alias)
+        assert not gpu.decode_info(info)["flags"].any()
+        o = obs.cpu().numpy()[0]
+    gpu.close()
