@@ -619,7 +619,12 @@ static __device__ __noinline__ int stability_check(const G &g, const typename G:
 #pragma unroll 1
         for (int q = pool.first_in[child]; q != EDGE_NIL; q = pool.next[q]) {
             if (!real && q == skip) continue;  // `involved` path member: its real load is replaced by the virtual one
-            const Stack4 e = pool.load(q);
+            Stack4 e = pool.load(q);
+            if constexpr (!REAL && ALIAS) {  // virtual check under the object semantics: an entry that IS the upper box's Stack object reads its field
+                // (differs from the stored load only after a FAILED real placement, i.e. for the terminal observation of the no-auto-reset facades)
+                EdgePoolA &pa = static_cast<EdgePoolA &>(pool);
+                if ((pa.e_alias[q >> 5] >> (q & 31)) & 1u) e = pa.box_st[pa.e_upper[q]];
+            }
             ccx += e.cx * e.m; ccy += e.cy * e.m; ccz += e.cz * e.m;
             mm += e.m;
         }

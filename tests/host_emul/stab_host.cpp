@@ -26,7 +26,7 @@ static inline double __longlong_as_double(long long v) { double d; memcpy(&d, &v
 using namespace pct;
 
 struct StabHost {
-    int setting, W, L, H;
+    int setting, W, L, H, nb_holder;
     int n_box, n_edge, n_poly, flags;
     int16_t box[NB_MAX][6];
     double density[NB_MAX];
@@ -51,9 +51,10 @@ extern "C" {
 StabHost *sh_create(int setting, int W, int L, int H) {
     StabHost *h = new StabHost();
     memset(h, 0, sizeof *h);
-    h->setting = setting; h->W = W; h->L = L; h->H = H;
+    h->setting = setting; h->W = W; h->L = L; h->H = H; h->nb_holder = NB_MAX;
     return h;
 }
+void sh_set_holder(StabHost *h, int nb) { h->nb_holder = nb; }
 void sh_destroy(StabHost *h) { delete h; }
 void sh_set_alias(StabHost *h, int on) { h->alias = on; }
 void sh_reset(StabHost *h) { h->n_box = 0; h->n_edge = 0; h->n_poly = 0; h->flags = 0; h->lock = 0; }
@@ -69,20 +70,22 @@ int sh_virtual(StabHost *h, int x, int y, int z, int lx, int ly, double density,
     if (h->setting == 2 || mh == 0) return 1;
     GeomD g{h->box, h->n_box, h->setting == 3 ? h->density : nullptr};
     NodeD root{lx, ly, mh, x, y, z, (double)(x * y * z) * density};
-    EdgePool pool = pool_of(h);
+    EdgePoolA pool;
+    static_cast<EdgePool &>(pool) = pool_of(h);
+    pool.box_st = h->box_st; pool.e_upper = h->e_upper; pool.e_alias = h->e_alias;
     int fl = 0;
-    const int ok = stability_check<false, GeomD>(g, root, pool, &h->big, &h->lock, 0, fl) != 0;
+    const int ok = (h->alias ? stability_check<false, GeomD, true>(g, root, pool, &h->big, &h->lock, 0, fl)
+                             : stability_check<false, GeomD>(g, root, pool, &h->big, &h->lock, 0, fl)) != 0;
     h->flags |= fl;
     return ok;
 }
 
 // Space.drop_box (D:space.py:347-391) as pct_apply_kernel performs it: 1 = placed, 0 = rejected (the episode ends)
 int sh_place(StabHost *h, int x, int y, int z, int lx, int ly, double density) {
-    const int n0 = h->n_box;
-    if (n0 >= NB_MAX) return 0;
+    const int n0 = h->n_box;  // may equal the holder size: the kernel (like the reference) runs the check first and rejects the box afterwards
     h->e_off[n0] = (uint16_t)h->n_edge;
     h->poly_off[n0] = (uint16_t)h->n_poly;
-    h->first_in[n0] = EDGE_NIL;
+    h->first_in[n0 < NB_MAX ? n0 : 0] = EDGE_NIL;
     const int mh = rest_height(h->box, 0, n0, 1, lx, ly, lx + x, ly + y);
     if (lx + x > h->W || ly + y > h->L) return 0;
     if (mh + z > h->H) return 0;
@@ -100,6 +103,7 @@ int sh_place(StabHost *h, int x, int y, int z, int lx, int ly, double density) {
         h->flags |= fl;
         if (!res) return 0;
     }
+    if (n0 >= h->nb_holder) return 0;  // PCT_FLAG_BOX_OVERFLOW in the kernel (IndexError in the reference, D:space.py:385)
     int16_t *b = h->box[n0];
     b[0] = (int16_t)lx; b[1] = (int16_t)ly; b[2] = (int16_t)mh; b[3] = (int16_t)(lx + x); b[4] = (int16_t)(ly + y); b[5] = (int16_t)(mh + z);
     h->density[n0] = density;
@@ -113,7 +117,7 @@ int sh_place(StabHost *h, int x, int y, int z, int lx, int ly, double density) {
 
 // ---- continuous domain (GeomC; what pctc_apply_kernel / pctc_feas_emit_kernel do around the routine, csrc/pct_continuous.cu) ----------
 struct StabHostC {
-    int setting;
+    int setting, nb_holder;
     double W, L, H;
     int n_box, n_edge, n_poly, flags;
     double box[NB_MAX][6];  // lx, ly, lz, x, y, z
@@ -136,9 +140,10 @@ extern "C" {
 StabHostC *shc_create(int setting, double W, double L, double H) {
     StabHostC *h = new StabHostC();
     memset(h, 0, sizeof *h);
-    h->setting = setting; h->W = W; h->L = L; h->H = H;
+    h->setting = setting; h->W = W; h->L = L; h->H = H; h->nb_holder = NB_MAX;
     return h;
 }
+void shc_set_holder(StabHostC *h, int nb) { h->nb_holder = nb; }
 void shc_destroy(StabHostC *h) { delete h; }
 void shc_set_alias(StabHostC *h, int on) { h->alias = on; }
 void shc_reset(StabHostC *h) { h->n_box = 0; h->n_edge = 0; h->n_poly = 0; h->flags = 0; h->lock = 0; }
@@ -155,9 +160,12 @@ int shc_virtual(StabHostC *h, const double t6[6], double density) {
     if (h->setting == 2 || fabs(mh) < 1e-6) return 1;
     GeomC g{h->box, h->den, h->n_box};
     NodeC root{lx, ly, mh, x, y, z, x * y * z * density};
-    EdgePool pool = pool_of(h);
+    EdgePoolA pool;
+    static_cast<EdgePool &>(pool) = pool_of(h);
+    pool.box_st = h->box_st; pool.e_upper = h->e_upper; pool.e_alias = h->e_alias;
     int fl = 0;
-    const int ok = stability_check<false, GeomC>(g, root, pool, &h->big, &h->lock, 0, fl) != 0;
+    const int ok = (h->alias ? stability_check<false, GeomC, true>(g, root, pool, &h->big, &h->lock, 0, fl)
+                             : stability_check<false, GeomC>(g, root, pool, &h->big, &h->lock, 0, fl)) != 0;
     h->flags |= fl;
     return ok;
 }
@@ -179,9 +187,8 @@ int shc_place_row(StabHostC *h, const double a[6], const double nb[3], double de
     }
     lx = around6(lx); ly = around6(ly);
     const int n0 = h->n_box;
-    if (n0 >= NB_MAX) return 0;
     bool ok = !(lx + x - 1e-6 > h->W || ly + y - 1e-6 > h->L) && !(lx + 1e-6 < 0 || ly + 1e-6 < 0);
-    h->e_off[n0] = (uint16_t)h->n_edge; h->poly_off[n0] = (uint16_t)h->n_poly; h->first_in[n0] = EDGE_NIL;
+    h->e_off[n0] = (uint16_t)h->n_edge; h->poly_off[n0] = (uint16_t)h->n_poly; h->first_in[n0 < NB_MAX ? n0 : 0] = EDGE_NIL;
     if (!ok) return 0;
     double mh = rest_height_c(h->box, 0, n0, 1, lx, ly, lx + x, ly + y);
     const double max_h = mh < 0 ? 0.0 : mh;
@@ -198,6 +205,7 @@ int shc_place_row(StabHostC *h, const double a[6], const double nb[3], double de
         h->n_edge = pool.n; h->n_poly = pool.n_poly; h->flags |= fl;
         if (!res) return 0;
     }
+    if (n0 >= h->nb_holder) return 0;  // PCT_FLAG_BOX_OVERFLOW in the kernel
     double *b = h->box[n0];
     b[0] = lx; b[1] = ly; b[2] = max_h; b[3] = x; b[4] = y; b[5] = z;
     h->den[n0] = density;
@@ -205,4 +213,13 @@ int shc_place_row(StabHostC *h, const double a[6], const double nb[3], double de
     h->e_off[n0 + 1] = (uint16_t)h->n_edge; h->poly_off[n0 + 1] = (uint16_t)h->n_poly;
     return 1;
 }
+}
+
+// debug / triage: the incoming loads of placed box i in pool order -> rows (edge position, cx, cy, cz, m); returns their number
+extern "C" int sh_incoming(StabHost *h, int i, double *out5, int cap) {
+    int n = 0;
+    for (int q = h->first_in[i]; q != EDGE_NIL && n < cap; q = h->e_next[q], n++) {
+        out5[5 * n] = q; out5[5 * n + 1] = h->e_st[q].cx; out5[5 * n + 2] = h->e_st[q].cy; out5[5 * n + 3] = h->e_st[q].cz; out5[5 * n + 4] = h->e_st[q].m;
+    }
+    return n;
 }

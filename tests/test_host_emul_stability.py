@@ -45,6 +45,7 @@ def lib():
     L.sh_virtual.argtypes = [C.c_void_p] + [C.c_int] * 5 + [C.c_double, C.POINTER(C.c_int)]
     L.sh_place.argtypes = [C.c_void_p] + [C.c_int] * 5 + [C.c_double]
     L.sh_set_alias.argtypes = [C.c_void_p, C.c_int]
+    L.sh_set_holder.argtypes = [C.c_void_p, C.c_int]
     dp = C.POINTER(C.c_double)
     L.shc_create.restype = C.c_void_p
     L.shc_create.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double]
@@ -69,6 +70,7 @@ def _placement(row, next_box):
 
 def _drive(L, env, setting, container, nb, nl, seed, env_id, steps, alias=False):
     h = L.sh_create(setting, *container)
+    L.sh_set_holder(h, nb)
     L.sh_set_alias(h, int(alias))
     L.sh_reset(h)
     o = env.reset()
@@ -90,6 +92,12 @@ def _drive(L, env, setting, container, nb, nl, seed, env_id, steps, alias=False)
         assert placed == (not done), "step %d real placement: host build %d, oracle done=%s" % (t, placed, done)
         n_real += 1
         if done:
+            # the terminal observation (gym.Env semantics): the virtual checks run on the state the FAILED real placement left behind
+            cand, feas = env.candidates()
+            for p, f in zip(cand, feas):
+                if f >= 0:
+                    got = L.sh_virtual(h, int(p[3] - p[0]), int(p[4] - p[1]), int(p[5] - p[2]), int(p[0]), int(p[1]), env.next_den, None)
+                    assert got == f, "terminal observation after step %d, candidate %s: host build %d, oracle %d" % (t, p.tolist(), got, f)
             o = env.reset()
             L.sh_reset(h)
     assert L.sh_flags(h) == 0
@@ -189,6 +197,11 @@ def _drive_c(L, env, setting, container, seed, env_id, steps, alias=False):
         placed = L.shc_place_row(h, _dpc(np.ascontiguousarray(row[:6], dtype=np.float64)), _dpc(nb), den)
         assert placed == (not done), "step %d real placement: host build %d, oracle done=%s" % (t, placed, done)
         if done:
+            cand, feas = env.candidates()  # terminal observation: virtual checks on the state the failed real placement left behind
+            for p, f in zip(cand, feas):
+                if f >= 0:
+                    got = L.shc_virtual(h, _dpc(np.ascontiguousarray(p, dtype=np.float64)), env.next_den)
+                    assert got == f, "terminal observation after step %d, candidate %s: host build %d, oracle %d" % (t, p.tolist(), got, f)
             o = env.reset()
             L.shc_reset(h)
     assert L.shc_flags(h) == 0
