@@ -11,7 +11,9 @@ run bench_default            $B
 PCT_B200_HOST_ZEROCOPY=1 run bench_zerocopy          $B
 PCT_B200_OBS_DELTA=1 run bench_delta                 $B
 PCT_B200_HOST_ZEROCOPY=1 PCT_B200_OBS_DELTA=1 run bench_zerocopy_delta $B
+PCT_B200_ALIAS=1 run bench_alias                     $B
 run bench_cont_default       $B --continuous
+PCT_B200_ALIAS=1 run bench_cont_alias                $B --continuous
 PCT_B200_CONT_PRE=1 run bench_cont_pre               $B --continuous
 python - <<'PY' | tee -a gpurun_out/r2_first/summary.txt
 import glob, json
