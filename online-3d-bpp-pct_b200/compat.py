@@ -182,6 +182,7 @@ def reference_evaluate(reference_root, args, env=None, policy=None, custom="pct_
     evaluate = importlib.import_module("evaluation_tools").evaluate
     time_str = custom + "-" + time.strftime("%Y.%m.%d-%H-%M-%S", time.localtime(time.time()))
     device = torch.device("cpu") if getattr(args, "no_cuda", False) else torch.device("cuda", args.device)
+    torch.set_num_threads(1)  # evaluation.py:22
     torch.manual_seed(args.seed)
     if device.type == "cuda":
         torch.cuda.set_device(args.device)

@@ -260,6 +260,14 @@ def test_make_vec_envs_takes_the_reference_args(fake, argv, continuous, monkeypa
     envs.close()
 
 
+@pytest.fixture
+def one_torch_thread():
+    n = torch.get_num_threads()
+    torch.set_num_threads(1)  # main.py:28 does the same; the network is tiny
+    yield
+    torch.set_num_threads(n)
+
+
 class _Stop(Exception):
     pass
 
@@ -289,7 +297,7 @@ class _Counting(object):
 @pytest.mark.reference
 @pytest.mark.skipif(not ref_shim.reference_available(), reason="reference not mounted")
 @pytest.mark.parametrize("acktr", [True, False])
-def test_reference_trainer_runs_on_the_vector_surface(fake, acktr, tmp_path, monkeypatch):
+def test_reference_trainer_runs_on_the_vector_surface(fake, acktr, tmp_path, monkeypatch, one_torch_thread):
     """train_tools.train_n_steps (train_tools.py:32-150: rollouts through envs.step(leaf rows), PCTRolloutStorage, ACKTR / A2C updates) —
     unmodified — on PctVecEnv and on the reference's own VecPyTorch(ShmemVecEnv(Monitor(env))) stack: same seeds, same item streams ->
     the trainer sees the same observations step after step and ends with the same network parameters."""

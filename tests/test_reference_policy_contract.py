@@ -22,6 +22,15 @@ pytestmark = [pytest.mark.reference, pytest.mark.skipif(not ref_shim.reference_a
 torch = pytest.importorskip("torch")
 
 
+@pytest.fixture(autouse=True)
+def _one_torch_thread():
+    """evaluation.py:22 / main.py:28 do the same; the network is tiny and 8 BLAS threads only fight over it"""
+    n = torch.get_num_threads()
+    torch.set_num_threads(1)
+    yield
+    torch.set_num_threads(n)
+
+
 def _policy(setting):
     model, tools = ref_shim.load_policy_module()
     args = types.SimpleNamespace(embedding_size=64, hidden_size=128, gat_layer_num=1, internal_node_holder=80,
