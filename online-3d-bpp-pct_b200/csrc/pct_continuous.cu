@@ -313,6 +313,7 @@ __global__ void __launch_bounds__(64) pctc_apply_kernel(const CParams p) {
                         DEnvAux *ax = g_pctc_alias_aux + e;
                         pool.box_st = ax->box_st; pool.e_upper = ax->e_upper; pool.e_alias = ax->e_alias;
                         res = stability_check<true, GeomC, true>(g, root, pool, &ev->big, lock, n_box0, fl);
+                        if (!res) alias_sync_loads(pool);
                         h.n_edge = pool.n; h.n_poly = pool.n_poly;
                     } else {
                     EdgePool pool{ev->e_lower, ev->e_next, ev->e_off, ev->first_in, ev->last_in, ev->e_st, ev->e_st, h.n_edge,

@@ -816,6 +816,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, K1_MINB) pct_apply_kerne
                         DEnvAux *ax = p.aux + e;
                         pool.box_st = ax->box_st; pool.e_upper = ax->e_upper; pool.e_alias = ax->e_alias;
                         res = stability_check<true, GeomD, true>(g, root, pool, &cold->big, lock, n_box0, fl);
+                        if (!res) alias_sync_loads(pool);
                         h.n_edge = pool.n;
                         h.n_poly = pool.n_poly;
                     } else {

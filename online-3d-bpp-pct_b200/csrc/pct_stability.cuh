@@ -390,6 +390,15 @@ static __device__ __forceinline__ void alias_set_edge(const G &g, EdgePoolA &pa,
     alias_recompute(g, pa, lower);
 }
 
+// After a real descent that FAILED midway the object-type entries of boxes whose stack was recomputed but not propagated still read the new
+// stack in the reference (the terminal observation's virtual checks see it); the stored snapshots are brought in line here, so the
+// read-only checks (stability_check<false>, which only knows snapshots) need no variant.  After a completed descent both are equal already.
+static __device__ __noinline__ void alias_sync_loads(EdgePoolA &pa) {
+#pragma unroll 1
+    for (int q = 0; q < pa.n; q++)
+        if ((pa.e_alias[q >> 5] >> (q & 31)) & 1u) pa.load(q) = pa.box_st[pa.e_upper[q]];
+}
+
 // The DFS keeps the CURRENT node in registers; frames are pushed to the lane-local stack only for nodes with
 // >= 2 supports, and descending into the last (or only) support is a tail call (nothing is left to do in the
 // parent once its last child returns True).
@@ -619,12 +628,7 @@ static __device__ __noinline__ int stability_check(const G &g, const typename G:
 #pragma unroll 1
         for (int q = pool.first_in[child]; q != EDGE_NIL; q = pool.next[q]) {
             if (!real && q == skip) continue;  // `involved` path member: its real load is replaced by the virtual one
-            Stack4 e = pool.load(q);
-            if constexpr (!REAL && ALIAS) {  // virtual check under the object semantics: an entry that IS the upper box's Stack object reads its field
-                // (differs from the stored load only after a FAILED real placement, i.e. for the terminal observation of the no-auto-reset facades)
-                EdgePoolA &pa = static_cast<EdgePoolA &>(pool);
-                if ((pa.e_alias[q >> 5] >> (q & 31)) & 1u) e = pa.box_st[pa.e_upper[q]];
-            }
+            const Stack4 e = pool.load(q);
             ccx += e.cx * e.m; ccy += e.cy * e.m; ccz += e.cz * e.m;
             mm += e.m;
         }

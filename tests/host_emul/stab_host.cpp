@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <cstdlib>
 using std::max;
 using std::min;
 static inline float __fdividef(float a, float b) { return a / b; }  // device: approximate; only a pre-filter whose verdict the exact path confirms
@@ -70,12 +71,9 @@ int sh_virtual(StabHost *h, int x, int y, int z, int lx, int ly, double density,
     if (h->setting == 2 || mh == 0) return 1;
     GeomD g{h->box, h->n_box, h->setting == 3 ? h->density : nullptr};
     NodeD root{lx, ly, mh, x, y, z, (double)(x * y * z) * density};
-    EdgePoolA pool;
-    static_cast<EdgePool &>(pool) = pool_of(h);
-    pool.box_st = h->box_st; pool.e_upper = h->e_upper; pool.e_alias = h->e_alias;
+    EdgePool pool = pool_of(h);  // the read-only check knows snapshots only, in both semantics (like pct_feas_emit_kernel)
     int fl = 0;
-    const int ok = (h->alias ? stability_check<false, GeomD, true>(g, root, pool, &h->big, &h->lock, 0, fl)
-                             : stability_check<false, GeomD>(g, root, pool, &h->big, &h->lock, 0, fl)) != 0;
+    const int ok = stability_check<false, GeomD>(g, root, pool, &h->big, &h->lock, 0, fl) != 0;
     h->flags |= fl;
     return ok;
 }
@@ -98,6 +96,7 @@ int sh_place(StabHost *h, int x, int y, int z, int lx, int ly, double density) {
         int fl = 0;
         const int res = h->alias ? stability_check<true, GeomD, true>(g, root, pool, &h->big, &h->lock, n0, fl)
                                  : stability_check<true, GeomD>(g, root, pool, &h->big, &h->lock, n0, fl);
+        if (h->alias && !res && !getenv("PCT_HOST_EMUL_NO_SYNC")) alias_sync_loads(pool);  // as the ALIAS instantiation of the apply kernel does (switch: sensitivity test)
         h->n_edge = pool.n;
         h->n_poly = pool.n_poly;
         h->flags |= fl;
@@ -160,12 +159,9 @@ int shc_virtual(StabHostC *h, const double t6[6], double density) {
     if (h->setting == 2 || fabs(mh) < 1e-6) return 1;
     GeomC g{h->box, h->den, h->n_box};
     NodeC root{lx, ly, mh, x, y, z, x * y * z * density};
-    EdgePoolA pool;
-    static_cast<EdgePool &>(pool) = pool_of(h);
-    pool.box_st = h->box_st; pool.e_upper = h->e_upper; pool.e_alias = h->e_alias;
+    EdgePool pool = pool_of(h);  // the read-only check knows snapshots only, in both semantics (like pct_feas_emit_kernel)
     int fl = 0;
-    const int ok = (h->alias ? stability_check<false, GeomC, true>(g, root, pool, &h->big, &h->lock, 0, fl)
-                             : stability_check<false, GeomC>(g, root, pool, &h->big, &h->lock, 0, fl)) != 0;
+    const int ok = stability_check<false, GeomC>(g, root, pool, &h->big, &h->lock, 0, fl) != 0;
     h->flags |= fl;
     return ok;
 }
@@ -202,6 +198,7 @@ int shc_place_row(StabHostC *h, const double a[6], const double nb[3], double de
         int fl = 0;
         const int res = h->alias ? stability_check<true, GeomC, true>(g, root, pool, &h->big, &h->lock, n0, fl)
                                  : stability_check<true, GeomC>(g, root, pool, &h->big, &h->lock, n0, fl);
+        if (h->alias && !res && !getenv("PCT_HOST_EMUL_NO_SYNC")) alias_sync_loads(pool);  // as the ALIAS instantiation of the apply kernel does (switch: sensitivity test)
         h->n_edge = pool.n; h->n_poly = pool.n_poly; h->flags |= fl;
         if (!res) return 0;
     }

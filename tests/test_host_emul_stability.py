@@ -238,3 +238,19 @@ def test_cross_check_is_sensitive_continuous(lib):
     env.set_alias_mode(True)
     with pytest.raises(AssertionError):
         _drive_c(lib, env, setting, (1.0, 1.0, 1.0), 4321, env_id, step + 20, alias=False)
+
+
+def test_terminal_observations_need_the_load_sync(lib, monkeypatch):
+    """after a FAILED real placement the ALIAS apply kernel brings the stored snapshots in line with the objects (alias_sync_loads), which
+    is what lets the snapshot-only read-only checks reproduce the reference's terminal observation; without it they do not"""
+    monkeypatch.setenv("PCT_HOST_EMUL_NO_SYNC", "1")
+    failing = 0
+    for setting, env_id, step in DIVERGING:
+        env = OracleDiscrete(setting, stream=make_stream(1234, env_id, 600, setting))
+        env.set_alias_mode(True)
+        try:
+            _drive(lib, env, setting, (10, 10, 10), 80, 50, 4321, env_id, step + 25, alias=True)
+        except AssertionError as ex:
+            assert "terminal observation" in str(ex)
+            failing += 1
+    assert failing >= 2
