@@ -119,3 +119,30 @@ def test_real_placement_semantics_on_the_parting_trajectories_continuous(setting
         assert not gpu.decode_info(info)["flags"].any()
         o = obs.cpu().numpy()[0]
     gpu.close()
+
+
+@pytest.mark.parametrize("setting,env_id,step", DIVERGING)
+def test_terminal_observation_of_the_facade_under_the_object_semantics(setting, env_id, step, monkeypatch):
+    """gym.Env semantics (no auto-reset): the observation returned WITH done=True is computed on the state the failed real placement left
+    behind, where objects and snapshots differ — the ALIAS apply kernel synchronises the stored loads (alias_sync_loads) so that the
+    ordinary feasibility kernel reproduces the alias oracle's terminal observation"""
+    import pct_b200
+    monkeypatch.setenv("PCT_B200_ALIAS", "1")
+    stream = make_stream(1234, env_id, 600, setting)
+    env = pct_b200.PackingDiscrete(setting=setting, container_size=[10, 10, 10], item_set=ITEM_SET, item_stream=stream[None])
+    orc = OracleDiscrete(setting, stream=stream)
+    orc.set_alias_mode(True)
+    o_ref, o = orc.reset(), env.reset()
+    terminals = 0
+    for t in range(step + 10):
+        assert np.array_equal(o_ref, o), "step %d" % t
+        _, row = policy_pick(o_ref, 80, 50, 4321, env_id, t)
+        o_ref, _, d_ref, _ = orc.step(row)
+        o, _, d, _ = env.step(row)
+        assert d == d_ref
+        if d:
+            assert np.array_equal(o_ref, o), "terminal observation after step %d" % t
+            terminals += 1
+            o_ref, o = orc.reset(), env.reset()
+    assert terminals >= 1
+    env.close()
