@@ -95,6 +95,7 @@ int pct_create(const pct_config *cfg, int32_t n_envs, int32_t device, pct_handle
     if (const char *zv = getenv("PCT_B200_HOST_ZEROCOPY")) h->host_zero_copy = atoi(zv) != 0;
     if (const char *dv = getenv("PCT_B200_OBS_DELTA")) h->obs_delta = atoi(dv) != 0;
     if (const char *av = getenv("PCT_B200_ALIAS")) h->alias_mode = atoi(av) != 0;
+    if (cfg->setting == 2) h->alias_mode = false;  // no stability check, no load entries
     if ((h->obs_delta || h->alias_mode) && e == cudaSuccess) {
         e = cudaMalloc(&h->d_aux, sizeof(DEnvAux) * (size_t)n_envs);
         if (e == cudaSuccess) e = cudaMemset(h->d_aux, 0, sizeof(DEnvAux) * (size_t)n_envs);

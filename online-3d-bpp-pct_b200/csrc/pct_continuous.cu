@@ -70,6 +70,7 @@ struct CParams {
     int mode, keep_draw, no_auto_reset;
     int32_t *ready;  // overlapped launch mode: per-env hand-over flags [2 * n_envs] (see pct_common.cuh), nullptr = off
     int32_t epoch;
+    DEnvAux *aux;    // per-env state of the ALIAS apply kernel (EdgePoolA arrays), nullptr with PCT_B200_ALIAS=0 / setting 2
 };
 
 // around6, NodeC / GeomC (geometry policy of the stability routine), rest_height_c, rest_height_pre: pct_geom_continuous.cuh
@@ -229,10 +230,8 @@ __device__ __noinline__ int genems_warp_c(CEnv *ev, const int n0, const double l
 }
 
 // ================= K1: apply =================
-// ALIAS variant (opt-in, PCT_B200_ALIAS=1): the reference's object semantics of the load entries (EdgePoolA).  CParams has no
-// free pointer slot (growing it would move the stack frames of the default kernels), so the per-env state is reached through this device
-// global, set on the launching stream right before the launch — one handle at a time while the switch is on.
-__device__ DEnvAux *g_pctc_alias_aux;
+// ALIAS variant (the default; PCT_B200_ALIAS=0 selects the snapshot kernels): the reference's object semantics of the load entries (EdgePoolA,
+// DESIGN.md section 3 (b)); per-env state through CParams::aux.
 
 template <bool STAB, bool ALIAS = false>
 __global__ void __launch_bounds__(64) pctc_apply_kernel(const CParams p) {
@@ -310,7 +309,7 @@ __global__ void __launch_bounds__(64) pctc_apply_kernel(const CParams p) {
                         EdgePoolA pool;
                         static_cast<EdgePool &>(pool) = EdgePool{ev->e_lower, ev->e_next, ev->e_off, ev->first_in, ev->last_in, ev->e_st, ev->e_st, h.n_edge,
                                                                  ev->poly_off, &ev->poly[0][0], &ev->poly[0][0], h.n_poly};
-                        DEnvAux *ax = g_pctc_alias_aux + e;
+                        DEnvAux *ax = p.aux + e;
                         pool.box_st = ax->box_st; pool.e_upper = ax->e_upper; pool.e_alias = ax->e_alias;
                         res = stability_check<true, GeomC, true>(g, root, pool, &ev->big, lock, n_box0, fl);
                         if (!res) alias_sync_loads(pool);
@@ -678,8 +677,7 @@ int continuous_launch(pct_env_batch *h, int mode, const void *actions, int actio
     const bool stab = p.setting != 2;
     const int b2 = (p.n_envs + 1) / 2;
     if (stab && h->alias_mode && h->d_aux) {
-        DEnvAux *aux = h->d_aux;
-        cudaMemcpyToSymbolAsync(g_pctc_alias_aux, &aux, sizeof aux, 0, cudaMemcpyHostToDevice, st);
+        p.aux = h->d_aux;
         pctc_apply_kernel<true, true><<<b2, 64, 0, st>>>(p);
     } else if (stab) pctc_apply_kernel<true><<<b2, 64, 0, st>>>(p);
     else pctc_apply_kernel<false><<<b2, 64, 0, st>>>(p);

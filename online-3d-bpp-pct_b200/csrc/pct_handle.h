@@ -27,9 +27,10 @@ struct pct_env_batch {
     // delta observation writes (PCT_B200_OBS_DELTA=1; not yet measured): the feasibility kernel writes only the rows that can differ from what the
     // SAME caller buffer already holds (DEnvAux::obs_prev = per env the internal / leaf rows of the tracked buffer that may be non-zero)
     bool obs_delta = false;
-    // object semantics of the load entries in the real placement (PCT_B200_ALIAS=1, discrete domain; logic verified on
-    // the host build of the stability routine, not yet run on hardware): pct_apply_kernel<STAB, ALIAS = true>
-    bool alias_mode = false;
+    // object semantics of the load entries in the real placement = what the reference's Python objects do:
+    // pct_apply_kernel<STAB, ALIAS = true> / pctc_apply_kernel<true, true>.  Default ON since round 2 (green on hardware, oracle default flipped with it);
+    // PCT_B200_ALIAS=0 selects the snapshot semantics of round 1 (kept for the sensitivity tests).
+    bool alias_mode = true;
     pct::DEnvAux *d_aux = nullptr;  // per-env state of the opt-in variants (allocated when one of them is on)
     const void *tracked_obs = nullptr;
     bool fill_pending = false;

@@ -481,7 +481,7 @@ static void cur_observation(pctc_env *e, double *obs) {
 
 pctc_env *pctc_create(int setting, double W, double L, double H, int nb_holder, int nl_holder, double low_bound) {
     pctc_env *e = calloc(1, sizeof(pctc_env));
-    { const char *am = getenv("PCT_ORACLE_ALIAS"); e->alias_mode = am && atoi(am) != 0; } /* default off: see pctc_set_alias_mode / DESIGN.md section 3 */
+    { const char *am = getenv("PCT_ORACLE_ALIAS"); e->alias_mode = am ? atoi(am) != 0 : 1; } /* default ON = the reference's object semantics; PCT_ORACLE_ALIAS=0: snapshot semantics */
     e->setting = setting; e->W = W; e->L = L; e->H = H; e->height = H;
     e->nb_holder = nb_holder; e->nl_holder = nl_holder; e->low_bound = low_bound;
     e->boxes = calloc(PC_MAX_BOXES, sizeof(Box));

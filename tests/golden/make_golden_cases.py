@@ -26,7 +26,7 @@ def record_case(D, c, seed, env_id):
     o = env.reset()
     rows, obs, rew, done, counter, ratio, ncand = [], [o.copy()], [], [], [], [], []
     for t in range(c["steps"]):
-        _, row = policy_pick(o, c["nb"], c["nl"], seed, env_id, t)
+        _, row = policy_pick(o, c["nb"], c["nl"], c.get("pseed", seed), env_id, t)
         o, r, d, info = env.step(row)
         rows.append(row); obs.append(o.copy()); rew.append(r); done.append(d)
         counter.append(info["counter"]); ratio.append(info.get("ratio", -1.0))
@@ -61,12 +61,17 @@ def record_cont_case(Cm, c, seed, env_id):
 
 def main():
     D, Cm = ref_shim.load_reference()
+    only = sys.argv[1:]  # optional: names of the cases to (re-)record
     for name, c in CASES.items():
+        if only and name not in only:
+            continue
         rec = record_case(D, c, c.get("seed", 517), c.get("env", 1))
         path = os.path.join(HERE, "case_%s.npz" % name)
         np.savez_compressed(path, name=name, **rec)
         print(path, os.path.getsize(path) // 1024, "KiB", "episodes", int(rec["done"].sum()), flush=True)
     for name, c in CONT_CASES.items():
+        if only and name not in only:
+            continue
         rec = record_cont_case(Cm, c, c.get("seed", 519), c.get("env", 2))
         path = os.path.join(HERE, "ccase_%s.npz" % name)
         np.savez_compressed(path, name=name, **rec)

@@ -34,7 +34,14 @@ CASES = {
     # found by scratch/soak_oracle_vs_reference.py: in extreme2D the dict newEps received key 2 before key 0 and the two points collide in
     # the 8-slot set table, so list(set(newEps.values())) lists them in the other order (D:PctTools.py:113-133)
     "ep_dictorder_s2": dict(_case(2, (14, 12, 10), ITEM_SET, steps=70, lnes="EP"), seed=134366, env=3),
+    # the BASELINE-stream trajectories (items seed 1234, policy seed 4321) on which the object-alias semantics of the reference's real placement and
+    # the snapshot semantics of round 1 part (scratch/alias_rate.py) — recorded from the reference through and 30 steps past
+    # the parting step; only the alias semantics (default since round 2) replays them
+    "alias_d1_e126": dict(_case(1, (10, 10, 10), ITEM_SET, steps=69), seed=1234, pseed=4321, env=126),
+    "alias_d1_e835": dict(_case(1, (10, 10, 10), ITEM_SET, steps=197), seed=1234, pseed=4321, env=835),
+    "alias_d3_e92": dict(_case(3, (10, 10, 10), ITEM_SET, steps=133), seed=1234, pseed=4321, env=92),
 }
+NEEDS_ALIAS_D = ("alias_d1_e126", "alias_d1_e835", "alias_d3_e92")
 
 
 def case_stream(c, seed, env, n):
@@ -54,9 +61,10 @@ def _ccase(setting, container, lo, hi, nb=80, nl=50, steps=110):
 CONT_CASES = {"box2_s1": _ccase(1, (2.0, 1.5, 2.5), 0.15, 0.75), "box2_s2": _ccase(2, (2.0, 1.5, 2.5), 0.15, 0.75),
               "box2_s3": _ccase(3, (2.0, 1.5, 2.5), 0.15, 0.75), "holders_s1": _ccase(1, (1.0, 1.0, 1.0), 0.1, 0.5, nb=60, nl=25),
               # found by scratch/soak_oracle_vs_reference.py: a real placement whose verdict depends on Python object aliasing in the reference
-              # (`up_edges[self] = self.thisStack` stores the live Stack object).  Replayed exactly only in the oracle's alias mode.
+              # (`up_edges[self] = self.thisStack` stores the live Stack object).  Replayed exactly only under the object-alias semantics (default since round 2).
               "alias_s1": dict(_ccase(1, (2.0, 1.5, 2.5), 0.15, 0.75, steps=95), seed=136818, env=2)}
-KNOWN_DIVERGENT = ("alias_s1",)  # records the default (GPU-equal) oracle mode does NOT reproduce; see tests/test_oracle_golden.py
+NEEDS_ALIAS = ("alias_s1",)  # records only the object-alias semantics (the default of the oracle AND of the kernels since round 2) reproduces; the
+#                              snapshot mode (PCT_ORACLE_ALIAS=0 / PCT_B200_ALIAS=0) must NOT: tests/test_oracle_golden.py
 
 
 def cont_case_stream(c, seed, env, n):

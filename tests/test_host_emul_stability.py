@@ -68,7 +68,7 @@ def _placement(row, next_box):
     return (x, y, int(z[0])), int(row[0]), int(row[1])
 
 
-def _drive(L, env, setting, container, nb, nl, seed, env_id, steps, alias=False):
+def _drive(L, env, setting, container, nb, nl, seed, env_id, steps, alias=True):  # alias: the default semantics of oracle and kernels since round 2
     h = L.sh_create(setting, *container)
     L.sh_set_holder(h, nb)
     L.sh_set_alias(h, int(alias))
@@ -142,6 +142,7 @@ def test_alias_variant_follows_the_alias_oracle(lib, setting, env_id, step, alia
 @pytest.mark.parametrize("setting,env_id,step", DIVERGING)
 def test_the_two_semantics_part_on_these_trajectories(setting, env_id, step):
     a, b = (OracleDiscrete(setting, stream=make_stream(1234, env_id, 600, setting)) for _ in range(2))
+    a.set_alias_mode(False)
     b.set_alias_mode(True)
     oa, ob = a.reset(), b.reset()
     for t in range(step + 1):
@@ -176,7 +177,7 @@ def _dpc(a):
     return a.ctypes.data_as(C.POINTER(C.c_double))
 
 
-def _drive_c(L, env, setting, container, seed, env_id, steps, alias=False):
+def _drive_c(L, env, setting, container, seed, env_id, steps, alias=True):
     h = L.shc_create(setting, *container)
     L.shc_set_alias(h, int(alias))
     L.shc_reset(h)

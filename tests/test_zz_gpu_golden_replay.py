@@ -5,9 +5,7 @@ single-env facades (PackingDiscrete / PackingContinuous = a GPU batch of one, gy
 rows; every float64 observation — terminal ones and the ones after reset() included —, reward, done, counter and ratio
 must equal the record.
 
-HARDWARE STATUS: written after round 1's GPU budget was spent — not yet run on a B200 (the same trajectories pass on the
-CPU oracle, tests/test_oracle_golden.py, and the oracle <-> GPU parity tests pass on hardware).  The file name sorts it
-behind every hardware-verified test file so that `pytest -x` reaches it last.
+Green on a B200 (driver GPUTEST_r01 and round 2).  No record is excluded.
 """
 import glob
 import os
@@ -16,15 +14,14 @@ import numpy as np
 import pytest
 
 torch = pytest.importorskip("torch")
-from harness import CASES, CONT_CASES, ITEM_SET, KNOWN_DIVERGENT  # noqa: E402
+from harness import CASES, CONT_CASES, ITEM_SET  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 G = os.path.join(os.path.dirname(__file__), "golden")
 DISCRETE = sorted(glob.glob(os.path.join(G, "discrete_*.npz"))) + sorted(glob.glob(os.path.join(G, "case_*.npz")))
 CONTINUOUS = sorted(glob.glob(os.path.join(G, "continuous_s*.npz"))) + sorted(glob.glob(os.path.join(G, "ccase_*.npz")))
-# the kernels hold snapshots of the loads (like the oracle's default mode); the record that needs the reference's object aliasing is the
-# documented divergence (tests/test_oracle_golden.py)
-CONTINUOUS = [p for p in CONTINUOUS if not any(os.path.basename(p) == "ccase_%s.npz" % n for n in KNOWN_DIVERGENT)]
+# no record is left out: the kernels implement the reference's object-alias semantics of the load entries by default since round 2, so
+# ccase_alias_s1.npz is replayed like every other record
 
 
 def _replay(env, g, exact_scalars):
@@ -47,7 +44,7 @@ def _replay(env, g, exact_scalars):
 
 
 def test_files_present():
-    assert len(DISCRETE) >= 14 + len(CASES) and len(CONTINUOUS) == 3 + len(CONT_CASES) - len(KNOWN_DIVERGENT)
+    assert len(DISCRETE) >= 14 + len(CASES) and len(CONTINUOUS) == 3 + len(CONT_CASES)
 
 
 @pytest.mark.parametrize("path", DISCRETE, ids=[os.path.basename(p) for p in DISCRETE])

@@ -1,9 +1,10 @@
-"""GPU: the opt-in ALIAS variant of the real placement (PCT_B200_ALIAS=1: pct_apply_kernel<STAB, ALIAS = true> -> stability_check<true, GeomD, true>,
-the reference's Python-object semantics of the load entries) against the oracle's alias mode — on the BASELINE-stream
-trajectories where the two semantics part (scratch/alias_rate.py) and on ordinary batches; the default build must keep following the
-default (snapshot) oracle on the same trajectories.
+"""GPU: the ALIAS variant of the real placement (the default since round 2; PCT_B200_ALIAS=0 selects the snapshot kernels of round 1:
+pct_apply_kernel<STAB, ALIAS = true> -> stability_check<true, GeomD, true>, the reference's Python-object semantics of the load entries,
+DESIGN.md section 3 (b)) against the oracle's alias mode — on the BASELINE-stream trajectories where the two semantics part
+(scratch/alias_rate.py) and on ordinary batches; the snapshot kernels must keep following the snapshot oracle on the same trajectories.
+Green on a B200 (driver GPUTEST_r01, round 2 call 1).
 
-HARDWARE STATUS: written after round 1's GPU budget was spent — not yet run on a B200.  The routine's logic is verified on its HOST build
+
 (tests/test_host_emul_stability.py); what is unverified is the kernel plumbing (DEnvAux, the K1 instantiation).  Sorted last.
 """
 import numpy as np
