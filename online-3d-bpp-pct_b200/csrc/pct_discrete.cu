@@ -607,14 +607,14 @@ __device__ __noinline__ void write_obs(const DParams &p, int e, const DEnvHot *h
 // hold how many internal / leaf rows of it may be non-zero.  75 % of the (NB + NL + 1) x 9 observation is zero padding, so only the
 // rows below max(now, prev) and the next-item row are written (and prev is updated); every other row is zero already.  The written
 // values are the ones write_obs computes.  The host resets prev to {NB, NL} whenever the buffer changes.
-template <typename OT>
+template <typename OT, bool WARP_SCOPE = false>
 __device__ __noinline__ void write_obs_delta(const DParams &p, int e, const DEnvHot *hot, const DEnvCold *cold, const int16_t (*leaf)[6], int n_leaf,
                                              int tid, int nthreads) {
     OT *obs = (OT *)p.obs + (size_t)e * (size_t)((p.nb + p.nl + 1) * 9);
     int32_t *prev = p.aux[e].obs_prev;
     const int n_box = hot->h.n_box;
     const int pb = min(prev[0], p.nb), pl = min(prev[1], p.nl);
-    __syncthreads();  // every thread has read prev before thread 0 replaces it below
+    if constexpr (WARP_SCOPE) __syncwarp(); else __syncthreads();  // every thread of the env has read prev before thread 0 replaces it below
     const int wb = max(max(n_box, pb), 1), wl = max(n_leaf, pl);  // row 0 always carries its valid flag (D:space.py:294-295)
     int s0 = hot->h.next_box[0], s1 = hot->h.next_box[1], s2 = hot->h.next_box[2];
     if (s1 < s0) { int t = s0; s0 = s1; s1 = t; }
@@ -1107,6 +1107,209 @@ __global__ void __launch_bounds__(FEAS_THREADS, K3_MINB) pct_feas_emit_kernel(co
     if (tid == 0) KT_END(p.env_id_base + e - p.env_id_base0, 2);
 }
 
+// ---- K3 (round 2): warp per env, dense feasibility lanes ----------------------------------------------------------
+// ncu of the thread-per-candidate kernel above at round 1's HEAD (profiles/r2_k3_head_*.txt): 22 % of the stall samples sit on its
+// block barrier (two warps per env, the first holds candidates 0-31, the second the ~6 that remain and waits), the DFS of
+// stability_check<false> holds 60 % of the warp instructions at 2-5 active lanes, and every candidate walks the placed boxes twice.
+// This kernel gives each env ONE warp and separates the work by kind:
+//   classify  lane per candidate, integer only: bounds + ONE pass over the boxes for the resting height and the supports
+//             (rest_height_supports) -> infeasible / feasible (floor, or no stability check) / needs the stability walk;
+//             feasibility bits per 32-candidate chunk, the walks are appended to a queue in shared memory (candidate order);
+//   walk      the first 32 queued placements, one per lane (dense: lanes 0..m-1), through stab_virtual — the warp-convergent
+//             restatement of the walk (light visits run ahead, heavy visits execute together);
+//   emit      the first `nl` set feasibility bits in candidate order -> leaf slots, observation (delta rows by default).
+// get_possible_position stops at `nl` feasible candidates (D:bin3D.py:117-136); here classification stops once `nl` candidates are KNOWN
+// feasible, and a queued walk is dropped when `nl` known-feasible candidates precede it — what is emitted is the same ordered prefix.
+#ifndef F2_MINB
+#define F2_MINB 8
+#endif
+#ifndef F2_WARPS_N
+#define F2_WARPS_N 2
+#endif
+constexpr int F2_WARPS = F2_WARPS_N;
+constexpr int F2_FBITS = 40;  // feasibility bits of <= 1280 candidates (K2 emits <= 1228)
+constexpr int F2_WL = 64;     // queue of pending walks: < 32 left over + <= 32 of one chunk
+struct WalkItem { uint16_t c; uint8_t mh, k; uint32_t pack; };
+static_assert(sizeof(WalkItem) == 8, "queue entry");
+constexpr int F2_OFF_LEAF = sizeof(DEnvHot);
+constexpr int F2_OFF_MISC = F2_OFF_LEAF + NL_MAX * 12;        // mbarrier (8) + lock (4) + pad; RotTab at +32
+constexpr int F2_OFF_FBITS = F2_OFF_MISC + 64;
+constexpr int F2_OFF_WL = F2_OFF_FBITS + F2_FBITS * 4;
+constexpr int F2_OFF_ST = F2_OFF_WL + F2_WL * 8;
+constexpr int F2_OFF_POLY = F2_OFF_ST + EDGE_STAGE * 32;
+constexpr int F2_SM_PER_WARP = F2_OFF_POLY + POLY_STAGE * 16;
+static_assert(F2_SM_PER_WARP % 16 == 0 && F2_OFF_ST % 16 == 0 && F2_OFF_POLY % 16 == 0, "TMA destinations are 16-byte aligned");
+
+template <typename OT, bool STAB, typename SlotT, bool DELTA>
+__global__ void __launch_bounds__(32 * F2_WARPS, F2_MINB) pct_feas_emit2_kernel(const DParams p) {
+    constexpr int BITS = sizeof(SlotT) == 2 ? 4 : 8;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int slot = blockIdx.x * F2_WARPS + warp;
+    if (slot >= p.n_envs) return;
+    const int e = (p.order && p.mode == 1) ? p.order[slot] : slot;  // same heaviest-first permutation as K1 / K2
+    unsigned char *sm = smem_raw + (size_t)warp * F2_SM_PER_WARP;
+    DEnvHot *hot = (DEnvHot *)sm;
+    int16_t (*leaf)[6] = (int16_t (*)[6])(sm + F2_OFF_LEAF);
+    uint64_t *mbar = (uint64_t *)(sm + F2_OFF_MISC);
+    int *lock = (int *)(mbar + 1);
+    RotTab *rt = (RotTab *)(sm + F2_OFF_MISC + 32);
+    uint32_t *fbits = (uint32_t *)(sm + F2_OFF_FBITS);
+    WalkItem *wl = (WalkItem *)(sm + F2_OFF_WL);
+    Stack4 *st_sm = (Stack4 *)(sm + F2_OFF_ST);
+    double *poly_sm = (double *)(sm + F2_OFF_POLY);
+    DEnvHot *ghot = p.hot + e;
+    DEnvCold *cold = p.cold + e;
+    const uint32_t lt = (1u << lane) - 1;
+    if (lane == 0) {
+        *lock = 0;
+        mbar_init(mbar, 1);
+        fence_proxy_async();
+    }
+    for (int t = lane; t < F2_FBITS; t += 32) fbits[t] = 0;
+    __syncwarp();
+    if (lane == 0) {
+        if (p.ready) {  // overlapped mode: wait for the candidates kernel's hand-over of THIS env
+            if (!env_wait(p.ready + p.n_envs + e, p.epoch)) atomicOr(&ghot->h.flags, PCT_FLAG_SYNC_TIMEOUT);
+            fence_proxy_async_all();
+        }
+        mbar_expect_tx(mbar, (uint32_t)sizeof(DEnvHot));
+        tma_load_1d(hot, ghot, (uint32_t)sizeof(DEnvHot), mbar);
+    }
+    mbar_wait(mbar, 0);
+    __syncwarp();  // every lane has observed phase 0 before the barrier is re-armed
+    const DHdr &h = hot->h;
+    if (STAB && h.n_edge > 0) {  // stage the load edges and stored support polygons (second phase of the same mbarrier)
+        const uint32_t bytes = (uint32_t)min(h.n_edge, EDGE_STAGE) * (uint32_t)sizeof(Stack4);
+        const uint32_t pbytes = (uint32_t)min(h.n_poly, POLY_STAGE) * 16u;
+        if (lane == 0) {
+            mbar_expect_tx(mbar, bytes + pbytes);
+            tma_load_1d(st_sm, cold->e_st, bytes, mbar);
+            if (pbytes) tma_load_1d(poly_sm, cold->poly, pbytes, mbar);
+        }
+        mbar_wait(mbar, 1);
+    }
+    const int nb3[3] = {h.next_box[0], h.next_box[1], h.next_box[2]};
+    if (lane == 0) make_rot_tab(nb3, p.setting == 2 ? 6 : 2, *rt);
+    __syncwarp();
+    const int n_cand = h.n_cand, n_box = h.n_box, nl = p.nl;
+    const double den = h.next_den;
+    const SlotT *cand = (const SlotT *)cold->cand;
+    GeomD g{hot->box, n_box, p.setting == 3 ? cold->density : nullptr};
+    const EdgePool pool{hot->e_lower, hot->e_next, hot->e_off, hot->first_in, hot->last_in, cold->e_st, st_sm, h.n_edge,
+                        hot->poly_off, &cold->poly[0][0], poly_sm, h.n_poly};
+    int pos = 0, nq = 0, nf = 0, fl = 0;
+#pragma unroll 1
+    for (;;) {
+        // ---- classify chunks of 32 candidates until a full batch of walks is queued ----
+#pragma unroll 1
+        while (nq < 32 && pos < n_cand && nf < nl) {
+            const int c = pos + lane;
+            bool feas = false, pend = false;
+            int mh = 0, k = 0;
+            uint32_t pack = 0;
+            if (c < n_cand) {
+                int xs, ys, zs, rot;
+                key_unpack<BITS>(cand[c], xs, ys, zs, rot);
+                const int sx = rt->d[rot][0], sy = rt->d[rot][1], sz = rt->d[rot][2];
+                // drop_box_virtual (D:space.py:393-433) + check_box (:436-454), integer part
+                bool far_out = false;
+                if (STAB) mh = rest_height_supports(hot->box, n_box, xs, ys, xs + sx, ys + sy, k, pack, far_out);
+                else mh = rest_height(hot->box, 0, n_box, 1, xs, ys, xs + sx, ys + sy);
+                if (xs + sx > p.W || ys + sy > p.L) feas = false;
+                else if (mh + sz > p.H) feas = false;
+                else if (!STAB || mh == 0) feas = true;
+                else pend = !far_out;  // far_out: the centre is outside the supports' bounding box -> the root test fails (rest_height_supports)
+            }
+            const uint32_t fm = __ballot_sync(FULL, feas), pm = __ballot_sync(FULL, pend);
+            if (lane == 0) fbits[pos >> 5] = fm;
+            nf += __popc(fm);
+            if (pend) {
+                WalkItem it;
+                it.c = (uint16_t)c; it.mh = (uint8_t)mh; it.k = (uint8_t)min(k, 255); it.pack = pack;
+                wl[nq + __popc(pm & lt)] = it;
+            }
+            nq += __popc(pm);
+            pos += 32;
+        }
+        __syncwarp();
+        if (nq == 0) break;
+        int m = min(nq, 32);
+        if (nf >= nl) {
+            // the cap may bind: a queued walk preceded by `nl` known-feasible candidates cannot be among the emitted leaves (nor can any later one)
+            bool drop = false;
+            if (lane < m) {
+                const int c = wl[lane].c;
+                int cnt = __popc(fbits[c >> 5] & ((1u << (c & 31)) - 1));
+#pragma unroll 1
+                for (int w = 0; w < (c >> 5); w++) cnt += __popc(fbits[w]);
+                drop = cnt >= nl;
+            }
+            const uint32_t dm = __ballot_sync(FULL, drop);
+            if (dm) { m = __ffs(dm) - 1; nq = m; }
+            if (m == 0) break;
+        }
+        // ---- walk: lanes 0..m-1 take the first m queued placements ----
+        const bool has = lane < m;
+        WalkItem it{};
+        if (has) it = wl[lane];
+        int xs = 0, ys = 0, zs = 0, rot = 0;
+        if (has) key_unpack<BITS>(cand[it.c], xs, ys, zs, rot);
+        const int sx = rt->d[rot][0], sy = rt->d[rot][1], sz = rt->d[rot][2];
+        const NodeD root{xs, ys, (int)it.mh, sx, sy, sz, (double)(sx * sy * sz) * den};
+        bool ok = false;
+        if constexpr (STAB) ok = stab_virtual<GeomD>(g, root, (int)it.k, it.pack, pool, &cold->big, lock, fl, has, FULL) != 0;
+        const bool feas = has && ok;
+        if (feas) atomicOr(&fbits[it.c >> 5], 1u << (it.c & 31));
+        nf += __popc(__ballot_sync(FULL, feas));
+        // the rest of the queue moves to the front
+        WalkItem mv{};
+        const bool keep = lane + m < nq;
+        if (keep) mv = wl[lane + m];
+        __syncwarp();
+        if (keep) wl[lane] = mv;
+        nq -= m;
+        __syncwarp();
+    }
+    // ---------------- leaves = the first `nl` feasible candidates in order ----------------
+    const int n_leaf = min(nf, nl);
+    {
+        int base = 0;
+        const int nw = pos >> 5;
+#pragma unroll 1
+        for (int w = 0; w < nw && base < nl; w++) {
+            const uint32_t bits = fbits[w];
+            if ((bits >> lane) & 1u) {
+                const int kk = base + __popc(bits & lt);
+                if (kk < nl) {
+                    int xs, ys, zs, rot;
+                    key_unpack<BITS>(cand[w * 32 + lane], xs, ys, zs, rot);
+                    leaf[kk][0] = (int16_t)xs; leaf[kk][1] = (int16_t)ys; leaf[kk][2] = (int16_t)zs;
+                    leaf[kk][3] = (int16_t)(xs + rt->d[rot][0]); leaf[kk][4] = (int16_t)(ys + rt->d[rot][1]); leaf[kk][5] = (int16_t)(zs + rt->d[rot][2]);
+                }
+            }
+            base += __popc(bits);
+        }
+    }
+    fl = __reduce_or_sync(FULL, fl);
+    if (fl && lane == 0) atomicOr(&ghot->h.flags, fl);
+    __syncwarp();
+    // persist the emitted leaves for the leaf-index action path; header / info
+    for (int t = lane; t < n_leaf * 6; t += 32) ((int16_t *)cold->leaf)[t] = ((int16_t *)leaf)[t];
+    if (lane == 0) {
+        ghot->h.n_leaf = n_leaf;
+        if (p.info) {
+            p.info[e].n_leaf = n_leaf;
+            p.info[e].n_cand = n_cand;
+            p.info[e].n_ems = h.n_ems;
+            p.info[e].flags |= h.flags | fl;
+        }
+    }
+    // ---------------- cur_observation (D:bin3D.py:70-93) ----------------
+    if constexpr (DELTA) write_obs_delta<OT, true>(p, e, hot, cold, leaf, n_leaf, lane, 32);
+    else write_obs<OT>(p, e, hot, cold, leaf, n_leaf, lane, 32);
+}
+
 // Block scheduling order.  A launch lasts as long as its slowest block, and blocks are dispatched in index order, so the
 // envs with the most expected work should get the lowest block indices (LPT rule).  One 1024-thread block counting-sorts
 // the envs by a work estimate read from the record headers: which = 0 -> order[0..n) for the NEXT step's apply kernel
@@ -1165,10 +1368,15 @@ static cudaError_t launch_t(const DParams &p, cudaStream_t st, cudaEvent_t *prof
     static bool attr_set = false;
     const size_t smem1 = (size_t)K1_SM_PER_WARP * WARPS_PER_BLOCK;
     const size_t smem2 = (size_t)Lay<SlotT, BIGSM>::PER_WARP * WARPS_PER_BLOCK;
+    const size_t smem3 = (size_t)F2_SM_PER_WARP * F2_WARPS;
+    const int blocks3 = (p.n_envs + F2_WARPS - 1) / F2_WARPS;
+    const bool k3_old = (p.opt & PCT_OPT_K3_BLOCK) != 0;  // PCT_B200_K3=block: round 1's block-per-env / thread-per-candidate kernel (A/B measurements)
     if (!attr_set) {
         cudaError_t err = set_smem(pct_apply_kernel<STAB>, smem1);
         if (err == cudaSuccess && STAB) err = set_smem(pct_apply_kernel<STAB, STAB>, smem1);  // the ALIAS variant (stability settings only)
         if (err == cudaSuccess) err = set_smem(pct_candidates_kernel<SlotT, BIGSM>, smem2);
+        if (err == cudaSuccess) err = set_smem(pct_feas_emit2_kernel<OT, STAB, SlotT, false>, smem3);
+        if (err == cudaSuccess) err = set_smem(pct_feas_emit2_kernel<OT, STAB, SlotT, true>, smem3);
         if (err != cudaSuccess) return err;
         attr_set = true;
     }
@@ -1187,17 +1395,28 @@ static cudaError_t launch_t(const DParams &p, cudaStream_t st, cudaEvent_t *prof
         cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(32 * WARPS_PER_BLOCK); cfg.dynamicSmemBytes = smem2;
         cudaError_t err = cudaLaunchKernelEx(&cfg, pct_candidates_kernel<SlotT, BIGSM>, p);
         if (err != cudaSuccess) return err;
-        cfg.gridDim = dim3(p.n_envs); cfg.blockDim = dim3(FEAS_THREADS); cfg.dynamicSmemBytes = 0;
-        err = (p.opt & PCT_OPT_DELTA) ? cudaLaunchKernelEx(&cfg, pct_feas_emit_kernel<OT, STAB, SlotT, true>, p)
-                         : cudaLaunchKernelEx(&cfg, pct_feas_emit_kernel<OT, STAB, SlotT>, p);
+        if (k3_old) {
+            cfg.gridDim = dim3(p.n_envs); cfg.blockDim = dim3(FEAS_THREADS); cfg.dynamicSmemBytes = 0;
+            err = (p.opt & PCT_OPT_DELTA) ? cudaLaunchKernelEx(&cfg, pct_feas_emit_kernel<OT, STAB, SlotT, true>, p)
+                             : cudaLaunchKernelEx(&cfg, pct_feas_emit_kernel<OT, STAB, SlotT>, p);
+        } else {
+            cfg.gridDim = dim3(blocks3); cfg.blockDim = dim3(32 * F2_WARPS); cfg.dynamicSmemBytes = smem3;
+            err = (p.opt & PCT_OPT_DELTA) ? cudaLaunchKernelEx(&cfg, pct_feas_emit2_kernel<OT, STAB, SlotT, true>, p)
+                             : cudaLaunchKernelEx(&cfg, pct_feas_emit2_kernel<OT, STAB, SlotT, false>, p);
+        }
         if (err == cudaSuccess && p.order) pct_order_kernel<<<1, 1024, 0, st>>>(p.hot, p.n_envs, p.order, 0);
         return err != cudaSuccess ? err : cudaGetLastError();
     }
     if (prof) cudaEventRecord(prof[1], st);
     pct_candidates_kernel<SlotT, BIGSM><<<blocks, 32 * WARPS_PER_BLOCK, smem2, st>>>(p);
     if (prof) cudaEventRecord(prof[2], st);
-    if (p.opt & PCT_OPT_DELTA) pct_feas_emit_kernel<OT, STAB, SlotT, true><<<p.n_envs, FEAS_THREADS, 0, st>>>(p);
-    else pct_feas_emit_kernel<OT, STAB, SlotT><<<p.n_envs, FEAS_THREADS, 0, st>>>(p);
+    if (k3_old) {
+        if (p.opt & PCT_OPT_DELTA) pct_feas_emit_kernel<OT, STAB, SlotT, true><<<p.n_envs, FEAS_THREADS, 0, st>>>(p);
+        else pct_feas_emit_kernel<OT, STAB, SlotT><<<p.n_envs, FEAS_THREADS, 0, st>>>(p);
+    } else {
+        if (p.opt & PCT_OPT_DELTA) pct_feas_emit2_kernel<OT, STAB, SlotT, true><<<blocks3, 32 * F2_WARPS, smem3, st>>>(p);
+        else pct_feas_emit2_kernel<OT, STAB, SlotT, false><<<blocks3, 32 * F2_WARPS, smem3, st>>>(p);
+    }
     if (p.order) pct_order_kernel<<<1, 1024, 0, st>>>(p.hot, p.n_envs, p.order, 0);
     if (prof) cudaEventRecord(prof[3], st);
     return cudaGetLastError();

@@ -24,18 +24,21 @@ struct pct_env_batch {
     int32_t epoch = 0;
     bool overlap = true;          // PCT_B200_OVERLAP=0: plain back-to-back kernels
     bool overlap_cont = false;    // continuous domain: measured slower overlapped (5.35 M -> 3.97 M env-steps/s), off unless PCT_B200_OVERLAP_CONT=1
-    // delta observation writes (PCT_B200_OBS_DELTA=1; not yet measured): the feasibility kernel writes only the rows that can differ from what the
-    // SAME caller buffer already holds (DEnvAux::obs_prev = per env the internal / leaf rows of the tracked buffer that may be non-zero)
-    bool obs_delta = false;
+    // delta observation writes (default ON since round 2: +3 % device path, and with zero-copy 5.2 -> 9.1 M env-steps/s through pct_step_host;
+    // PCT_B200_OBS_DELTA=0 disables): the feasibility kernel writes only the rows that can differ from what the SAME caller buffer already holds
+    // (DEnvAux::obs_prev = per env the internal / leaf rows of the tracked buffer that may be non-zero).  Contract (include/pct_b200.h): a caller
+    // that hands the same observation pointer to consecutive calls must not have modified the buffer in between.
+    bool obs_delta = true;
     // object semantics of the load entries in the real placement = what the reference's Python objects do:
     // pct_apply_kernel<STAB, ALIAS = true> / pctc_apply_kernel<true, true>.  Default ON since round 2 (green on hardware, oracle default flipped with it);
     // PCT_B200_ALIAS=0 selects the snapshot semantics of round 1 (kept for the sensitivity tests).
     bool alias_mode = true;
+    bool k3_block = false;        // PCT_B200_K3=block: round 1's block-per-env feasibility kernel instead of the warp-per-env one (A/B measurements)
     pct::DEnvAux *d_aux = nullptr;  // per-env state of the opt-in variants (allocated when one of them is on)
     const void *tracked_obs = nullptr;
     bool fill_pending = false;
-    bool host_zero_copy = false;  // pct_step_host: kernels write the observation straight into the pinned host buffer (PCT_B200_HOST_ZEROCOPY=1; not yet measured)
-    bool cont_pre = false;        // continuous feas_emit: resting heights from pre-rounded rectangles (PCT_B200_CONT_PRE=1; exact, not yet measured)
+    bool host_zero_copy = true;   // pct_step_host: kernels write the observation straight into the pinned (mapped) host buffer; PCT_B200_HOST_ZEROCOPY=0: staged copies
+    bool cont_pre = true;         // continuous feas_emit: resting heights from pre-rounded rectangles (exact, +2 %; PCT_B200_CONT_PRE=0 disables)
     int32_t *d_hstate = nullptr;  // (n_envs, 4) LSAH footprint state (pct_heuristic_actions)
     double *d_hstate_c = nullptr; // same for the continuous domain (pct_heuristic_actions_f64)
     double *d_query_c = nullptr;  // 2 doubles: result of pct_query_placement_f64

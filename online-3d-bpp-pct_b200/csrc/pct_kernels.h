@@ -166,7 +166,7 @@ struct DParams {
     int32_t epoch;   // value published in `ready` by this launch
     int32_t opt;     // opt-in variants served by `aux`: PCT_OPT_DELTA (K3 delta observation writes), PCT_OPT_ALIAS (K1 object semantics of the loads)
 };
-constexpr int PCT_OPT_DELTA = 1, PCT_OPT_ALIAS = 2;
+constexpr int PCT_OPT_DELTA = 1, PCT_OPT_ALIAS = 2, PCT_OPT_K3_BLOCK = 4;
 
 // heuristic baselines (pct_heuristics.cuh)
 struct HParams {

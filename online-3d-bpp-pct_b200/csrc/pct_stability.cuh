@@ -643,4 +643,255 @@ static __device__ __noinline__ int stability_check(const G &g, const typename G:
     }
 }
 
+// =====================================================================================================================
+// stab_virtual: the read-only feasibility check (calculated_impact_virtual, D:space.py:166-267) for a WARP of placements,
+// one lane per placement, restructured for SIMT convergence (round 2).
+//
+// ncu of round 1's thread-per-candidate kernel (profiles/r2_k3_head_source.txt): the DFS of stability_check<false> holds 60 % of
+// the kernel's warp instructions at 2-5 active lanes — every lane walks its own support DAG, and a visit is either LIGHT (no or
+// one support: a rectangle test in registers) or HEAVY (>= 2 supports: hull / stored polygon, load split, frame push), 10x the
+// instructions; with both kinds present in nearly every round a warp pays light + heavy per round.  Here the walk is a per-lane state machine with
+// two warp-synchronous phases per round: lanes RUN AHEAD through their light visits (diverging only in trip count) until they
+// either finish or stand in front of a heavy visit; then all lanes with a heavy visit pending execute it together.  The number
+// of heavy phases is the maximum over lanes of the heavy visits on a lane's path, not the number of rounds with any heavy visit.
+//
+// Semantics, operation order and capacities are those of stability_check<false, G> (same helpers, same FP64 expressions): the
+// verdicts are bit-identical, which tests/test_host_emul_stability.py checks on the host build for whole trajectories.
+// Every lane of `mask` must call; lanes without work pass has_work = false.  k_root >= 0: the root's supports were found by the
+// caller's fused resting-height scan (sup_pack = the first 4 ids, 8 bits each, scan order); k_root < 0: scan here.
+#ifdef __CUDA_ARCH__
+#define PCT_ANY(mask, p) __any_sync(mask, p)
+#else
+#define PCT_ANY(mask, p) (p)
+#endif
+#ifndef PCT_STAT
+#define PCT_STAT(i)   // statistics hook of the host build (tests/host_emul/stab_host.cpp)
+#endif
+template <class G>
+static __device__ __noinline__ int stab_virtual(const G &g, const typename G::Node &root, int k_root, uint32_t sup_pack, const EdgePool &pool,
+                                                BigScratch *big, int *lock, int &flags, bool has_work, unsigned mask) {
+    typedef typename G::Node Node;
+    StabFrame fr[STAB_DEPTH];
+    uint8_t sup_id[STAB_SUP_POOL];
+    double sup_m[STAB_SUP_POOL];
+    int depth = 0, node = NODE_NEW, base = 0;
+    Stack4 st;
+    g.centre(root, st.cx, st.cy, st.cz);
+    st.m = root.mass;
+    bool active = has_work, need_adv = false;
+    int result = 0;
+    int child = -1, skip = EDGE_NIL;
+    double vx = 0, vy = 0, vm = 0;
+    if (active && k_root < 0) {  // supports of the placement itself (D:space.py:360-376), scan order
+        int k = 0;
+        const int limit = g.n_boxes();
+        double r[4];
+        sup_pack = 0;
+#pragma unroll 1
+        for (int t = 0; t < limit; t++) {
+            if (!g.support(root, t, r)) continue;
+            if (k < 4) sup_pack |= (uint32_t)t << (8 * k);
+            k++;
+        }
+        k_root = k;
+    }
+#pragma unroll 1
+    for (;;) {
+        bool heavy = false;
+        int k = 0, eoff = 0;
+        // ---------------- light phase: run ahead until finished or in front of a node with >= 2 supports ----------------
+#pragma unroll 1
+        while (active) {
+            if (need_adv) {
+                if (child < 0) {
+                    // the subtree below the last entered node returned True: continue with the top frame's next support
+#pragma unroll 1
+                    for (;;) {
+                        if (depth == 0) { active = false; result = 1; break; }
+                        StabFrame &f = fr[depth - 1];
+                        if (f.i == f.k) { depth--; continue; }
+                        const int s = f.i++;
+                        child = sup_id[f.base + s];
+                        const int parent = f.node;
+                        skip = (parent == NODE_NEW) ? EDGE_NIL : (int)f.eoff + s;
+                        st = f.st;
+                        vm = sup_m[f.base + s];
+                        vx = st.cx; vy = st.cy;
+                        if (!f.whole) {  // the load sits at the centre of this support's contact rectangle with the parent
+                            Node par;
+                            if (parent != NODE_NEW) g.node_box(parent, par);
+                            else par = root;
+                            double r[4];
+                            g.support(par, child, r);
+                            vx = (r[0] + r[2]) * 0.5; vy = (r[1] + r[3]) * 0.5;
+                        }
+                        base = f.base + f.k;
+                        if (s == f.k - 1) { depth--; base = f.base; }  // tail call: the parent frame is finished
+                        break;
+                    }
+                    if (!active) break;
+                }
+                // calculate_new_com of `child` (D:space.py:51-71) under the virtual load (vx, vy, st.cz, vm)
+                Node sb;
+                g.node_box(child, sb);
+                double ccx, ccy, ccz, mm = sb.mass;
+                g.centre(sb, ccx, ccy, ccz);
+                ccx *= mm; ccy *= mm; ccz *= mm;
+#pragma unroll 1
+                for (int q = pool.first_in[child]; q != EDGE_NIL; q = pool.next[q]) {
+                    if (q == skip) continue;  // `involved` path member: its real load is replaced by the virtual one
+                    const Stack4 e = pool.load(q);
+                    ccx += e.cx * e.m; ccy += e.cy * e.m; ccz += e.cz * e.m;
+                    mm += e.m;
+                }
+                if (vm != 0.0) {  // zero-mass virtual loads add +0.0 to every sum: skipped (exact)
+                    ccx += vx * vm; ccy += vy * vm; ccz += st.cz * vm;
+                    mm += vm;
+                }
+                st.cx = ddiv(ccx, mm); st.cy = ddiv(ccy, mm); st.cz = ddiv(ccz, mm); st.m = mm;
+                node = child;
+                need_adv = false;
+            }
+            // ENTER(node, st): how many supports?
+            if (node == NODE_NEW) { k = k_root; eoff = pool.n; }
+            else { eoff = (int)pool.off[node]; k = (int)pool.off[node + 1] - eoff; }
+            if (k >= 2) { heavy = true; break; }
+            child = -1;
+            PCT_STAT(k);  // 0 / 1: light visits
+            if (k == 1) {
+                const int sid0 = (node == NODE_NEW) ? (int)(sup_pack & 0xFFu) : (int)pool.lower[eoff];
+                Node cur;
+                if (node != NODE_NEW) g.node_box(node, cur);
+                else cur = root;
+                double r0[4];
+                g.support(cur, sid0, r0);
+                const double t1 = r0[1] * 1e-6, t2 = r0[3] * 1e-6;
+                const bool fast = (r0[0] + t1 < r0[0] + t2) && (r0[0] + t2 < r0[2] + t1) && (r0[2] + t1 < r0[2] + t2);
+                bool ok;
+                if (fast) ok = pip_rect(r0[0], r0[1], r0[2], r0[3], t1, t2, st.cx, st.cy);
+                else {
+                    double px[4] = {r0[0] + t1, r0[0] + t2, r0[2] + t1, r0[2] + t2}, py[4] = {r0[1], r0[3], r0[1], r0[3]};
+                    double hx[8], hy[8];
+                    const int m = hull_coords(px, py, 4, hx, hy);
+                    ok = pip_shrunk(hx, hy, 1, m, st.cx, st.cy);
+                }
+                if (!ok) PCT_STAT(node == NODE_NEW ? 17 : 18);  // light visit failed: root / placed box
+                if (!ok) { active = false; result = 0; break; }
+                child = sid0;  // the whole stack goes to the single support
+                skip = (node == NODE_NEW) ? EDGE_NIL : eoff;
+                vx = st.cx; vy = st.cy; vm = st.m;
+            }
+            need_adv = true;
+        }
+        if (!PCT_ANY(mask, heavy)) break;
+        // ---------------- heavy phase: every lane standing in front of a node with >= 2 supports enters it ----------------
+        if (heavy) {
+            PCT_STAT(node == NODE_NEW ? 2 : 3);  // heavy visits: root / placed box
+            PCT_STAT(4 + (k < 8 ? k : 8));       // by number of supports
+            Node cur;
+            if (node != NODE_NEW) g.node_box(node, cur);
+            else cur = root;
+            bool ok = true;
+            if (node == NODE_NEW) {
+                if (k > KSUP_MAX || k > STAB_SUP_POOL) { flags |= PCT_FLAG_SUPPORT_OVERFLOW; ok = false; }
+                else if (k <= 4) {
+#pragma unroll 1
+                    for (int j = 0; j < k; j++) sup_id[base + j] = (uint8_t)((sup_pack >> (8 * j)) & 0xFFu);
+                } else {
+                    int kk = 0;
+                    const int limit = g.n_boxes();
+                    double r[4];
+#pragma unroll 1
+                    for (int t = 0; t < limit && kk < k; t++)
+                        if (g.support(cur, t, r)) sup_id[base + kk++] = (uint8_t)t;
+                }
+            } else {
+                if (base + k > STAB_SUP_POOL) { flags |= PCT_FLAG_SUPPORT_OVERFLOW; ok = false; }
+                else {
+#pragma unroll 1
+                    for (int j = 0; j < k; j++) sup_id[base + j] = pool.lower[eoff + j];
+                }
+            }
+            int whole = 2;
+            if (ok) {
+                double lrect[KSUP_SMALL][4], lpx[4 * KSUP_SMALL], lpy[4 * KSUP_SMALL], lhx[8 * KSUP_SMALL], lhy[8 * KSUP_SMALL];
+                const bool small = k <= KSUP_SMALL;
+                double (*rect)[4] = lrect;
+                double *px = lpx, *py = lpy, *hx = lhx, *hy = lhy;
+                if (!small) {  // rare: serialise the lanes of this env on the per-env HBM scratch
+                    while (atomicCAS(lock, 0, 1) != 0) { }
+                    __threadfence_block();
+                    rect = big->rect; px = big->px; py = big->py; hx = big->hx; hy = big->hy;
+                }
+#pragma unroll 1
+                for (int s = 0; s < k; s++) g.support(cur, sup_id[base + s], rect[s]);
+                const int pv = node == NODE_NEW ? 0 : (int)pool.poly_off[node], pm = node == NODE_NEW ? 0 : (int)pool.poly_off[node + 1] - pv;
+                if (pm > 0 && (pv + pm <= POLY_STAGE || pv >= POLY_STAGE)) {
+                    const double *xy = pool.poly_at(pv);  // a placed box: its support polygon was stored when it was placed
+                    ok = pip_shrunk(xy, xy + 1, 2, pm, st.cx, st.cy);
+                } else {
+#pragma unroll 1
+                    for (int s = 0; s < k; s++) {
+                        const double x1 = rect[s][0], y1 = rect[s][1], x2 = rect[s][2], y2 = rect[s][3];
+                        const double t1 = y1 * 1e-6, t2 = y2 * 1e-6;
+                        px[4 * s + 0] = x1 + t1; py[4 * s + 0] = y1;
+                        px[4 * s + 1] = x1 + t2; py[4 * s + 1] = y2;
+                        px[4 * s + 2] = x2 + t1; py[4 * s + 2] = y1;
+                        px[4 * s + 3] = x2 + t2; py[4 * s + 3] = y2;
+                    }
+                    const int m = hull_coords(px, py, 4 * k, hx, hy);
+                    ok = pip_shrunk(hx, hy, 1, m, st.cx, st.cy);
+                }
+                if (ok) {
+                    int direct = -1;
+#pragma unroll 1
+                    for (int s = 0; s < k; s++)
+                        if (g.strictly_inside(st.cx, st.cy, rect[s])) { direct = s; break; }
+                    if (direct >= 0) {
+#pragma unroll 1
+                        for (int s = 0; s < k; s++) sup_m[base + s] = (s == direct) ? st.m : 0.0;
+                    } else {
+                        whole = 0;
+#pragma unroll 1
+                        for (int s = 0; s < k; s++) {
+                            px[s] = (rect[s][0] + rect[s][2]) * 0.5;
+                            py[s] = (rect[s][1] + rect[s][3]) * 0.5;
+                        }
+                        if (k == 2) {
+                            double lx = px[0] - px[1], ly = py[0] - py[1];
+                            const double len = dsqrt(fma(ly, ly, lx * lx));
+                            const double len2 = len * len;
+                            lx = ddiv(lx, len2); ly = ddiv(ly, len2);
+                            sup_m[base + 0] = st.m * fabs(dot2(st.cx - px[1], st.cy - py[1], lx, ly));
+                            sup_m[base + 1] = st.m * fabs(dot2(st.cx - px[0], st.cy - py[0], lx, ly));
+                        } else {
+                            PCT_STAT(14);
+                            double lR[KSUP_SMALL * KSUP_SMALL], lV[KSUP_SMALL * KSUP_SMALL], ly_[KSUP_SMALL], lrow[KSUP_SMALL], lx_[KSUP_SMALL];
+                            LsWork w;
+                            w.R = small ? lR : big->R; w.V = small ? lV : big->V; w.y = small ? ly_ : big->y;
+                            w.row = small ? lrow : big->row; w.x = small ? lx_ : big->x; w.ld = small ? KSUP_SMALL : KSUP_MAX;
+                            lstsq_ratios(w, k, px, py, st.cx, st.cy);
+#pragma unroll 1
+                            for (int s = 0; s < k; s++) sup_m[base + s] = st.m * w.x[s];
+                        }
+                    }
+                }
+                if (!small) { __threadfence_block(); atomicExch(lock, 0); }
+            }
+            if (ok && depth >= STAB_DEPTH) { flags |= PCT_FLAG_SUPPORT_OVERFLOW; ok = false; }
+            if (!ok) PCT_STAT(node == NODE_NEW ? 15 : 16);  // heavy visit failed: root / placed box
+            if (!ok) { active = false; result = 0; }
+            else {
+                StabFrame &f = fr[depth++];
+                f.st = st; f.node = (uint8_t)node; f.base = (uint8_t)base; f.k = (uint8_t)k; f.i = 0; f.whole = (uint8_t)whole;
+                f.eoff = (uint8_t)eoff;
+                child = -1;
+                need_adv = true;
+            }
+        }
+    }
+    return result;
+}
+
+
 }  // namespace pct

@@ -85,9 +85,9 @@ class _PackingBase(object):
         if load_test_data:
             # LoadBoxCreator (binCreator.py:41-72): one trajectory per episode (reset() pre-increments the index, so
             # trajectory 0 is never used), each followed by the [100,100,100] sentinel that ends the episode.
-            trajs = [np.array(t, dtype=np.float64) for t in torch.load(data_name)][1:]
+            from .evaluation import load_trajectories, round3
+            trajs = load_trajectories(data_name)[1:]  # torch.load(..., weights_only=False): the datasets are pickled lists (binCreator.py:48-49)
             if self._continuous:  # test mode rounds the item sizes to 3 decimals (C:bin3D.py:84-87)
-                from .evaluation import round3
                 trajs = round3(trajs)
             traj_len = max(len(t) for t in trajs) + 1
             seq = np.full((len(trajs), traj_len, 4), 100.0)
@@ -177,8 +177,17 @@ class PackingDiscrete(_PackingBase):
 
 
 class PackingContinuous(_PackingBase):
-    """Drop-in for pct_envs.PctContinuous0.PackingContinuous."""
+    """Drop-in for pct_envs.PctContinuous0.PackingContinuous — including its class defaults sample_from_distribution=True, U(0.1, 0.5)
+    (C:bin3D.py:14-16), which set Space.low_bound = 0.1 even when a dataset supplies the items (heuristic.py:585-591 relies on them)."""
     _continuous = True
+
+    def __init__(self, setting, container_size=(10, 10, 10), item_set=None, data_name=None, load_test_data=False,
+                 internal_node_holder=80, leaf_node_holder=50, next_holder=1, shuffle=False,
+                 sample_from_distribution=True, sample_left_bound=0.1, sample_right_bound=0.5, **kwags):
+        super().__init__(setting, container_size=container_size, item_set=item_set, data_name=data_name, load_test_data=load_test_data,
+                         internal_node_holder=internal_node_holder, leaf_node_holder=leaf_node_holder, next_holder=next_holder,
+                         shuffle=shuffle, sample_from_distribution=sample_from_distribution, sample_left_bound=sample_left_bound,
+                         sample_right_bound=sample_right_bound, **kwags)
 
 
 def make_vec_envs(args, log_dir=None, allow_early_resets=True):

@@ -13,7 +13,7 @@ import torch
 
 from . import _lib
 from .batch import PctBatch
-from .evaluation import _streams, load_trajectories
+from .evaluation import _streams, load_trajectories, round3
 
 HEURISTICS = tuple(_lib.HEURISTIC_CODES)  # LSAH, OnlineBPH, BR, MACS, DBL, HM, RANDOM (tools.py:209)
 CONTINUOUS_HEURISTICS = ("LSAH", "OnlineBPH", "BR")  # tools.py:217-218
@@ -40,6 +40,8 @@ def run_heuristic(name, setting, episodes, container_size=(10, 10, 10), item_set
     stream = traj_len = None
     if data is not None:
         trajs = load_trajectories(data)
+        if continuous:  # PackingContinuous in test mode rounds the item sizes to 3 decimals (C:bin3D.py:84-87), like evaluate_batched and the facade
+            trajs = round3(trajs)
         if not 0 < episodes <= len(trajs) - 1:
             raise ValueError("episodes must be in 1..len(dataset)-1")
         stream, traj_len, quota = _streams(trajs, episodes, n)
@@ -119,10 +121,11 @@ def main(argv=None):
     cs = a.container_size or ([1.0, 1.0, 1.0] if a.continuous else [10, 10, 10])  # givenData.py:4-5
     if not a.continuous:
         cs = [int(c) for c in cs]
-    # heuristic.py:585-591 builds PackingContinuous with its defaults: sample_from_distribution=True, U(0.1, 0.5) (C:bin3D.py:14-16)
+    # heuristic.py:585-591 builds PackingContinuous with its class defaults — sample_from_distribution=True, U(0.1, 0.5) (C:bin3D.py:14-16) —
+    # also under --load-dataset: the dataset then supplies the items, but Space.low_bound stays sample_left_bound = 0.1 (C:bin3D.py:25-27)
     mean, var, length = run_heuristic(a.heuristic, a.setting, a.evaluation_episodes, container_size=cs, item_set=item_set,
                                       data=a.dataset_path if a.load_dataset else None, n_envs=a.num_envs, device=a.device,
-                                      continuous=a.continuous, sample_from_distribution=a.continuous and not a.load_dataset,
+                                      continuous=a.continuous, sample_from_distribution=a.continuous,
                                       sample_left_bound=0.1 if a.continuous else None, sample_right_bound=0.5 if a.continuous else None)
     print("The average space utilization:", mean)
     print("The variance of space utilization:", var)

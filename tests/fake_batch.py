@@ -31,6 +31,7 @@ class FakeBatch(object):
                     sample_left_bound, sample_right_bound = 0.1 * min(container_size), 0.5 * min(container_size)
                     if size_minimum is None or size_minimum == 1.0:
                         size_minimum = sample_left_bound
+        self.size_minimum = size_minimum
         if continuous:
             self.envs = [OracleContinuous(setting, container_size=container_size, internal_node_holder=self.nb, leaf_node_holder=self.nl,
                                           size_minimum=size_minimum, stream=s) for s in self._streams]

@@ -16,6 +16,10 @@ static inline int atomicCAS(int *p, int cmp, int val) { int o = *p; if (o == cmp
 static inline int atomicExch(int *p, int v) { int o = *p; *p = v; return o; }
 static inline void __threadfence_block() {}
 static inline double __longlong_as_double(long long v) { double d; memcpy(&d, &v, 8); return d; }
+static long long g_far_out = 0, g_walks = 0;  // statistics of the quick reject (sh_stats)
+static long long g_stat[32];
+#define PCT_STAT(i) g_stat[(i)]++
+static int g_use_v2 = 0;  // sh_use_v2: route the virtual checks through stab_virtual (the warp-convergent restatement used by the round-2 feasibility kernels)
 #include <cuda_runtime.h>
 #ifndef __noinline__
 #define __noinline__ __attribute__((noinline))
@@ -73,10 +77,22 @@ int sh_virtual(StabHost *h, int x, int y, int z, int lx, int ly, double density,
     NodeD root{lx, ly, mh, x, y, z, (double)(x * y * z) * density};
     EdgePool pool = pool_of(h);  // the read-only check knows snapshots only, in both semantics (like pct_feas_emit_kernel)
     int fl = 0;
-    const int ok = stability_check<false, GeomD>(g, root, pool, &h->big, &h->lock, 0, fl) != 0;
+    int ok;
+    if (g_use_v2 == 1) {  // as pct_feas_emit_kernel calls it: supports from the fused resting-height scan
+        int k; uint32_t pack; bool far_out;
+        const int mh2 = rest_height_supports(h->box, h->n_box, lx, ly, lx + x, ly + y, k, pack, far_out);
+        if (mh2 != mh) { h->flags |= 1 << 20; return -1; }
+        if (far_out) { g_far_out++; return 0; }  // the kernel's integer quick reject
+        g_walks++;
+        ok = stab_virtual<GeomD>(g, root, k, pack, pool, &h->big, &h->lock, fl, true, 0xffffffffu);
+    } else if (g_use_v2 == 2) ok = stab_virtual<GeomD>(g, root, -1, 0, pool, &h->big, &h->lock, fl, true, 0xffffffffu);
+    else ok = stability_check<false, GeomD>(g, root, pool, &h->big, &h->lock, 0, fl) != 0;
     h->flags |= fl;
     return ok;
 }
+void sh_use_v2(int on) { g_use_v2 = on; }
+void sh_stats(long long *out2) { out2[0] = g_far_out; out2[1] = g_walks; }
+void sh_stats_visits(long long *out32) { memcpy(out32, g_stat, sizeof g_stat); }
 
 // Space.drop_box (D:space.py:347-391) as pct_apply_kernel performs it: 1 = placed, 0 = rejected (the episode ends)
 int sh_place(StabHost *h, int x, int y, int z, int lx, int ly, double density) {
@@ -161,7 +177,8 @@ int shc_virtual(StabHostC *h, const double t6[6], double density) {
     NodeC root{lx, ly, mh, x, y, z, x * y * z * density};
     EdgePool pool = pool_of(h);  // the read-only check knows snapshots only, in both semantics (like pct_feas_emit_kernel)
     int fl = 0;
-    const int ok = stability_check<false, GeomC>(g, root, pool, &h->big, &h->lock, 0, fl) != 0;
+    const int ok = g_use_v2 ? stab_virtual<GeomC>(g, root, -1, 0, pool, &h->big, &h->lock, fl, true, 0xffffffffu)
+                            : (int)(stability_check<false, GeomC>(g, root, pool, &h->big, &h->lock, 0, fl) != 0);
     h->flags |= fl;
     return ok;
 }

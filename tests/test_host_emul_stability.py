@@ -46,6 +46,7 @@ def lib():
     L.sh_place.argtypes = [C.c_void_p] + [C.c_int] * 5 + [C.c_double]
     L.sh_set_alias.argtypes = [C.c_void_p, C.c_int]
     L.sh_set_holder.argtypes = [C.c_void_p, C.c_int]
+    L.sh_use_v2.argtypes = [C.c_int]
     dp = C.POINTER(C.c_double)
     L.shc_create.restype = C.c_void_p
     L.shc_create.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double]
@@ -55,6 +56,13 @@ def lib():
     L.shc_virtual.argtypes = [C.c_void_p, dp, C.c_double]
     L.shc_place_row.argtypes = [C.c_void_p, dp, dp, C.c_double]
     return L
+
+
+@pytest.fixture(autouse=True)
+def _default_routine(lib):
+    lib.sh_use_v2(0)
+    yield
+    lib.sh_use_v2(0)
 
 
 def _placement(row, next_box):
@@ -105,8 +113,12 @@ def _drive(L, env, setting, container, nb, nl, seed, env_id, steps, alias=True):
     return n_virtual, n_real
 
 
+# routine: 0 = stability_check<false> (K1's twin, heuristics), 1 = stab_virtual with the supports of the fused resting-height scan (what
+# pct_feas_emit_kernel runs since round 2), 2 = stab_virtual scanning the supports itself (continuous kernels)
+@pytest.mark.parametrize("routine", [0, 1, 2], ids=["stability_check", "stab_virtual_fused", "stab_virtual_scan"])
 @pytest.mark.parametrize("setting", [1, 3, 2])
-def test_device_stability_source_follows_the_oracle(lib, setting):
+def test_device_stability_source_follows_the_oracle(lib, setting, routine):
+    lib.sh_use_v2(routine)
     tot = 0
     for env_id in range(6):
         seed = 300 + setting
@@ -116,8 +128,10 @@ def test_device_stability_source_follows_the_oracle(lib, setting):
     assert tot > 20000
 
 
+@pytest.mark.parametrize("routine", [0, 1], ids=["stability_check", "stab_virtual_fused"])
 @pytest.mark.parametrize("name", ["big_s1", "dense16_s1", "flat_s1", "holders_s1"])
-def test_device_stability_source_on_other_configurations(lib, name):
+def test_device_stability_source_on_other_configurations(lib, name, routine):
+    lib.sh_use_v2(routine)
     c = CASES[name]
     env = OracleDiscrete(c["setting"], container_size=c["container"], internal_node_holder=c["nb"], leaf_node_holder=c["nl"],
                          size_minimum=min(min(i) for i in c["items"]), stream=case_stream(c, 91, 2, 600))
@@ -210,9 +224,11 @@ def _drive_c(L, env, setting, container, seed, env_id, steps, alias=True):
     return n_virtual
 
 
+@pytest.mark.parametrize("routine", [0, 2], ids=["stability_check", "stab_virtual_scan"])
 @pytest.mark.parametrize("setting", [1, 3, 2])
-def test_device_stability_source_follows_the_continuous_oracle(lib, setting):
+def test_device_stability_source_follows_the_continuous_oracle(lib, setting, routine):
     from pct_oracle import OracleContinuous, make_continuous_stream
+    lib.sh_use_v2(routine)
     tot = 0
     for env_id in range(4):
         env = OracleContinuous(setting, stream=make_continuous_stream(77 + setting, env_id, 600, setting))

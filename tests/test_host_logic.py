@@ -346,3 +346,40 @@ def test_reference_trainer_runs_on_the_vector_surface(fake, acktr, tmp_path, mon
     assert results[0][2] == results[1][2] == 4
     assert torch.equal(results[0][0], results[1][0])
     assert all(torch.equal(a, b) for a, b in zip(results[0][1], results[1][1]))
+
+
+# ---- reference-default kwargs: PackingContinuous' class defaults are sample_from_distribution=True, U(0.1, 0.5) (C:bin3D.py:14-16),
+# so Space.low_bound is 0.1 even when a dataset supplies the items (heuristic.py:585-591 builds the env exactly like that) -----------------------
+class _Recorder(FakeBatch):
+    seen = None
+
+    def __init__(self, *a, **kw):
+        _Recorder.seen = dict(kw)
+        super().__init__(*a, **kw)
+
+
+def test_continuous_facade_has_the_reference_defaults(monkeypatch, tmp_path):
+    import pct_b200.envs as E
+    monkeypatch.setattr(E, "PctBatch", _Recorder)
+    g = np.load(sorted(glob.glob(os.path.join(G, "eval_cont_s*.npz")))[0])
+    path = os.path.join(str(tmp_path), "data.pt")
+    torch.save([np.asarray(t) for t in g["data"]], path)
+    env = E.PackingContinuous(setting=int(g["setting"]), container_size=[1.0, 1.0, 1.0], item_set=CONT_ITEM_SET, data_name=path, load_test_data=True,
+                              internal_node_holder=80, leaf_node_holder=50)
+    kw = _Recorder.seen
+    assert kw["sample_from_distribution"] is True and kw["sample_left_bound"] == 0.1 and kw["sample_right_bound"] == 0.5
+    assert kw["item_stream"] is not None  # the dataset supplies the items
+    assert env._batch.size_minimum == 0.1
+    o = env.reset()
+    assert o.shape == (131 * 9,)
+
+
+def test_run_heuristic_continuous_dataset_uses_reference_bounds_and_rounding(monkeypatch):
+    import pct_b200.heuristics as Hm
+    monkeypatch.setattr(Hm, "PctBatch", _Recorder)
+    data = [np.array([[0.30004, 0.2, 0.1], [0.25, 0.25, 0.25]]) for _ in range(3)]
+    Hm.run_heuristic("LSAH", 2, 2, container_size=(1.0, 1.0, 1.0), data=data, n_envs=2, continuous=True, sample_from_distribution=True,
+                     sample_left_bound=0.1, sample_right_bound=0.5)
+    kw = _Recorder.seen
+    assert kw["sample_from_distribution"] is True and kw["sample_left_bound"] == 0.1
+    assert kw["item_stream"][0, 0, 0] == 0.3  # round3 (C:bin3D.py:84-87) applied to the dataset
