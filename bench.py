@@ -1,23 +1,27 @@
 #!/usr/bin/env python
 """bench.py — env-steps/s of the batched PCT step (BASELINE.json metric) on N B200s of one node.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--setting S] [--envs-per-gpu E]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--setting S] [--envs-per-gpu E] [--continuous]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-A "step" is ONE batched environment step over all envs of a rank: the synthetic uniform-valid-leaf policy
-kernel + the PCT step kernel (action -> placement -> EMS update -> candidate leaves -> feasibility ->
-observation / reward / done, with auto-reset).  Workload at N=1 = BASELINE.json configs[1]: setting 1
-discrete, 10x10x10 bin, items {1..5}^3, 80 internal / 50 leaf holders, EMS scheme, 4096 envs; weak scaling
-(4096 envs per GPU, env streams keyed by the GLOBAL env index).
+A "step" is ONE batched environment step over all envs of a rank: the synthetic uniform-valid-leaf policy kernel + the PCT step
+kernels (action -> placement -> EMS update -> candidate leaves -> feasibility -> observation / reward / done, with auto-reset).
+
+Headline workload (`value`, `e2e`, `roofline`, `vec_env`) = BASELINE.json configs[1]: setting 1 discrete, 10x10x10 bin, items {1..5}^3,
+80 internal / 50 leaf holders, EMS scheme, 4096 envs per GPU; weak scaling (env streams keyed by the GLOBAL env index).
+The same JSON line carries the other BASELINE configs as sub-records under `configs` (device-timed exactly like `value`):
+    N = 1:  "3" setting 2 / 8192 envs, "4" continuous / 4096 envs, "5_shard" setting 1 / 8192 envs (one GPU's shard of config 5)
+    N > 1:  "5" setting 1 / 8192 envs per GPU (N = 8: the 65 536 envs of config 5), and `allgather` = the one optional collective
+            of the path (NCCL all-gather of the rollout observation buffer), timed separately — the step itself has no collective.
 
 `value`    : device-timed (CUDA events, L2 flushed between steps, max over ranks), inputs resident in HBM.
-`e2e`      : the same metric through the C-ABI host-buffer call (pct_step_host): actions come from pinned
-             host memory, observation / reward / done / info are copied back to pinned host memory every
-             step and the policy runs on the host from that observation.
-`roofline` : HBM roofline of the dominant kernel (pct_feas_emit_kernel), algorithmic bytes per launch
-              / its mean launch duration measured here with CUDA events.
-`cpu_baseline` / `--impl reference`: the CPU restatement of the reference env (oracle/, C, pthreads over
-             envs like the reference's ShmemVecEnv workers) on this box's host cores.
+`e2e`      : the same metric through the C-ABI host-buffer call (pct_step_host): actions come from pinned host memory, observation /
+             reward / done / info land in pinned host memory every step and the policy runs on the host from those records.
+`vec_env`  : the same metric through the reference-facing VecEnv surface (PctVecEnv.step: device observation, host reward / done / infos).
+`roofline` : HBM roofline of the dominant kernel group, algorithmic bytes per launch / its mean duration measured here
+             with CUDA events (second pass with events between the kernels).
+`cpu_baseline` / `--impl reference`: the CPU restatement of the reference env (oracle/, C, pthreads over envs like the reference's
+             ShmemVecEnv workers) on this box's host cores; >= 3 repeats of >= 1 s each, median reported (min / max beside it).
 """
 import argparse
 import json
@@ -33,6 +37,7 @@ sys.path.insert(0, ROOT)
 ITEM_SET = [(i, j, k) for i in range(1, 6) for j in range(1, 6) for k in range(1, 6)]  # givenData.py:7-14
 ITEM_SEED, POLICY_SEED = 1234, 4321
 METRIC = "env-steps/s (batched PCT step)"
+PREROLL = 256  # steps after the synchronised reset before anything is timed: the batch reaches its steady-state episode mix
 
 
 def parse():
@@ -46,16 +51,17 @@ def parse():
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between steps (diagnostic only)")
     ap.add_argument("--e2e-steps", type=int, default=200)
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-configs", action="store_true", help="headline only: no sub-records for the other BASELINE configs")
     ap.add_argument("--continuous", action="store_true", help="BASELINE config 4: PctContinuous, sample_from_distribution, bin 1x1x1")
+    ap.add_argument("--preroll", type=int, default=PREROLL)
     return ap.parse_args()
 
 
-def workload_name(a, n_gpus):
-    if a.continuous:
+def workload_name(setting, continuous, envs_per_gpu, n_gpus):
+    if continuous:
         return "setting %d continuous (sample_from_distribution U(0.1,0.5)), bin 1x1x1, 80 internal / 50 leaf, EMS, %d envs/GPU x %d GPU" % (
-            a.setting, a.envs_per_gpu, n_gpus)
-    return "setting %d discrete, bin 10x10x10, items 1-5, 80 internal / 50 leaf, EMS, %d envs/GPU x %d GPU" % (
-        a.setting, a.envs_per_gpu, n_gpus)
+            setting, envs_per_gpu, n_gpus)
+    return "setting %d discrete, bin 10x10x10, items 1-5, 80 internal / 50 leaf, EMS, %d envs/GPU x %d GPU" % (setting, envs_per_gpu, n_gpus)
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -112,7 +118,7 @@ def measured_peak():
 
 
 def ncu_traffic():
-    """DRAM bytes per launch of the dominant kernel from the committed ncu summary (profiles/), or None."""
+    """DRAM bytes per launch of the kernels from the committed ncu captures (profiles/traffic.json: per kernel, with the commit they were taken at)."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(p):
         try:
@@ -123,19 +129,33 @@ def ncu_traffic():
 
 
 # ------------------------------------------------------------------------------------------------------------
-def cpu_port_rate(setting, n_envs, warm, steps, threads=None, continuous=False):
+def cpu_port_rate(setting, n_envs, min_steps, threads=None, continuous=False, min_seconds=1.0, repeats=3, warm_seconds=0.5):
+    """The CPU arm: the C restatement of the reference env (oracle/), one pthread per host core over the envs.  Warm up for >= warm_seconds,
+    then `repeats` timed runs of >= min_steps vector steps AND >= min_seconds each (run length adapted from the warm-up rate).
+    -> dict(value = median env-steps/s, min, max, runs, steps_per_run, seconds, cores)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import pct_oracle  # the ONLY place bench.py touches oracle/: the CPU baseline / reference arm
     if continuous:  # BASELINE config 4: PackingContinuous, sample_from_distribution U(0.1, 0.5), unit container
         b = pct_oracle.OracleBatchContinuous(n_envs, setting, ITEM_SEED, POLICY_SEED, threads=threads)
     else:
         b = pct_oracle.OracleBatch(n_envs, setting, ITEM_SET, ITEM_SEED, POLICY_SEED, threads=threads)
-    if warm:
-        b.run(warm)
-    dt = b.run(steps)
+    warm_steps, warm_t = 0, 0.0
+    chunk = max(4, min_steps // 4)
+    while warm_t < warm_seconds:
+        warm_t += b.run(chunk)
+        warm_steps += chunk
+    per_step = warm_t / warm_steps
+    steps = max(int(min_steps), int(min_seconds / per_step) + 1)
+    rates, secs = [], []
+    for _ in range(repeats):
+        dt = b.run(steps)
+        rates.append(n_envs * steps / dt)
+        secs.append(dt)
     cores = b.threads
     b.close()
-    return n_envs * steps / dt, dt, cores
+    rates_sorted = sorted(rates)
+    return {"value": rates_sorted[len(rates_sorted) // 2], "min": rates_sorted[0], "max": rates_sorted[-1], "runs": rates, "steps_per_run": steps,
+            "seconds": secs, "cores": cores, "warm_steps": warm_steps}
 
 
 def run_reference(a):
@@ -143,110 +163,187 @@ def run_reference(a):
     if rank != 0:
         return
     n = a.envs_per_gpu * a.gpus  # whole-job workload of the GPU arm, stepped by all host threads
-    # bounded sample: the CPU steps at most 8192 envs per vector step
-    n_s = min(n, 8192)
-    rate, dt, cores = cpu_port_rate(a.setting, n_s, a.warmup, a.steps, continuous=a.continuous)
+    r = cpu_port_rate(a.setting, n, max(a.steps, 1), continuous=a.continuous)
+    rate = r["value"]
+    sample = "%d envs x %d vector steps per run, %d runs of %.2f-%.2f s (median; min %.3g, max %.3g env-steps/s) after %d warm-up steps" % (
+        n, r["steps_per_run"], len(r["runs"]), min(r["seconds"]), max(r["seconds"]), r["min"], r["max"], r["warm_steps"])
     line = {"metric": METRIC, "value": rate, "unit": "env-steps/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
-            "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "timed_steps_per_run": r["steps_per_run"], "warmup_steps_run": r["warm_steps"], "ms_per_step": 1e3 * n / rate, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64" if a.continuous else "int32+f64",
             "data": "synthetic", "impl": "reference",
-            "config": {"workload": workload_name(a, a.gpus), "note": "reference's CPU env path: C restatement (oracle/, kind=port; the "
-                       "reference itself is pure Python and does not travel to the GPU box), pthreads over envs like ShmemVecEnv workers"},
-            "cpu_baseline": {"value": rate, "unit": "env-steps/s", "cores": cores, "kind": "port",
-                             "sample": "%d envs x %d vector steps (+%d warm-up)" % (n_s, a.steps, a.warmup)},
+            "config": {"workload": workload_name(a.setting, a.continuous, a.envs_per_gpu, a.gpus),
+                       "note": "reference's CPU env path: C restatement (oracle/, kind=port; the reference itself is pure Python and does not "
+                               "travel to the GPU box), pthreads over envs like ShmemVecEnv workers; --steps is the MINIMUM run length: every "
+                               "timed run lasts >= 1 s, median of 3"},
+            "cpu_baseline": {"value": rate, "unit": "env-steps/s", "cores": r["cores"], "kind": "port", "sample": sample,
+                             "min": r["min"], "max": r["max"]},
             "e2e": {"value": rate, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------------------------------
-def run_ours(a):
-    import numpy as np
-    import torch
+class Ctx(object):
+    pass
+
+
+def make_batch(setting, continuous, n, rank, local):
     import pct_b200
+    if continuous:
+        return pct_b200.PctBatch(n, setting, container_size=(1.0, 1.0, 1.0), continuous=True, sample_from_distribution=True,
+                                 seed=ITEM_SEED, env_id_base=rank * n, device=local)
+    return pct_b200.PctBatch(n, setting, item_set=ITEM_SET, seed=ITEM_SEED, env_id_base=rank * n, device=local)
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    n = a.envs_per_gpu
-    K, W = a.steps, max(a.warmup, 3)
 
-    if a.continuous:
-        batch = pct_b200.PctBatch(n, a.setting, container_size=(1.0, 1.0, 1.0), continuous=True, sample_from_distribution=True,
-                                  seed=ITEM_SEED, env_id_base=rank * n, device=local)
-    else:
-        batch = pct_b200.PctBatch(n, a.setting, item_set=ITEM_SET, seed=ITEM_SEED, env_id_base=rank * n, device=local)
-    launches0 = batch.kernel_launches
-    flush = None if a.no_flush else torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    obs = batch.reset()
-    for t in range(W):
-        idx = batch.random_policy(POLICY_SEED, t)
-        batch.step(leaf_idx=idx)
+def measure(cx, setting, continuous, n, K, W, preroll, kernels=True, keep=False):
+    """Device-timed throughput of one configuration on this rank's GPU (all ranks call it together): reset, `preroll` + W untimed steps,
+    K timed steps (CUDA events per step, L2 flushed before each, barrier on both sides), then — discrete only — a second pass of K steps
+    with events between the kernels for the per-kernel durations."""
+    import torch
+    batch = make_batch(setting, continuous, n, cx.rank, cx.local)
+    batch.reset()
+    for t in range(preroll + W):
+        batch.step(leaf_idx=batch.random_policy(POLICY_SEED, t))
     torch.cuda.synchronize()
-
+    T0 = preroll + W
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
-    stats = torch.zeros((4,), dtype=torch.float64, device=dev)  # sums of counter, n_leaf, n_cand, n_ems
-    sampler = ClockSampler(local) if rank == 0 else None
-    if sampler:
-        sampler.start()
-        time.sleep(0.3)
-    barrier()
+    stats = torch.zeros((4,), dtype=torch.float64, device=cx.dev)  # sums of counter, n_leaf, n_cand, n_ems
+    cx.barrier()
     l0 = batch.kernel_launches
     t_wall0 = time.perf_counter()
     for t in range(K):
-        if flush is not None:
-            flush.zero_()  # L2 flush (256 MiB > 126 MB L2), outside the timed interval of the step
+        if cx.flush is not None:
+            cx.flush.zero_()  # L2 flush (256 MiB > 126 MB L2), outside the timed interval of the step
         ev[t][0].record()
-        idx = batch.random_policy(POLICY_SEED, W + t)
+        idx = batch.random_policy(POLICY_SEED, T0 + t)
         ev[t][1].record()
         _, _, _, info = batch.step(leaf_idx=idx)
         ev[t][2].record()
         if t % 16 == 0:
             stats += torch.stack([info[:, 0].double().mean(), info[:, 5].double().mean(), info[:, 6].double().mean(), info[:, 7].double().mean()])
-    barrier()
+    cx.barrier()
     wall = time.perf_counter() - t_wall0
     launches = batch.kernel_launches - l0
-    # Per-kernel durations for the roofline: a second pass over the same number of steps with CUDA events between the three
-    # kernels (pct_profile_enable).  Events between the kernels serialise them, i.e. this pass runs WITHOUT the overlapped
-    # launch mode the timed region above uses (programmatic dependent launch + per-env hand-over flags), so a kernel's duration
-    # here is its stand-alone duration; the step time of the timed region is shorter than their sum.
     kms, ksteps = {}, 0
-    if not a.continuous:
+    if kernels and not continuous:
         batch.profile(True)
         for t in range(K):
-            if flush is not None:
-                flush.zero_()
-            batch.step(leaf_idx=batch.random_policy(POLICY_SEED, W + K + t))
+            if cx.flush is not None:
+                cx.flush.zero_()
+            batch.step(leaf_idx=batch.random_policy(POLICY_SEED, T0 + K + t))
         torch.cuda.synchronize()
         kms, ksteps = batch.profile_read()
         batch.profile(False)
-    clocks = sampler.finish() if sampler else None
     per_step = sorted(ev[t][0].elapsed_time(ev[t][2]) for t in range(K))
     step_ms = sum(per_step)
     kern_ms = sum(ev[t][1].elapsed_time(ev[t][2]) for t in range(K))
-    tt = torch.tensor([step_ms, kern_ms], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    tt = torch.tensor([step_ms, kern_ms], dtype=torch.float64, device=cx.dev)
+    if cx.dist is not None:
+        cx.dist.all_reduce(tt, op=cx.dist.ReduceOp.MAX)
     step_ms, kern_ms = float(tt[0]), float(tt[1])
     nsamp = len(range(0, K, 16))
     mean_boxes, mean_leaf, mean_cand, mean_ems = [float(x) / nsamp for x in stats.cpu()]
-    value = world * n * K / (step_ms * 1e-3)
+    rec = {"value": cx.world * n * K / (step_ms * 1e-3), "ms_per_step": step_ms / K, "kernel_ms_per_step": kern_ms / K,
+           "ms_per_step_p50": per_step[K // 2], "ms_per_step_p99": per_step[min(K - 1, int(K * 0.99))], "wall_s_timed_loop": wall,
+           "gpu_launches": int(launches), "mean_boxes": mean_boxes, "mean_ems": mean_ems, "mean_valid_leaves": mean_leaf,
+           "mean_candidates": mean_cand, "kernel_ms": {k: v / ksteps for k, v in kms.items()} if ksteps else None, "steps": K, "warmup": W,
+           "preroll": preroll, "envs_per_gpu": n}
+    if keep:
+        return rec, batch
+    batch.close()
+    return rec
 
-    # ---- e2e: host buffers through pct_step_host, host policy on the returned observation ----
-    Ke, We = max(3, min(a.e2e_steps, K)), 5
+
+def roofline_of(rec, setting, continuous, n, obs_len, delta_obs):
+    """HBM roofline of the dominant kernel group from the per-kernel CUDA-event durations; algorithmic bytes per env as in DESIGN.md section 5."""
+    peak, peak_src = measured_peak()
+    hot, prefix, stage = 3584, 2576, 1040  # sizeof(DEnvHot), HOT_PREFIX, header + boxes
+    stab = setting != 2
+    nb_, nl_, nc_ = rec["mean_boxes"], rec["mean_valid_leaves"], rec["mean_candidates"]
+    edges = nb_ if stab else 0.0
+    loads = (32 * edges + 16 * 0.3 * edges) if stab else 0.0
+    walks = 0.45 * nc_ if stab else 0.0  # candidates that need a stability walk (host statistics of the BASELINE streams: 45 %)
+    obs_b = (max(nb_, 1.0) + nl_ + 1.0) * 36.0 if delta_obs else obs_len * 4.0
+    groups = {
+        "apply": 2 * hot + 2 * loads + 4 + 4 + 1 + 32,
+        "candidates": prefix + 2 * nc_ + 4 * (nc_ / 32.0 + 1) + 20 * walks,
+        "feas_emit": 20 * walks + (hot + loads if stab else 0) + stage + 2 * nc_ + 4 * (nc_ / 32.0 + 1) + 12 * nl_ * 2 + obs_b + 32,
+    }
+    b_step = sum(groups.values())
+    out = {"bound": "hbm", "peak": peak, "unit": "GB/s", "peak_source": peak_src, "algorithmic_bytes_per_env_step": b_step,
+           "step_achieved": b_step * n / (rec["kernel_ms_per_step"] * 1e-3) / 1e9}
+    out["step_fraction_of_peak"] = out["step_achieved"] / peak
+    km = rec.get("kernel_ms")
+    if km:
+        dom = max(km, key=lambda k: km[k])
+        ach = groups[dom] * n / (km[dom] * 1e-3) / 1e9
+        names = {"apply": "pct_apply_kernel", "candidates": "pct_candidates_kernel (+ classify)", "feas_emit": "pct_walk_kernel + pct_emit_kernel"}
+        out.update(achieved=ach, frac=ach / peak, kernel=names[dom], kernel_ms=km[dom], algorithmic_bytes_per_env_kernel=groups[dom],
+                   all_kernels_ms=km,
+                   all_kernels_frac={k: groups[k] * n / (km[k] * 1e-3) / 1e9 / peak for k in km},
+                   kernel_timing="second pass of %d steps right after the timed region with CUDA events between the kernel groups; the events "
+                                 "serialise the kernels, the timed region itself overlaps apply -> candidates (programmatic dependent launch + "
+                                 "per-env hand-over flags), so ms_per_step < sum of these" % rec["steps"])
+    else:
+        out.update(achieved=out["step_achieved"], frac=out["step_fraction_of_peak"], kernel="whole step (continuous kernels: pctc_apply / pctc_candidates / pctc_feas_emit)",
+                   kernel_ms=rec["kernel_ms_per_step"])
+    # SURVEY.md 8(d) / BASELINE.md 3.5 figure for the WHOLE step, independent of this implementation's record layout
+    b_survey = 5593.0 + 24.0 * nb_ + 48.0 * rec["mean_ems"]
+    ach_survey = b_survey * n / (rec["kernel_ms_per_step"] * 1e-3) / 1e9
+    out["survey_formula"] = {"bytes_per_env_step": b_survey, "achieved": ach_survey, "frac": ach_survey / peak,
+                             "note": "SURVEY 8(d): (5593 + 24 N + 48 E) B x env-steps/s of one GPU / peak, whole step"}
+    tr = ncu_traffic()
+    out["traffic"] = None
+    if tr:
+        key = out["kernel"].split(" ")[0]
+        ent = tr.get("kernels", {}).get(key) or tr.get("kernels", {}).get("pct_walk_kernel")
+        if ent:
+            out["traffic"] = ent.get("dram_bytes_per_launch")
+            out["traffic_source"] = "ncu --set full capture of commit %s (profiles/%s), %s" % (tr.get("commit"), tr.get("file"), ent.get("note", ""))
+        out["traffic_all_kernels"] = tr.get("kernels")
+    return out
+
+
+def run_ours(a):
+    import numpy as np
+    import torch
+    import pct_b200
+
+    cx = Ctx()
+    cx.world = int(os.environ.get("WORLD_SIZE", "1"))
+    cx.rank = int(os.environ.get("RANK", "0"))
+    cx.local = int(os.environ.get("LOCAL_RANK", "0"))
+    cx.dist = None
+    if cx.world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(cx.local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", cx.local))
+        cx.dist = dist
+    torch.cuda.set_device(cx.local)
+    cx.dev = torch.device("cuda", cx.local)
+    cx.flush = None if a.no_flush else torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=cx.dev)
+
+    def barrier():
+        if cx.dist is not None:
+            cx.dist.barrier()
+        torch.cuda.synchronize()
+    cx.barrier = barrier
+    world, rank, local, dev = cx.world, cx.rank, cx.local, cx.dev
+    n = a.envs_per_gpu
+    K, W = a.steps, max(a.warmup, 3)
+    switches = {k: v for k, v in sorted(os.environ.items()) if k.startswith("PCT_B200_")}
+    delta_obs = os.environ.get("PCT_B200_OBS_DELTA", "1") != "0" and not a.continuous
+    zero_copy = os.environ.get("PCT_B200_HOST_ZEROCOPY", "1") != "0"
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.3)
+    head, batch = measure(cx, a.setting, a.continuous, n, K, W, a.preroll, keep=True)
+    clocks = sampler.finish() if sampler else None
     ol = batch.obs_len
+
+    # ---- e2e: host buffers through pct_step_host, host policy on the returned records ----
+    Ke, We = max(3, min(a.e2e_steps, K)), 5
     obs_h = torch.empty((n, ol), dtype=torch.float32, pin_memory=True).numpy()
     rew_h = torch.empty((n,), dtype=torch.float32, pin_memory=True).numpy()
     done_h = torch.empty((n,), dtype=torch.uint8, pin_memory=True).numpy()
@@ -284,69 +381,117 @@ def run_ours(a):
     torch.cuda.synchronize()
     e2e_dt = time.perf_counter() - t0
     te = torch.tensor([e2e_dt], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    if cx.dist is not None:
+        cx.dist.all_reduce(te, op=cx.dist.ReduceOp.MAX)
     e2e_value = world * n * Ke / float(te[0])
     h2d = idx_h.nbytes
-    d2h = obs_h.nbytes + rew_h.nbytes + done_h.nbytes + info_h.nbytes
+    rows_changed = (max(head["mean_boxes"], 1.0) + head["mean_valid_leaves"] + 1.0) * 36.0
+    d2h_full = obs_h.nbytes + rew_h.nbytes + done_h.nbytes + info_h.nbytes
+    d2h = int(n * rows_changed + rew_h.nbytes + done_h.nbytes + info_h.nbytes) if (delta_obs and zero_copy) else d2h_full
+    batch.close()
+
+    # ---- the reference-facing VecEnv surface: PctVecEnv.step (device observation; reward / done / infos on the host, one sync per step) ----
+    vec = None
+    try:
+        kw = dict(container_size=(1.0, 1.0, 1.0), continuous=True, sample_from_distribution=True) if a.continuous else dict(item_set=ITEM_SET)
+        venv = pct_b200.PctVecEnv(n, a.setting, seed=ITEM_SEED, env_id_base=rank * n, device=local, **kw)
+        venv.reset()
+        Kv = max(3, min(a.e2e_steps, K))
+        n_done = 0
+        for t in range(20):
+            venv.step(venv.batch.random_policy(POLICY_SEED, t))
+        barrier()
+        t0 = time.perf_counter()
+        for t in range(Kv):
+            _, _, d_, infos = venv.step(venv.batch.random_policy(POLICY_SEED, 20 + t))
+            for i in np.nonzero(d_)[0]:  # what train_tools.py:72-79 reads: the finished envs' episode records
+                n_done += 1 if "ratio" in infos[i] else 0
+        torch.cuda.synchronize()
+        tv = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if cx.dist is not None:
+            cx.dist.all_reduce(tv, op=cx.dist.ReduceOp.MAX)
+        vec = {"value": world * n * Kv / float(tv[0]), "unit": "env-steps/s", "steps": Kv, "episodes_read": n_done,
+               "path": "PctVecEnv.step(leaf indices on the device): device observation (fresh tensor per step), reward / done / lazy infos on the "
+                       "host, finished envs' info dicts materialised; wall clock"}
+        venv.close()
+    except Exception as ex:  # never fail the headline on the convenience surface
+        vec = {"value": None, "error": repr(ex)}
+
+    # ---- the other BASELINE configs, device-timed the same way ----
+    configs = {}
+    default_head = (a.setting == 1 and not a.continuous and n == 4096)
+    Kc, Wc = max(20, min(K, 300)), W
+    if not a.skip_configs and default_head:
+        if world == 1:
+            plan = [("3", 2, False, 8192), ("4", 1, True, 4096), ("5_shard", 1, False, 8192)]
+        else:
+            plan = [("5", 1, False, 8192)]
+        for key, s_, c_, n_ in plan:
+            r = measure(cx, s_, c_, n_, Kc, Wc, a.preroll)
+            r["workload"] = workload_name(s_, c_, n_, world)
+            if rank == 0:
+                r["roofline"] = roofline_of(r, s_, c_, n_, ol, (not c_) and os.environ.get("PCT_B200_OBS_DELTA", "1") != "0")
+            configs[key] = r
+
+    # ---- the one optional collective of the path: NCCL all-gather of the rollout observation buffer (not part of the step) ----
+    allgather = None
+    if cx.dist is not None:
+        from pct_b200.distributed import gather_observations
+        o_loc = torch.zeros((8192 if default_head else n, ol), dtype=torch.float32, device=dev)
+        for _ in range(3):
+            gather_observations(o_loc)
+        barrier()
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        reps = 20
+        evs[0].record()
+        for _ in range(reps):
+            g_all = gather_observations(o_loc)
+        evs[1].record()
+        barrier()
+        tg = torch.tensor([evs[0].elapsed_time(evs[1]) / reps], dtype=torch.float64, device=dev)
+        cx.dist.all_reduce(tg, op=cx.dist.ReduceOp.MAX)
+        allgather = {"ms": float(tg[0]), "bytes_per_rank": int(o_loc.numel() * 4), "bytes_gathered": int(g_all.numel() * 4),
+                     "algbw_GBps": g_all.numel() * 4 / (float(tg[0]) * 1e-3) / 1e9,
+                     "note": "optional rollout-buffer gather (pct_b200.distributed.gather_observations); NOT inside `value`: the step has no collective"}
 
     if rank == 0:
-        peak, peak_src = measured_peak()
-        # algorithmic bytes per env-step.  Dominant kernel = pct_feas_emit_kernel (K3): it reads the
-        # hot record, the staged loads / polygons and the candidate list, writes the observation, the leaf list and info.
-        hot, prefix = 3584, 2576  # sizeof(DEnvHot), HOT_PREFIX
-        stab = a.setting != 2
-        edges = mean_boxes if stab else 0.0
-        b_k3 = hot + (32 * edges + 16 * 0.3 * edges if stab else 0) + 2 * mean_cand + ol * 4 + 12 * mean_leaf + 16
-        b_step = 2 * hot + prefix + 2 * 2 * mean_cand + b_k3 + (2 * 32 * edges if stab else 0) + 4 + 4 + 1 + 32
-        if ksteps:
-            k3_ms = kms["feas_emit"] / ksteps
-            ach = b_k3 * n / (k3_ms * 1e-3) / 1e9
-        else:
-            k3_ms = None
-            ach = b_step * n / (kern_ms / K * 1e-3) / 1e9
-        # SURVEY.md 8(d) / BASELINE.md 3.5 figure for the WHOLE step, independent of this implementation's record layout:
-        # B_step = 5593 + 24 N + 48 E bytes (action, item, boxes, EMS before / after, height map, observation, reward / done)
-        b_survey = 5593.0 + 24.0 * mean_boxes + 48.0 * mean_ems
-        ach_survey = b_survey * n / (kern_ms / K * 1e-3) / 1e9  # per GPU: n envs of this rank over this rank's kernel time
-        traffic = ncu_traffic()
-        line = {"metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
-                "ms_per_step": step_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "int16/int32 geometry + f64 stability, f32 observations", "data": "synthetic",
-                "config": {"workload": workload_name(a, world), "items": "device counter-based RNG seed %d, uniform over 125 sizes" % ITEM_SEED,
-                           "policy": "uniform over valid leaves (device kernel)", "launch_mode": os.environ.get("PCT_B200_OVERLAP", "1") != "0" and
-                           "overlapped (PDL + per-env flags)" or "back-to-back kernels", "l2": "not flushed (diagnostic)" if a.no_flush else
-                           "flushed between steps (256 MiB memset outside the timed interval)",
-                           "mean_boxes": mean_boxes, "mean_ems": mean_ems, "mean_valid_leaves": mean_leaf, "mean_candidates": mean_cand,
-                           "switches": {k: v for k, v in sorted(os.environ.items()) if k.startswith("PCT_B200_")}},
+        roof = roofline_of(head, a.setting, a.continuous, n, ol, delta_obs)
+        line = {"metric": METRIC, "value": head["value"], "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64 geometry and stability, f32 observations" if a.continuous else "int16/int32 geometry + f64 stability, f32 observations",
+                "data": "synthetic",
+                "config": {"workload": workload_name(a.setting, a.continuous, n, world),
+                           "items": "device counter-based RNG seed %d, uniform over 125 sizes" % ITEM_SEED,
+                           "policy": "uniform over valid leaves (device kernel)",
+                           "launch_mode": os.environ.get("PCT_B200_OVERLAP", "1") != "0" and "overlapped apply -> candidates (PDL + per-env flags), pooled walks"
+                                          or "back-to-back kernels",
+                           "l2": "not flushed (diagnostic)" if a.no_flush else "flushed between steps (256 MiB memset outside the timed interval)",
+                           "phase": "steady-state episode mix: %d pre-roll steps after the synchronised reset, then %d warm-up steps, then the timed steps" % (a.preroll, W),
+                           "mean_boxes": head["mean_boxes"], "mean_ems": head["mean_ems"], "mean_valid_leaves": head["mean_valid_leaves"],
+                           "mean_candidates": head["mean_candidates"], "switches": switches},
                 "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                        "steps": Ke, "path": ("pct_step_host (C ABI, pinned host buffers, zero-copy: kernels write the observation into the mapped host buffer)"
-                                 if os.environ.get("PCT_B200_HOST_ZEROCOPY", "0") != "0" else
-                                 "pct_step_host (C ABI, pinned host buffers, 4 pipelined env ranges)") + " + numpy policy on the host from the returned step records"},
-                "gpu_launches": int(launches), "kernel_ms_per_step": kern_ms / K,
-                "ms_per_step_p50": per_step[K // 2], "ms_per_step_p99": per_step[min(K - 1, int(K * 0.99))], "wall_s_timed_loop": wall,
-                "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                             "traffic": traffic.get("dram_bytes_per_launch") if traffic else None, "kernel": "pct_feas_emit_kernel",
-                             "peak_source": peak_src, "algorithmic_bytes_per_env_kernel": b_k3, "algorithmic_bytes_per_env_step": b_step,
-                             "kernel_ms": k3_ms, "all_kernels_ms": {k: v / ksteps for k, v in kms.items()} if ksteps else None,
-                             "kernel_timing": "second pass of %d steps right after the timed region with CUDA events between the three kernels; "
-                                              "the events serialise the kernels, the timed region itself runs them overlapped (programmatic "
-                                              "dependent launch + per-env hand-over flags), so ms_per_step < sum of these" % ksteps,
-                             "step_fraction_of_peak": b_step * n / (kern_ms / K * 1e-3) / 1e9 / peak,
-                             "survey_formula": {"bytes_per_env_step": b_survey, "achieved": ach_survey, "frac": ach_survey / peak,
-                                                "note": "SURVEY 8(d): (5593 + 24 N + 48 E) B x env-steps/s of one GPU / peak, whole step"}},
-                "clocks": clocks}
+                        "d2h_bytes_per_step_full_observation": int(d2h_full), "steps": Ke,
+                        "path": ("pct_step_host (C ABI, pinned host buffers, zero-copy: the emit kernel writes the changed observation rows straight into the "
+                                 "mapped host buffer)" if zero_copy else "pct_step_host (C ABI, pinned host buffers, 4 pipelined env ranges)")
+                                + " + numpy policy on the host from the returned step records"},
+                "vec_env": vec,
+                "gpu_launches": head["gpu_launches"], "kernel_ms_per_step": head["kernel_ms_per_step"],
+                "ms_per_step_p50": head["ms_per_step_p50"], "ms_per_step_p99": head["ms_per_step_p99"], "wall_s_timed_loop": head["wall_s_timed_loop"],
+                "roofline": roof, "clocks": clocks, "configs": configs}
+        if allgather:
+            line["allgather"] = allgather
         if world == 1 and not a.skip_cpu:
             try:
-                rate, dt, cores = cpu_port_rate(a.setting, 2048, 20, 300, continuous=a.continuous)
-                line["cpu_baseline"] = {"value": rate, "unit": "env-steps/s", "cores": cores, "kind": "port",
-                                        "sample": "2048 envs x 300 vector steps (+20 warm-up), same items / policy"}
+                r = cpu_port_rate(a.setting, 4096, 50, continuous=a.continuous)
+                line["cpu_baseline"] = {"value": r["value"], "unit": "env-steps/s", "cores": r["cores"], "kind": "port", "min": r["min"], "max": r["max"],
+                                        "sample": "4096 envs x %d vector steps per run, %d runs of %.2f-%.2f s (median) after %d warm-up steps, same items / policy"
+                                                  % (r["steps_per_run"], len(r["runs"]), min(r["seconds"]), max(r["seconds"]), r["warm_steps"])}
             except Exception as ex:  # the oracle is test infrastructure; never fail the GPU number on it
                 line["cpu_baseline"] = {"value": None, "error": str(ex)}
         print(json.dumps(line))
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
+    if cx.dist is not None:
+        cx.dist.barrier()
+        cx.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

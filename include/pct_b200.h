@@ -85,6 +85,11 @@ typedef struct pct_config {
                                   /*    wrapper/shmem_vec_env.py:141-142); 1: plain gym.Env semantics (the       */
                                   /*    terminal observation is returned, the caller resets; D:bin3D.py:160-165) */
     int32_t lnes;                 /* leaf-node expansion scheme (D:bin3D.py:101-112): pct_lnes, 0 = EMS (reference default) */
+    int32_t shuffle;              /* `shuffle` kwarg (D:bin3D.py:114-115, C:bin3D.py:126-127; tools.py:136 defaults it to True for training): the   */
+                                  /*   ordered candidate list is permuted before the feasibility tests and the leaf cap.  The reference draws from  */
+                                  /*   the global numpy RNG (no parity definition); here the permutation is the stable argsort of counter-based     */
+                                  /*   keys rnd_u64(seed ^ 0x5AFE5EED, global env id, draws << 16 | i) — uniform, reproducible, independent of the  */
+                                  /*   sharding — and the oracle (test infrastructure) implements the same definition.                              */
 } pct_config;
 
 /* Terminal-step info (the dict built at D:bin3D.py:163-164 plus what Monitor adds, wrapper/monitor.py:58-77) */

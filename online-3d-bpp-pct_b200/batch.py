@@ -20,7 +20,9 @@ class PctBatch(object):
     def __init__(self, n_envs, setting, container_size=(10, 10, 10), item_set=None, internal_node_holder=80,
                  leaf_node_holder=50, continuous=False, obs_dtype=torch.float32, seed=0, env_id_base=0, device=0,
                  sample_from_distribution=False, sample_left_bound=None, sample_right_bound=None, item_stream=None,
-                 size_minimum=None, auto_reset=True, LNES="EMS"):
+                 size_minimum=None, auto_reset=True, LNES="EMS", shuffle=False):
+        """shuffle: the reference's `shuffle` kwarg (D:bin3D.py:114-115; tools.py:136 defaults --shuffle to True for training): the ordered candidate list
+        is permuted before the feasibility tests and the leaf cap, by a keyed counter-based permutation (include/pct_b200.h, pct_config::shuffle)."""
         if not torch.cuda.is_available():
             raise PctError("pct_b200 needs a CUDA device (sm_100a kernels; there is no CPU fallback)")
         self.L = _lib.lib()
@@ -58,6 +60,7 @@ class PctBatch(object):
         cfg.env_id_base = int(env_id_base)
         cfg.no_auto_reset = 0 if auto_reset else 1
         cfg.lnes = _lib.LNES_CODES[LNES]
+        cfg.shuffle = int(bool(shuffle))
         self.cfg = cfg
         h = C.c_void_p()
         rc = self.L.pct_create(C.byref(cfg), self.n_envs, int(device), C.byref(h))

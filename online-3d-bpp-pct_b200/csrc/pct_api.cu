@@ -122,6 +122,11 @@ int pct_create(const pct_config *cfg, int32_t n_envs, int32_t device, pct_handle
             if (e == cudaSuccess) e = cudaMalloc(&h->d_ready, sizeof(int32_t) * 2 * (size_t)n_envs);
             if (e == cudaSuccess) e = cudaMemset(h->d_ready, 0, sizeof(int32_t) * 2 * (size_t)n_envs);
             if (e == cudaSuccess) e = cudaMemset(h->d_cold, 0, sizeof(DEnvCold) * (size_t)n_envs);
+            if (e == cudaSuccess && !h->k3_block) {  // the step's pool of stability walks: worst-case capacity, only the used prefix is ever touched
+                e = cudaMalloc(&h->d_walkq, sizeof(WalkItem) * (size_t)CAND_MAX * (size_t)n_envs);
+                if (e == cudaSuccess) e = cudaMalloc(&h->d_walk_ctr, sizeof(int32_t) * (size_t)n_envs);
+                if (e == cudaSuccess) e = cudaMemset(h->d_walk_ctr, 0, sizeof(int32_t) * (size_t)n_envs);
+            }
             if (e == cudaSuccess) e = cudaMalloc(&h->d_order, sizeof(int32_t) * 2 * (size_t)n_envs);
             if (e == cudaSuccess) {
                 std::vector<int32_t> id(2 * (size_t)n_envs);
@@ -149,6 +154,7 @@ void pct_destroy(pct_handle h) {
     cudaSetDevice(h->device);
     if (h->cfg.domain == PCT_CONTINUOUS) continuous_destroy(h);
     cudaFree(h->d_order);
+    cudaFree(h->d_walkq); cudaFree(h->d_walk_ctr);
     cudaFree(h->d_hstate); cudaFree(h->d_hstate_c); cudaFree(h->d_query_c); cudaFree(h->d_query); cudaFree(h->d_aux);
     cudaFree(h->d_ready);
     cudaFree(h->d_hot); cudaFree(h->d_cold); cudaFree(h->d_item_set); cudaFree(h->d_stream);
@@ -209,7 +215,7 @@ static int launch_range(pct_handle h, int mode, int off, int cnt, const void *ac
     p.hot = h->d_hot + off; p.cold = h->d_cold + off; p.n_envs = cnt;
     p.W = (int)h->cfg.container_size[0]; p.L = (int)h->cfg.container_size[1]; p.H = (int)h->cfg.container_size[2];
     p.nb = h->cfg.internal_node_holder; p.nl = h->cfg.leaf_node_holder; p.setting = h->cfg.setting;
-    p.low_bound = h->cfg.size_minimum; p.lnes = h->cfg.lnes;
+    p.low_bound = h->cfg.size_minimum; p.lnes = h->cfg.lnes; p.shuffle = h->cfg.shuffle;
     p.item_mode = h->item_mode; p.item_set = h->d_item_set; p.n_items = h->n_items;
     p.stream = h->d_stream ? h->d_stream + (size_t)off * h->stream_len * 4 : nullptr; p.stream_len = h->stream_len; p.traj_len = h->traj_len;
     p.seed = h->cfg.seed; p.env_id_base = h->cfg.env_id_base + off; p.env_id_base0 = h->cfg.env_id_base;
@@ -244,8 +250,10 @@ static int launch_range(pct_handle h, int mode, int off, int cnt, const void *ac
         prof = &h->prof_ev[(size_t)h->prof_steps * 4];
         h->prof_steps++;
     }
+    p.walkq = h->d_walkq ? h->d_walkq + (size_t)off * CAND_MAX : nullptr;  // env ranges stepped concurrently (pct_step_host's staged path) own disjoint slices
+    p.walk_ctr = h->d_walk_ctr ? h->d_walk_ctr + off : nullptr;
     CK(h, launch_discrete(p, gs, prof));
-    h->launches += discrete_kernels_per_step();
+    h->launches += discrete_kernels_per_step(p);
     return PCT_OK;
 }
 

@@ -146,6 +146,30 @@ __device__ __forceinline__ bool env_wait(const int32_t *flag, int32_t epoch) {
     return false;
 }
 
+// shuffle=True (D:bin3D.py:114-115 / C:bin3D.py:126-127): one warp permutes the ordered candidate list list[0..n) in place.  Definition
+// (include/pct_b200.h, pct_config::shuffle): stable argsort of the keys rnd_u64(seed ^ SALT, global env id, draws << 16 | i).  Rank by
+// counting (n^2 / 32 key comparisons per warp; n is 38 on average, <= 1228); keys[n] and tmp[n] are scratch in global memory.
+constexpr uint64_t SHUFFLE_SALT = 0x5AFE5EEDull;
+template <typename T>
+__device__ __noinline__ void shuffle_candidates(T *list, int n, uint64_t *keys, T *tmp, uint64_t seed, uint64_t gid, uint64_t draws, int lane) {
+    if (n < 2) return;
+    for (int i = lane; i < n; i += 32) keys[i] = rnd_u64(seed ^ SHUFFLE_SALT, gid, (draws << 16) | (uint64_t)i);
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) {
+        const uint64_t ki = keys[i];
+        int r = 0;
+#pragma unroll 4
+        for (int j = 0; j < n; j++) {
+            const uint64_t kj = keys[j];
+            r += (int)(kj < ki || (kj == ki && j < i));
+        }
+        tmp[r] = list[i];
+    }
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) list[i] = tmp[i];
+    __syncwarp();
+}
+
 __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {

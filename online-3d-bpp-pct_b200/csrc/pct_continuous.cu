@@ -70,6 +70,7 @@ struct CParams {
     int mode, keep_draw, no_auto_reset;
     int32_t *ready;  // overlapped launch mode: per-env hand-over flags [2 * n_envs] (see pct_common.cuh), nullptr = off
     int32_t epoch;
+    int shuffle;     // pct_config::shuffle: keyed permutation of the ordered candidate list (shuffle_candidates)
     DEnvAux *aux;    // per-env state of the ALIAS apply kernel (EdgePoolA arrays), nullptr with PCT_B200_ALIAS=0 / setting 2
 };
 
@@ -510,6 +511,11 @@ __global__ void __launch_bounds__(32) pctc_candidates_kernel(const CParams p) {
         cnt += __popc(em);
     }
     __syncwarp();
+    if (p.shuffle) {  // scratch: the GENEMS temp list (24 KB, idle between apply kernels): keys at 0, permuted codes at 10 KB
+        static_assert(sizeof(ev->ems_tmp) >= 10240 + sizeof(ev->cand), "shuffle scratch fits");
+        shuffle_candidates<uint16_t>(ev->cand, cnt, (uint64_t *)ev->ems_tmp, (uint16_t *)((char *)ev->ems_tmp + 10240), p.seed, (uint64_t)(p.env_id_base + e),
+                                     (uint64_t)h.draw_pos, lane);
+    }
     if (lane == 0) {
         ev->h.n_cand = cnt;
         if (fl) ev->h.flags |= fl;
@@ -667,7 +673,7 @@ int continuous_launch(pct_env_batch *h, int mode, const void *actions, int actio
     p.item_mode = h->item_mode; p.sample_dist = h->cfg.sample_from_distribution;
     p.sample_a = h->cfg.sample_left_bound; p.sample_b = h->cfg.sample_right_bound;
     p.item_set = h->d_item_set; p.n_items = h->n_items; p.stream = h->d_stream; p.stream_len = h->stream_len; p.traj_len = h->traj_len;
-    p.seed = h->cfg.seed; p.env_id_base = h->cfg.env_id_base;
+    p.seed = h->cfg.seed; p.env_id_base = h->cfg.env_id_base; p.shuffle = h->cfg.shuffle;
     p.actions = actions; p.action_f64 = action_f64; p.leaf_idx = leaf_idx;
     p.obs = obs; p.obs_f64 = h->cfg.obs_dtype == PCT_F64; p.reward = rew; p.done = done; p.info = info;
     p.mode = mode; p.keep_draw = h->did_reset ? 1 : 0; p.no_auto_reset = h->cfg.no_auto_reset;

@@ -97,7 +97,7 @@ __device__ __noinline__ uint64_t key_hash(uint32_t k, const RotTab *rt) {
 }
 
 // ---- EMS update (GENEMS + Difference + EliminateInscribedEMS, D:space.py:457-531) -------------------------
-__device__ __noinline__ int genems_warp(int16_t (*ems)[6], const int n0, int16_t (*tmp)[6], const int16_t *it, double low_bound, int lane,
+__device__ __noinline__ int genems_warp(int16_t (*ems)[6], const int n0, int16_t (*tmp)[6], uint2 *pk, const int16_t *it, double low_bound, int lane,
                                         int &flags) {
     const double lb = low_bound == 0 ? 0.1 : low_bound;
     const int nch = (n0 + 31) >> 5;
@@ -165,22 +165,32 @@ __device__ __noinline__ int genems_warp(int16_t (*ems)[6], const int n0, int16_t
     if (__any_sync(FULL, overflow)) flags |= PCT_FLAG_EMS_OVERFLOW;
     const int n = off < EMS_TMP_MAX ? off : EMS_TMP_MAX;  // intermediate list (survivors + children), before the inscribed-EMS purge
     __syncwarp();
-    // EliminateInscribedEMS: drop i if some j != i contains it (non-strict; identical twins delete each other)
+    // EliminateInscribedEMS: drop i if some j != i contains it (non-strict; identical twins delete each other).
+    // The O(n^2) containment test was 28 % of the apply kernel's warp instructions (ncu r2, profiles/r2_k1_head_source.txt): six 16-bit loads and
+    // six compares per pair.  Coordinates are <= 255 (pct_create), so an EMS packs into two words of three 9-bit fields — lows as they are, highs
+    // as 255 - v, which turns all six tests into "field of a >= field of b" — and with a guard bit per field one subtraction tests three fields:
+    // ((a | G) - b) keeps the guard of a field iff a_f >= b_f (fields are >= 1 after the OR, so no borrow crosses a field).
+    constexpr uint32_t G = (1u << 8) | (1u << 17) | (1u << 26);
+    for (int i = lane; i < n; i += 32) {
+        const int16_t *m = tmp[i];
+        pk[i] = make_uint2((uint32_t)m[0] | ((uint32_t)m[1] << 9) | ((uint32_t)m[2] << 18),
+                           (uint32_t)(255 - m[3]) | ((uint32_t)(255 - m[4]) << 9) | ((uint32_t)(255 - m[5]) << 18));
+    }
+    __syncwarp();
     int w = 0;
     const int nch2 = (n + 31) >> 5;
 #pragma unroll 1
     for (int c = 0; c < nch2; c++) {
         const int i = c * 32 + lane;
         bool keep = false;
-        int16_t a[6];
         if (i < n) {
-#pragma unroll
-            for (int t = 0; t < 6; t++) a[t] = tmp[i][t];
+            const uint2 a = pk[i];
+            const uint32_t aL = a.x | G, aH = a.y | G;
             int hit = 0;
 #pragma unroll 4
             for (int j = 0; j < n; j++) {
-                const int16_t *b = tmp[j];
-                hit |= (int)(j != i && a[0] >= b[0] && a[1] >= b[1] && a[2] >= b[2] && a[3] <= b[3] && a[4] <= b[4] && a[5] <= b[5]);
+                const uint2 b = pk[j];
+                hit |= (int)(((aL - b.x) & (aH - b.y) & G) == G && j != i);
             }
             keep = !hit;
         }
@@ -189,7 +199,7 @@ __device__ __noinline__ int genems_warp(int16_t (*ems)[6], const int n0, int16_t
             const int p = w + __popc(bm & ((1u << lane) - 1));
             if (p < E_MAX) {
 #pragma unroll
-                for (int t = 0; t < 6; t++) ems[p][t] = a[t];
+                for (int t = 0; t < 6; t++) ems[p][t] = tmp[i][t];
             }
         }
         w += __popc(bm);
@@ -683,7 +693,7 @@ __device__ __forceinline__ long long gtime() { long long t; asm volatile("mov.u6
 #ifndef K3_MINB
 #define K3_MINB 8   // sweep (r1): 128 regs / 8 blocks per SM
 #endif
-constexpr int K1_SM_PER_WARP = sizeof(DEnvHot) + EMS_TMP_MAX * 12 + 16 + EDGE_STAGE * 32 + POLY_STAGE * 16;  // record + EMS temp + mbarrier/lock + staged loads
+constexpr int K1_SM_PER_WARP = sizeof(DEnvHot) + EMS_TMP_MAX * 12 + 16 + EDGE_STAGE * 32 + POLY_STAGE * 16 + EMS_TMP_MAX * 8;  // record + EMS temp + mbarrier/lock + staged loads + packed EMS temp
 static_assert(K1_SM_PER_WARP % 16 == 0, "alignment");
 
 template <bool STAB, bool ALIAS = false>
@@ -700,6 +710,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, K1_MINB) pct_apply_kerne
     int *lock = (int *)(mbar + 1);
     Stack4 *st_sm = (Stack4 *)(sm + sizeof(DEnvHot) + EMS_TMP_MAX * 12 + 16);
     double *poly_sm = (double *)(st_sm + EDGE_STAGE);
+    uint2 *ems_pk = (uint2 *)(poly_sm + 2 * POLY_STAGE);
     DEnvHot *ghot = p.hot + e;
     DEnvCold *cold = p.cold + e;
     DHdr &h = hot->h;
@@ -853,7 +864,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, K1_MINB) pct_apply_kerne
             __syncwarp();
             int fl = 0;
             // GENEMS only runs for LNES == 'EMS' (D:bin3D.py:172-175)
-            const int n_ems = p.lnes == 0 ? genems_warp(hot->ems, n_ems0, ems_tmp, b, p.low_bound, lane, fl) : n_ems0;
+            const int n_ems = p.lnes == 0 ? genems_warp(hot->ems, n_ems0, ems_tmp, ems_pk, b, p.low_bound, lane, fl) : n_ems0;
             const double rw = (double)(nb0 * nb1 * nb2) / binvol * 10;  // D:bin3D.py:180-183
             reward = (float)rw;
             info.counter = n_box0 + 1;
@@ -962,6 +973,55 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) pct_candidates_kernel(co
         for (int t = lane; t < n_cand; t += 32) out[t] = cand[t];
     fl |= sync_fl;
     __syncwarp();
+    if (p.shuffle) {  // scratch: cold->raw + cold->tab_big (contiguous, 16 KB, free once the list is in `out`): keys at 0, permuted list at 10 KB
+        static_assert(offsetof(DEnvCold, tab_big) == offsetof(DEnvCold, raw) + sizeof(uint32_t) * RAW_MAX, "raw and tab_big are contiguous");
+        static_assert(CAND_MAX * 8 <= 10240 && 10240 + CAND_MAX * 4 <= (RAW_MAX + TAB_A) * 4, "shuffle scratch fits");
+        shuffle_candidates<SlotT>(out, n_cand, (uint64_t *)cold->raw, (SlotT *)((char *)cold->raw + 10240), p.seed, (uint64_t)(p.env_id_base + e),
+                                  (uint64_t)h.draw_pos, lane);
+        cand = out;
+    }
+    if (p.walkq) {
+        // ---- classify (round 2; see "K3 (round 2)" below): drop_box_virtual (D:space.py:393-433) + check_box (:436-454), integer part ----
+        constexpr bool STAB = !BIGSM;
+        const int n_box = h.n_box, nl = p.nl;
+        const uint32_t lt = (1u << lane) - 1;
+        int pos = 0, nf = 0;
+#pragma unroll 1
+        while (pos < n_cand && nf < nl) {
+            const int c = pos + lane;
+            bool feas = false, pend = false;
+            int mh = 0, k = 0, xs = 0, ys = 0, zs = 0, rot = 0, sx = 0, sy = 0, sz = 0;
+            uint32_t pack = 0;
+            if (c < n_cand) {
+                key_unpack<KB>((uint32_t)cand[c], xs, ys, zs, rot);
+                sx = rt->d[rot][0]; sy = rt->d[rot][1]; sz = rt->d[rot][2];
+                bool far_out = false;
+                if (STAB) mh = rest_height_supports(hot->box, n_box, xs, ys, xs + sx, ys + sy, k, pack, far_out);
+                else mh = rest_height(hot->box, 0, n_box, 1, xs, ys, xs + sx, ys + sy);
+                if (xs + sx > p.W || ys + sy > p.L) feas = false;
+                else if (mh + sz > p.H) feas = false;
+                else if (!STAB || mh == 0) feas = true;
+                else pend = !far_out;  // far_out: the centre is outside the supports' bounding box -> the root test fails (rest_height_supports)
+            }
+            const uint32_t fm = __ballot_sync(FULL, feas), pm = __ballot_sync(FULL, pend);
+            if (lane == 0) cold->fbits[pos >> 5] = fm;
+            nf += __popc(fm);
+            if (pm) {
+                int qb = 0;
+                if (lane == 0) qb = atomicAdd(p.walk_ctr, __popc(pm));
+                qb = __shfl_sync(FULL, qb, 0);
+                if (pend) {
+                    WalkItem it;
+                    it.env = (uint32_t)e; it.pack = pack; it.c = (uint16_t)c;
+                    it.xs = (uint8_t)xs; it.ys = (uint8_t)ys; it.mh = (uint8_t)mh; it.sx = (uint8_t)sx; it.sy = (uint8_t)sy; it.sz = (uint8_t)sz;
+                    it.k = (uint8_t)min(k, 255); it.pad_ = 0;
+                    p.walkq[qb + __popc(pm & lt)] = it;
+                }
+            }
+            pos += 32;
+        }
+        if (lane == 0) cold->n_fw = pos >> 5;
+    }
     if (lane == 0) {
         ghot->h.n_cand = n_cand;
         if (fl) ghot->h.flags = h.flags | fl;
@@ -1107,192 +1167,105 @@ __global__ void __launch_bounds__(FEAS_THREADS, K3_MINB) pct_feas_emit_kernel(co
     if (tid == 0) KT_END(p.env_id_base + e - p.env_id_base0, 2);
 }
 
-// ---- K3 (round 2): warp per env, dense feasibility lanes ----------------------------------------------------------
-// ncu of the thread-per-candidate kernel above at round 1's HEAD (profiles/r2_k3_head_*.txt): 22 % of the stall samples sit on its
-// block barrier (two warps per env, the first holds candidates 0-31, the second the ~6 that remain and waits), the DFS of
-// stability_check<false> holds 60 % of the warp instructions at 2-5 active lanes, and every candidate walks the placed boxes twice.
-// This kernel gives each env ONE warp and separates the work by kind:
-//   classify  lane per candidate, integer only: bounds + ONE pass over the boxes for the resting height and the supports
-//             (rest_height_supports) -> infeasible / feasible (floor, or no stability check) / needs the stability walk;
-//             feasibility bits per 32-candidate chunk, the walks are appended to a queue in shared memory (candidate order);
-//   walk      the first 32 queued placements, one per lane (dense: lanes 0..m-1), through stab_virtual — the warp-convergent
-//             restatement of the walk (light visits run ahead, heavy visits execute together);
-//   emit      the first `nl` set feasibility bits in candidate order -> leaf slots, observation (delta rows by default).
+// ---- K3 (round 2): pooled stability walks + emit ---------------------------------------------------------------------
+// ncu of the kernel above at round 1's HEAD (profiles/r2_k3_head_*.txt) and of a warp-per-env variant (profiles/r2_k3_warp_per_env.txt):
+// the launch lasts 2x the SMs' mean active time — it ends when the env with the most and deepest stability walks ends (a serial chain
+// inside one block) —, 60 % of the warp instructions sit in the walk at 2-5 active lanes, every candidate scans the boxes twice, and capping
+// registers for occupancy only trades stalls for spills.  Round 2 cuts the work by KIND instead of by env:
+//   classify  (end of K2, warp per env, integer only) bounds + ONE pass over the boxes for resting height, supports and the exact
+//             quick reject (rest_height_supports) -> infeasible / feasible / needs a stability walk; feasibility bits per 32-candidate
+//             chunk; the walks of ALL envs go into one global pool;
+//   walk      pct_walk_kernel: 32 walks per warp, from whichever envs, through stab_virtual (warp-convergent light / heavy phases).
+//             Lanes are dense, a heavy env's walks spread over many warps and SMs, the longest serial chain is ONE walk;
+//   emit      pct_emit_kernel (warp per env): the first `nl` set feasibility bits in candidate order -> leaf slots, observation.
 // get_possible_position stops at `nl` feasible candidates (D:bin3D.py:117-136); here classification stops once `nl` candidates are KNOWN
-// feasible, and a queued walk is dropped when `nl` known-feasible candidates precede it — what is emitted is the same ordered prefix.
-#ifndef F2_MINB
-#define F2_MINB 8
+// feasible and the emit kernel takes the first `nl` set bits: the same ordered prefix (walks past the cut are wasted work, not wrong).
+#ifndef WALK_MINB
+#define WALK_MINB 8
 #endif
-#ifndef F2_WARPS_N
-#define F2_WARPS_N 2
-#endif
-constexpr int F2_WARPS = F2_WARPS_N;
-constexpr int F2_FBITS = 40;  // feasibility bits of <= 1280 candidates (K2 emits <= 1228)
-constexpr int F2_WL = 64;     // queue of pending walks: < 32 left over + <= 32 of one chunk
-struct WalkItem { uint16_t c; uint8_t mh, k; uint32_t pack; };
-static_assert(sizeof(WalkItem) == 8, "queue entry");
-constexpr int F2_OFF_LEAF = sizeof(DEnvHot);
-constexpr int F2_OFF_MISC = F2_OFF_LEAF + NL_MAX * 12;        // mbarrier (8) + lock (4) + pad; RotTab at +32
-constexpr int F2_OFF_FBITS = F2_OFF_MISC + 64;
-constexpr int F2_OFF_WL = F2_OFF_FBITS + F2_FBITS * 4;
-constexpr int F2_OFF_ST = F2_OFF_WL + F2_WL * 8;
-constexpr int F2_OFF_POLY = F2_OFF_ST + EDGE_STAGE * 32;
-constexpr int F2_SM_PER_WARP = F2_OFF_POLY + POLY_STAGE * 16;
-static_assert(F2_SM_PER_WARP % 16 == 0 && F2_OFF_ST % 16 == 0 && F2_OFF_POLY % 16 == 0, "TMA destinations are 16-byte aligned");
+constexpr int WALK_WARPS = 2;
 
-template <typename OT, bool STAB, typename SlotT, bool DELTA>
-__global__ void __launch_bounds__(32 * F2_WARPS, F2_MINB) pct_feas_emit2_kernel(const DParams p) {
+__global__ void __launch_bounds__(32 * WALK_WARPS, WALK_MINB) pct_walk_kernel(const DParams p) {
+    const int lane = threadIdx.x & 31;
+    const int total = *(volatile const int32_t *)p.walk_ctr;
+    const int nwarps = gridDim.x * WALK_WARPS;
+#pragma unroll 1
+    for (int base = (blockIdx.x * WALK_WARPS + (threadIdx.x >> 5)) * 32; base < total; base += nwarps * 32) {
+        const int i = base + lane;
+        const bool has = i < total;
+        WalkItem it{};
+        if (has) it = p.walkq[i];
+        const DEnvHot *hot = p.hot + it.env;
+        DEnvCold *cold = p.cold + it.env;
+        const DHdr &h = hot->h;
+        GeomD g{hot->box, has ? h.n_box : 0, p.setting == 3 ? cold->density : nullptr};
+        // the record stays in global memory (L1 / L2): the lanes of a warp belong to different envs
+        const EdgePool pool{const_cast<uint8_t *>(hot->e_lower), const_cast<uint8_t *>(hot->e_next), const_cast<uint16_t *>(hot->e_off),
+                            const_cast<uint8_t *>(hot->first_in), const_cast<uint8_t *>(hot->last_in), cold->e_st, cold->e_st, has ? h.n_edge : 0,
+                            const_cast<uint16_t *>(hot->poly_off), &cold->poly[0][0], &cold->poly[0][0], has ? h.n_poly : 0};
+        const int sx = it.sx, sy = it.sy, sz = it.sz;
+        const NodeD root{(int)it.xs, (int)it.ys, (int)it.mh, sx, sy, sz, (double)(sx * sy * sz) * (has ? h.next_den : 1.0)};
+        int fl = 0;
+        const bool ok = stab_virtual<GeomD>(g, root, (int)it.k, it.pack, pool, &cold->big, &cold->lock, fl, has, FULL) != 0;
+        if (has && ok) atomicOr(&cold->fbits[it.c >> 5], 1u << (it.c & 31));
+        if (has && fl) atomicOr(const_cast<int32_t *>(&hot->h.flags), fl);
+    }
+}
+
+constexpr int EMIT_WARPS = 4;
+constexpr int EMIT_STAGE = sizeof(DHdr) + NB_MAX * 12;  // header + placed boxes: all the observation needs from the hot record
+constexpr int EMIT_SM_PER_WARP = EMIT_STAGE + NL_MAX * 12 + 48;
+static_assert(EMIT_STAGE % 16 == 0 && EMIT_SM_PER_WARP % 16 == 0, "TMA bulk copies move multiples of 16 bytes");
+
+template <typename OT, typename SlotT, bool DELTA>
+__global__ void __launch_bounds__(32 * EMIT_WARPS) pct_emit_kernel(const DParams p) {
     constexpr int BITS = sizeof(SlotT) == 2 ? 4 : 8;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ __align__(16) unsigned char smem[EMIT_WARPS * EMIT_SM_PER_WARP];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int slot = blockIdx.x * F2_WARPS + warp;
-    if (slot >= p.n_envs) return;
-    const int e = (p.order && p.mode == 1) ? p.order[slot] : slot;  // same heaviest-first permutation as K1 / K2
-    unsigned char *sm = smem_raw + (size_t)warp * F2_SM_PER_WARP;
-    DEnvHot *hot = (DEnvHot *)sm;
-    int16_t (*leaf)[6] = (int16_t (*)[6])(sm + F2_OFF_LEAF);
-    uint64_t *mbar = (uint64_t *)(sm + F2_OFF_MISC);
-    int *lock = (int *)(mbar + 1);
-    RotTab *rt = (RotTab *)(sm + F2_OFF_MISC + 32);
-    uint32_t *fbits = (uint32_t *)(sm + F2_OFF_FBITS);
-    WalkItem *wl = (WalkItem *)(sm + F2_OFF_WL);
-    Stack4 *st_sm = (Stack4 *)(sm + F2_OFF_ST);
-    double *poly_sm = (double *)(sm + F2_OFF_POLY);
+    const int e = blockIdx.x * EMIT_WARPS + warp;
+    if (e >= p.n_envs) return;
+    unsigned char *sm = smem + warp * EMIT_SM_PER_WARP;
+    DEnvHot *hot = (DEnvHot *)sm;  // only the header and the boxes are staged
+    int16_t (*leaf)[6] = (int16_t (*)[6])(sm + EMIT_STAGE);
+    uint64_t *mbar = (uint64_t *)(sm + EMIT_STAGE + NL_MAX * 12);
+    RotTab *rt = (RotTab *)(sm + EMIT_STAGE + NL_MAX * 12 + 16);
     DEnvHot *ghot = p.hot + e;
     DEnvCold *cold = p.cold + e;
     const uint32_t lt = (1u << lane) - 1;
     if (lane == 0) {
-        *lock = 0;
         mbar_init(mbar, 1);
         fence_proxy_async();
     }
-    for (int t = lane; t < F2_FBITS; t += 32) fbits[t] = 0;
     __syncwarp();
     if (lane == 0) {
-        if (p.ready) {  // overlapped mode: wait for the candidates kernel's hand-over of THIS env
-            if (!env_wait(p.ready + p.n_envs + e, p.epoch)) atomicOr(&ghot->h.flags, PCT_FLAG_SYNC_TIMEOUT);
-            fence_proxy_async_all();
-        }
-        mbar_expect_tx(mbar, (uint32_t)sizeof(DEnvHot));
-        tma_load_1d(hot, ghot, (uint32_t)sizeof(DEnvHot), mbar);
+        mbar_expect_tx(mbar, (uint32_t)EMIT_STAGE);
+        tma_load_1d(hot, ghot, (uint32_t)EMIT_STAGE, mbar);
     }
     mbar_wait(mbar, 0);
-    __syncwarp();  // every lane has observed phase 0 before the barrier is re-armed
+    __syncwarp();
     const DHdr &h = hot->h;
-    if (STAB && h.n_edge > 0) {  // stage the load edges and stored support polygons (second phase of the same mbarrier)
-        const uint32_t bytes = (uint32_t)min(h.n_edge, EDGE_STAGE) * (uint32_t)sizeof(Stack4);
-        const uint32_t pbytes = (uint32_t)min(h.n_poly, POLY_STAGE) * 16u;
-        if (lane == 0) {
-            mbar_expect_tx(mbar, bytes + pbytes);
-            tma_load_1d(st_sm, cold->e_st, bytes, mbar);
-            if (pbytes) tma_load_1d(poly_sm, cold->poly, pbytes, mbar);
-        }
-        mbar_wait(mbar, 1);
-    }
     const int nb3[3] = {h.next_box[0], h.next_box[1], h.next_box[2]};
     if (lane == 0) make_rot_tab(nb3, p.setting == 2 ? 6 : 2, *rt);
     __syncwarp();
-    const int n_cand = h.n_cand, n_box = h.n_box, nl = p.nl;
-    const double den = h.next_den;
+    const int nl = p.nl, nw = cold->n_fw;
     const SlotT *cand = (const SlotT *)cold->cand;
-    GeomD g{hot->box, n_box, p.setting == 3 ? cold->density : nullptr};
-    const EdgePool pool{hot->e_lower, hot->e_next, hot->e_off, hot->first_in, hot->last_in, cold->e_st, st_sm, h.n_edge,
-                        hot->poly_off, &cold->poly[0][0], poly_sm, h.n_poly};
-    int pos = 0, nq = 0, nf = 0, fl = 0;
-#pragma unroll 1
-    for (;;) {
-        // ---- classify chunks of 32 candidates until a full batch of walks is queued ----
-#pragma unroll 1
-        while (nq < 32 && pos < n_cand && nf < nl) {
-            const int c = pos + lane;
-            bool feas = false, pend = false;
-            int mh = 0, k = 0;
-            uint32_t pack = 0;
-            if (c < n_cand) {
-                int xs, ys, zs, rot;
-                key_unpack<BITS>(cand[c], xs, ys, zs, rot);
-                const int sx = rt->d[rot][0], sy = rt->d[rot][1], sz = rt->d[rot][2];
-                // drop_box_virtual (D:space.py:393-433) + check_box (:436-454), integer part
-                bool far_out = false;
-                if (STAB) mh = rest_height_supports(hot->box, n_box, xs, ys, xs + sx, ys + sy, k, pack, far_out);
-                else mh = rest_height(hot->box, 0, n_box, 1, xs, ys, xs + sx, ys + sy);
-                if (xs + sx > p.W || ys + sy > p.L) feas = false;
-                else if (mh + sz > p.H) feas = false;
-                else if (!STAB || mh == 0) feas = true;
-                else pend = !far_out;  // far_out: the centre is outside the supports' bounding box -> the root test fails (rest_height_supports)
-            }
-            const uint32_t fm = __ballot_sync(FULL, feas), pm = __ballot_sync(FULL, pend);
-            if (lane == 0) fbits[pos >> 5] = fm;
-            nf += __popc(fm);
-            if (pend) {
-                WalkItem it;
-                it.c = (uint16_t)c; it.mh = (uint8_t)mh; it.k = (uint8_t)min(k, 255); it.pack = pack;
-                wl[nq + __popc(pm & lt)] = it;
-            }
-            nq += __popc(pm);
-            pos += 32;
-        }
-        __syncwarp();
-        if (nq == 0) break;
-        int m = min(nq, 32);
-        if (nf >= nl) {
-            // the cap may bind: a queued walk preceded by `nl` known-feasible candidates cannot be among the emitted leaves (nor can any later one)
-            bool drop = false;
-            if (lane < m) {
-                const int c = wl[lane].c;
-                int cnt = __popc(fbits[c >> 5] & ((1u << (c & 31)) - 1));
-#pragma unroll 1
-                for (int w = 0; w < (c >> 5); w++) cnt += __popc(fbits[w]);
-                drop = cnt >= nl;
-            }
-            const uint32_t dm = __ballot_sync(FULL, drop);
-            if (dm) { m = __ffs(dm) - 1; nq = m; }
-            if (m == 0) break;
-        }
-        // ---- walk: lanes 0..m-1 take the first m queued placements ----
-        const bool has = lane < m;
-        WalkItem it{};
-        if (has) it = wl[lane];
-        int xs = 0, ys = 0, zs = 0, rot = 0;
-        if (has) key_unpack<BITS>(cand[it.c], xs, ys, zs, rot);
-        const int sx = rt->d[rot][0], sy = rt->d[rot][1], sz = rt->d[rot][2];
-        const NodeD root{xs, ys, (int)it.mh, sx, sy, sz, (double)(sx * sy * sz) * den};
-        bool ok = false;
-        if constexpr (STAB) ok = stab_virtual<GeomD>(g, root, (int)it.k, it.pack, pool, &cold->big, lock, fl, has, FULL) != 0;
-        const bool feas = has && ok;
-        if (feas) atomicOr(&fbits[it.c >> 5], 1u << (it.c & 31));
-        nf += __popc(__ballot_sync(FULL, feas));
-        // the rest of the queue moves to the front
-        WalkItem mv{};
-        const bool keep = lane + m < nq;
-        if (keep) mv = wl[lane + m];
-        __syncwarp();
-        if (keep) wl[lane] = mv;
-        nq -= m;
-        __syncwarp();
-    }
     // ---------------- leaves = the first `nl` feasible candidates in order ----------------
-    const int n_leaf = min(nf, nl);
-    {
-        int base = 0;
-        const int nw = pos >> 5;
+    int base = 0;
 #pragma unroll 1
-        for (int w = 0; w < nw && base < nl; w++) {
-            const uint32_t bits = fbits[w];
-            if ((bits >> lane) & 1u) {
-                const int kk = base + __popc(bits & lt);
-                if (kk < nl) {
-                    int xs, ys, zs, rot;
-                    key_unpack<BITS>(cand[w * 32 + lane], xs, ys, zs, rot);
-                    leaf[kk][0] = (int16_t)xs; leaf[kk][1] = (int16_t)ys; leaf[kk][2] = (int16_t)zs;
-                    leaf[kk][3] = (int16_t)(xs + rt->d[rot][0]); leaf[kk][4] = (int16_t)(ys + rt->d[rot][1]); leaf[kk][5] = (int16_t)(zs + rt->d[rot][2]);
-                }
+    for (int w = 0; w < nw && base < nl; w++) {
+        const uint32_t bits = cold->fbits[w];
+        if ((bits >> lane) & 1u) {
+            const int kk = base + __popc(bits & lt);
+            if (kk < nl) {
+                int xs, ys, zs, rot;
+                key_unpack<BITS>(cand[w * 32 + lane], xs, ys, zs, rot);
+                leaf[kk][0] = (int16_t)xs; leaf[kk][1] = (int16_t)ys; leaf[kk][2] = (int16_t)zs;
+                leaf[kk][3] = (int16_t)(xs + rt->d[rot][0]); leaf[kk][4] = (int16_t)(ys + rt->d[rot][1]); leaf[kk][5] = (int16_t)(zs + rt->d[rot][2]);
             }
-            base += __popc(bits);
         }
+        base += __popc(bits);
     }
-    fl = __reduce_or_sync(FULL, fl);
-    if (fl && lane == 0) atomicOr(&ghot->h.flags, fl);
+    const int n_leaf = min(base, nl);
     __syncwarp();
     // persist the emitted leaves for the leaf-index action path; header / info
     for (int t = lane; t < n_leaf * 6; t += 32) ((int16_t *)cold->leaf)[t] = ((int16_t *)leaf)[t];
@@ -1300,9 +1273,9 @@ __global__ void __launch_bounds__(32 * F2_WARPS, F2_MINB) pct_feas_emit2_kernel(
         ghot->h.n_leaf = n_leaf;
         if (p.info) {
             p.info[e].n_leaf = n_leaf;
-            p.info[e].n_cand = n_cand;
+            p.info[e].n_cand = h.n_cand;
             p.info[e].n_ems = h.n_ems;
-            p.info[e].flags |= h.flags | fl;
+            p.info[e].flags |= h.flags;
         }
     }
     // ---------------- cur_observation (D:bin3D.py:70-93) ----------------
@@ -1315,9 +1288,11 @@ __global__ void __launch_bounds__(32 * F2_WARPS, F2_MINB) pct_feas_emit2_kernel(
 // the envs by a work estimate read from the record headers: which = 0 -> order[0..n) for the NEXT step's apply kernel
 // (boxes already placed drive the real stability DFS and the EMS update), which = 1 -> order[n..2n) for feas_emit
 // (candidates x stack depth).
-__global__ void __launch_bounds__(1024) pct_order_kernel(const DEnvHot *hot, int n_envs, int32_t *order, int which) {
+__global__ void __launch_bounds__(1024) pct_order_kernel(const DEnvHot *hot, int n_envs, int32_t *order, int which, int32_t *walk_ctr) {
     __shared__ int hist[64], base[64];
     const int tid = threadIdx.x;
+    if (tid == 0 && walk_ctr) *walk_ctr = 0;  // last kernel of every launch sequence: the next step's walk pool starts empty
+    if (!order) return;
     if (tid < 64) hist[tid] = 0;
     __syncthreads();
     for (int e = tid; e < n_envs; e += 1024) {
@@ -1363,20 +1338,22 @@ static cudaError_t set_smem(K kernel, size_t smem) {
 }
 
 template <typename OT, bool STAB, typename SlotT>
-static cudaError_t launch_t(const DParams &p, cudaStream_t st, cudaEvent_t *prof) {
+static cudaError_t launch_t(const DParams &p_in, cudaStream_t st, cudaEvent_t *prof) {
     constexpr bool BIGSM = !STAB;
     static bool attr_set = false;
+    static int n_sm = 0;
     const size_t smem1 = (size_t)K1_SM_PER_WARP * WARPS_PER_BLOCK;
     const size_t smem2 = (size_t)Lay<SlotT, BIGSM>::PER_WARP * WARPS_PER_BLOCK;
-    const size_t smem3 = (size_t)F2_SM_PER_WARP * F2_WARPS;
-    const int blocks3 = (p.n_envs + F2_WARPS - 1) / F2_WARPS;
-    const bool k3_old = (p.opt & PCT_OPT_K3_BLOCK) != 0;  // PCT_B200_K3=block: round 1's block-per-env / thread-per-candidate kernel (A/B measurements)
+    DParams p = p_in;
+    const bool k3_old = (p.opt & PCT_OPT_K3_BLOCK) != 0 || !p.walkq;  // PCT_B200_K3=block: round 1's block-per-env / thread-per-candidate kernel (A/B measurements)
+    if (k3_old) p.walkq = nullptr;  // K2 then skips the classification
     if (!attr_set) {
         cudaError_t err = set_smem(pct_apply_kernel<STAB>, smem1);
         if (err == cudaSuccess && STAB) err = set_smem(pct_apply_kernel<STAB, STAB>, smem1);  // the ALIAS variant (stability settings only)
         if (err == cudaSuccess) err = set_smem(pct_candidates_kernel<SlotT, BIGSM>, smem2);
-        if (err == cudaSuccess) err = set_smem(pct_feas_emit2_kernel<OT, STAB, SlotT, false>, smem3);
-        if (err == cudaSuccess) err = set_smem(pct_feas_emit2_kernel<OT, STAB, SlotT, true>, smem3);
+        int dev = 0;
+        if (err == cudaSuccess) err = cudaGetDevice(&dev);
+        if (err == cudaSuccess) err = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
         if (err != cudaSuccess) return err;
         attr_set = true;
     }
@@ -1384,40 +1361,42 @@ static cudaError_t launch_t(const DParams &p, cudaStream_t st, cudaEvent_t *prof
     if (prof) cudaEventRecord(prof[0], st);
     if (STAB && (p.opt & PCT_OPT_ALIAS)) pct_apply_kernel<STAB, STAB><<<blocks, 32 * WARPS_PER_BLOCK, smem1, st>>>(p);
     else pct_apply_kernel<STAB><<<blocks, 32 * WARPS_PER_BLOCK, smem1, st>>>(p);
+    if (prof) cudaEventRecord(prof[1], st);
+    cudaError_t err = cudaSuccess;
     if (p.ready) {
-        // overlapped mode (programmatic dependent launch): the candidates / feas_emit blocks become resident while the
-        // previous kernel's tail is still running and pick their env up through the per-env hand-over flags
+        // overlapped mode (programmatic dependent launch): the candidates blocks become resident while the apply kernel's tail is
+        // still running and pick their env up through the per-env hand-over flags
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         at[0].val.programmaticStreamSerializationAllowed = 1;
         cudaLaunchConfig_t cfg{};
         cfg.stream = st; cfg.attrs = at; cfg.numAttrs = 1;
         cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(32 * WARPS_PER_BLOCK); cfg.dynamicSmemBytes = smem2;
-        cudaError_t err = cudaLaunchKernelEx(&cfg, pct_candidates_kernel<SlotT, BIGSM>, p);
+        err = cudaLaunchKernelEx(&cfg, pct_candidates_kernel<SlotT, BIGSM>, p);
         if (err != cudaSuccess) return err;
         if (k3_old) {
             cfg.gridDim = dim3(p.n_envs); cfg.blockDim = dim3(FEAS_THREADS); cfg.dynamicSmemBytes = 0;
             err = (p.opt & PCT_OPT_DELTA) ? cudaLaunchKernelEx(&cfg, pct_feas_emit_kernel<OT, STAB, SlotT, true>, p)
                              : cudaLaunchKernelEx(&cfg, pct_feas_emit_kernel<OT, STAB, SlotT>, p);
-        } else {
-            cfg.gridDim = dim3(blocks3); cfg.blockDim = dim3(32 * F2_WARPS); cfg.dynamicSmemBytes = smem3;
-            err = (p.opt & PCT_OPT_DELTA) ? cudaLaunchKernelEx(&cfg, pct_feas_emit2_kernel<OT, STAB, SlotT, true>, p)
-                             : cudaLaunchKernelEx(&cfg, pct_feas_emit2_kernel<OT, STAB, SlotT, false>, p);
+            if (err != cudaSuccess) return err;
         }
-        if (err == cudaSuccess && p.order) pct_order_kernel<<<1, 1024, 0, st>>>(p.hot, p.n_envs, p.order, 0);
-        return err != cudaSuccess ? err : cudaGetLastError();
-    }
-    if (prof) cudaEventRecord(prof[1], st);
-    pct_candidates_kernel<SlotT, BIGSM><<<blocks, 32 * WARPS_PER_BLOCK, smem2, st>>>(p);
-    if (prof) cudaEventRecord(prof[2], st);
-    if (k3_old) {
-        if (p.opt & PCT_OPT_DELTA) pct_feas_emit_kernel<OT, STAB, SlotT, true><<<p.n_envs, FEAS_THREADS, 0, st>>>(p);
-        else pct_feas_emit_kernel<OT, STAB, SlotT><<<p.n_envs, FEAS_THREADS, 0, st>>>(p);
     } else {
-        if (p.opt & PCT_OPT_DELTA) pct_feas_emit2_kernel<OT, STAB, SlotT, true><<<blocks3, 32 * F2_WARPS, smem3, st>>>(p);
-        else pct_feas_emit2_kernel<OT, STAB, SlotT, false><<<blocks3, 32 * F2_WARPS, smem3, st>>>(p);
+        pct_candidates_kernel<SlotT, BIGSM><<<blocks, 32 * WARPS_PER_BLOCK, smem2, st>>>(p);
+        if (prof) cudaEventRecord(prof[2], st);
+        if (k3_old) {
+            if (p.opt & PCT_OPT_DELTA) pct_feas_emit_kernel<OT, STAB, SlotT, true><<<p.n_envs, FEAS_THREADS, 0, st>>>(p);
+            else pct_feas_emit_kernel<OT, STAB, SlotT><<<p.n_envs, FEAS_THREADS, 0, st>>>(p);
+        }
     }
-    if (p.order) pct_order_kernel<<<1, 1024, 0, st>>>(p.hot, p.n_envs, p.order, 0);
+    if (!k3_old) {
+        // the pooled walks need EVERY env's classification (plain stream order = full dependency), the emit kernel every walk
+        if (p.ready && prof) cudaEventRecord(prof[2], st);
+        if (STAB) pct_walk_kernel<<<n_sm * WALK_MINB, 32 * WALK_WARPS, 0, st>>>(p);
+        const int eb = (p.n_envs + EMIT_WARPS - 1) / EMIT_WARPS;
+        if (p.opt & PCT_OPT_DELTA) pct_emit_kernel<OT, SlotT, true><<<eb, 32 * EMIT_WARPS, 0, st>>>(p);
+        else pct_emit_kernel<OT, SlotT, false><<<eb, 32 * EMIT_WARPS, 0, st>>>(p);
+    }
+    if (p.order || p.walk_ctr) pct_order_kernel<<<1, 1024, 0, st>>>(p.hot, p.n_envs, p.order, 0, p.walk_ctr);
     if (prof) cudaEventRecord(prof[3], st);
     return cudaGetLastError();
 }
@@ -1427,8 +1406,11 @@ static cudaError_t launch_s(const DParams &p, cudaStream_t st, cudaEvent_t *prof
     return launch_t<OT, STAB, uint32_t>(p, st, prof);
 }
 
-// number of kernels one reset / step enqueues (for pct_kernel_launches)
-int discrete_kernels_per_step() { return 3; }
+// number of kernels one reset / step enqueues (for pct_kernel_launches): apply, candidates (+ classify), [walk], emit, order / pool reset
+int discrete_kernels_per_step(const DParams &p) {
+    if ((p.opt & PCT_OPT_K3_BLOCK) || !p.walkq) return 3 + (p.order ? 1 : 0);
+    return 4 + (p.setting != 2 ? 1 : 0);
+}
 
 cudaError_t launch_discrete(const DParams &p, cudaStream_t st, cudaEvent_t *prof) {
     const bool stab = p.setting != 2;

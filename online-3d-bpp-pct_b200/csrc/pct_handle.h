@@ -53,6 +53,8 @@ struct pct_env_batch {
     cudaStream_t own_stream = nullptr;
     void *dbg = nullptr;
     int32_t *d_order = nullptr;   // block -> env permutations (LPT scheduling)
+    pct::WalkItem *d_walkq = nullptr;  // [n_envs * CAND_MAX] pool of stability walks of the current step (pct_walk_kernel)
+    int32_t *d_walk_ctr = nullptr;     // [n_envs] fill counters (index = first env of the launched range)
     bool lpt = false;
     int prof_on = 0;
     std::vector<cudaEvent_t> prof_ev;   // 4 events per recorded step

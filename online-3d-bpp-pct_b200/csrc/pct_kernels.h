@@ -13,6 +13,8 @@ constexpr int E_MAX = 128;    // EMS list capacity (reference: unbounded python 
 constexpr int TAB_A = 2048;   // CPython-set emulation: largest table (<= 1228 distinct candidates)
 constexpr int TAB_B = 512;
 constexpr int WARPS_PER_BLOCK = 2;
+constexpr int CAND_MAX = 1232;    // ordered candidate list capacity (K2 emits <= 1228 distinct candidates)
+constexpr int FBITS_WORDS = 40;   // feasibility bits of <= 1280 candidates
 
 constexpr int PCT_FLAG_BOX_OVERFLOW_ = PCT_FLAG_BOX_OVERFLOW;
 constexpr int PCT_FLAG_BAD_ACTION_ = PCT_FLAG_BAD_ACTION;
@@ -121,11 +123,27 @@ struct alignas(16) DEnvCold {
     double density[NB_MAX];   // per placed box (setting 3)
     Stack4 e_st[EDGE_MAX + 1];
     double poly[POLY_MAX][2];
-    uint32_t cand[1232];      // ordered candidate keys written by K2, read by K3 (<= 1228 distinct candidates)
+    uint32_t cand[CAND_MAX];  // ordered candidate keys written by K2, read by K3 (<= 1228 distinct candidates)
     uint32_t raw[2048];       // insertion sequence produced by the EV / EP / CP / FC generators
     uint32_t tab_big[TAB_A];  // 2048-slot stage of the set emulation when it does not live in shared memory
     BigScratch big;
+    // feasibility of the candidates of the CURRENT observation, one bit per candidate in candidate order: written per 32-candidate chunk by
+    // the classification at the end of K2 (bounds / resting height / floor), completed by the pooled stability walks (atomicOr), read by the emit kernel
+    uint32_t fbits[FBITS_WORDS];
+    int32_t n_fw;             // chunks classified (classification stops once `leaf_node_holder` candidates are known feasible)
+    int32_t lock;             // serialises the rare > KSUP_SMALL-support visits of this env on `big` (walk lanes of one env sit in different warps)
+    int32_t pad_[2];
 };
+
+// One stability walk (calculated_impact_virtual of one candidate placement) of the step's global pool: produced by the classification at
+// the end of K2 for every candidate that is in bounds, fits under the lid and rests on boxes (not on the floor), consumed by pct_walk_kernel.
+struct WalkItem {
+    uint32_t env;             // launch-local env index
+    uint32_t pack;            // the first four supports of the placement (8 bits each, scan order)
+    uint16_t c;               // candidate index (bit position in DEnvCold::fbits)
+    uint8_t xs, ys, mh, sx, sy, sz, k, pad_;  // footprint corner, resting height, oriented dims, number of supports
+};
+static_assert(sizeof(WalkItem) == 20, "queue entry");
 
 struct DParams {
     DEnvHot *hot;
@@ -151,6 +169,7 @@ struct DParams {
     uint8_t *done;
     pct_step_info *info;
     int lnes;  // leaf-node expansion scheme: 0 EMS, 1 EV, 2 EP, 3 CP, 4 FC
+    int shuffle;  // pct_config::shuffle: keyed permutation of the ordered candidate list (shuffle_candidates)
     int mode;  // 0 = reset all, 1 = step
     int keep_draw;      // mode 0: continue the item source instead of rewinding it (env.reset() after an episode)
     int no_auto_reset;  // mode 1: leave a finished env untouched (gym.Env semantics)
@@ -164,9 +183,11 @@ struct DParams {
     int32_t *order;  // [2 * n_envs] block -> env permutations (apply, feas_emit), nullptr = identity
     int32_t *ready;  // [2 * n_envs] per-env hand-over flags (apply -> candidates, candidates -> feas_emit); nullptr = kernels run back to back
     int32_t epoch;   // value published in `ready` by this launch
+    WalkItem *walkq;    // [n_envs * CAND_MAX] the step's pool of stability walks (worst-case capacity; only the used prefix is touched)
+    int32_t *walk_ctr;  // its fill counter; reset by pct_order_kernel at the end of every launch sequence
     int32_t opt;     // opt-in variants served by `aux`: PCT_OPT_DELTA (K3 delta observation writes), PCT_OPT_ALIAS (K1 object semantics of the loads)
 };
-constexpr int PCT_OPT_DELTA = 1, PCT_OPT_ALIAS = 2, PCT_OPT_K3_BLOCK = 4;
+constexpr int PCT_OPT_DELTA = 1, PCT_OPT_ALIAS = 2, PCT_OPT_K3_BLOCK = 4;  // K3_BLOCK: round 1's block-per-env feasibility kernel (A/B)
 
 // heuristic baselines (pct_heuristics.cuh)
 struct HParams {
@@ -195,7 +216,7 @@ cudaError_t launch_heuristic_discrete(const DParams &p, const HParams &hp, cudaS
 // delta observation writes: aux[i].obs_prev = {nb, nl} for n envs ("every row of the buffer may be non-zero")
 void launch_fill_prev(DEnvAux *aux, int n_envs, int nb, int nl, cudaStream_t st);
 
-int discrete_kernels_per_step();
+int discrete_kernels_per_step(const DParams &p);
 cudaError_t launch_discrete(const DParams &p, cudaStream_t st, cudaEvent_t *prof = nullptr);
 cudaError_t launch_policy_random_discrete(const DEnvHot *hot, int n_envs, int64_t env_id_base, uint64_t seed, int64_t t, int32_t *leaf_idx,
                                           cudaStream_t st, const int64_t *t_dev = nullptr);

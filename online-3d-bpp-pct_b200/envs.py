@@ -71,8 +71,6 @@ class _PackingBase(object):
                  item_stream=None, size_minimum=None, **kwags):
         if next_holder != 1:
             raise NotImplementedError("next_holder must be 1 (reference default)")
-        if shuffle:
-            raise NotImplementedError("shuffle=True has no parity definition (global numpy RNG in the reference)")
         self.internal_node_holder, self.leaf_node_holder, self.next_holder = internal_node_holder, leaf_node_holder, next_holder
         self.bin_size = container_size
         self.setting = setting
@@ -99,7 +97,7 @@ class _PackingBase(object):
                                leaf_node_holder=leaf_node_holder, continuous=self._continuous, obs_dtype=torch.float64, seed=seed,
                                device=device, sample_from_distribution=sample_from_distribution and self._continuous,
                                sample_left_bound=sample_left_bound, sample_right_bound=sample_right_bound, item_stream=stream,
-                               size_minimum=size_minimum, auto_reset=False, LNES=LNES)
+                               size_minimum=size_minimum, auto_reset=False, LNES=LNES, shuffle=shuffle)
         if traj_len:
             self._batch.set_trajectory_length(traj_len)
         self.observation_space = _make_box(0.0, float(container_size[2]), (self._batch.obs_len,))
@@ -199,7 +197,7 @@ def make_vec_envs(args, log_dir=None, allow_early_resets=True):
                      continuous=getattr(args, "continuous", False) or str(getattr(args, "id", "")).startswith("PctContinuous"),
                      device=dev, seed=args.seed, sample_from_distribution=getattr(args, "sample_from_distribution", False),
                      sample_left_bound=getattr(args, "sample_left_bound", None), sample_right_bound=getattr(args, "sample_right_bound", None),
-                     LNES=getattr(args, "lnes", "EMS"), shuffle=False)
+                     LNES=getattr(args, "lnes", "EMS"), shuffle=bool(getattr(args, "shuffle", False)))  # tools.py:136: --shuffle defaults to True
 
 
 def registration_envs():

@@ -90,6 +90,11 @@ class OracleDiscrete(object):
         self.L.pcto_set_alias_mode.argtypes = [C.c_void_p, C.c_int]
         self.L.pcto_set_alias_mode(self.h, int(on))
 
+    def set_shuffle(self, seed, gid, on=True):
+        """shuffle=True (D:bin3D.py:114-115) with the product's keyed permutation: stable argsort of rnd_u64(seed ^ SALT, gid, draws << 16 | i)"""
+        self.L.pcto_set_shuffle.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64]
+        self.L.pcto_set_shuffle(self.h, int(on), int(seed) & ((1 << 64) - 1), int(gid))
+
     def set_random_items(self, item_set, seed, gid):
         """RandomBoxCreator draws from the counter-based generator the device uses (item_set[rnd(seed, gid, d) % n], density for setting 3)"""
         self._items = np.ascontiguousarray(np.array(item_set, dtype=np.float64).reshape(-1, 3))
@@ -330,6 +335,11 @@ class OracleContinuous(object):
     def set_alias_mode(self, on=True):
         self.L.pctc_set_alias_mode.argtypes = [C.c_void_p, C.c_int]
         self.L.pctc_set_alias_mode(self.h, int(on))
+
+    def set_shuffle(self, seed, gid, on=True):
+        """shuffle=True (C:bin3D.py:126-127) with the product's keyed permutation (see OracleDiscrete.set_shuffle)"""
+        self.L.pctc_set_shuffle.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64]
+        self.L.pctc_set_shuffle(self.h, int(on), int(seed) & ((1 << 64) - 1), int(gid))
 
     def set_random_sample(self, seed, gid, lo, hi):
         """sample_from_distribution draws (C:bin3D.py:103-115) from the counter-based generator the device uses"""

@@ -52,6 +52,7 @@ typedef struct pctc_env {
     const double *stream; int stream_len, stream_pos; int have_item;
     int alias_mode; /* 1: up_edges values that are the upper box's own Stack object are read live (pctc_set_alias_mode) */
     int traj_len; /* > 0: LoadBoxCreator.reset discipline, every reset jumps to the next trajectory boundary (C:binCreator.py:51-62) */
+    int shuffle_on; uint64_t shuf_seed, shuf_gid; /* keyed candidate shuffle (pctc_set_shuffle), same definition as the discrete oracle */
     int use_rng; uint64_t rng_seed, rng_gid; double rng_lo, rng_hi; /* sample_from_distribution draws (C:bin3D.py:103-115), counter-based */
     double cur_item[4];
     double next_box[3];
@@ -455,6 +456,19 @@ static void cur_observation(pctc_env *e, double *obs) {
     double *leaf = obs + 9 * nbh;
     memset(leaf, 0, sizeof(double) * 9 * nlh);
     int nc = ems_point(e, e->next_box, e->last_cand, PC_MAX_CAND);
+    if (e->shuffle_on && nc > 1) { /* C:bin3D.py:126-127; keyed permutation, see pct_oracle_discrete.c cur_observation */
+        static __thread uint64_t keys[PC_MAX_CAND];
+        static __thread int perm[PC_MAX_CAND];
+        static __thread double tmpc[PC_MAX_CAND][6];
+        for (int i = 0; i < nc; i++) { keys[i] = pcto_rnd_u64(e->shuf_seed ^ 0x5AFE5EEDULL, e->shuf_gid, ((uint64_t)e->stream_pos << 16) | (uint64_t)i); perm[i] = i; }
+        for (int i = 1; i < nc; i++) {
+            int v = perm[i], j = i - 1;
+            while (j >= 0 && keys[perm[j]] > keys[v]) { perm[j + 1] = perm[j]; j--; }
+            perm[j + 1] = v;
+        }
+        for (int i = 0; i < nc; i++) memcpy(tmpc[i], e->last_cand[perm[i]], sizeof(double[6]));
+        memcpy(e->last_cand, tmpc, sizeof(double[6]) * nc);
+    }
     e->last_ncand = nc;
     int nleaf = 0;
     for (int i = 0; i < nc; i++) e->last_feas[i] = -1;
@@ -500,6 +514,7 @@ int pctc_obs_len(pctc_env *e) { return (e->nb_holder + e->nl_holder + 1) * 9; }
 /* C:bin3D.py:69-75 + C:space.py:281-303 */
 void pctc_set_trajectory_length(pctc_env *e, int n) { e->traj_len = n; }
 void pctc_set_alias_mode(pctc_env *e, int on) { e->alias_mode = on; }
+void pctc_set_shuffle(pctc_env *e, int on, uint64_t seed, uint64_t gid) { e->shuffle_on = on; e->shuf_seed = seed; e->shuf_gid = gid; }
 void pctc_reset(pctc_env *e, double *obs) {
     e->have_item = 0;
     if (e->traj_len > 0 && e->stream_pos % e->traj_len) e->stream_pos += e->traj_len - e->stream_pos % e->traj_len;

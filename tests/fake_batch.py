@@ -12,7 +12,7 @@ from pct_oracle import OracleContinuous, OracleDiscrete
 class FakeBatch(object):
     def __init__(self, n_envs, setting, container_size=(10, 10, 10), item_set=None, internal_node_holder=80, leaf_node_holder=50,
                  continuous=False, obs_dtype=torch.float32, seed=0, env_id_base=0, device=0, sample_from_distribution=False,
-                 sample_left_bound=None, sample_right_bound=None, item_stream=None, size_minimum=None, auto_reset=True, LNES="EMS"):
+                 sample_left_bound=None, sample_right_bound=None, item_stream=None, size_minimum=None, auto_reset=True, LNES="EMS", shuffle=False):
         self.n_envs, self.setting, self.continuous = int(n_envs), int(setting), bool(continuous)
         self.nb, self.nl = int(internal_node_holder), int(leaf_node_holder)
         self.obs_len = (self.nb + self.nl + 1) * 9
@@ -38,6 +38,9 @@ class FakeBatch(object):
         else:
             self.envs = [OracleDiscrete(setting, container_size=container_size, internal_node_holder=self.nb, leaf_node_holder=self.nl,
                                         size_minimum=size_minimum, stream=s, lnes=LNES) for s in self._streams]
+        if shuffle:
+            for i, e in enumerate(self.envs):
+                e.set_shuffle(seed, env_id_base + i)
         if item_stream is None:
             for i, e in enumerate(self.envs):
                 if continuous and sample_from_distribution:

@@ -91,6 +91,7 @@ int sh_virtual(StabHost *h, int x, int y, int z, int lx, int ly, double density,
     return ok;
 }
 void sh_use_v2(int on) { g_use_v2 = on; }
+double sh_around6(double v) { return around6(v); }  // the device's np.around(v, 6) (fast division by 1e6, pct_geom_continuous.cuh)
 void sh_stats(long long *out2) { out2[0] = g_far_out; out2[1] = g_walks; }
 void sh_stats_visits(long long *out32) { memcpy(out32, g_stat, sizeof g_stat); }
 

@@ -271,3 +271,18 @@ def test_terminal_observations_need_the_load_sync(lib, monkeypatch):
             assert "terminal observation" in str(ex)
             failing += 1
     assert failing >= 2
+
+
+def test_fast_around6_equals_the_division(lib):
+    """around6 (csrc/pct_geom_continuous.cuh) divides by 1e6 with one FMA correction instead of the IEEE division subroutine; it must equal
+    np.around(v, 6) = rint(v * 1e6) / 1e6 bit for bit.  Exhaustive proof over every integer numerator |a| <= 2.2e9: scratch/around6_exhaustive.c;
+    here: random, half-way, huge (fallback path) and tiny operands through the host build of the device function."""
+    lib.sh_around6.restype = C.c_double
+    lib.sh_around6.argtypes = [C.c_double]
+    rng = np.random.default_rng(11)
+    k = rng.integers(-3000000, 3000000, 20000).astype(np.float64)
+    vals = np.concatenate([rng.uniform(-3, 3, 60000), rng.uniform(-2300, 2300, 20000), (k + 0.5) / 1e6, np.nextafter((k + 0.5) / 1e6, 9.0),
+                           rng.uniform(-1e7, 1e7, 5000), [0.0, -0.0, 1e-7, 4.9999995e-7, 5e-7, 2199.9999995, 2200.0000005, 1e12, -1e12]])
+    want = np.rint(vals * 1e6) / 1e6
+    got = np.array([lib.sh_around6(float(v)) for v in vals])
+    assert np.array_equal(got.view(np.uint64), want.view(np.uint64))
