@@ -140,12 +140,20 @@ int pct_reset(pct_handle h, void *d_obs, void *stream);
  *   d_actions  : n_envs x 9 leaf rows (float32 if action_f64==0 else float64), or NULL
  *   d_leaf_idx : n_envs int32 indices into the previous observation's leaf rows (fast path), or NULL;
  *                an index >= the env's n_leaf selects the all-zero row.  Exactly one of the two is non-NULL.
- *   d_reward   : n_envs float32;  d_done: n_envs uint8;  d_info: n_envs pct_step_info (may be NULL) */
+ *   d_reward   : n_envs float32;  d_done: n_envs uint8;  d_info: n_envs pct_step_info (may be NULL)
+ * Observation buffer contract (delta rows, default; PCT_B200_OBS_DELTA=0 restores full rewrites): 75 % of the (internal + leaf + 1) x 9
+ * observation is zero padding and the internal-node rows are append-only within an episode, so when a call receives the SAME d_obs pointer
+ * as the previous reset / step of this handle, only the rows that can have changed are rewritten (the rows below max(rows now, rows the
+ * buffer may hold non-zero) and the item row).  A caller that hands the same buffer to consecutive calls must therefore not modify it in
+ * between (reading is fine); a caller that alternates buffers, or passes a fresh one, always gets every row written.  The continuous
+ * domain always writes every row. */
 int pct_step(pct_handle h, const void *d_actions, int32_t action_f64, const int32_t *d_leaf_idx, void *d_obs,
              float *d_reward, uint8_t *d_done, pct_step_info *d_info, void *stream);
 
-/* Same call with HOST buffers (what the reference's VecEnv.step exchanges over its pipes):
- * copies actions host->device, steps, copies obs/reward/done/info back, synchronises. */
+/* Same call with HOST buffers (what the reference's VecEnv.step exchanges over its pipes): copies actions host->device, steps, delivers
+ * obs / reward / done / info to the host, synchronises.  When h_obs is pinned (cudaHostAlloc / cudaHostRegister, i.e. mapped under UVA) the
+ * emit kernel writes the observation rows STRAIGHT into it over PCIe (zero-copy, default; PCT_B200_HOST_ZEROCOPY=0 or an unpinned buffer:
+ * staged device buffer + pipelined copies); the buffer contract of pct_step applies to h_obs in that mode. */
 int pct_step_host(pct_handle h, const void *h_actions, int32_t action_f64, const int32_t *h_leaf_idx, void *h_obs,
                   float *h_reward, uint8_t *h_done, pct_step_info *h_info);
 int pct_reset_host(pct_handle h, void *h_obs);

@@ -74,9 +74,12 @@ class PctBatch(object):
             self.set_item_stream(item_stream)
         with torch.cuda.device(self.device):
             self._obs = torch.empty((self.n_envs, self.obs_len), dtype=obs_dtype, device=self.device)
-            self._rew = torch.zeros((self.n_envs,), dtype=torch.float32, device=self.device)
-            self._done = torch.zeros((self.n_envs,), dtype=torch.uint8, device=self.device)
-            self._info = torch.zeros((self.n_envs, 8), dtype=torch.int32, device=self.device)
+            # reward (N f32) | info (N x 8 i32) | done (N u8) live in ONE allocation, so that a host-facing caller fetches all three with one copy
+            n = self.n_envs
+            self._pack = torch.zeros((n * 4 + n * 32 + n,), dtype=torch.uint8, device=self.device)
+            self._rew = self._pack[:4 * n].view(torch.float32)
+            self._info = self._pack[4 * n:36 * n].view(torch.int32).view(n, 8)
+            self._done = self._pack[36 * n:]
             self._idx = torch.zeros((self.n_envs,), dtype=torch.int32, device=self.device)
 
     # -- plumbing ------------------------------------------------------------------------------------------

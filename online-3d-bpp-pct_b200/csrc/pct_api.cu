@@ -12,6 +12,7 @@
 using namespace pct;
 
 static thread_local std::string g_create_err;
+static_assert(sizeof(pct_config) == 112 && sizeof(pct_step_info) == 32, "C ABI layout (tests/test_cabi.py checks the ctypes mirror against the same numbers)");
 
 #define CK(h, call)                                                                                        \
     do {                                                                                                   \
@@ -96,6 +97,7 @@ int pct_create(const pct_config *cfg, int32_t n_envs, int32_t device, pct_handle
     if (const char *dv = getenv("PCT_B200_OBS_DELTA")) h->obs_delta = atoi(dv) != 0;
     if (const char *av = getenv("PCT_B200_ALIAS")) h->alias_mode = atoi(av) != 0;
     if (const char *kv = getenv("PCT_B200_K3")) h->k3_block = strcmp(kv, "block") == 0;
+    if (const char *wv = getenv("PCT_B200_WALK_LANES")) { h->walk_lanes = atoi(wv); if (h->walk_lanes < 1) h->walk_lanes = 1; if (h->walk_lanes > 32) h->walk_lanes = 32; }
     if (cfg->setting == 2) h->alias_mode = false;  // no stability check, no load entries
     if ((h->obs_delta || h->alias_mode) && e == cudaSuccess) {
         e = cudaMalloc(&h->d_aux, sizeof(DEnvAux) * (size_t)n_envs);
@@ -126,6 +128,9 @@ int pct_create(const pct_config *cfg, int32_t n_envs, int32_t device, pct_handle
                 e = cudaMalloc(&h->d_walkq, sizeof(WalkItem) * (size_t)CAND_MAX * (size_t)n_envs);
                 if (e == cudaSuccess) e = cudaMalloc(&h->d_walk_ctr, sizeof(int32_t) * (size_t)n_envs);
                 if (e == cudaSuccess) e = cudaMemset(h->d_walk_ctr, 0, sizeof(int32_t) * (size_t)n_envs);
+                if (e == cudaSuccess) e = cudaMalloc(&h->d_contq, sizeof(WalkCont) * (size_t)WALK_CONT_PER_ENV * (size_t)n_envs);
+                if (e == cudaSuccess) e = cudaMalloc(&h->d_cont_ctr, sizeof(int32_t) * (size_t)n_envs);
+                if (e == cudaSuccess) e = cudaMemset(h->d_cont_ctr, 0, sizeof(int32_t) * (size_t)n_envs);
             }
             if (e == cudaSuccess) e = cudaMalloc(&h->d_order, sizeof(int32_t) * 2 * (size_t)n_envs);
             if (e == cudaSuccess) {
@@ -154,7 +159,7 @@ void pct_destroy(pct_handle h) {
     cudaSetDevice(h->device);
     if (h->cfg.domain == PCT_CONTINUOUS) continuous_destroy(h);
     cudaFree(h->d_order);
-    cudaFree(h->d_walkq); cudaFree(h->d_walk_ctr);
+    cudaFree(h->d_walkq); cudaFree(h->d_walk_ctr); cudaFree(h->d_contq); cudaFree(h->d_cont_ctr);
     cudaFree(h->d_hstate); cudaFree(h->d_hstate_c); cudaFree(h->d_query_c); cudaFree(h->d_query); cudaFree(h->d_aux);
     cudaFree(h->d_ready);
     cudaFree(h->d_hot); cudaFree(h->d_cold); cudaFree(h->d_item_set); cudaFree(h->d_stream);
@@ -252,6 +257,9 @@ static int launch_range(pct_handle h, int mode, int off, int cnt, const void *ac
     }
     p.walkq = h->d_walkq ? h->d_walkq + (size_t)off * CAND_MAX : nullptr;  // env ranges stepped concurrently (pct_step_host's staged path) own disjoint slices
     p.walk_ctr = h->d_walk_ctr ? h->d_walk_ctr + off : nullptr;
+    p.contq = h->d_contq ? h->d_contq + (size_t)off * WALK_CONT_PER_ENV : nullptr;
+    p.cont_ctr = h->d_cont_ctr ? h->d_cont_ctr + off : nullptr;
+    p.walk_lanes = h->walk_lanes;
     CK(h, launch_discrete(p, gs, prof));
     h->launches += discrete_kernels_per_step(p);
     return PCT_OK;

@@ -44,7 +44,18 @@ struct alignas(16) CEnv {
     double leaf[NL_MAX][6];
     uint16_t cand[1232];
     BigScratch big;
+    uint32_t fbits[FBITS_WORDS];  // feasibility bits of the current observation's candidates (classification at the end of K2, pooled walks, emit kernel)
+    int32_t n_fw, lock, pad_[2];
 };
+
+// one pooled stability walk of the continuous domain (cf. WalkItem): the candidate's tuple is rebuilt from `code` (cand_tuple)
+struct WalkItemC {
+    uint32_t env, pack;
+    uint16_t c, code;
+    int32_t k;
+    double mh;
+};
+static_assert(sizeof(WalkItemC) == 24, "queue entry");
 
 struct CParams {
     CEnv *env;
@@ -71,6 +82,11 @@ struct CParams {
     int32_t *ready;  // overlapped launch mode: per-env hand-over flags [2 * n_envs] (see pct_common.cuh), nullptr = off
     int32_t epoch;
     int shuffle;     // pct_config::shuffle: keyed permutation of the ordered candidate list (shuffle_candidates)
+    WalkItemC *walkq;   // pooled stability walks (round 2, see pct_discrete.cu "K3 (round 2)"); nullptr: round 1's block kernel does everything
+    int32_t *walk_ctr;
+    WalkCont *contq;
+    int32_t *cont_ctr;
+    int32_t walk_lanes;
     DEnvAux *aux;    // per-env state of the ALIAS apply kernel (EdgePoolA arrays), nullptr with PCT_B200_ALIAS=0 / setting 2
 };
 
@@ -516,12 +532,196 @@ __global__ void __launch_bounds__(32) pctc_candidates_kernel(const CParams p) {
         shuffle_candidates<uint16_t>(ev->cand, cnt, (uint64_t *)ev->ems_tmp, (uint16_t *)((char *)ev->ems_tmp + 10240), p.seed, (uint64_t)(p.env_id_base + e),
                                      (uint64_t)h.draw_pos, lane);
     }
+    if (p.walkq) {
+        // ---- classify (round 2): drop_box_virtual's bounds / resting height (C:space.py:380-398) on pre-rounded box rectangles, supports + exact
+        // quick reject for the placements that rest on boxes; the stability walks of all envs go to one pool (pctc_walk_light / pctc_walk kernels) ----
+        __shared__ double rb[NB_MAX][5];
+        const int n_box = h.n_box, nl = p.nl;
+        const bool stab = p.setting != 2;
+        for (int t = lane; t < n_box; t += 32) {
+            const double *b = ev->box[t];
+            rb[t][0] = around6(-b[0]); rb[t][1] = around6(-b[1]); rb[t][2] = around6(b[0] + b[3]); rb[t][3] = around6(b[1] + b[4]);
+            rb[t][4] = b[2] + b[5];
+        }
+        __syncwarp();
+        const uint32_t lt = (1u << lane) - 1;
+        const double margin = 2e-6 * (1.0 + fmax(p.W, p.L));  // the support polygon lies inside the contact rectangles' bounding box up to the 1e-6 * y perturbation
+        int pos = 0, nf = 0;
+#pragma unroll 1
+        while (pos < cnt && nf < nl) {
+            const int c = pos + lane;
+            bool feas = false, pend = false;
+            int k = 0;
+            uint32_t pack = 0;
+            uint16_t code = 0;
+            double mh = 0;
+            if (c < cnt) {
+                code = ev->cand[c];
+                double t6[6];
+                cand_tuple(code, ev->ems, nb, t6);
+                const double x = t6[3] - t6[0], y = t6[4] - t6[1], z = t6[5] - t6[2], lx = t6[0], ly = t6[1];
+                bool chk = !(lx + x - 1e-6 > p.W || ly + y - 1e-6 > p.L) && !(lx + 1e-6 < 0 || ly + 1e-6 < 0);
+                const double c0 = around6(-lx), c1 = around6(-ly), c2 = around6(lx + x), c3 = around6(ly + y);
+                mh = rest_height_pre(rb, n_box, c0, c1, c2, c3);
+                if (mh < 0) mh = 0.0;
+                if (mh + z - 1e-6 > p.H) chk = false;
+                if (!chk) feas = false;
+                else if (!stab || fabs(mh) < 1e-6) feas = true;
+                else {
+                    // supports = GeomC::support(root, t): top within 1e-6 of the resting height and a positive rounded intersection (C:space.py:350-359)
+                    double X1 = 0, Y1 = 0, X2 = 0, Y2 = 0;
+#pragma unroll 1
+                    for (int t = 0; t < n_box; t++) {
+                        const double *b = rb[t];
+                        if (!(fabs(b[4] - mh) < 1e-6)) continue;
+                        const double i0 = fmin(c0, b[0]), i1 = fmin(c1, b[1]), i2 = fmin(c2, b[2]), i3 = fmin(c3, b[3]);
+                        if (!((i0 + i2 > 0) && (i1 + i3 > 0))) continue;
+                        if (k == 0) { X1 = -i0; Y1 = -i1; X2 = i2; Y2 = i3; }
+                        else { X1 = fmin(X1, -i0); Y1 = fmin(Y1, -i1); X2 = fmax(X2, i2); Y2 = fmax(Y2, i3); }
+                        if (k < 4) pack |= (uint32_t)t << (8 * k);
+                        k++;
+                    }
+                    const double cx = lx + x * 0.5, cy = ly + y * 0.5;
+                    const bool far_out = k > 0 && (cx < X1 - margin || cx > X2 + margin || cy < Y1 - margin || cy > Y2 + margin);
+                    pend = !far_out;  // centre outside the supports' bounding box: the root test fails (cf. rest_height_supports, pct_geom.cuh)
+                }
+            }
+            const uint32_t fm = __ballot_sync(FULL, feas), pm = __ballot_sync(FULL, pend);
+            if (lane == 0) ev->fbits[pos >> 5] = fm;
+            nf += __popc(fm);
+            if (pm) {
+                int qb = 0;
+                if (lane == 0) qb = atomicAdd(p.walk_ctr, __popc(pm));
+                qb = __shfl_sync(FULL, qb, 0);
+                if (pend) p.walkq[qb + __popc(pm & lt)] = WalkItemC{(uint32_t)e, pack, (uint16_t)c, code, k, mh};
+            }
+            pos += 32;
+        }
+        if (lane == 0) ev->n_fw = pos >> 5;
+    }
     if (lane == 0) {
         ev->h.n_cand = cnt;
         if (fl) ev->h.flags |= fl;
         if (p.ready) env_publish(p.ready + p.n_envs + e, p.epoch);
     }
 }
+
+// ---- pooled walks (round 2): see pct_discrete.cu — light prefix for every walk, continuation kernel for the walks that reach a node with >= 2 supports ----
+struct WalkViewC {
+    GeomC g;
+    EdgePool pool;
+    NodeC root;
+    CEnv *ev;
+};
+__device__ __forceinline__ WalkViewC walk_view_c(const CParams &p, const WalkItemC &it, bool has) {
+    CEnv *ev = p.env + it.env;
+    const CHdr &h = ev->h;
+    double t6[6] = {0, 0, 0, 0, 0, 0};
+    if (has) {
+        const double nb[3] = {h.next_box[0], h.next_box[1], h.next_box[2]};
+        cand_tuple(it.code, ev->ems, nb, t6);
+    }
+    const double x = t6[3] - t6[0], y = t6[4] - t6[1], z = t6[5] - t6[2];
+    return WalkViewC{GeomC{ev->box, ev->den, has ? h.n_box : 0},
+                     EdgePool{ev->e_lower, ev->e_next, ev->e_off, ev->first_in, ev->last_in, ev->e_st, ev->e_st, has ? h.n_edge : 0, ev->poly_off,
+                              &ev->poly[0][0], &ev->poly[0][0], has ? h.n_poly : 0},
+                     NodeC{t6[0], t6[1], it.mh, x, y, z, x * y * z * (has ? h.next_den : 1.0)}, ev};
+}
+
+__global__ void __launch_bounds__(128, 4) pctc_walk_light_kernel(const CParams p) {
+    const int lane = threadIdx.x & 31;
+    const int total = *(volatile const int32_t *)p.walk_ctr;
+    const int nwarps = gridDim.x * 4;
+    const int cap = p.n_envs * WALK_CONT_PER_ENV;
+#pragma unroll 1
+    for (int base = (blockIdx.x * 4 + (threadIdx.x >> 5)) * 32; base < total; base += nwarps * 32) {
+        const int i = base + lane;
+        const bool has = i < total;
+        WalkItemC it{};
+        if (has) it = p.walkq[i];
+        const WalkViewC v = walk_view_c(p, it, has);
+        int node = NODE_NEW, res = 0;
+        Stack4 st{};
+        if (has) res = stab_light<GeomC>(v.g, v.root, it.k, it.pack, v.pool, node, st);
+        if (res == 1) atomicOr(&v.ev->fbits[it.c >> 5], 1u << (it.c & 31));
+        const uint32_t pm = __ballot_sync(FULL, res == 2);
+        if (pm) {
+            int qb = 0;
+            if (lane == 0) qb = atomicAdd(p.cont_ctr, __popc(pm));
+            qb = __shfl_sync(FULL, qb, 0);
+            if (res == 2) {
+                const int slot = qb + __popc(pm & ((1u << lane) - 1));
+                if (slot < cap) p.contq[slot] = WalkCont{(uint32_t)i, (uint32_t)node, st};
+                else atomicOr(&v.ev->h.flags, PCT_FLAG_CAND_OVERFLOW);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(64, 8) pctc_walk_kernel(const CParams p) {
+    const int lane = threadIdx.x & 31;
+    const int total = min(*(volatile const int32_t *)p.cont_ctr, p.n_envs * WALK_CONT_PER_ENV);
+    const int nwarps = gridDim.x * 2, L = p.walk_lanes;
+    const unsigned mask = L >= 32 ? FULL : ((1u << L) - 1u);
+    if (lane >= L) return;
+#pragma unroll 1
+    for (int base = (blockIdx.x * 2 + (threadIdx.x >> 5)) * L; base < total; base += nwarps * L) {
+        const int i = base + lane;
+        const bool has = i < total;
+        WalkCont ct{};
+        WalkItemC it{};
+        if (has) { ct = p.contq[i]; it = p.walkq[ct.item]; }
+        const WalkViewC v = walk_view_c(p, it, has);
+        int fl = 0;
+        const bool ok = stab_virtual<GeomC>(v.g, v.root, it.k, it.pack, v.pool, &v.ev->big, &v.ev->lock, fl, has, mask, has ? (int)ct.node : NODE_NEW, &ct.st) != 0;
+        if (has && ok) atomicOr(&v.ev->fbits[it.c >> 5], 1u << (it.c & 31));
+        if (has && fl) atomicOr(&v.ev->h.flags, fl);
+    }
+}
+
+template <typename OT> __device__ __noinline__ void write_obs_c(const CParams &p, int e, const CEnv *ev, const double (*leaf)[6], int n_leaf, int tid, int nthreads);
+
+// emit (round 2): the first `nl` set feasibility bits in candidate order -> leaf rows, observation; 64 threads per env
+template <typename OT>
+__global__ void __launch_bounds__(64) pctc_emit_kernel(const CParams p) {
+    __shared__ double leaf[NL_MAX][6];
+    __shared__ int s_nleaf;
+    const int tid = threadIdx.x, lane = tid & 31, e = blockIdx.x;
+    CEnv *ev = p.env + e;
+    const CHdr &h = ev->h;
+    const double nb[3] = {h.next_box[0], h.next_box[1], h.next_box[2]};
+    if (e == 0 && tid == 0) { *p.walk_ctr = 0; *p.cont_ctr = 0; }  // both walk kernels have completed (stream order): empty the pools for the next step
+    if (tid < 32) {
+        const int nl = p.nl, nw = ev->n_fw;
+        const uint32_t lt = (1u << lane) - 1;
+        int base = 0;
+#pragma unroll 1
+        for (int w = 0; w < nw && base < nl; w++) {
+            const uint32_t bits = ev->fbits[w];
+            if ((bits >> lane) & 1u) {
+                const int kk = base + __popc(bits & lt);
+                if (kk < nl) {
+                    double t6[6];
+                    cand_tuple(ev->cand[w * 32 + lane], ev->ems, nb, t6);
+                    for (int t = 0; t < 6; t++) leaf[kk][t] = t6[t];
+                }
+            }
+            base += __popc(bits);
+        }
+        if (lane == 0) s_nleaf = min(base, nl);
+    }
+    __syncthreads();
+    const int n_leaf = s_nleaf;
+    for (int t = tid; t < n_leaf * 6; t += 64) ((double *)ev->leaf)[t] = ((double *)leaf)[t];
+    if (tid == 0) {
+        ev->h.n_leaf = n_leaf;
+        if (p.info) {
+            p.info[e].n_leaf = n_leaf; p.info[e].n_cand = h.n_cand; p.info[e].n_ems = h.n_ems; p.info[e].flags |= h.flags;
+        }
+    }
+    write_obs_c<OT>(p, e, ev, leaf, n_leaf, tid, 64);
+}
+
 
 // ================= K3: feasibility per candidate + leaf compaction + observation =================
 template <typename OT>
@@ -657,10 +857,16 @@ int continuous_create(pct_env_batch *h) {
     if (e == cudaSuccess) e = cudaMemset(h->c_state, 0, sizeof(CEnv) * (size_t)h->n_envs);
     if (e == cudaSuccess) e = cudaMalloc(&h->d_ready, sizeof(int32_t) * 2 * (size_t)h->n_envs);
     if (e == cudaSuccess) e = cudaMemset(h->d_ready, 0, sizeof(int32_t) * 2 * (size_t)h->n_envs);
+    if (e == cudaSuccess && !h->k3_block) {  // pools of the round-2 walk kernels (worst-case capacity for the walks; only the used prefix is touched)
+        e = cudaMalloc(&h->c_walkq, sizeof(WalkItemC) * (size_t)CAND_MAX * (size_t)h->n_envs);
+        if (e == cudaSuccess) e = cudaMalloc(&h->d_walk_ctr, sizeof(int32_t) * 2);
+        if (e == cudaSuccess) e = cudaMemset(h->d_walk_ctr, 0, sizeof(int32_t) * 2);
+        if (e == cudaSuccess) e = cudaMalloc(&h->d_contq, sizeof(WalkCont) * (size_t)WALK_CONT_PER_ENV * (size_t)h->n_envs);
+    }
     if (e != cudaSuccess) { h->err = std::string("continuous_create: ") + cudaGetErrorString(e); return PCT_ERR_CUDA; }
     return PCT_OK;
 }
-void continuous_destroy(pct_env_batch *h) { cudaFree(h->c_state); h->c_state = nullptr; }
+void continuous_destroy(pct_env_batch *h) { cudaFree(h->c_state); h->c_state = nullptr; cudaFree(h->c_walkq); h->c_walkq = nullptr; }
 int64_t continuous_state_bytes() { return (int64_t)sizeof(CEnv); }
 
 int continuous_launch(pct_env_batch *h, int mode, const void *actions, int action_f64, const int32_t *leaf_idx, void *obs, float *rew,
@@ -694,8 +900,26 @@ int continuous_launch(pct_env_batch *h, int mode, const void *actions, int actio
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cudaLaunchConfig_t cfg{};
     cfg.stream = st; cfg.attrs = at; cfg.numAttrs = p.ready ? 1 : 0;
+    const bool pooled = h->c_walkq != nullptr && !h->k3_block;
+    if (pooled) {
+        p.walkq = (WalkItemC *)h->c_walkq; p.walk_ctr = h->d_walk_ctr; p.contq = h->d_contq; p.cont_ctr = h->d_walk_ctr + 1; p.walk_lanes = h->walk_lanes;
+    }
     cfg.gridDim = dim3(p.n_envs); cfg.blockDim = dim3(32);
     cudaLaunchKernelEx(&cfg, pctc_candidates_kernel, p);
+    if (pooled) {
+        static int n_sm = 0;
+        if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
+        if (stab) {
+            pctc_walk_light_kernel<<<n_sm * 4, 128, 0, st>>>(p);
+            pctc_walk_kernel<<<n_sm * 8 * (p.walk_lanes <= 4 ? 4 : p.walk_lanes <= 16 ? 2 : 1), 64, 0, st>>>(p);
+        }
+        if (p.obs_f64) pctc_emit_kernel<double><<<p.n_envs, 64, 0, st>>>(p);
+        else pctc_emit_kernel<float><<<p.n_envs, 64, 0, st>>>(p);
+        cudaError_t e2 = cudaGetLastError();
+        if (e2 != cudaSuccess) { h->err = std::string("continuous launch: ") + cudaGetErrorString(e2); return PCT_ERR_CUDA; }
+        h->launches += stab ? 4 : 2;  // apply, candidates, [light, walk], emit; the caller counts one
+        return PCT_OK;
+    }
     cfg.blockDim = dim3(64);
     if (h->cont_pre) {
         if (p.obs_f64) { if (stab) cudaLaunchKernelEx(&cfg, pctc_feas_emit_kernel<double, true, true>, p); else cudaLaunchKernelEx(&cfg, pctc_feas_emit_kernel<double, false, true>, p); }

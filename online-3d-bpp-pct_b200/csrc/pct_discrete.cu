@@ -1175,40 +1175,96 @@ __global__ void __launch_bounds__(FEAS_THREADS, K3_MINB) pct_feas_emit_kernel(co
 //   classify  (end of K2, warp per env, integer only) bounds + ONE pass over the boxes for resting height, supports and the exact
 //             quick reject (rest_height_supports) -> infeasible / feasible / needs a stability walk; feasibility bits per 32-candidate
 //             chunk; the walks of ALL envs go into one global pool;
-//   walk      pct_walk_kernel: 32 walks per warp, from whichever envs, through stab_virtual (warp-convergent light / heavy phases).
-//             Lanes are dense, a heavy env's walks spread over many warps and SMs, the longest serial chain is ONE walk;
+//   walk      two kernels over the pool, 32 walks per warp from whichever envs (a heavy env's walks spread over many warps and SMs):
+//             pct_walk_light_kernel runs every walk's LIGHT PREFIX (stab_light: visits of nodes with <= 1 support; 81 % of the walks are
+//             nothing else) and hands the rest — walks standing in front of a node with >= 2 supports, with (node, stack) — to
+//             pct_walk_kernel, whose lanes therefore all START with a heavy visit (dense) and finish through stab_virtual;
 //   emit      pct_emit_kernel (warp per env): the first `nl` set feasibility bits in candidate order -> leaf slots, observation.
 // get_possible_position stops at `nl` feasible candidates (D:bin3D.py:117-136); here classification stops once `nl` candidates are KNOWN
 // feasible and the emit kernel takes the first `nl` set bits: the same ordered prefix (walks past the cut are wasted work, not wrong).
 #ifndef WALK_MINB
 #define WALK_MINB 8
 #endif
-constexpr int WALK_WARPS = 2;
+#ifndef LIGHT_MINB
+#define LIGHT_MINB 6
+#endif
+constexpr int WALK_WARPS = 2, LIGHT_WARPS = 4;
 
-__global__ void __launch_bounds__(32 * WALK_WARPS, WALK_MINB) pct_walk_kernel(const DParams p) {
+// per-lane view of one pooled walk: the env's record stays in global memory (L1 / L2) — the lanes of a warp belong to different envs
+struct WalkView {
+    GeomD g;
+    EdgePool pool;
+    NodeD root;
+    DEnvCold *cold;
+    const DEnvHot *hot;
+};
+__device__ __forceinline__ WalkView walk_view(const DParams &p, const WalkItem &it, bool has) {
+    const DEnvHot *hot = p.hot + it.env;
+    DEnvCold *cold = p.cold + it.env;
+    const DHdr &h = hot->h;
+    const int sx = it.sx, sy = it.sy, sz = it.sz;
+    return WalkView{GeomD{hot->box, has ? h.n_box : 0, p.setting == 3 ? cold->density : nullptr},
+                    EdgePool{const_cast<uint8_t *>(hot->e_lower), const_cast<uint8_t *>(hot->e_next), const_cast<uint16_t *>(hot->e_off),
+                             const_cast<uint8_t *>(hot->first_in), const_cast<uint8_t *>(hot->last_in), cold->e_st, cold->e_st, has ? h.n_edge : 0,
+                             const_cast<uint16_t *>(hot->poly_off), &cold->poly[0][0], &cold->poly[0][0], has ? h.n_poly : 0},
+                    NodeD{(int)it.xs, (int)it.ys, (int)it.mh, sx, sy, sz, (double)(sx * sy * sz) * (has ? h.next_den : 1.0)}, cold, hot};
+}
+
+// walk, stage 1: the light prefix of EVERY pooled walk, one lane per walk (stab_light: single-support visits only — small code, no local arrays).
+// 81 % of the walks end here; the rest goes to the continuation pool with (node, stack).
+__global__ void __launch_bounds__(32 * LIGHT_WARPS, LIGHT_MINB) pct_walk_light_kernel(const DParams p) {
     const int lane = threadIdx.x & 31;
     const int total = *(volatile const int32_t *)p.walk_ctr;
-    const int nwarps = gridDim.x * WALK_WARPS;
+    const int nwarps = gridDim.x * LIGHT_WARPS;
+    const int cap = p.n_envs * WALK_CONT_PER_ENV;
 #pragma unroll 1
-    for (int base = (blockIdx.x * WALK_WARPS + (threadIdx.x >> 5)) * 32; base < total; base += nwarps * 32) {
+    for (int base = (blockIdx.x * LIGHT_WARPS + (threadIdx.x >> 5)) * 32; base < total; base += nwarps * 32) {
         const int i = base + lane;
         const bool has = i < total;
         WalkItem it{};
         if (has) it = p.walkq[i];
-        const DEnvHot *hot = p.hot + it.env;
-        DEnvCold *cold = p.cold + it.env;
-        const DHdr &h = hot->h;
-        GeomD g{hot->box, has ? h.n_box : 0, p.setting == 3 ? cold->density : nullptr};
-        // the record stays in global memory (L1 / L2): the lanes of a warp belong to different envs
-        const EdgePool pool{const_cast<uint8_t *>(hot->e_lower), const_cast<uint8_t *>(hot->e_next), const_cast<uint16_t *>(hot->e_off),
-                            const_cast<uint8_t *>(hot->first_in), const_cast<uint8_t *>(hot->last_in), cold->e_st, cold->e_st, has ? h.n_edge : 0,
-                            const_cast<uint16_t *>(hot->poly_off), &cold->poly[0][0], &cold->poly[0][0], has ? h.n_poly : 0};
-        const int sx = it.sx, sy = it.sy, sz = it.sz;
-        const NodeD root{(int)it.xs, (int)it.ys, (int)it.mh, sx, sy, sz, (double)(sx * sy * sz) * (has ? h.next_den : 1.0)};
+        const WalkView v = walk_view(p, it, has);
+        int node = NODE_NEW, res = 0;
+        Stack4 st{};
+        if (has) res = stab_light<GeomD>(v.g, v.root, (int)it.k, it.pack, v.pool, node, st);
+        if (res == 1) atomicOr(&v.cold->fbits[it.c >> 5], 1u << (it.c & 31));
+        const uint32_t pm = __ballot_sync(FULL, res == 2);
+        if (pm) {
+            int qb = 0;
+            if (lane == 0) qb = atomicAdd(p.cont_ctr, __popc(pm));
+            qb = __shfl_sync(FULL, qb, 0);
+            if (res == 2) {
+                const int slot = qb + __popc(pm & ((1u << lane) - 1));
+                if (slot < cap) p.contq[slot] = WalkCont{(uint32_t)i, (uint32_t)node, st};
+                else atomicOr(const_cast<int32_t *>(&v.hot->h.flags), PCT_FLAG_CAND_OVERFLOW);  // never silent: the candidate stays infeasible and the env is flagged
+            }
+        }
+    }
+}
+
+// walk, stage 2: the continuations — every lane starts with the heavy visit its walk stopped at, then runs the general light / heavy state
+// machine to the end of the walk.  Only `p.walk_lanes` lanes of a warp carry a walk (default 8): there are few continuations (3 per env) and each
+// is a long serial chain, so a full warp of them (ncu r2, profiles/r2_walk_two_stage_32lanes.txt: 400 warps on 592 schedulers, 20 k instructions
+// per warp, SMs 4 % occupied, 116 us) is latency-bound on the SUM of its lanes' divergent paths; fewer walks per warp = more warps, shorter chains.
+__global__ void __launch_bounds__(32 * WALK_WARPS, WALK_MINB) pct_walk_kernel(const DParams p) {
+    const int lane = threadIdx.x & 31;
+    const int total = min(*(volatile const int32_t *)p.cont_ctr, p.n_envs * WALK_CONT_PER_ENV);
+    const int nwarps = gridDim.x * WALK_WARPS, L = p.walk_lanes;
+    const unsigned mask = L >= 32 ? FULL : ((1u << L) - 1u);
+    if (lane >= L) return;
+#pragma unroll 1
+    for (int base = (blockIdx.x * WALK_WARPS + (threadIdx.x >> 5)) * L; base < total; base += nwarps * L) {
+        const int i = base + lane;
+        const bool has = i < total;
+        WalkCont ct{};
+        WalkItem it{};
+        if (has) { ct = p.contq[i]; it = p.walkq[ct.item]; }
+        const WalkView v = walk_view(p, it, has);
         int fl = 0;
-        const bool ok = stab_virtual<GeomD>(g, root, (int)it.k, it.pack, pool, &cold->big, &cold->lock, fl, has, FULL) != 0;
-        if (has && ok) atomicOr(&cold->fbits[it.c >> 5], 1u << (it.c & 31));
-        if (has && fl) atomicOr(const_cast<int32_t *>(&hot->h.flags), fl);
+        const bool ok = stab_virtual<GeomD>(v.g, v.root, (int)it.k, it.pack, v.pool, &v.cold->big, &v.cold->lock, fl, has, mask,
+                                            has ? (int)ct.node : NODE_NEW, &ct.st) != 0;
+        if (has && ok) atomicOr(&v.cold->fbits[it.c >> 5], 1u << (it.c & 31));
+        if (has && fl) atomicOr(const_cast<int32_t *>(&v.hot->h.flags), fl);
     }
 }
 
@@ -1223,6 +1279,8 @@ __global__ void __launch_bounds__(32 * EMIT_WARPS) pct_emit_kernel(const DParams
     __shared__ __align__(16) unsigned char smem[EMIT_WARPS * EMIT_SM_PER_WARP];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int e = blockIdx.x * EMIT_WARPS + warp;
+    // last kernel of the launch sequence that touches the walk pools (both walk kernels have completed: plain stream order): empty them for the next step
+    if (blockIdx.x == 0 && threadIdx.x == 0 && p.walk_ctr) { *p.walk_ctr = 0; *p.cont_ctr = 0; }
     if (e >= p.n_envs) return;
     unsigned char *sm = smem + warp * EMIT_SM_PER_WARP;
     DEnvHot *hot = (DEnvHot *)sm;  // only the header and the boxes are staged
@@ -1288,11 +1346,9 @@ __global__ void __launch_bounds__(32 * EMIT_WARPS) pct_emit_kernel(const DParams
 // the envs by a work estimate read from the record headers: which = 0 -> order[0..n) for the NEXT step's apply kernel
 // (boxes already placed drive the real stability DFS and the EMS update), which = 1 -> order[n..2n) for feas_emit
 // (candidates x stack depth).
-__global__ void __launch_bounds__(1024) pct_order_kernel(const DEnvHot *hot, int n_envs, int32_t *order, int which, int32_t *walk_ctr) {
+__global__ void __launch_bounds__(1024) pct_order_kernel(const DEnvHot *hot, int n_envs, int32_t *order, int which) {
     __shared__ int hist[64], base[64];
     const int tid = threadIdx.x;
-    if (tid == 0 && walk_ctr) *walk_ctr = 0;  // last kernel of every launch sequence: the next step's walk pool starts empty
-    if (!order) return;
     if (tid < 64) hist[tid] = 0;
     __syncthreads();
     for (int e = tid; e < n_envs; e += 1024) {
@@ -1391,12 +1447,15 @@ static cudaError_t launch_t(const DParams &p_in, cudaStream_t st, cudaEvent_t *p
     if (!k3_old) {
         // the pooled walks need EVERY env's classification (plain stream order = full dependency), the emit kernel every walk
         if (p.ready && prof) cudaEventRecord(prof[2], st);
-        if (STAB) pct_walk_kernel<<<n_sm * WALK_MINB, 32 * WALK_WARPS, 0, st>>>(p);
+        if (STAB) {
+            pct_walk_light_kernel<<<n_sm * LIGHT_MINB, 32 * LIGHT_WARPS, 0, st>>>(p);
+            pct_walk_kernel<<<n_sm * WALK_MINB * (p.walk_lanes <= 4 ? 4 : p.walk_lanes <= 16 ? 2 : 1), 32 * WALK_WARPS, 0, st>>>(p);
+        }
         const int eb = (p.n_envs + EMIT_WARPS - 1) / EMIT_WARPS;
         if (p.opt & PCT_OPT_DELTA) pct_emit_kernel<OT, SlotT, true><<<eb, 32 * EMIT_WARPS, 0, st>>>(p);
         else pct_emit_kernel<OT, SlotT, false><<<eb, 32 * EMIT_WARPS, 0, st>>>(p);
     }
-    if (p.order || p.walk_ctr) pct_order_kernel<<<1, 1024, 0, st>>>(p.hot, p.n_envs, p.order, 0, p.walk_ctr);
+    if (p.order) pct_order_kernel<<<1, 1024, 0, st>>>(p.hot, p.n_envs, p.order, 0);
     if (prof) cudaEventRecord(prof[3], st);
     return cudaGetLastError();
 }
@@ -1409,7 +1468,7 @@ static cudaError_t launch_s(const DParams &p, cudaStream_t st, cudaEvent_t *prof
 // number of kernels one reset / step enqueues (for pct_kernel_launches): apply, candidates (+ classify), [walk], emit, order / pool reset
 int discrete_kernels_per_step(const DParams &p) {
     if ((p.opt & PCT_OPT_K3_BLOCK) || !p.walkq) return 3 + (p.order ? 1 : 0);
-    return 4 + (p.setting != 2 ? 1 : 0);
+    return 3 + (p.setting != 2 ? 2 : 0) + (p.order ? 1 : 0);
 }
 
 cudaError_t launch_discrete(const DParams &p, cudaStream_t st, cudaEvent_t *prof) {

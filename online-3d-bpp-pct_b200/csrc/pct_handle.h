@@ -15,6 +15,7 @@ struct pct_env_batch {
     pct::DEnvHot *d_hot = nullptr;
     pct::DEnvCold *d_cold = nullptr;
     void *c_state = nullptr;  // continuous-domain state (pct_continuous.cu)
+    void *c_walkq = nullptr;  // continuous-domain pool of stability walks (WalkItemC, pct_continuous.cu)
     double *d_item_set = nullptr;
     int n_items = 0;
     double *d_stream = nullptr;
@@ -55,6 +56,9 @@ struct pct_env_batch {
     int32_t *d_order = nullptr;   // block -> env permutations (LPT scheduling)
     pct::WalkItem *d_walkq = nullptr;  // [n_envs * CAND_MAX] pool of stability walks of the current step (pct_walk_kernel)
     int32_t *d_walk_ctr = nullptr;     // [n_envs] fill counters (index = first env of the launched range)
+    pct::WalkCont *d_contq = nullptr;  // [n_envs * WALK_CONT_PER_ENV] continuations: light-prefix kernel -> pct_walk_kernel
+    int32_t *d_cont_ctr = nullptr;
+    int walk_lanes = 8;                // continuations per warp of pct_walk_kernel (PCT_B200_WALK_LANES; few long serial chains: more warps beat fuller warps)
     bool lpt = false;
     int prof_on = 0;
     std::vector<cudaEvent_t> prof_ev;   // 4 events per recorded step

@@ -144,6 +144,15 @@ struct WalkItem {
     uint8_t xs, ys, mh, sx, sy, sz, k, pad_;  // footprint corner, resting height, oriented dims, number of supports
 };
 static_assert(sizeof(WalkItem) == 20, "queue entry");
+// A walk that the light-prefix kernel could not finish: it stands in front of placed box / the placement itself (`node`, NODE_NEW = 255) with
+// the stack `st`; pct_walk_kernel continues it (stab_virtual's continuation entry).
+struct WalkCont {
+    uint32_t item;            // index of its WalkItem in the pool
+    uint32_t node;
+    Stack4 st;
+};
+static_assert(sizeof(WalkCont) == 40, "queue entry");
+constexpr int WALK_CONT_PER_ENV = 256;  // capacity of the continuation pool = n_envs x this (mean use: 3 per env); overflow -> PCT_FLAG_CAND_OVERFLOW
 
 struct DParams {
     DEnvHot *hot;
@@ -185,6 +194,9 @@ struct DParams {
     int32_t epoch;   // value published in `ready` by this launch
     WalkItem *walkq;    // [n_envs * CAND_MAX] the step's pool of stability walks (worst-case capacity; only the used prefix is touched)
     int32_t *walk_ctr;  // its fill counter; reset by pct_order_kernel at the end of every launch sequence
+    WalkCont *contq;    // [n_envs * WALK_CONT_PER_ENV] walks the light-prefix kernel hands to the continuation kernel
+    int32_t *cont_ctr;
+    int32_t walk_lanes; // continuations per warp of pct_walk_kernel (1..32)
     int32_t opt;     // opt-in variants served by `aux`: PCT_OPT_DELTA (K3 delta observation writes), PCT_OPT_ALIAS (K1 object semantics of the loads)
 };
 constexpr int PCT_OPT_DELTA = 1, PCT_OPT_ALIAS = 2, PCT_OPT_K3_BLOCK = 4;  // K3_BLOCK: round 1's block-per-env feasibility kernel (A/B)

@@ -53,6 +53,9 @@ __device__ __forceinline__ int orient_of(double s1, double s2) {
 __device__ __forceinline__ int orient3(double ax, double ay, double bx, double by, double cx, double cy) {
     const double d1x = bx - ax, d1y = by - ay, d2x = cx - bx, d2y = cy - by;
     if (d1x != 0 && d2x != 0) {
+        // three corners on one horizontal line (every contact rectangle contributes two such pairs): both slopes are (+-0) / dx = +-0, their
+        // difference is 0 -> collinear (0), without the two IEEE divisions the float estimate below would fall through to
+        if (d1y == 0 && d2y == 0) return 0;
         const float f1 = __fdividef((float)d1y, (float)d1x), f2 = __fdividef((float)d2y, (float)d2x);
         const float gap = f2 - f1, tol = 1e-4f * (fabsf(f1) + fabsf(f2));
         if (fabsf(gap) > tol && fabsf(f1) < 1e30f && fabsf(f2) < 1e30f) return gap > 0 ? -1 : 1;
@@ -667,9 +670,67 @@ static __device__ __noinline__ int stability_check(const G &g, const typename G:
 #ifndef PCT_STAT
 #define PCT_STAT(i)   // statistics hook of the host build (tests/host_emul/stab_host.cpp)
 #endif
+
+// stab_light: the LIGHT PREFIX of a feasibility walk — visits of nodes with no or one support (81 % of the walks of the BASELINE streams
+// consist of nothing else; host statistics, scratch/stats_farout.py): a rectangle test in registers and the centre-of-mass update, no frames,
+// no hull, no local arrays, so the kernel that runs it is small, register-light and convergent (lanes differ in trip count only).
+// Returns 0 infeasible / 1 feasible / 2 the walk stands in front of a node with >= 2 supports (or the rare single support whose perturbed
+// corners are not in the proven order): (node_out, st_out) is where stab_virtual continues.  Same expressions as stab_virtual's light phase.
+template <class G>
+static __device__ __forceinline__ int stab_light(const G &g, const typename G::Node &root, int k_root, uint32_t sup_pack, const EdgePool &pool,
+                                                 int &node_out, Stack4 &st_out) {
+    typedef typename G::Node Node;
+    int node = NODE_NEW;
+    Stack4 st;
+    g.centre(root, st.cx, st.cy, st.cz);
+    st.m = root.mass;
+#pragma unroll 1
+    for (;;) {
+        int k, eoff;
+        if (node == NODE_NEW) { k = k_root; eoff = pool.n; }
+        else { eoff = (int)pool.off[node]; k = (int)pool.off[node + 1] - eoff; }
+        if (k == 0) return 1;  // rests on the floor: every support test above passed
+        if (k >= 2) { node_out = node; st_out = st; return 2; }
+        PCT_STAT(1);
+        const int sid0 = (node == NODE_NEW) ? (int)(sup_pack & 0xFFu) : (int)pool.lower[eoff];
+        Node cur;
+        if (node != NODE_NEW) g.node_box(node, cur);
+        else cur = root;
+        double r0[4];
+        g.support(cur, sid0, r0);
+        const double t1 = r0[1] * 1e-6, t2 = r0[3] * 1e-6;
+        const bool fast = (r0[0] + t1 < r0[0] + t2) && (r0[0] + t2 < r0[2] + t1) && (r0[2] + t1 < r0[2] + t2);
+        if (!fast) { node_out = node; st_out = st; return 2; }
+        if (!pip_rect(r0[0], r0[1], r0[2], r0[3], t1, t2, st.cx, st.cy)) return 0;
+        // calculate_new_com of the single support under the whole stack (D:space.py:51-71); its real load from `node` is replaced
+        const int skip = (node == NODE_NEW) ? EDGE_NIL : eoff;
+        Node sb;
+        g.node_box(sid0, sb);
+        double ccx, ccy, ccz, mm = sb.mass;
+        g.centre(sb, ccx, ccy, ccz);
+        ccx *= mm; ccy *= mm; ccz *= mm;
+#pragma unroll 1
+        for (int q = pool.first_in[sid0]; q != EDGE_NIL; q = pool.next[q]) {
+            if (q == skip) continue;
+            const Stack4 e = pool.load(q);
+            ccx += e.cx * e.m; ccy += e.cy * e.m; ccz += e.cz * e.m;
+            mm += e.m;
+        }
+        if (st.m != 0.0) {
+            ccx += st.cx * st.m; ccy += st.cy * st.m; ccz += st.cz * st.m;
+            mm += st.m;
+        }
+        st.cx = ddiv(ccx, mm); st.cy = ddiv(ccy, mm); st.cz = ddiv(ccz, mm); st.m = mm;
+        node = sid0;
+    }
+}
+
+// start_node != NODE_NEW: continue a walk that stab_light ran as far as its first node with >= 2 supports (its frame stack is empty there:
+// every earlier visit was a tail call) — enter `start_node` with the stack *start_st.
 template <class G>
 static __device__ __noinline__ int stab_virtual(const G &g, const typename G::Node &root, int k_root, uint32_t sup_pack, const EdgePool &pool,
-                                                BigScratch *big, int *lock, int &flags, bool has_work, unsigned mask) {
+                                                BigScratch *big, int *lock, int &flags, bool has_work, unsigned mask,
+                                                int start_node = NODE_NEW, const Stack4 *start_st = nullptr) {
     typedef typename G::Node Node;
     StabFrame fr[STAB_DEPTH];
     uint8_t sup_id[STAB_SUP_POOL];
@@ -678,6 +739,7 @@ static __device__ __noinline__ int stab_virtual(const G &g, const typename G::No
     Stack4 st;
     g.centre(root, st.cx, st.cy, st.cz);
     st.m = root.mass;
+    if (start_node != NODE_NEW) { node = start_node; st = *start_st; }
     bool active = has_work, need_adv = false;
     int result = 0;
     int child = -1, skip = EDGE_NIL;

@@ -134,10 +134,12 @@ class PctVecEnv(object):
                 a = torch.cat([a, torch.zeros((a.shape[0], 9 - a.shape[1]), dtype=a.dtype, device=a.device)], dim=1)
             obs, rew, done, info = self.batch.step(actions=a)
         n = self.num_envs
-        pk = self._dev_pack
-        pk[:4 * n].view(torch.float32).copy_(rew)
-        pk[4 * n:36 * n].view(torch.int32).copy_(info.reshape(-1))
-        pk[36 * n:].copy_(done)
+        pk = getattr(self.batch, "_pack", None)  # PctBatch keeps reward | info | done in one allocation: one device -> host copy
+        if pk is None:
+            pk = self._dev_pack
+            pk[:4 * n].view(torch.float32).copy_(rew)
+            pk[4 * n:36 * n].view(torch.int32).copy_(info.reshape(-1))
+            pk[36 * n:].copy_(done)
         self._host.copy_(pk, non_blocking=True)
         if self.copy_obs:
             obs = obs.clone()

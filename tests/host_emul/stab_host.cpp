@@ -85,6 +85,14 @@ int sh_virtual(StabHost *h, int x, int y, int z, int lx, int ly, double density,
         if (far_out) { g_far_out++; return 0; }  // the kernel's integer quick reject
         g_walks++;
         ok = stab_virtual<GeomD>(g, root, k, pack, pool, &h->big, &h->lock, fl, true, 0xffffffffu);
+    } else if (g_use_v2 == 3) {  // as the round-2 kernels run it: light prefix (pct_walk_light_kernel), then the continuation (pct_walk_kernel)
+        int k; uint32_t pack; bool far_out;
+        const int mh2 = rest_height_supports(h->box, h->n_box, lx, ly, lx + x, ly + y, k, pack, far_out);
+        if (mh2 != mh) { h->flags |= 1 << 20; return -1; }
+        if (far_out) { g_far_out++; return 0; }
+        int node = NODE_NEW; Stack4 st{};
+        ok = stab_light<GeomD>(g, root, k, pack, pool, node, st);
+        if (ok == 2) { g_walks++; ok = stab_virtual<GeomD>(g, root, k, pack, pool, &h->big, &h->lock, fl, true, 0xffffffffu, node, &st); }
     } else if (g_use_v2 == 2) ok = stab_virtual<GeomD>(g, root, -1, 0, pool, &h->big, &h->lock, fl, true, 0xffffffffu);
     else ok = stability_check<false, GeomD>(g, root, pool, &h->big, &h->lock, 0, fl) != 0;
     h->flags |= fl;
@@ -178,8 +186,23 @@ int shc_virtual(StabHostC *h, const double t6[6], double density) {
     NodeC root{lx, ly, mh, x, y, z, x * y * z * density};
     EdgePool pool = pool_of(h);  // the read-only check knows snapshots only, in both semantics (like pct_feas_emit_kernel)
     int fl = 0;
-    const int ok = g_use_v2 ? stab_virtual<GeomC>(g, root, -1, 0, pool, &h->big, &h->lock, fl, true, 0xffffffffu)
-                            : (int)(stability_check<false, GeomC>(g, root, pool, &h->big, &h->lock, 0, fl) != 0);
+    int ok;
+    if (g_use_v2 == 3) {  // as the round-2 continuous kernels run it: supports + quick reject (classification), light prefix, continuation
+        int k = 0; uint32_t pack = 0; double r[4], X1 = 0, Y1 = 0, X2 = 0, Y2 = 0;
+        for (int t = 0; t < h->n_box; t++) {
+            if (!g.support(root, t, r)) continue;
+            if (k == 0) { X1 = r[0]; Y1 = r[1]; X2 = r[2]; Y2 = r[3]; }
+            else { X1 = fmin(X1, r[0]); Y1 = fmin(Y1, r[1]); X2 = fmax(X2, r[2]); Y2 = fmax(Y2, r[3]); }
+            if (k < 4) pack |= (uint32_t)t << (8 * k);
+            k++;
+        }
+        const double margin = 2e-6 * (1.0 + fmax(h->W, h->L)), cx = lx + x * 0.5, cy = ly + y * 0.5;
+        if (k > 0 && (cx < X1 - margin || cx > X2 + margin || cy < Y1 - margin || cy > Y2 + margin)) { g_far_out++; return 0; }
+        int node = NODE_NEW; Stack4 st{};
+        ok = stab_light<GeomC>(g, root, k, pack, pool, node, st);
+        if (ok == 2) { g_walks++; ok = stab_virtual<GeomC>(g, root, k, pack, pool, &h->big, &h->lock, fl, true, 0xffffffffu, node, &st); }
+    } else ok = g_use_v2 ? stab_virtual<GeomC>(g, root, -1, 0, pool, &h->big, &h->lock, fl, true, 0xffffffffu)
+                         : (int)(stability_check<false, GeomC>(g, root, pool, &h->big, &h->lock, 0, fl) != 0);
     h->flags |= fl;
     return ok;
 }

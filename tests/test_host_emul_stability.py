@@ -113,9 +113,9 @@ def _drive(L, env, setting, container, nb, nl, seed, env_id, steps, alias=True):
     return n_virtual, n_real
 
 
-# routine: 0 = stability_check<false> (K1's twin, heuristics), 1 = stab_virtual with the supports of the fused resting-height scan (what
-# pct_feas_emit_kernel runs since round 2), 2 = stab_virtual scanning the supports itself (continuous kernels)
-@pytest.mark.parametrize("routine", [0, 1, 2], ids=["stability_check", "stab_virtual_fused", "stab_virtual_scan"])
+# routine: 0 = stability_check<false> (K1's twin, heuristics, round 1's block kernel), 1 = stab_virtual with the supports of the fused
+# resting-height scan, 2 = stab_virtual scanning the supports itself, 3 = stab_light + stab_virtual continuation (what the round-2 walk kernels run)
+@pytest.mark.parametrize("routine", [0, 1, 2, 3], ids=["stability_check", "stab_virtual_fused", "stab_virtual_scan", "light_then_continuation"])
 @pytest.mark.parametrize("setting", [1, 3, 2])
 def test_device_stability_source_follows_the_oracle(lib, setting, routine):
     lib.sh_use_v2(routine)
@@ -128,7 +128,7 @@ def test_device_stability_source_follows_the_oracle(lib, setting, routine):
     assert tot > 20000
 
 
-@pytest.mark.parametrize("routine", [0, 1], ids=["stability_check", "stab_virtual_fused"])
+@pytest.mark.parametrize("routine", [0, 1, 3], ids=["stability_check", "stab_virtual_fused", "light_then_continuation"])
 @pytest.mark.parametrize("name", ["big_s1", "dense16_s1", "flat_s1", "holders_s1"])
 def test_device_stability_source_on_other_configurations(lib, name, routine):
     lib.sh_use_v2(routine)
@@ -224,7 +224,7 @@ def _drive_c(L, env, setting, container, seed, env_id, steps, alias=True):
     return n_virtual
 
 
-@pytest.mark.parametrize("routine", [0, 2], ids=["stability_check", "stab_virtual_scan"])
+@pytest.mark.parametrize("routine", [0, 2, 3], ids=["stability_check", "stab_virtual_scan", "classify_light_continuation"])
 @pytest.mark.parametrize("setting", [1, 3, 2])
 def test_device_stability_source_follows_the_continuous_oracle(lib, setting, routine):
     from pct_oracle import OracleContinuous, make_continuous_stream

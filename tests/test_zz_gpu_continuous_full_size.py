@@ -3,8 +3,7 @@ item generator) stepped with the synthetic policy — every one of the final flo
 reward sums must equal the threaded CPU oracle's (oracle/pct_oracle_batch_continuous.c).  Trajectories are chaotic, so equality of
 the final state certifies every intermediate step.  Settings 1 (stability) and 2 (six orientations).
 
-HARDWARE STATUS: written after round 1's GPU budget was spent — not yet run on a B200 (the small lock-step tests of the same path,
-tests/test_gpu_continuous_parity.py, pass on hardware).  Sorted behind every hardware-verified file.
+Green on a B200 (driver GPUTEST_r01 and round 2).
 """
 import numpy as np
 import pytest

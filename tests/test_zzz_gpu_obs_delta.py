@@ -1,10 +1,9 @@
-"""GPU: the opt-in delta observation writes of the discrete feasibility kernel (PCT_B200_OBS_DELTA=1: when the caller hands back the
+"""GPU: the delta observation writes (default since round 2) of the discrete feasibility kernel (PCT_B200_OBS_DELTA, default 1: when the caller hands back the
 same observation buffer, only the rows that can differ from its contents are written) must leave exactly the observation the default
 path writes — on the library-owned buffer, with alternating caller buffers (every switch falls back to a full write), inside a captured
 CUDA graph, and through the zero-copy host path.
 
-HARDWARE STATUS: written after round 1's GPU budget was spent — not yet run on a B200 (the default kernels' SASS is byte-identical to the
-hardware-verified build: scratch/sass_diff.sh).  Sorted behind every hardware-verified file.
+Green on a B200 (driver GPUTEST_r01; round 2: the delta rows are the default, this file also pins the full-rewrite mode).
 """
 import numpy as np
 import pytest
