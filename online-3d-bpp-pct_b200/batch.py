@@ -115,7 +115,10 @@ class PctBatch(object):
 
     def step(self, actions=None, leaf_idx=None, out=None):
         """actions: (N,9) float32/float64 CUDA tensor of leaf rows, or leaf_idx: (N,) int32 CUDA tensor.
-        Returns (obs, reward(N,), done(N,) uint8, info(N,8) int32 raw pct_step_info records) — all on the GPU."""
+        Returns (obs, reward(N,), done(N,) uint8, info(N,8) int32 raw pct_step_info records) — all on the GPU.
+        NOTE: without `out`, the four tensors are the library-owned buffers, rewritten IN PLACE by the next reset / step (zero-copy; and with the
+        delta observation rows, include/pct_b200.h, the observation buffer must not be modified by the caller).  Keep a result across steps with
+        .clone(), or pass your own `out` buffers (e.g. a rollout storage, GraphedRollout); PctVecEnv hands out fresh observation tensors."""
         obs = self._obs if out is None else out
         a_ptr, i_ptr, f64 = None, None, 0
         if actions is not None:
@@ -201,6 +204,18 @@ class PctBatch(object):
                     "pct_step_host")
 
     # -- introspection -------------------------------------------------------------------------------------
+    @staticmethod
+    def check_flags(flags, ignore=0, what="pct_step"):
+        """Raise PctError when any env's step record carries a capacity / hand-over flag (pct_step_info.flags) outside `ignore`: a flagged env's
+        results are not the reference's (which would have raised IndexError / ValueError, or has no such limit).  Used by PctVecEnv,
+        evaluate_batched and run_heuristic; low-level PctBatch.step callers check `decode_info(info)['flags']` themselves."""
+        f = np.asarray(flags).astype(np.int64) & ~int(ignore)
+        if f.any():
+            bad = np.nonzero(f)[0]
+            names = sorted({nm for v in f[bad] for bit, nm in _lib.FLAG_NAMES.items() if v & bit})
+            raise PctError("%s flagged %d env(s) (first: env %d, flags %d = %s) — results of flagged envs are not the reference's"
+                           % (what, len(bad), int(bad[0]), int(f[bad[0]]), "|".join(names)))
+
     @staticmethod
     def decode_info(info_cpu):
         """(N,8) int32 tensor/array of pct_step_info records -> dict of numpy arrays."""

@@ -3,6 +3,7 @@
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
+#include "pct_pyhash.cuh"  // hash_double: _Py_HashDouble, shared with the host build of the tests
 
 namespace pct {
 
@@ -53,31 +54,6 @@ __device__ __forceinline__ uint64_t tuple_hash_n(const uint64_t *lane, int n) {
     if (acc == ~0ull) return 1546275796ull;
     return acc;
 }
-// _Py_HashDouble (Python/pyhash.c) for finite doubles: value mod (2^61 - 1) with sign, -1 -> -2
-__device__ __forceinline__ uint64_t hash_double(double v) {
-    const uint64_t MOD = (1ull << 61) - 1;
-    if (v == 0.0) return 0;
-    int e;
-    double m = frexp(v, &e);
-    int sign = 1;
-    if (m < 0) { sign = -1; m = -m; }
-    uint64_t x = 0;
-    while (m != 0.0) {
-        x = ((x << 28) & MOD) | (x >> (61 - 28));
-        m *= 268435456.0;
-        e -= 28;
-        uint64_t y = (uint64_t)m;
-        m -= (double)y;
-        x += y;
-        if (x >= MOD) x -= MOD;
-    }
-    e = e >= 0 ? e % 61 : 61 - 1 - ((-1 - e) % 61);
-    x = ((x << e) & MOD) | (x >> (61 - e));
-    int64_t r = (int64_t)x * sign;
-    if (r == -1) r = -2;
-    return (uint64_t)r;
-}
-
 // ---- TMA 1-D bulk copies + mbarrier (PTX ISA 8.x; SASS: UBLKCP / SYNCS) ---------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {

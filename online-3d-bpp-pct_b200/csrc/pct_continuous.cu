@@ -153,7 +153,8 @@ __device__ __noinline__ void reset_space_c(CEnv *ev, const CParams &p, int e, in
 }
 
 // GENEMS (C:space.py:441-528): same ballot / scan compaction as the discrete kernel, float64 with rounded intersections
-__device__ __noinline__ int genems_warp_c(CEnv *ev, const int n0, const double loc[6], double lb, int lane, int &flags) {
+constexpr int CE_STAGE = 128;  // intermediate EMS entries staged in shared memory for the inscribed-EMS purge (6 KB per warp)
+__device__ __noinline__ int genems_warp_c(CEnv *ev, const int n0, const double loc[6], double lb, int lane, int &flags, double (*stage)[6]) {
     double (*ems)[6] = ev->ems, (*tmp)[6] = ev->ems_tmp;
     const int nch = (n0 + 31) >> 5;
     const double itn[6] = {-loc[0], -loc[1], -loc[2], loc[3], loc[4], loc[5]};
@@ -213,6 +214,14 @@ __device__ __noinline__ int genems_warp_c(CEnv *ev, const int n0, const double l
     flags = __reduce_or_sync(FULL, flags);
     const int n = off < CE_TMP ? off : CE_TMP;
     __syncwarp();
+    // EliminateInscribedEMS (C:space.py:505-528): the O(n^2) containment test read every candidate container b from the env record in global memory
+    // (ncu r2, profiles/r2_cont_head.txt: 30 % of this kernel's stall samples on that line); the intermediate list is staged in shared memory first
+    // (lists longer than CE_STAGE entries — not seen on the BASELINE streams — keep reading the record).
+    const bool staged = n <= CE_STAGE;
+    if (staged)
+        for (int t = lane; t < n * 6; t += 32) (&stage[0][0])[t] = (&tmp[0][0])[t];
+    __syncwarp();
+    const double (*src)[6] = staged ? stage : tmp;
     int w = 0;
     const int nch2 = (n + 31) >> 5;
 #pragma unroll 1
@@ -222,11 +231,11 @@ __device__ __noinline__ int genems_warp_c(CEnv *ev, const int n0, const double l
         double a[6];
         if (i < n) {
 #pragma unroll
-            for (int t = 0; t < 6; t++) a[t] = tmp[i][t];
+            for (int t = 0; t < 6; t++) a[t] = src[i][t];
             int hit = 0;
 #pragma unroll 2
             for (int j = 0; j < n; j++) {
-                const double *b = tmp[j];
+                const double *b = src[j];
                 hit |= (int)(j != i && a[0] >= b[0] && a[1] >= b[1] && a[2] >= b[2] && a[3] <= b[3] && a[4] <= b[4] && a[5] <= b[5]);
             }
             keep = !hit;
@@ -256,6 +265,7 @@ __global__ void __launch_bounds__(64) pctc_apply_kernel(const CParams p) {
     const int e = blockIdx.x * 2 + warp;
     if (e >= p.n_envs) return;
     __shared__ int lock_s[2];
+    __shared__ double ems_stage[2][CE_STAGE][6];
     int *lock = &lock_s[warp];
     CEnv *ev = p.env + e;
     CHdr &h = ev->h;
@@ -358,7 +368,7 @@ __global__ void __launch_bounds__(64) pctc_apply_kernel(const CParams p) {
             __syncwarp();
             int fl = 0;
             const double loc[6] = {lx, ly, max_h, around6(lx + x), around6(ly + y), around6(max_h + z)};  // C:bin3D.py:191-194
-            const int n_ems = genems_warp_c(ev, n_ems0, loc, p.low_bound, lane, fl);
+            const int n_ems = genems_warp_c(ev, n_ems0, loc, p.low_bound, lane, fl, ems_stage[warp]);
             const double rw = (nb0 * nb1 * nb2) / binvol * 10;
             reward = (float)rw;
             info.counter = n_box0 + 1;
@@ -389,8 +399,20 @@ __global__ void __launch_bounds__(64) pctc_apply_kernel(const CParams p) {
 }
 
 // ================= K2: candidates in CPython-set order (C:space.py:531-568) =================
+// Table slots are 32 bits: candidate code | 16-bit tag (the top bits of the tuple hash — CPython compares the stored hash before the keys, setobject.c).
+// A probe rejects a non-matching slot on the tag alone; the exact 6-double comparison (tuples rebuilt from the two codes) runs only on a tag match,
+// i.e. practically only for true duplicates.  Round 1 rebuilt and compared the tuple of EVERY probed slot and broadcast the six doubles of every
+// inserted key through shuffles (ncu r2, profiles/r2_cont_head.txt: 25 % of this kernel in _Py_HashDouble's frexp loop — now an integer rotation,
+// pct_pyhash.cuh —, 15 % in shuffles).
+__device__ __forceinline__ bool cand_equal(uint16_t a, uint16_t b, const double (*ems)[6], const double nb[3]) {
+    double u[6], v[6];
+    cand_tuple(a, ems, nb, u);
+    cand_tuple(b, ems, nb, v);
+    return u[0] == v[0] && u[1] == v[1] && u[2] == v[2] && u[3] == v[3] && u[4] == v[4] && u[5] == v[5];
+}
+
 __global__ void __launch_bounds__(32) pctc_candidates_kernel(const CParams p) {
-    __shared__ uint16_t tabA[CC_TAB], tabB[512];
+    __shared__ uint32_t tabA[CC_TAB], tabB[512];
     const int lane = threadIdx.x, e = blockIdx.x;
     CEnv *ev = p.env + e;
     int fl = 0;
@@ -402,8 +424,8 @@ __global__ void __launch_bounds__(32) pctc_candidates_kernel(const CParams p) {
     const CHdr &h = ev->h;
     const double nb[3] = {h.next_box[0], h.next_box[1], h.next_box[2]};
     const int R = p.setting == 2 ? 6 : 2, n_ems = h.n_ems;
-    constexpr uint16_t EMPTY = 0xFFFF;
-    uint16_t *tab = tabA;
+    constexpr uint32_t EMPTY = 0xFFFFFFFFu;
+    uint32_t *tab = tabA;
     uint32_t mask = 7;
     int fill = 0;
     if (lane < 8) tab[lane] = EMPTY;
@@ -416,7 +438,6 @@ __global__ void __launch_bounds__(32) pctc_candidates_kernel(const CParams p) {
         bool valid = false;
         uint64_t hash = 0;
         uint16_t code = 0;
-        double t6[6];
         if (r < raw) {
             const int q = r & 3, er = r >> 2, rot = er % R, ei = er / R;
             double sx, sy, sz;
@@ -425,6 +446,7 @@ __global__ void __launch_bounds__(32) pctc_candidates_kernel(const CParams p) {
                 if (m[3] - m[0] + 1e-6 >= sx && m[4] - m[1] + 1e-6 >= sy && m[5] - m[2] + 1e-6 >= sz) {
                     valid = true;
                     code = (uint16_t)((ei << 5) | (rot << 2) | q);
+                    double t6[6];
                     cand_tuple(code, ev->ems, nb, t6);
                     hash = cand_hash_c(t6);
                 }
@@ -432,17 +454,16 @@ __global__ void __launch_bounds__(32) pctc_candidates_kernel(const CParams p) {
         }
         // already present? (read-only probe; present keys sit on their own probe sequence)
         if (valid) {
+            const uint32_t tag = (uint32_t)(hash >> 48);
             uint64_t perturb = hash;
             uint32_t i = (uint32_t)hash & mask;
             bool open = true;
             while (open) {
                 const int probes = (i + 9 <= mask) ? 9 : 0;
                 for (int j = 0; j <= probes; j++) {
-                    const uint16_t s = tab[i + j];
+                    const uint32_t s = tab[i + j];
                     if (s == EMPTY) { open = false; break; }
-                    double u[6];
-                    cand_tuple(s, ev->ems, nb, u);
-                    if (u[0] == t6[0] && u[1] == t6[1] && u[2] == t6[2] && u[3] == t6[3] && u[4] == t6[4] && u[5] == t6[5]) { open = false; valid = false; break; }
+                    if ((s >> 16) == tag && cand_equal((uint16_t)s, code, ev->ems, nb)) { open = false; valid = false; break; }
                 }
                 perturb >>= 5;
                 i = (uint32_t)((uint64_t)i * 5 + 1 + perturb) & mask;
@@ -455,9 +476,7 @@ __global__ void __launch_bounds__(32) pctc_candidates_kernel(const CParams p) {
             vm &= vm - 1;
             const uint64_t hk = __shfl_sync(FULL, hash, k);
             const uint16_t ck = (uint16_t)__shfl_sync(FULL, (int)code, k);
-            double tk[6];
-#pragma unroll
-            for (int t = 0; t < 6; t++) tk[t] = __shfl_sync(FULL, t6[t], k);
+            const uint32_t tagk = (uint32_t)(hk >> 48);
             // set_add_entry, uniform across the warp (earlier lanes of this chunk may have inserted the same tuple)
             uint64_t perturb = hk;
             uint32_t i = (uint32_t)hk & mask;
@@ -467,11 +486,9 @@ __global__ void __launch_bounds__(32) pctc_candidates_kernel(const CParams p) {
                 const int probes = (i + 9 <= mask) ? 9 : 0;
 #pragma unroll 1
                 for (int j = 0; j <= probes; j++) {
-                    const uint16_t s = tab[i + j];
-                    if (s == EMPTY) { __syncwarp(); if (lane == 0) tab[i + j] = ck; state = 1; break; }  // every lane has read the slot before lane 0 fills it
-                    double u[6];
-                    cand_tuple(s, ev->ems, nb, u);
-                    if (u[0] == tk[0] && u[1] == tk[1] && u[2] == tk[2] && u[3] == tk[3] && u[4] == tk[4] && u[5] == tk[5]) { state = 2; break; }
+                    const uint32_t s = tab[i + j];
+                    if (s == EMPTY) { __syncwarp(); if (lane == 0) tab[i + j] = (tagk << 16) | ck; state = 1; break; }  // every lane has read the slot before lane 0 fills it
+                    if ((s >> 16) == tagk && cand_equal((uint16_t)s, ck, ev->ems, nb)) { state = 2; break; }
                 }
                 perturb >>= 5;
                 i = (uint32_t)((uint64_t)i * 5 + 1 + perturb) & mask;
@@ -481,22 +498,22 @@ __global__ void __launch_bounds__(32) pctc_candidates_kernel(const CParams p) {
                 uint32_t newsize = 8;
                 while (newsize <= (uint32_t)fill * 4) newsize <<= 1;
                 if (newsize > CC_TAB) { fl |= PCT_FLAG_CAND_OVERFLOW; stop = true; break; }
-                uint16_t *nt = (tab == tabA) ? tabB : tabA;
+                uint32_t *nt = (tab == tabA) ? tabB : tabA;
                 for (uint32_t t = lane; t < newsize; t += 32) nt[t] = EMPTY;
                 __syncwarp();
 #pragma unroll 1
                 for (uint32_t b2 = 0; b2 <= mask; b2 += 32) {
                     const uint32_t s = b2 + lane;
-                    const uint16_t c2 = s <= mask ? tab[s] : EMPTY;
+                    const uint32_t c2 = s <= mask ? tab[s] : EMPTY;
                     uint64_t eh = 0;
-                    if (c2 != EMPTY) { double u[6]; cand_tuple(c2, ev->ems, nb, u); eh = cand_hash_c(u); }
+                    if (c2 != EMPTY) { double u[6]; cand_tuple((uint16_t)c2, ev->ems, nb, u); eh = cand_hash_c(u); }
                     uint32_t em = __ballot_sync(FULL, c2 != EMPTY);
 #pragma unroll 1
                     while (em) {
                         const int kk = __ffs(em) - 1;
                         em &= em - 1;
                         const uint64_t hh = __shfl_sync(FULL, eh, kk);
-                        const uint16_t cc = (uint16_t)__shfl_sync(FULL, (int)c2, kk);
+                        const uint32_t cc = __shfl_sync(FULL, c2, kk);
                         uint64_t pt = hh;
                         uint32_t ii = (uint32_t)hh & (newsize - 1);
                         bool placed = false;
@@ -521,9 +538,9 @@ __global__ void __launch_bounds__(32) pctc_candidates_kernel(const CParams p) {
 #pragma unroll 1
     for (uint32_t b2 = 0; b2 <= mask; b2 += 32) {
         const uint32_t s = b2 + lane;
-        const uint16_t c2 = s <= mask ? tab[s] : EMPTY;
+        const uint32_t c2 = s <= mask ? tab[s] : EMPTY;
         const uint32_t em = __ballot_sync(FULL, c2 != EMPTY);
-        if (c2 != EMPTY) ev->cand[cnt + __popc(em & ((1u << lane) - 1))] = c2;
+        if (c2 != EMPTY) ev->cand[cnt + __popc(em & ((1u << lane) - 1))] = (uint16_t)c2;
         cnt += __popc(em);
     }
     __syncwarp();

@@ -110,7 +110,9 @@ def evaluate_batched(data, setting, policy=None, container_size=(10, 10, 10), it
         who = np.nonzero(done_h & (played < quota))[0]
         if len(who) == 0:
             continue
-        counter = info[:, 0].cpu().numpy()
+        info_h = info.cpu().numpy()
+        counter = info_h[:, 0]
+        PctBatch.check_flags(info_h[who, 1], what="evaluate_batched")  # a flagged episode would not be the reference's: never silent
         rows = prev[torch.from_numpy(who).to(prev.device)].cpu().numpy().reshape(len(who), nb, 9)
         for k, e in enumerate(who):
             ep = int(e + played[e] * n)

@@ -76,6 +76,9 @@ def run_heuristic(name, setting, episodes, container_size=(10, 10, 10), item_set
         if len(who) == 0:
             continue
         rec = PctBatch.decode_info(info)
+        # "no feasible placement" is delivered as a row no item matches (PCT_FLAG_BAD_ACTION, include/pct_b200.h) and ends the episode like the
+        # reference's `done = True` without stepping: expected here; every other flag means the episode is not the reference's
+        PctBatch.check_flags(rec["flags"][who], ignore=2, what="run_heuristic")
         boxes = prev[torch.from_numpy(who).to(prev.device)].cpu().numpy().reshape(len(who), nb, 9) if prev is not None else None
         for k, e in enumerate(who):
             ep = int(e + played[e] * n)

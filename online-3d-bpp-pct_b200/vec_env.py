@@ -150,13 +150,8 @@ class PctVecEnv(object):
         rec_raw = hb[4 * n:36 * n].view(np.int32).reshape(n, 8).copy()
         done_h = hb[36 * n:].astype(bool)
         rec = PctBatch.decode_info(rec_raw)
-        if self.raise_on_flags and rec["flags"].any():
-            from . import _lib
-            from .batch import PctError
-            bad = np.nonzero(rec["flags"])[0]
-            names = sorted({nm for f in rec["flags"][bad] for bit, nm in _lib.FLAG_NAMES.items() if f & bit})
-            raise PctError("pct_step flagged %d env(s) (first: env %d, flags %d = %s) — results of flagged envs are not the reference's"
-                           % (len(bad), int(bad[0]), int(rec["flags"][bad[0]]), "|".join(names)))
+        if self.raise_on_flags:
+            PctBatch.check_flags(rec["flags"], what="PctVecEnv.step")
         infos = LazyInfos(rec, done_h, round(time.time() - self._tstart, 6))
         return obs, reward, done_h, infos
 

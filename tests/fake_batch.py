@@ -123,6 +123,11 @@ class FakeBatch(object):
         return dict(n_boxes=n, boxes=boxes, ems=np.asarray(e.ems(), dtype=np.float64), next_box=list(nb), next_den=e.next_den, flags=0)
 
     @staticmethod
+    def check_flags(flags, ignore=0, what="pct_step"):
+        from pct_b200.batch import PctBatch
+        return PctBatch.check_flags(flags, ignore=ignore, what=what)
+
+    @staticmethod
     def decode_info(info_cpu):
         a = info_cpu.cpu().numpy() if hasattr(info_cpu, "cpu") else np.asarray(info_cpu)
         f = a.view(np.float32)

@@ -25,6 +25,7 @@ static int g_use_v2 = 0;  // sh_use_v2: route the virtual checks through stab_vi
 #define __noinline__ __attribute__((noinline))
 #endif
 #include "pct_stability.cuh"
+#include "pct_pyhash.cuh"
 #include "pct_geom.cuh"
 #include "pct_geom_continuous.cuh"
 
@@ -99,7 +100,8 @@ int sh_virtual(StabHost *h, int x, int y, int z, int lx, int ly, double density,
     return ok;
 }
 void sh_use_v2(int on) { g_use_v2 = on; }
-double sh_around6(double v) { return around6(v); }  // the device's np.around(v, 6) (fast division by 1e6, pct_geom_continuous.cuh)
+double sh_around6(double v) { return around6(v); }
+long long sh_hash_double(double v, int loop) { return (long long)(loop ? hash_double_loop(v) : hash_double(v)); }  // _Py_HashDouble: integer restatement / frexp loop  // the device's np.around(v, 6) (fast division by 1e6, pct_geom_continuous.cuh)
 void sh_stats(long long *out2) { out2[0] = g_far_out; out2[1] = g_walks; }
 void sh_stats_visits(long long *out32) { memcpy(out32, g_stat, sizeof g_stat); }
 

@@ -31,7 +31,7 @@ def lib():
     inc = _cuda_include()
     if inc is None:
         pytest.skip("CUDA headers not found")
-    deps = [SRC] + [os.path.join(CSRC, f) for f in ("pct_stability.cuh", "pct_geom.cuh", "pct_geom_continuous.cuh", "pct_kernels.h")]
+    deps = [SRC] + [os.path.join(CSRC, f) for f in ("pct_stability.cuh", "pct_geom.cuh", "pct_geom_continuous.cuh", "pct_kernels.h", "pct_pyhash.cuh")]
     if not os.path.exists(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in deps):
         os.makedirs(os.path.dirname(OUT), exist_ok=True)
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-w", "-I" + CSRC,
@@ -286,3 +286,17 @@ def test_fast_around6_equals_the_division(lib):
     want = np.rint(vals * 1e6) / 1e6
     got = np.array([lib.sh_around6(float(v)) for v in vals])
     assert np.array_equal(got.view(np.uint64), want.view(np.uint64))
+
+
+def test_integer_hash_double_equals_cpython(lib):
+    """hash_double (csrc/pct_pyhash.cuh: _Py_HashDouble as a 61-bit rotation of the integer mantissa) against Python's own hash() of the float — the
+    value CPython feeds into the tuple hash that orders the continuous candidate set (C:space.py:563-567) — and against the frexp-loop restatement."""
+    lib.sh_hash_double.restype = C.c_longlong
+    lib.sh_hash_double.argtypes = [C.c_double, C.c_int]
+    rng = np.random.default_rng(3)
+    vals = np.concatenate([rng.uniform(-3, 3, 40000), np.round(rng.uniform(0, 1, 40000), 3), np.round(rng.uniform(0, 2.5, 20000), 6),
+                           rng.integers(-10**6, 10**6, 5000).astype(np.float64), 2.0 ** rng.integers(-60, 60, 2000), rng.uniform(-1e12, 1e12, 5000),
+                           [0.0, -0.0, 1.0, -1.0, 0.5, 0.1, 0.30000000000000004, 1e-300, 5e-324, 2.0 ** 61, 2.0 ** 61 - 1, float(2 ** 61 - 1) * 3, 1e308]])
+    for v in vals:
+        v = float(v)
+        assert lib.sh_hash_double(v, 0) == hash(v) == lib.sh_hash_double(v, 1), v
