@@ -404,15 +404,16 @@ def run_ours(a):
         t0 = time.perf_counter()
         for t in range(Kv):
             _, _, d_, infos = venv.step(venv.batch.random_policy(POLICY_SEED, 20 + t))
-            for i in np.nonzero(d_)[0]:  # what train_tools.py:72-79 reads: the finished envs' episode records
-                n_done += 1 if "ratio" in infos[i] else 0
+            if t % 5 == 4:  # train_tools.py:63-79: after every num_steps (= 5, tools.py) steps the trainer reads the LAST step's infos of the finished envs
+                for i in np.nonzero(d_)[0]:
+                    n_done += 1 if "ratio" in infos[i] else 0
         torch.cuda.synchronize()
         tv = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
         if cx.dist is not None:
             cx.dist.all_reduce(tv, op=cx.dist.ReduceOp.MAX)
         vec = {"value": world * n * Kv / float(tv[0]), "unit": "env-steps/s", "steps": Kv, "episodes_read": n_done,
                "path": "PctVecEnv.step(leaf indices on the device): device observation (fresh tensor per step), reward / done / lazy infos on the "
-                       "host, finished envs' info dicts materialised; wall clock"}
+                       "host, finished envs' info dicts materialised after every 5th step like the trainer's n-step loop (train_tools.py:63-79); wall clock"}
         venv.close()
     except Exception as ex:  # never fail the headline on the convenience surface
         vec = {"value": None, "error": repr(ex)}

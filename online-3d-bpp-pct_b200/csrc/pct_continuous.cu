@@ -45,7 +45,7 @@ struct alignas(16) CEnv {
     uint16_t cand[1232];
     BigScratch big;
     uint32_t fbits[FBITS_WORDS];  // feasibility bits of the current observation's candidates (classification at the end of K2, pooled walks, emit kernel)
-    int32_t n_fw, lock, pad_[2];
+    int32_t n_fw, lock, n_pending, pad_;  // n_pending: stability walks still running (classification sets, walk kernels decrement, emit kernel polls)
 };
 
 // one pooled stability walk of the continuous domain (cf. WalkItem): the candidate's tuple is rebuilt from `code` (cand_tuple)
@@ -563,7 +563,7 @@ __global__ void __launch_bounds__(32) pctc_candidates_kernel(const CParams p) {
         __syncwarp();
         const uint32_t lt = (1u << lane) - 1;
         const double margin = 2e-6 * (1.0 + fmax(p.W, p.L));  // the support polygon lies inside the contact rectangles' bounding box up to the 1e-6 * y perturbation
-        int pos = 0, nf = 0;
+        int pos = 0, nf = 0, n_walk = 0;
 #pragma unroll 1
         while (pos < cnt && nf < nl) {
             const int c = pos + lane;
@@ -606,6 +606,7 @@ __global__ void __launch_bounds__(32) pctc_candidates_kernel(const CParams p) {
             const uint32_t fm = __ballot_sync(FULL, feas), pm = __ballot_sync(FULL, pend);
             if (lane == 0) ev->fbits[pos >> 5] = fm;
             nf += __popc(fm);
+            n_walk += __popc(pm);
             if (pm) {
                 int qb = 0;
                 if (lane == 0) qb = atomicAdd(p.walk_ctr, __popc(pm));
@@ -614,7 +615,7 @@ __global__ void __launch_bounds__(32) pctc_candidates_kernel(const CParams p) {
             }
             pos += 32;
         }
-        if (lane == 0) ev->n_fw = pos >> 5;
+        if (lane == 0) { ev->n_fw = pos >> 5; ev->n_pending = n_walk; }
     }
     if (lane == 0) {
         ev->h.n_cand = cnt;
@@ -661,6 +662,7 @@ __global__ void __launch_bounds__(128, 4) pctc_walk_light_kernel(const CParams p
         Stack4 st{};
         if (has) res = stab_light<GeomC>(v.g, v.root, it.k, it.pack, v.pool, node, st);
         if (res == 1) atomicOr(&v.ev->fbits[it.c >> 5], 1u << (it.c & 31));
+        if (has && res != 2) { __threadfence(); atomicSub(&v.ev->n_pending, 1); }
         const uint32_t pm = __ballot_sync(FULL, res == 2);
         if (pm) {
             int qb = 0;
@@ -669,7 +671,7 @@ __global__ void __launch_bounds__(128, 4) pctc_walk_light_kernel(const CParams p
             if (res == 2) {
                 const int slot = qb + __popc(pm & ((1u << lane) - 1));
                 if (slot < cap) p.contq[slot] = WalkCont{(uint32_t)i, (uint32_t)node, st};
-                else atomicOr(&v.ev->h.flags, PCT_FLAG_CAND_OVERFLOW);
+                else { atomicOr(&v.ev->h.flags, PCT_FLAG_CAND_OVERFLOW); __threadfence(); atomicSub(&v.ev->n_pending, 1); }
             }
         }
     }
@@ -678,6 +680,8 @@ __global__ void __launch_bounds__(128, 4) pctc_walk_light_kernel(const CParams p
 __global__ void __launch_bounds__(64, 8) pctc_walk_kernel(const CParams p) {
     const int lane = threadIdx.x & 31;
     const int total = min(*(volatile const int32_t *)p.cont_ctr, p.n_envs * WALK_CONT_PER_ENV);
+    __syncthreads();
+    pdl_launch_dependents();  // the emit kernel may follow: its blocks wait for their env's last walk (CEnv::n_pending)
     const int nwarps = gridDim.x * 2, L = p.walk_lanes;
     const unsigned mask = L >= 32 ? FULL : ((1u << L) - 1u);
     if (lane >= L) return;
@@ -693,6 +697,7 @@ __global__ void __launch_bounds__(64, 8) pctc_walk_kernel(const CParams p) {
         const bool ok = stab_virtual<GeomC>(v.g, v.root, it.k, it.pack, v.pool, &v.ev->big, &v.ev->lock, fl, has, mask, has ? (int)ct.node : NODE_NEW, &ct.st) != 0;
         if (has && ok) atomicOr(&v.ev->fbits[it.c >> 5], 1u << (it.c & 31));
         if (has && fl) atomicOr(&v.ev->h.flags, fl);
+        if (has) { __threadfence(); atomicSub(&v.ev->n_pending, 1); }
     }
 }
 
@@ -707,7 +712,16 @@ __global__ void __launch_bounds__(64) pctc_emit_kernel(const CParams p) {
     CEnv *ev = p.env + e;
     const CHdr &h = ev->h;
     const double nb[3] = {h.next_box[0], h.next_box[1], h.next_box[2]};
-    if (e == 0 && tid == 0) { *p.walk_ctr = 0; *p.cont_ctr = 0; }  // both walk kernels have completed (stream order): empty the pools for the next step
+    if (e == 0 && tid == 0) { *p.walk_ctr = 0; *p.cont_ctr = 0; }  // every walk-kernel block has read them (programmatic dependency): empty the pools for the next step
+    if (tid == 0) {  // may run while this env's walks are still in flight (programmatic dependent of the continuation kernel)
+        int spins = 0;
+        while (*(volatile const int32_t *)&ev->n_pending > 0) {
+            __nanosleep(spins < 16 ? 100 : 1000);
+            if (++spins > (1 << 22)) { atomicOr(&ev->h.flags, PCT_FLAG_SYNC_TIMEOUT); break; }
+        }
+        __threadfence();
+    }
+    __syncthreads();
     if (tid < 32) {
         const int nl = p.nl, nw = ev->n_fw;
         const uint32_t lt = (1u << lane) - 1;
@@ -928,10 +942,18 @@ int continuous_launch(pct_env_batch *h, int mode, const void *actions, int actio
         if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
         if (stab) {
             pctc_walk_light_kernel<<<n_sm * 4, 128, 0, st>>>(p);
-            pctc_walk_kernel<<<n_sm * 8 * (p.walk_lanes <= 4 ? 4 : p.walk_lanes <= 16 ? 2 : 1), 64, 0, st>>>(p);
+            pctc_walk_kernel<<<n_sm * 8, 64, 0, st>>>(p);  // one resident wave
         }
-        if (p.obs_f64) pctc_emit_kernel<double><<<p.n_envs, 64, 0, st>>>(p);
-        else pctc_emit_kernel<float><<<p.n_envs, 64, 0, st>>>(p);
+        {
+            cudaLaunchAttribute at2[1];
+            at2[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at2[0].val.programmaticStreamSerializationAllowed = 1;
+            cudaLaunchConfig_t c2{};
+            c2.stream = st; c2.attrs = at2; c2.numAttrs = (stab && cap == cudaStreamCaptureStatusNone) ? 1 : 0;
+            c2.gridDim = dim3(p.n_envs); c2.blockDim = dim3(64);
+            if (p.obs_f64) cudaLaunchKernelEx(&c2, pctc_emit_kernel<double>, p);
+            else cudaLaunchKernelEx(&c2, pctc_emit_kernel<float>, p);
+        }
         cudaError_t e2 = cudaGetLastError();
         if (e2 != cudaSuccess) { h->err = std::string("continuous launch: ") + cudaGetErrorString(e2); return PCT_ERR_CUDA; }
         h->launches += stab ? 4 : 2;  // apply, candidates, [light, walk], emit; the caller counts one

@@ -985,7 +985,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) pct_candidates_kernel(co
         constexpr bool STAB = !BIGSM;
         const int n_box = h.n_box, nl = p.nl;
         const uint32_t lt = (1u << lane) - 1;
-        int pos = 0, nf = 0;
+        int pos = 0, nf = 0, n_walk = 0;
 #pragma unroll 1
         while (pos < n_cand && nf < nl) {
             const int c = pos + lane;
@@ -1006,6 +1006,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) pct_candidates_kernel(co
             const uint32_t fm = __ballot_sync(FULL, feas), pm = __ballot_sync(FULL, pend);
             if (lane == 0) cold->fbits[pos >> 5] = fm;
             nf += __popc(fm);
+            n_walk += __popc(pm);
             if (pm) {
                 int qb = 0;
                 if (lane == 0) qb = atomicAdd(p.walk_ctr, __popc(pm));
@@ -1020,7 +1021,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) pct_candidates_kernel(co
             }
             pos += 32;
         }
-        if (lane == 0) cold->n_fw = pos >> 5;
+        if (lane == 0) { cold->n_fw = pos >> 5; cold->n_pending = n_walk; }
     }
     if (lane == 0) {
         ghot->h.n_cand = n_cand;
@@ -1190,6 +1191,12 @@ __global__ void __launch_bounds__(FEAS_THREADS, K3_MINB) pct_feas_emit_kernel(co
 #endif
 constexpr int WALK_WARPS = 2, LIGHT_WARPS = 4;
 
+// a walk of this env has delivered its verdict (fbits / flags written before): release-decrement the env's counter of running walks
+__device__ __forceinline__ void walk_done(int32_t *n_pending) {
+    __threadfence();
+    atomicSub(n_pending, 1);
+}
+
 // per-lane view of one pooled walk: the env's record stays in global memory (L1 / L2) — the lanes of a warp belong to different envs
 struct WalkView {
     GeomD g;
@@ -1228,6 +1235,7 @@ __global__ void __launch_bounds__(32 * LIGHT_WARPS, LIGHT_MINB) pct_walk_light_k
         Stack4 st{};
         if (has) res = stab_light<GeomD>(v.g, v.root, (int)it.k, it.pack, v.pool, node, st);
         if (res == 1) atomicOr(&v.cold->fbits[it.c >> 5], 1u << (it.c & 31));
+        if (has && res != 2) walk_done(&v.cold->n_pending);
         const uint32_t pm = __ballot_sync(FULL, res == 2);
         if (pm) {
             int qb = 0;
@@ -1236,7 +1244,7 @@ __global__ void __launch_bounds__(32 * LIGHT_WARPS, LIGHT_MINB) pct_walk_light_k
             if (res == 2) {
                 const int slot = qb + __popc(pm & ((1u << lane) - 1));
                 if (slot < cap) p.contq[slot] = WalkCont{(uint32_t)i, (uint32_t)node, st};
-                else atomicOr(const_cast<int32_t *>(&v.hot->h.flags), PCT_FLAG_CAND_OVERFLOW);  // never silent: the candidate stays infeasible and the env is flagged
+                else { atomicOr(const_cast<int32_t *>(&v.hot->h.flags), PCT_FLAG_CAND_OVERFLOW); walk_done(&v.cold->n_pending); }  // never silent: the candidate stays infeasible and the env is flagged
             }
         }
     }
@@ -1249,6 +1257,8 @@ __global__ void __launch_bounds__(32 * LIGHT_WARPS, LIGHT_MINB) pct_walk_light_k
 __global__ void __launch_bounds__(32 * WALK_WARPS, WALK_MINB) pct_walk_kernel(const DParams p) {
     const int lane = threadIdx.x & 31;
     const int total = min(*(volatile const int32_t *)p.cont_ctr, p.n_envs * WALK_CONT_PER_ENV);
+    __syncthreads();
+    pdl_launch_dependents();  // the emit kernel's blocks may become resident now (it also empties the pool counters: read above); each waits for ITS env's last walk
     const int nwarps = gridDim.x * WALK_WARPS, L = p.walk_lanes;
     const unsigned mask = L >= 32 ? FULL : ((1u << L) - 1u);
     if (lane >= L) return;
@@ -1265,6 +1275,7 @@ __global__ void __launch_bounds__(32 * WALK_WARPS, WALK_MINB) pct_walk_kernel(co
                                             has ? (int)ct.node : NODE_NEW, &ct.st) != 0;
         if (has && ok) atomicOr(&v.cold->fbits[it.c >> 5], 1u << (it.c & 31));
         if (has && fl) atomicOr(const_cast<int32_t *>(&v.hot->h.flags), fl);
+        if (has) walk_done(&v.cold->n_pending);
     }
 }
 
@@ -1293,6 +1304,15 @@ __global__ void __launch_bounds__(32 * EMIT_WARPS) pct_emit_kernel(const DParams
     if (lane == 0) {
         mbar_init(mbar, 1);
         fence_proxy_async();
+        // launched as a programmatic dependent of the continuation kernel: this block may run while walks are still in flight.  The classification
+        // (a fully completed kernel) set n_pending; the walk kernels release-decrement it after their last write of this env.
+        int spins = 0;
+        while (*(volatile const int32_t *)&cold->n_pending > 0) {
+            __nanosleep(spins < 16 ? 100 : 1000);
+            if (++spins > (1 << 22)) { atomicOr(&ghot->h.flags, PCT_FLAG_SYNC_TIMEOUT); break; }
+        }
+        __threadfence();
+        fence_proxy_async_all();
     }
     __syncwarp();
     if (lane == 0) {
@@ -1449,11 +1469,19 @@ static cudaError_t launch_t(const DParams &p_in, cudaStream_t st, cudaEvent_t *p
         if (p.ready && prof) cudaEventRecord(prof[2], st);
         if (STAB) {
             pct_walk_light_kernel<<<n_sm * LIGHT_MINB, 32 * LIGHT_WARPS, 0, st>>>(p);
-            pct_walk_kernel<<<n_sm * WALK_MINB * (p.walk_lanes <= 4 ? 4 : p.walk_lanes <= 16 ? 2 : 1), 32 * WALK_WARPS, 0, st>>>(p);
+            pct_walk_kernel<<<n_sm * WALK_MINB, 32 * WALK_WARPS, 0, st>>>(p);  // one resident wave (every block starts at once: the emit kernel may follow)
         }
         const int eb = (p.n_envs + EMIT_WARPS - 1) / EMIT_WARPS;
-        if (p.opt & PCT_OPT_DELTA) pct_emit_kernel<OT, SlotT, true><<<eb, 32 * EMIT_WARPS, 0, st>>>(p);
-        else pct_emit_kernel<OT, SlotT, false><<<eb, 32 * EMIT_WARPS, 0, st>>>(p);
+        {   // programmatic dependent of the continuation kernel (setting 2: of the candidates kernel, whose blocks never trigger early -> plain order)
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at[0].val.programmaticStreamSerializationAllowed = 1;
+            cudaLaunchConfig_t cfg{};
+            cfg.stream = st; cfg.attrs = at; cfg.numAttrs = (STAB && p.ready) ? 1 : 0;
+            cfg.gridDim = dim3(eb); cfg.blockDim = dim3(32 * EMIT_WARPS); cfg.dynamicSmemBytes = 0;
+            err = (p.opt & PCT_OPT_DELTA) ? cudaLaunchKernelEx(&cfg, pct_emit_kernel<OT, SlotT, true>, p) : cudaLaunchKernelEx(&cfg, pct_emit_kernel<OT, SlotT, false>, p);
+            if (err != cudaSuccess) return err;
+        }
     }
     if (p.order) pct_order_kernel<<<1, 1024, 0, st>>>(p.hot, p.n_envs, p.order, 0);
     if (prof) cudaEventRecord(prof[3], st);

@@ -132,7 +132,8 @@ struct alignas(16) DEnvCold {
     uint32_t fbits[FBITS_WORDS];
     int32_t n_fw;             // chunks classified (classification stops once `leaf_node_holder` candidates are known feasible)
     int32_t lock;             // serialises the rare > KSUP_SMALL-support visits of this env on `big` (walk lanes of one env sit in different warps)
-    int32_t pad_[2];
+    int32_t n_pending;        // stability walks of this env still running (set by the classification, decremented by the walk kernels, polled by the emit kernel)
+    int32_t pad_;
 };
 
 // One stability walk (calculated_impact_virtual of one candidate placement) of the step's global pool: produced by the classification at
