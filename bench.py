@@ -276,7 +276,8 @@ def roofline_of(rec, setting, continuous, n, obs_len, delta_obs):
     if km:
         dom = max(km, key=lambda k: km[k])
         ach = groups[dom] * n / (km[dom] * 1e-3) / 1e9
-        names = {"apply": "pct_apply_kernel", "candidates": "pct_candidates_kernel (+ classify)", "feas_emit": "pct_walk_kernel + pct_emit_kernel"}
+        names = {"apply": "pct_apply_kernel", "candidates": "pct_candidates_kernel (+ classify)",
+                 "feas_emit": "pct_walk_light_kernel + pct_walk_kernel + pct_emit_kernel"}
         out.update(achieved=ach, frac=ach / peak, kernel=names[dom], kernel_ms=km[dom], algorithmic_bytes_per_env_kernel=groups[dom],
                    all_kernels_ms=km,
                    all_kernels_frac={k: groups[k] * n / (km[k] * 1e-3) / 1e9 / peak for k in km},
@@ -293,13 +294,14 @@ def roofline_of(rec, setting, continuous, n, obs_len, delta_obs):
                              "note": "SURVEY 8(d): (5593 + 24 N + 48 E) B x env-steps/s of one GPU / peak, whole step"}
     tr = ncu_traffic()
     out["traffic"] = None
-    if tr:
-        key = out["kernel"].split(" ")[0]
-        ent = tr.get("kernels", {}).get(key) or tr.get("kernels", {}).get("pct_walk_kernel")
-        if ent:
-            out["traffic"] = ent.get("dram_bytes_per_launch")
-            out["traffic_source"] = "ncu --set full capture of commit %s (profiles/%s), %s" % (tr.get("commit"), tr.get("file"), ent.get("note", ""))
-        out["traffic_all_kernels"] = tr.get("kernels")
+    if tr and not continuous:
+        ks = [k for k in tr.get("kernels", {}) if k in out["kernel"]]  # the kernels of the dominant group
+        if ks:
+            out["traffic"] = sum(tr["kernels"][k]["dram_bytes_per_launch"] for k in ks)
+            out["traffic_source"] = "dram__bytes_read + write of %s from the ncu --set full captures of %s (profiles/%s; 4096 envs, setting 1, caches flushed per replay)" % (
+                " + ".join(ks), tr.get("commit"), tr.get("file"))
+        out["traffic_all_kernels"] = {k: v["dram_bytes_per_launch"] for k, v in tr.get("kernels", {}).items()}
+        out["traffic_step_total"] = tr.get("step_total_dram_bytes")
     return out
 
 

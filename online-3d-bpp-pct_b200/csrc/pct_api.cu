@@ -97,6 +97,7 @@ int pct_create(const pct_config *cfg, int32_t n_envs, int32_t device, pct_handle
     if (const char *dv = getenv("PCT_B200_OBS_DELTA")) h->obs_delta = atoi(dv) != 0;
     if (const char *av = getenv("PCT_B200_ALIAS")) h->alias_mode = atoi(av) != 0;
     if (const char *kv = getenv("PCT_B200_K3")) h->k3_block = strcmp(kv, "block") == 0;
+    if (const char *ev = getenv("PCT_B200_EMIT_PDL")) h->no_emit_pdl = atoi(ev) == 0;
     if (const char *wv = getenv("PCT_B200_WALK_LANES")) { h->walk_lanes = atoi(wv); if (h->walk_lanes < 1) h->walk_lanes = 1; if (h->walk_lanes > 32) h->walk_lanes = 32; }
     if (cfg->setting == 2) h->alias_mode = false;  // no stability check, no load entries
     if ((h->obs_delta || h->alias_mode) && e == cudaSuccess) {
@@ -245,6 +246,7 @@ static int launch_range(pct_handle h, int mode, int off, int cnt, const void *ac
         p.opt = (h->obs_delta ? PCT_OPT_DELTA : 0) | (h->alias_mode ? PCT_OPT_ALIAS : 0);
     }
     if (h->k3_block) p.opt |= PCT_OPT_K3_BLOCK;
+    if (h->no_emit_pdl) p.opt |= PCT_OPT_NO_EMIT_PDL;
     cudaEvent_t *prof = nullptr;
     if (h->prof_on && mode == 1 && whole_batch) {
         if ((size_t)(h->prof_steps + 1) * 4 > h->prof_ev.size()) {

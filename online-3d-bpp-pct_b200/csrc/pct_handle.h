@@ -34,6 +34,7 @@ struct pct_env_batch {
     // pct_apply_kernel<STAB, ALIAS = true> / pctc_apply_kernel<true, true>.  Default ON since round 2 (green on hardware, oracle default flipped with it);
     // PCT_B200_ALIAS=0 selects the snapshot semantics of round 1 (kept for the sensitivity tests).
     bool alias_mode = true;
+    bool no_emit_pdl = false;     // PCT_B200_EMIT_PDL=0: launch the emit kernel in plain stream order (A/B measurement of the emit / walk-tail overlap)
     bool k3_block = false;        // PCT_B200_K3=block: round 1's block-per-env feasibility kernel instead of the warp-per-env one (A/B measurements)
     pct::DEnvAux *d_aux = nullptr;  // per-env state of the opt-in variants (allocated when one of them is on)
     const void *tracked_obs = nullptr;

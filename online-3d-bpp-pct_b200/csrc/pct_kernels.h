@@ -200,7 +200,7 @@ struct DParams {
     int32_t walk_lanes; // continuations per warp of pct_walk_kernel (1..32)
     int32_t opt;     // opt-in variants served by `aux`: PCT_OPT_DELTA (K3 delta observation writes), PCT_OPT_ALIAS (K1 object semantics of the loads)
 };
-constexpr int PCT_OPT_DELTA = 1, PCT_OPT_ALIAS = 2, PCT_OPT_K3_BLOCK = 4;  // K3_BLOCK: round 1's block-per-env feasibility kernel (A/B)
+constexpr int PCT_OPT_DELTA = 1, PCT_OPT_ALIAS = 2, PCT_OPT_K3_BLOCK = 4, PCT_OPT_NO_EMIT_PDL = 8;  // K3_BLOCK: round 1's block-per-env feasibility kernel (A/B)
 
 // heuristic baselines (pct_heuristics.cuh)
 struct HParams {

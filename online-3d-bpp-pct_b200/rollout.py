@@ -86,7 +86,16 @@ class GraphedRollout(object):
             self._steps()
         else:
             if self.graph is None:
-                # start() already launched every kernel once (first launches set kernel attributes, which cannot be captured)
+                # start() already launched every env kernel once (first launches set kernel attributes, which cannot be captured); a torch policy gets
+                # one eager call on a side stream for the same reason (lazy cuBLAS / cuDNN handle creation and autotuning are not capturable)
+                if self.policy is not None:
+                    side = torch.cuda.Stream(device=self.batch.device)
+                    side.wait_stream(torch.cuda.current_stream(self.batch.device))
+                    with torch.cuda.stream(side):
+                        for _ in range(2):
+                            self.policy(self.obs[0], self.t_dev)
+                    torch.cuda.current_stream(self.batch.device).wait_stream(side)
+                    torch.cuda.synchronize(self.batch.device)
                 self.graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(self.graph):
                     self._steps()
