@@ -117,9 +117,15 @@ def _argv(argv):
         sys.argv = old
 
 
-def load_policy_modules(reference_root):
-    """-> (model, tools): the reference's `model` (DRL_GAT) and `tools` modules; attention_model.py gets its one-line accommodation in memory."""
+def load_policy_modules(reference_root, strip_asserts=False):
+    """-> (model, tools): the reference's `model` (DRL_GAT) and `tools` modules; attention_model.py gets its one-line accommodation in memory.
+    strip_asserts: compile attention_model.py like `python -O` does (source text untouched): its forward pass contains
+    `assert not torch.isnan(log_p).any()` (attention_model.py:198), a device -> host synchronisation that a CUDA graph cannot capture — needed by
+    GraphedRollout(use_graph=True) with the real network; the trainer / evaluator paths keep the asserts."""
     enable(reference_root)
+    if strip_asserts and "attention_model" in sys.modules and not getattr(sys.modules["attention_model"], "_pct_b200_optimized", False):
+        for m in ("attention_model", "model"):
+            sys.modules.pop(m, None)
     if "attention_model" not in sys.modules:
         path = os.path.join(reference_root, "attention_model.py")
         src = open(path).read()
@@ -131,7 +137,8 @@ def load_policy_modules(reference_root):
         sys.modules["attention_model"] = mod
         try:
             with _argv([]):
-                exec(compile(src.replace(old, "return tuple.__getitem__(self, key)"), path, "exec"), mod.__dict__)
+                exec(compile(src.replace(old, "return tuple.__getitem__(self, key)"), path, "exec", optimize=1 if strip_asserts else -1), mod.__dict__)
+                mod._pct_b200_optimized = bool(strip_asserts)
         except Exception:
             sys.modules.pop("attention_model", None)
             raise

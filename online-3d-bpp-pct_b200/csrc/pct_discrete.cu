@@ -569,23 +569,26 @@ __device__ __noinline__ void reset_space(DEnvHot *hot, const DParams &p, int e, 
     __syncwarp();
 }
 
-template <typename OT>
+// PART: 0 = the whole observation (round 1's block kernel), 1 = internal-node rows + item row (written by the candidates kernel since round 2: they
+// are final after the apply kernel, and on the zero-copy host path their PCIe traffic then overlaps the walk kernels), 2 = leaf rows (emit kernel).
+template <typename OT, int PART = 0>
 __device__ __noinline__ void write_obs(const DParams &p, int e, const DEnvHot *hot, const DEnvCold *cold, const int16_t (*leaf)[6], int n_leaf,
                                        int tid, int nthreads) {
     OT *obs = (OT *)p.obs + (size_t)e * (size_t)((p.nb + p.nl + 1) * 9);
     const int n_box = hot->h.n_box;
-    const int total = (p.nb + p.nl + 1) * 9;
     int s0 = hot->h.next_box[0], s1 = hot->h.next_box[1], s2 = hot->h.next_box[2];
     if (s1 < s0) { int t = s0; s0 = s1; s1 = t; }
     if (s2 < s1) { int t = s1; s1 = s2; s2 = t; }
     if (s1 < s0) { int t = s0; s0 = s1; s1 = t; }
     const OT den = (OT)hot->h.next_den;
     const bool s3 = p.setting == 3;
-    // flat index f = nthreads*it + tid; (row, col) advance by (nthreads / 9, nthreads % 9) per iteration
-    int row = tid / 9, col = tid - row * 9;
-    const int dr = nthreads / 9, dc = nthreads - dr * 9;
+    const int r_lo = PART == 2 ? p.nb : 0, r_hi = PART == 1 ? p.nb : (PART == 2 ? p.nb + p.nl : p.nb + p.nl + 1);
+    const int f_lo = r_lo * 9, f_hi = r_hi * 9;
 #pragma unroll 4
-    for (int f = tid; f < total; f += nthreads) {
+    for (int f = f_lo + tid; f < f_hi + (PART == 1 ? 9 : 0); f += nthreads) {
+        int row = f / 9;
+        const int col = f - row * 9;
+        if (PART == 1 && row >= p.nb) row = p.nb + p.nl;  // the 9 extra elements of PART 1 are the item row
         OT v = 0;
         if (row < p.nb) {
             if (row < n_box) {
@@ -607,17 +610,15 @@ __device__ __noinline__ void write_obs(const DParams &p, int e, const DEnvHot *h
             else if (col == 5) v = (OT)s2;
             else if (col == 8) v = 1;
         }
-        obs[f] = v;
-        row += dr; col += dc;
-        if (col >= 9) { col -= 9; row++; }
+        obs[row * 9 + col] = v;
     }
 }
 
-// Delta variant (opt-in, PCT_B200_OBS_DELTA=1): the caller hands back the SAME observation buffer every step, and prev[0] / prev[1]
+// Delta variant (default, PCT_B200_OBS_DELTA=0 disables): the caller hands back the SAME observation buffer every step, and prev[0] / prev[1]
 // hold how many internal / leaf rows of it may be non-zero.  75 % of the (NB + NL + 1) x 9 observation is zero padding, so only the
 // rows below max(now, prev) and the next-item row are written (and prev is updated); every other row is zero already.  The written
 // values are the ones write_obs computes.  The host resets prev to {NB, NL} whenever the buffer changes.
-template <typename OT, bool WARP_SCOPE = false>
+template <typename OT, bool WARP_SCOPE = false, int PART = 0>
 __device__ __noinline__ void write_obs_delta(const DParams &p, int e, const DEnvHot *hot, const DEnvCold *cold, const int16_t (*leaf)[6], int n_leaf,
                                              int tid, int nthreads) {
     OT *obs = (OT *)p.obs + (size_t)e * (size_t)((p.nb + p.nl + 1) * 9);
@@ -625,14 +626,15 @@ __device__ __noinline__ void write_obs_delta(const DParams &p, int e, const DEnv
     const int n_box = hot->h.n_box;
     const int pb = min(prev[0], p.nb), pl = min(prev[1], p.nl);
     if constexpr (WARP_SCOPE) __syncwarp(); else __syncthreads();  // every thread of the env has read prev before thread 0 replaces it below
-    const int wb = max(max(n_box, pb), 1), wl = max(n_leaf, pl);  // row 0 always carries its valid flag (D:space.py:294-295)
+    const int wb = PART == 2 ? 0 : max(max(n_box, pb), 1);  // row 0 always carries its valid flag (D:space.py:294-295)
+    const int wl = PART == 1 ? 0 : max(n_leaf, pl);
     int s0 = hot->h.next_box[0], s1 = hot->h.next_box[1], s2 = hot->h.next_box[2];
     if (s1 < s0) { int t = s0; s0 = s1; s1 = t; }
     if (s2 < s1) { int t = s1; s1 = s2; s2 = t; }
     if (s1 < s0) { int t = s0; s0 = s1; s1 = t; }
     const OT den = (OT)hot->h.next_den;
     const bool s3 = p.setting == 3;
-    const int total = (wb + wl + 1) * 9;
+    const int total = (wb + wl + (PART == 2 ? 0 : 1)) * 9;
 #pragma unroll 1
     for (int f = tid; f < total; f += nthreads) {
         const int r = f / 9, col = f - r * 9;
@@ -663,7 +665,10 @@ __device__ __noinline__ void write_obs_delta(const DParams &p, int e, const DEnv
         }
         obs[row * 9 + col] = v;
     }
-    if (tid == 0) { prev[0] = max(n_box, 1); prev[1] = n_leaf; }
+    if (tid == 0) {
+        if (PART != 2) prev[0] = max(n_box, 1);
+        if (PART != 1) prev[1] = n_leaf;
+    }
 }
 
 // ======================================================================================================
@@ -1022,6 +1027,12 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) pct_candidates_kernel(co
             pos += 32;
         }
         if (lane == 0) { cold->n_fw = pos >> 5; cold->n_pending = n_walk; }
+        // cur_observation, part 1 (D:bin3D.py:70-93): internal-node rows + item row are final since the apply kernel
+        if (p.obs) {
+            const bool delta = (p.opt & PCT_OPT_DELTA) != 0;
+            if (p.obs_f64) { if (delta) write_obs_delta<double, true, 1>(p, e, hot, cold, nullptr, 0, lane, 32); else write_obs<double, 1>(p, e, hot, cold, nullptr, 0, lane, 32); }
+            else { if (delta) write_obs_delta<float, true, 1>(p, e, hot, cold, nullptr, 0, lane, 32); else write_obs<float, 1>(p, e, hot, cold, nullptr, 0, lane, 32); }
+        }
     }
     if (lane == 0) {
         ghot->h.n_cand = n_cand;
@@ -1357,8 +1368,8 @@ __global__ void __launch_bounds__(32 * EMIT_WARPS) pct_emit_kernel(const DParams
         }
     }
     // ---------------- cur_observation (D:bin3D.py:70-93) ----------------
-    if constexpr (DELTA) write_obs_delta<OT, true>(p, e, hot, cold, leaf, n_leaf, lane, 32);
-    else write_obs<OT>(p, e, hot, cold, leaf, n_leaf, lane, 32);
+    if constexpr (DELTA) write_obs_delta<OT, true, 2>(p, e, hot, cold, leaf, n_leaf, lane, 32);  // leaf rows: the rest was written by the candidates kernel
+    else write_obs<OT, 2>(p, e, hot, cold, leaf, n_leaf, lane, 32);
 }
 
 // Block scheduling order.  A launch lasts as long as its slowest block, and blocks are dispatched in index order, so the
