@@ -97,6 +97,7 @@ int pct_create(const pct_config *cfg, int32_t n_envs, int32_t device, pct_handle
     if (const char *dv = getenv("PCT_B200_OBS_DELTA")) h->obs_delta = atoi(dv) != 0;
     if (const char *av = getenv("PCT_B200_ALIAS")) h->alias_mode = atoi(av) != 0;
     if (const char *kv = getenv("PCT_B200_K3")) h->k3_block = strcmp(kv, "block") == 0;
+    if (const char *wv = getenv("PCT_B200_WALK_LANES_TALL")) { h->walk_lanes_tall = atoi(wv); if (h->walk_lanes_tall < 1) h->walk_lanes_tall = 1; if (h->walk_lanes_tall > 32) h->walk_lanes_tall = 32; }
     if (const char *ev = getenv("PCT_B200_EMIT_PDL")) h->no_emit_pdl = atoi(ev) == 0;
     if (const char *wv = getenv("PCT_B200_WALK_LANES")) { h->walk_lanes = atoi(wv); if (h->walk_lanes < 1) h->walk_lanes = 1; if (h->walk_lanes > 32) h->walk_lanes = 32; }
     if (cfg->setting == 2) h->alias_mode = false;  // no stability check, no load entries
@@ -130,8 +131,8 @@ int pct_create(const pct_config *cfg, int32_t n_envs, int32_t device, pct_handle
                 if (e == cudaSuccess) e = cudaMalloc(&h->d_walk_ctr, sizeof(int32_t) * (size_t)n_envs);
                 if (e == cudaSuccess) e = cudaMemset(h->d_walk_ctr, 0, sizeof(int32_t) * (size_t)n_envs);
                 if (e == cudaSuccess) e = cudaMalloc(&h->d_contq, sizeof(WalkCont) * (size_t)WALK_CONT_PER_ENV * (size_t)n_envs);
-                if (e == cudaSuccess) e = cudaMalloc(&h->d_cont_ctr, sizeof(int32_t) * (size_t)n_envs);
-                if (e == cudaSuccess) e = cudaMemset(h->d_cont_ctr, 0, sizeof(int32_t) * (size_t)n_envs);
+                if (e == cudaSuccess) e = cudaMalloc(&h->d_cont_ctr, sizeof(int32_t) * ((size_t)n_envs + 1));
+                if (e == cudaSuccess) e = cudaMemset(h->d_cont_ctr, 0, sizeof(int32_t) * ((size_t)n_envs + 1));
             }
             if (e == cudaSuccess) e = cudaMalloc(&h->d_order, sizeof(int32_t) * 2 * (size_t)n_envs);
             if (e == cudaSuccess) {
@@ -261,7 +262,7 @@ static int launch_range(pct_handle h, int mode, int off, int cnt, const void *ac
     p.walk_ctr = h->d_walk_ctr ? h->d_walk_ctr + off : nullptr;
     p.contq = h->d_contq ? h->d_contq + (size_t)off * WALK_CONT_PER_ENV : nullptr;
     p.cont_ctr = h->d_cont_ctr ? h->d_cont_ctr + off : nullptr;
-    p.walk_lanes = h->walk_lanes;
+    p.walk_lanes = h->walk_lanes; p.walk_lanes_tall = h->walk_lanes_tall;
     CK(h, launch_discrete(p, gs, prof));
     h->launches += discrete_kernels_per_step(p);
     return PCT_OK;

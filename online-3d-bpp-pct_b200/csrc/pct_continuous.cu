@@ -86,7 +86,7 @@ struct CParams {
     int32_t *walk_ctr;
     WalkCont *contq;
     int32_t *cont_ctr;
-    int32_t walk_lanes;
+    int32_t walk_lanes, walk_lanes_tall;
     DEnvAux *aux;    // per-env state of the ALIAS apply kernel (EdgePoolA arrays), nullptr with PCT_B200_ALIAS=0 / setting 2
 };
 
@@ -690,14 +690,20 @@ __global__ void __launch_bounds__(128, 4) pctc_walk_light_kernel(const CParams p
         if (has) res = stab_light<GeomC>(v.g, v.root, it.k, it.pack, v.pool, node, st);
         if (res == 1) atomicOr(&v.ev->fbits[it.c >> 5], 1u << (it.c & 31));
         if (has && res != 2) { __threadfence(); atomicSub(&v.ev->n_pending, 1); }
-        const uint32_t pm = __ballot_sync(FULL, res == 2);
-        if (pm) {
-            int qb = 0;
-            if (lane == 0) qb = atomicAdd(p.cont_ctr, __popc(pm));
-            qb = __shfl_sync(FULL, qb, 0);
+        const bool tall = it.mh >= 0.6 * p.H;  // the longest chains: pooled from the end, fewer lanes per warp (see pct_discrete.cu)
+        const uint32_t ps = __ballot_sync(FULL, res == 2 && !tall), pt = __ballot_sync(FULL, res == 2 && tall);
+        if (ps | pt) {
+            int qs = 0, qt = 0;
+            if (lane == 0) {
+                if (ps) qs = atomicAdd(p.cont_ctr, __popc(ps));
+                if (pt) qt = atomicAdd(p.cont_ctr + 1, __popc(pt));
+            }
+            qs = __shfl_sync(FULL, qs, 0);
+            qt = __shfl_sync(FULL, qt, 0);
             if (res == 2) {
-                const int slot = qb + __popc(pm & ((1u << lane) - 1));
-                if (slot < cap) p.contq[slot] = WalkCont{(uint32_t)i, (uint32_t)node, st};
+                const uint32_t lt = (1u << lane) - 1;
+                const int idx = tall ? qt + __popc(pt & lt) : qs + __popc(ps & lt);
+                if (idx < cap / 2) p.contq[tall ? cap - 1 - idx : idx] = WalkCont{(uint32_t)i, (uint32_t)node, st};
                 else { atomicOr(&v.ev->h.flags, PCT_FLAG_CAND_OVERFLOW); __threadfence(); atomicSub(&v.ev->n_pending, 1); }
             }
         }
@@ -706,19 +712,23 @@ __global__ void __launch_bounds__(128, 4) pctc_walk_light_kernel(const CParams p
 
 __global__ void __launch_bounds__(64, 8) pctc_walk_kernel(const CParams p) {
     const int lane = threadIdx.x & 31;
-    const int total = min(*(volatile const int32_t *)p.cont_ctr, p.n_envs * WALK_CONT_PER_ENV);
+    const int cap = p.n_envs * WALK_CONT_PER_ENV;
+    const int n_short = min(*(volatile const int32_t *)p.cont_ctr, cap / 2), n_tall = min(*(volatile const int32_t *)(p.cont_ctr + 1), cap / 2);
     __syncthreads();
     pdl_launch_dependents();  // the emit kernel may follow: its blocks wait for their env's last walk (CEnv::n_pending)
-    const int nwarps = gridDim.x * 2, L = p.walk_lanes;
-    const unsigned mask = L >= 32 ? FULL : ((1u << L) - 1u);
-    if (lane >= L) return;
+    const int nwarps = gridDim.x * 2, Ls = p.walk_lanes, Lt = p.walk_lanes_tall;
+    const int w_tall = (n_tall + Lt - 1) / Lt, w_all = w_tall + (n_short + Ls - 1) / Ls;
 #pragma unroll 1
-    for (int base = (blockIdx.x * 2 + (threadIdx.x >> 5)) * L; base < total; base += nwarps * L) {
-        const int i = base + lane;
-        const bool has = i < total;
+    for (int w = blockIdx.x * 2 + (threadIdx.x >> 5); w < w_all; w += nwarps) {
+        const bool tw = w < w_tall;
+        const int L = tw ? Lt : Ls;
+        const unsigned mask = L >= 32 ? FULL : ((1u << L) - 1u);
+        if (lane >= L) continue;
+        const int i = tw ? w * Lt + lane : (w - w_tall) * Ls + lane;
+        const bool has = i < (tw ? n_tall : n_short);
         WalkCont ct{};
         WalkItemC it{};
-        if (has) { ct = p.contq[i]; it = p.walkq[ct.item]; }
+        if (has) { ct = p.contq[tw ? cap - 1 - i : i]; it = p.walkq[ct.item]; }
         const WalkViewC v = walk_view_c(p, it, has);
         int fl = 0;
         const bool ok = stab_virtual<GeomC>(v.g, v.root, it.k, it.pack, v.pool, &v.ev->big, &v.ev->lock, fl, has, mask, has ? (int)ct.node : NODE_NEW, &ct.st) != 0;
@@ -739,7 +749,7 @@ __global__ void __launch_bounds__(64) pctc_emit_kernel(const CParams p) {
     CEnv *ev = p.env + e;
     const CHdr &h = ev->h;
     const double nb[3] = {h.next_box[0], h.next_box[1], h.next_box[2]};
-    if (e == 0 && tid == 0) { *p.walk_ctr = 0; *p.cont_ctr = 0; }  // every walk-kernel block has read them (programmatic dependency): empty the pools for the next step
+    if (e == 0 && tid == 0) { *p.walk_ctr = 0; p.cont_ctr[0] = 0; p.cont_ctr[1] = 0; }  // every walk-kernel block has read them (programmatic dependency): empty the pools for the next step
     if (tid == 0) {  // may run while this env's walks are still in flight (programmatic dependent of the continuation kernel)
         int spins = 0;
         while (*(volatile const int32_t *)&ev->n_pending > 0) {
@@ -917,8 +927,8 @@ int continuous_create(pct_env_batch *h) {
     if (e == cudaSuccess) e = cudaMemset(h->d_ready, 0, sizeof(int32_t) * 2 * (size_t)h->n_envs);
     if (e == cudaSuccess && !h->k3_block) {  // pools of the round-2 walk kernels (worst-case capacity for the walks; only the used prefix is touched)
         e = cudaMalloc(&h->c_walkq, sizeof(WalkItemC) * (size_t)CAND_MAX * (size_t)h->n_envs);
-        if (e == cudaSuccess) e = cudaMalloc(&h->d_walk_ctr, sizeof(int32_t) * 2);
-        if (e == cudaSuccess) e = cudaMemset(h->d_walk_ctr, 0, sizeof(int32_t) * 2);
+        if (e == cudaSuccess) e = cudaMalloc(&h->d_walk_ctr, sizeof(int32_t) * 4);  // [0] walk pool, [1] / [2] continuation pool (ordinary / tall)
+        if (e == cudaSuccess) e = cudaMemset(h->d_walk_ctr, 0, sizeof(int32_t) * 4);
         if (e == cudaSuccess) e = cudaMalloc(&h->d_contq, sizeof(WalkCont) * (size_t)WALK_CONT_PER_ENV * (size_t)h->n_envs);
     }
     if (e != cudaSuccess) { h->err = std::string("continuous_create: ") + cudaGetErrorString(e); return PCT_ERR_CUDA; }
@@ -960,7 +970,7 @@ int continuous_launch(pct_env_batch *h, int mode, const void *actions, int actio
     cfg.stream = st; cfg.attrs = at; cfg.numAttrs = p.ready ? 1 : 0;
     const bool pooled = h->c_walkq != nullptr && !h->k3_block;
     if (pooled) {
-        p.walkq = (WalkItemC *)h->c_walkq; p.walk_ctr = h->d_walk_ctr; p.contq = h->d_contq; p.cont_ctr = h->d_walk_ctr + 1; p.walk_lanes = h->walk_lanes;
+        p.walkq = (WalkItemC *)h->c_walkq; p.walk_ctr = h->d_walk_ctr; p.contq = h->d_contq; p.cont_ctr = h->d_walk_ctr + 1; p.walk_lanes = h->walk_lanes; p.walk_lanes_tall = h->walk_lanes_tall;
     }
     cfg.gridDim = dim3(p.n_envs); cfg.blockDim = dim3(32);
     cudaLaunchKernelEx(&cfg, pctc_candidates_kernel, p);

@@ -1247,14 +1247,22 @@ __global__ void __launch_bounds__(32 * LIGHT_WARPS, LIGHT_MINB) pct_walk_light_k
         if (has) res = stab_light<GeomD>(v.g, v.root, (int)it.k, it.pack, v.pool, node, st);
         if (res == 1) atomicOr(&v.cold->fbits[it.c >> 5], 1u << (it.c & 31));
         if (has && res != 2) walk_done(&v.cold->n_pending);
-        const uint32_t pm = __ballot_sync(FULL, res == 2);
-        if (pm) {
-            int qb = 0;
-            if (lane == 0) qb = atomicAdd(p.cont_ctr, __popc(pm));
-            qb = __shfl_sync(FULL, qb, 0);
+        // continuations: walks high up in the bin descend through the deepest support DAGs (host statistics: resting height >= 0.6 H -> up to 8 heavy
+        // visits, below -> at most 2), so they are pooled apart (from the END of the pool) and get fewer lanes per warp in pct_walk_kernel
+        const bool tall = (int)it.mh * 5 >= p.H * 3;
+        const uint32_t ps = __ballot_sync(FULL, res == 2 && !tall), pt = __ballot_sync(FULL, res == 2 && tall);
+        if (ps | pt) {
+            int qs = 0, qt = 0;
+            if (lane == 0) {
+                if (ps) qs = atomicAdd(p.cont_ctr, __popc(ps));
+                if (pt) qt = atomicAdd(p.cont_ctr + 1, __popc(pt));
+            }
+            qs = __shfl_sync(FULL, qs, 0);
+            qt = __shfl_sync(FULL, qt, 0);
             if (res == 2) {
-                const int slot = qb + __popc(pm & ((1u << lane) - 1));
-                if (slot < cap) p.contq[slot] = WalkCont{(uint32_t)i, (uint32_t)node, st};
+                const uint32_t lt = (1u << lane) - 1;
+                const int idx = tall ? qt + __popc(pt & lt) : qs + __popc(ps & lt);  // each class owns half of the pool (the counters may overshoot; the consumer clamps)
+                if (idx < cap / 2) p.contq[tall ? cap - 1 - idx : idx] = WalkCont{(uint32_t)i, (uint32_t)node, st};
                 else { atomicOr(const_cast<int32_t *>(&v.hot->h.flags), PCT_FLAG_CAND_OVERFLOW); walk_done(&v.cold->n_pending); }  // never silent: the candidate stays infeasible and the env is flagged
             }
         }
@@ -1267,19 +1275,23 @@ __global__ void __launch_bounds__(32 * LIGHT_WARPS, LIGHT_MINB) pct_walk_light_k
 // per warp, SMs 4 % occupied, 116 us) is latency-bound on the SUM of its lanes' divergent paths; fewer walks per warp = more warps, shorter chains.
 __global__ void __launch_bounds__(32 * WALK_WARPS, WALK_MINB) pct_walk_kernel(const DParams p) {
     const int lane = threadIdx.x & 31;
-    const int total = min(*(volatile const int32_t *)p.cont_ctr, p.n_envs * WALK_CONT_PER_ENV);
+    const int cap = p.n_envs * WALK_CONT_PER_ENV;
+    const int n_short = min(*(volatile const int32_t *)p.cont_ctr, cap / 2), n_tall = min(*(volatile const int32_t *)(p.cont_ctr + 1), cap / 2);
     __syncthreads();
     pdl_launch_dependents();  // the emit kernel's blocks may become resident now (it also empties the pool counters: read above); each waits for ITS env's last walk
-    const int nwarps = gridDim.x * WALK_WARPS, L = p.walk_lanes;
-    const unsigned mask = L >= 32 ? FULL : ((1u << L) - 1u);
-    if (lane >= L) return;
+    const int nwarps = gridDim.x * WALK_WARPS, Ls = p.walk_lanes, Lt = p.walk_lanes_tall;
+    const int w_tall = (n_tall + Lt - 1) / Lt, w_all = w_tall + (n_short + Ls - 1) / Ls;
 #pragma unroll 1
-    for (int base = (blockIdx.x * WALK_WARPS + (threadIdx.x >> 5)) * L; base < total; base += nwarps * L) {
-        const int i = base + lane;
-        const bool has = i < total;
+    for (int w = blockIdx.x * WALK_WARPS + (threadIdx.x >> 5); w < w_all; w += nwarps) {  // the tall walks (longest chains) are dealt first
+        const bool tw = w < w_tall;
+        const int L = tw ? Lt : Ls;
+        const unsigned mask = L >= 32 ? FULL : ((1u << L) - 1u);
+        if (lane >= L) continue;
+        const int i = tw ? w * Lt + lane : (w - w_tall) * Ls + lane;
+        const bool has = i < (tw ? n_tall : n_short);
         WalkCont ct{};
         WalkItem it{};
-        if (has) { ct = p.contq[i]; it = p.walkq[ct.item]; }
+        if (has) { ct = p.contq[tw ? cap - 1 - i : i]; it = p.walkq[ct.item]; }
         const WalkView v = walk_view(p, it, has);
         int fl = 0;
         const bool ok = stab_virtual<GeomD>(v.g, v.root, (int)it.k, it.pack, v.pool, &v.cold->big, &v.cold->lock, fl, has, mask,
@@ -1302,7 +1314,7 @@ __global__ void __launch_bounds__(32 * EMIT_WARPS) pct_emit_kernel(const DParams
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int e = blockIdx.x * EMIT_WARPS + warp;
     // last kernel of the launch sequence that touches the walk pools (both walk kernels have completed: plain stream order): empty them for the next step
-    if (blockIdx.x == 0 && threadIdx.x == 0 && p.walk_ctr) { *p.walk_ctr = 0; *p.cont_ctr = 0; }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && p.walk_ctr) { *p.walk_ctr = 0; p.cont_ctr[0] = 0; p.cont_ctr[1] = 0; }
     if (e >= p.n_envs) return;
     unsigned char *sm = smem + warp * EMIT_SM_PER_WARP;
     DEnvHot *hot = (DEnvHot *)sm;  // only the header and the boxes are staged

@@ -196,8 +196,8 @@ struct DParams {
     WalkItem *walkq;    // [n_envs * CAND_MAX] the step's pool of stability walks (worst-case capacity; only the used prefix is touched)
     int32_t *walk_ctr;  // its fill counter; reset by pct_order_kernel at the end of every launch sequence
     WalkCont *contq;    // [n_envs * WALK_CONT_PER_ENV] walks the light-prefix kernel hands to the continuation kernel
-    int32_t *cont_ctr;
-    int32_t walk_lanes; // continuations per warp of pct_walk_kernel (1..32)
+    int32_t *cont_ctr;  // [2]: continuations pooled from the front (ordinary) / from the end (tall walks) of contq
+    int32_t walk_lanes, walk_lanes_tall; // continuations per warp of pct_walk_kernel (1..32): ordinary / tall (resting height >= 0.6 H) walks
     int32_t opt;     // opt-in variants served by `aux`: PCT_OPT_DELTA (K3 delta observation writes), PCT_OPT_ALIAS (K1 object semantics of the loads)
 };
 constexpr int PCT_OPT_DELTA = 1, PCT_OPT_ALIAS = 2, PCT_OPT_K3_BLOCK = 4, PCT_OPT_NO_EMIT_PDL = 8;  // K3_BLOCK: round 1's block-per-env feasibility kernel (A/B)
