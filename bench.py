@@ -237,7 +237,11 @@ def measure(cx, setting, continuous, n, K, W, preroll, kernels=True, keep=False)
     step_ms = sum(per_step)
     kern_ms = sum(ev[t][1].elapsed_time(ev[t][2]) for t in range(K))
     tt = torch.tensor([step_ms, kern_ms], dtype=torch.float64, device=cx.dev)
+    per_rank = None
     if cx.dist is not None:
+        allr = [torch.zeros_like(tt) for _ in range(cx.world)]
+        cx.dist.all_gather(allr, tt)  # every rank's own device time: the spread attributes the weak-scaling loss (the step has no collective)
+        per_rank = [float(x[0]) / K for x in allr]
         cx.dist.all_reduce(tt, op=cx.dist.ReduceOp.MAX)
     step_ms, kern_ms = float(tt[0]), float(tt[1])
     nsamp = len(range(0, K, 16))
@@ -247,6 +251,8 @@ def measure(cx, setting, continuous, n, K, W, preroll, kernels=True, keep=False)
            "gpu_launches": int(launches), "mean_boxes": mean_boxes, "mean_ems": mean_ems, "mean_valid_leaves": mean_leaf,
            "mean_candidates": mean_cand, "kernel_ms": {k: v / ksteps for k, v in kms.items()} if ksteps else None, "steps": K, "warmup": W,
            "preroll": preroll, "envs_per_gpu": n}
+    if per_rank:
+        rec["per_rank_ms_per_step"] = per_rank  # value uses the MAX: a launch lasts as long as its heaviest env, and N ranks sample N times more tails
     if keep:
         return rec, batch
     batch.close()
@@ -362,12 +368,15 @@ def run_ours(a):
             z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
             return z ^ (z >> np.uint64(31))
 
+    with np.errstate(over="ignore"):
+        pol_base = sm64(np.uint64(POLICY_SEED) ^ (gid * GOLD))  # the per-env half of rnd_u64(seed, env, t): constant over the run
+
     def host_policy(t):
         # uniform choice among the valid leaves, on the HOST from the step's returned records: the number of valid leaf rows
         # is pct_step_info.n_leaf (== the count of 1s in column 8 of the leaf rows of the returned observation)
         nvalid = info_h[:, 5].astype(np.uint64)
         with np.errstate(over="ignore"):
-            r = sm64(sm64(np.uint64(POLICY_SEED) ^ (gid * GOLD)) + np.uint64(t))
+            r = sm64(pol_base + np.uint64(t))
         idx_h[:] = np.where(nvalid > 0, r % np.maximum(nvalid, np.uint64(1)), 0).astype(np.int32)
 
     batch.reset_host(obs_h)
@@ -481,6 +490,8 @@ def run_ours(a):
                 "gpu_launches": head["gpu_launches"], "kernel_ms_per_step": head["kernel_ms_per_step"],
                 "ms_per_step_p50": head["ms_per_step_p50"], "ms_per_step_p99": head["ms_per_step_p99"], "wall_s_timed_loop": head["wall_s_timed_loop"],
                 "roofline": roof, "clocks": clocks, "configs": configs}
+        if head.get("per_rank_ms_per_step"):
+            line["per_rank_ms_per_step"] = head["per_rank_ms_per_step"]
         if allgather:
             line["allgather"] = allgather
         if world == 1 and not a.skip_cpu:

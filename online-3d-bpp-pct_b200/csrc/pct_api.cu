@@ -369,13 +369,29 @@ int pct_step_host(pct_handle h, const void *h_actions, int32_t action_f64, const
         if (cudaHostGetDevicePointer(&obs_alias, h_obs, 0) == cudaSuccess && obs_alias) {
             cudaStream_t st = h->own_stream;
             const size_t n = (size_t)h->n_envs;
-            if (h_actions) CK(h, cudaMemcpyAsync(h->d_act, h_actions, n * 9 * asz, cudaMemcpyHostToDevice, st));
-            else CK(h, cudaMemcpyAsync(h->d_idx, h_leaf_idx, n * 4, cudaMemcpyHostToDevice, st));
-            rc = launch(h, 1, h_actions ? h->d_act : nullptr, action_f64, h_actions ? nullptr : h->d_idx, obs_alias, h->d_rew, h->d_done, h->d_info, st);
+            // reward / done are write-only for the kernels too: when their buffers are pinned the apply kernel writes them straight into the mapped
+            // host buffers (posted PCIe writes), saving two of the four staging copies.  Actions / leaf indices (READ by the apply kernel) and info
+            // (read-modify-write by the emit kernel) keep their staged copies: measured (round 2, call 14), device-side READS of mapped host memory
+            // put a PCIe round trip on every env's critical path — pct_step_host went from 426 to 661 us per step with everything mapped.
+            auto alias = [](const void *hp) -> void * {
+                void *d = nullptr;
+                if (hp && cudaHostGetDevicePointer(&d, const_cast<void *>(hp), 0) == cudaSuccess && d) return d;
+                (void)cudaGetLastError();
+                return nullptr;
+            };
+            void *a_act = nullptr, *a_rew = alias(h_reward), *a_done = alias(h_done), *a_info = nullptr;
+            if (!a_act) {
+                if (h_actions) CK(h, cudaMemcpyAsync(h->d_act, h_actions, n * 9 * asz, cudaMemcpyHostToDevice, st));
+                else CK(h, cudaMemcpyAsync(h->d_idx, h_leaf_idx, n * 4, cudaMemcpyHostToDevice, st));
+            }
+            const void *k_act = h_actions ? (a_act ? a_act : h->d_act) : nullptr;
+            const int32_t *k_idx = h_actions ? nullptr : (a_act ? (const int32_t *)a_act : h->d_idx);
+            pct_step_info *k_info = h_info ? (a_info ? (pct_step_info *)a_info : h->d_info) : h->d_info;
+            rc = launch(h, 1, k_act, action_f64, k_idx, obs_alias, a_rew ? (float *)a_rew : h->d_rew, a_done ? (uint8_t *)a_done : h->d_done, k_info, st);
             if (rc) return rc;
-            CK(h, cudaMemcpyAsync(h_reward, h->d_rew, n * 4, cudaMemcpyDeviceToHost, st));
-            CK(h, cudaMemcpyAsync(h_done, h->d_done, n, cudaMemcpyDeviceToHost, st));
-            if (h_info) CK(h, cudaMemcpyAsync(h_info, h->d_info, n * sizeof(pct_step_info), cudaMemcpyDeviceToHost, st));
+            if (!a_rew) CK(h, cudaMemcpyAsync(h_reward, h->d_rew, n * 4, cudaMemcpyDeviceToHost, st));
+            if (!a_done) CK(h, cudaMemcpyAsync(h_done, h->d_done, n, cudaMemcpyDeviceToHost, st));
+            if (h_info && !a_info) CK(h, cudaMemcpyAsync(h_info, h->d_info, n * sizeof(pct_step_info), cudaMemcpyDeviceToHost, st));
             CK(h, cudaStreamSynchronize(st));
             return PCT_OK;
         }
