@@ -145,8 +145,7 @@ int pct_reset(pct_handle h, void *d_obs, void *stream);
  * observation is zero padding and the internal-node rows are append-only within an episode, so when a call receives the SAME d_obs pointer
  * as the previous reset / step of this handle, only the rows that can have changed are rewritten (the rows below max(rows now, rows the
  * buffer may hold non-zero) and the item row).  A caller that hands the same buffer to consecutive calls must therefore not modify it in
- * between (reading is fine); a caller that alternates buffers, or passes a fresh one, always gets every row written.  The continuous
- * domain always writes every row. */
+ * between (reading is fine); a caller that alternates buffers, or passes a fresh one, always gets every row written.  Both domains. */
 int pct_step(pct_handle h, const void *d_actions, int32_t action_f64, const int32_t *d_leaf_idx, void *d_obs,
              float *d_reward, uint8_t *d_done, pct_step_info *d_info, void *stream);
 

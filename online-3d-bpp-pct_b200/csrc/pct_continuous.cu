@@ -87,6 +87,7 @@ struct CParams {
     WalkCont *contq;
     int32_t *cont_ctr;
     int32_t walk_lanes, walk_lanes_tall;
+    int32_t delta;   // delta observation rows (DEnvAux::obs_prev), emit kernel only
     DEnvAux *aux;    // per-env state of the ALIAS apply kernel (EdgePoolA arrays), nullptr with PCT_B200_ALIAS=0 / setting 2
 };
 
@@ -739,6 +740,7 @@ __global__ void __launch_bounds__(64, 8) pctc_walk_kernel(const CParams p) {
 }
 
 template <typename OT> __device__ __noinline__ void write_obs_c(const CParams &p, int e, const CEnv *ev, const double (*leaf)[6], int n_leaf, int tid, int nthreads);
+template <typename OT> __device__ __noinline__ void write_obs_c_delta(const CParams &p, int e, const CEnv *ev, const double (*leaf)[6], int n_leaf, int tid, int nthreads);
 
 // emit (round 2): the first `nl` set feasibility bits in candidate order -> leaf rows, observation; 64 threads per env
 template <typename OT>
@@ -787,7 +789,8 @@ __global__ void __launch_bounds__(64) pctc_emit_kernel(const CParams p) {
             p.info[e].n_leaf = n_leaf; p.info[e].n_cand = h.n_cand; p.info[e].n_ems = h.n_ems; p.info[e].flags |= h.flags;
         }
     }
-    write_obs_c<OT>(p, e, ev, leaf, n_leaf, tid, 64);
+    if (p.delta) write_obs_c_delta<OT>(p, e, ev, leaf, n_leaf, tid, 64);
+    else write_obs_c<OT>(p, e, ev, leaf, n_leaf, tid, 64);
 }
 
 
@@ -827,6 +830,55 @@ __device__ __noinline__ void write_obs_c(const CParams &p, int e, const CEnv *ev
         }
         obs[f] = (OT)v;
     }
+}
+
+// Delta variant of write_obs_c (cf. write_obs_delta, pct_discrete.cu): the caller hands back the same observation buffer, obs_prev[0] / [1] say how
+// many internal / leaf rows of it may be non-zero; only the rows below max(now, prev) and the item row are written.  Same values as write_obs_c.
+template <typename OT>
+__device__ __noinline__ void write_obs_c_delta(const CParams &p, int e, const CEnv *ev, const double (*leaf)[6], int n_leaf, int tid, int nthreads) {
+    OT *obs = (OT *)p.obs + (size_t)e * (size_t)((p.nb + p.nl + 1) * 9);
+    int32_t *prev = p.aux[e].obs_prev;
+    const int n_box = ev->h.n_box;
+    const int pb = min(prev[0], p.nb), pl = min(prev[1], p.nl);
+    __syncthreads();  // every thread of the block (= env) has read prev before thread 0 replaces it
+    const int wb = max(max(n_box, pb), 1), wl = max(n_leaf, pl);
+    double s0 = ev->h.next_box[0], s1 = ev->h.next_box[1], s2 = ev->h.next_box[2];
+    if (s1 < s0) { double t = s0; s0 = s1; s1 = t; }
+    if (s2 < s1) { double t = s1; s1 = s2; s2 = t; }
+    if (s1 < s0) { double t = s0; s0 = s1; s1 = t; }
+    const int total = (wb + wl + 1) * 9;
+#pragma unroll 1
+    for (int f = tid; f < total; f += nthreads) {
+        const int r = f / 9, col = f - r * 9;
+        double v = 0;
+        int row;
+        if (r < wb) {
+            row = r;
+            if (row < n_box) {
+                const double *b = ev->box[row];
+                if (col < 3) v = b[col];
+                else if (col < 6) v = b[col - 3] + b[col];
+                else if (col == 8) v = 1;
+            } else if (row == 0 && col == 8) v = 1;
+        } else if (r < wb + wl) {
+            const int k = r - wb;
+            row = p.nb + k;
+            if (k < n_leaf) {
+                if (col < 5) v = leaf[k][col];
+                else if (col == 5) v = p.H;
+                else if (col == 8) v = 1;
+            }
+        } else {
+            row = p.nb + p.nl;
+            if (col == 0) v = ev->h.next_den;
+            else if (col == 3) v = s0;
+            else if (col == 4) v = s1;
+            else if (col == 5) v = s2;
+            else if (col == 8) v = 1;
+        }
+        obs[row * 9 + col] = (OT)v;
+    }
+    if (tid == 0) { prev[0] = max(n_box, 1); prev[1] = n_leaf; }
 }
 
 template <bool PRE>
@@ -969,6 +1021,12 @@ int continuous_launch(pct_env_batch *h, int mode, const void *actions, int actio
     cudaLaunchConfig_t cfg{};
     cfg.stream = st; cfg.attrs = at; cfg.numAttrs = p.ready ? 1 : 0;
     const bool pooled = h->c_walkq != nullptr && !h->k3_block;
+    if (pooled && h->obs_delta && h->d_aux) {  // delta observation rows (emit kernel): a buffer other than the tracked one may hold anything -> "all rows"
+        if (h->fill_pending) launch_fill_prev(h->d_aux, p.n_envs, p.nb, p.nl, st);
+        p.aux = h->d_aux;
+        p.delta = 1;
+    }
+    h->fill_pending = false;
     if (pooled) {
         p.walkq = (WalkItemC *)h->c_walkq; p.walk_ctr = h->d_walk_ctr; p.contq = h->d_contq; p.cont_ctr = h->d_walk_ctr + 1; p.walk_lanes = h->walk_lanes; p.walk_lanes_tall = h->walk_lanes_tall;
     }

@@ -37,6 +37,28 @@ def test_delta_equals_full_on_the_library_buffer(setting, monkeypatch):
     assert np.array_equal(ref, got)
 
 
+@pytest.mark.parametrize("setting", [1, 2])
+def test_delta_equals_full_continuous(setting, monkeypatch):
+    """the continuous emit kernel's delta rows (round 2): library buffer and alternating caller buffers, float32 and float64"""
+    import pct_b200
+    res = []
+    for delta in ("0", "1"):
+        monkeypatch.setenv("PCT_B200_OBS_DELTA", delta)
+        n = 200
+        b = pct_b200.PctBatch(n, setting, container_size=(1.0, 1.0, 1.0), continuous=True, sample_from_distribution=True, seed=12,
+                              obs_dtype=torch.float64 if setting == 2 else torch.float32)
+        bufs = [torch.full((n, b.obs_len), 7.0, dtype=b.obs_dtype, device=b.device) for _ in range(2)]
+        out = [b.reset().clone()]
+        for t in range(60):
+            tgt = None if t < 30 else bufs[0 if (t // 3) % 2 else 1]  # library buffer first, then caller buffers switched every third step
+            obs, _, _, info = b.step(leaf_idx=b.random_policy(5, t), out=tgt)
+            out.append(obs.clone())
+        assert not b.decode_info(info)["flags"].any()
+        res.append(torch.stack(out).cpu().numpy())
+        b.close()
+    assert np.array_equal(res[0], res[1])
+
+
 def test_delta_with_alternating_buffers_and_f64(monkeypatch):
     ref = _trace(1, 300, 40, False, monkeypatch, alternate=True, obs_dtype=torch.float64)
     got = _trace(1, 300, 40, True, monkeypatch, alternate=True, obs_dtype=torch.float64)
