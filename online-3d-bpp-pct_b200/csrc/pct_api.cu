@@ -134,14 +134,21 @@ int pct_create(const pct_config *cfg, int32_t n_envs, int32_t device, pct_handle
                 if (e == cudaSuccess) e = cudaMalloc(&h->d_cont_ctr, sizeof(int32_t) * ((size_t)n_envs + 1));
                 if (e == cudaSuccess) e = cudaMemset(h->d_cont_ctr, 0, sizeof(int32_t) * ((size_t)n_envs + 1));
             }
-            if (e == cudaSuccess) e = cudaMalloc(&h->d_order, sizeof(int32_t) * 2 * (size_t)n_envs);
-            if (e == cudaSuccess) {
-                std::vector<int32_t> id(2 * (size_t)n_envs);
-                for (int i = 0; i < n_envs; i++) id[i] = id[n_envs + i] = i;
-                e = cudaMemcpy(h->d_order, id.data(), sizeof(int32_t) * id.size(), cudaMemcpyHostToDevice);
+            h->lpt = !h->k3_block;   // heaviest-env-first block order (pct_discrete.cu, order_lookup / order_file); PCT_B200_LPT=0 disables
+            if (const char *lv = getenv("PCT_B200_LPT")) h->lpt = atoi(lv) != 0 && !h->k3_block;
+            if (e == cudaSuccess && h->lpt) {
+                // parity + two 64-bucket histograms + two sets of per-bucket env lists; starts as "every env in the lightest bucket, in env order"
+                const size_t words = 2 + 2 * 64 + 2 * 64 * (size_t)n_envs;
+                e = cudaMalloc(&h->d_order, sizeof(int32_t) * words);
+                if (e == cudaSuccess) e = cudaMemset(h->d_order, 0, sizeof(int32_t) * words);
+                if (e == cudaSuccess) {
+                    std::vector<int32_t> id((size_t)n_envs);
+                    for (int i = 0; i < n_envs; i++) id[i] = i;
+                    const int32_t n32 = n_envs;
+                    e = cudaMemcpy(h->d_order + 2 + 63, &n32, sizeof n32, cudaMemcpyHostToDevice);
+                    if (e == cudaSuccess) e = cudaMemcpy(h->d_order + 2 + 128 + 63 * (size_t)n_envs, id.data(), sizeof(int32_t) * id.size(), cudaMemcpyHostToDevice);
+                }
             }
-            h->lpt = true;   // heaviest-env-first block order: no gain with back-to-back kernels, +9 % on top of the overlapped launch mode; PCT_B200_LPT=0 disables
-            if (const char *lv = getenv("PCT_B200_LPT")) h->lpt = atoi(lv) != 0;
         } else {
             int rc = continuous_create(h);
             if (rc != PCT_OK) { g_create_err = h->err; delete h; return rc; }

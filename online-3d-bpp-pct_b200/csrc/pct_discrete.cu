@@ -698,6 +698,39 @@ __device__ __forceinline__ long long gtime() { long long t; asm volatile("mov.u6
 #ifndef K3_MINB
 #define K3_MINB 8   // sweep (r1): 128 regs / 8 blocks per SM
 #endif
+// ---- block scheduling order (longest-processing-time-first) --------------------------------------------------------------------------
+// A launch lasts as long as its slowest block and blocks are dispatched in index order, so the envs with the most expected work (boxes placed
+// drive the real stability descent and the EMS update) get the lowest slots.  No sorting pass: pct_apply_kernel files every env under its
+// work key for the NEXT step (one atomicAdd into a 64-bucket histogram + one store into that bucket's list), and the apply / candidates
+// kernels of the next step turn their slot into an env with a 64-entry warp scan.  Two parities: a step reads what the previous step
+// wrote; the emit kernel (last of the sequence) empties the buckets just consumed and flips the parity ON THE DEVICE, so captured graphs replay
+// correctly.  Layout of DParams::order (int32): [0] parity, [2 + 64 * par + j] count of bucket j = 63 - key, [ORD_LIST + (64 * par + j) * n_envs + i] envs.
+constexpr int ORD_BUCKETS = 64, ORD_CNT = 2, ORD_LIST = ORD_CNT + 2 * ORD_BUCKETS;
+__device__ __forceinline__ int order_lookup(const int32_t *ord, int n_envs, int slot, int lane) {
+    const int par = *(volatile const int32_t *)ord & 1;
+    const int32_t *cnt = ord + ORD_CNT + ORD_BUCKETS * par;
+    const int a = cnt[2 * lane], b = cnt[2 * lane + 1];
+    int incl = a + b;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(FULL, incl, d);
+        if (lane >= d) incl += t;
+    }
+    const uint32_t m = __ballot_sync(FULL, slot < incl);
+    if (m == 0) return slot;  // not a whole-batch history (cannot happen after pct_create's initialisation): identity
+    const int f = __ffs(m) - 1;
+    const int incl_f = __shfl_sync(FULL, incl, f), a_f = __shfl_sync(FULL, a, f), b_f = __shfl_sync(FULL, b, f);
+    int off = slot - (incl_f - a_f - b_f), j = 2 * f;
+    if (off >= a_f) { off -= a_f; j++; }
+    return ord[ORD_LIST + (size_t)(ORD_BUCKETS * par + j) * n_envs + off];
+}
+__device__ __forceinline__ void order_file(int32_t *ord, int n_envs, int e, int n_box, int n_ems) {
+    const int par = *(volatile const int32_t *)ord & 1;
+    const int j = 63 - min(63, n_box + (n_ems >> 1));
+    const int pos = atomicAdd(ord + ORD_CNT + ORD_BUCKETS * (par ^ 1) + j, 1);
+    if (pos < n_envs) ord[ORD_LIST + (size_t)(ORD_BUCKETS * (par ^ 1) + j) * n_envs + pos] = e;
+}
+
 constexpr int K1_SM_PER_WARP = sizeof(DEnvHot) + EMS_TMP_MAX * 12 + 16 + EDGE_STAGE * 32 + POLY_STAGE * 16 + EMS_TMP_MAX * 8;  // record + EMS temp + mbarrier/lock + staged loads + packed EMS temp
 static_assert(K1_SM_PER_WARP % 16 == 0, "alignment");
 
@@ -707,7 +740,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, K1_MINB) pct_apply_kerne
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int slot = blockIdx.x * WARPS_PER_BLOCK + warp;
     if (slot >= p.n_envs) return;
-    const int e = (p.order && p.mode == 1) ? p.order[slot] : slot;  // heaviest envs first (longest-processing-time-first)
+    const int e = (p.order && p.mode == 1) ? order_lookup(p.order, p.n_envs, slot, lane) : slot;  // heaviest envs first (longest-processing-time-first)
     unsigned char *sm = smem_raw + (size_t)warp * K1_SM_PER_WARP;
     DEnvHot *hot = (DEnvHot *)sm;
     int16_t (*ems_tmp)[6] = (int16_t (*)[6])(sm + sizeof(DEnvHot));
@@ -900,6 +933,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, K1_MINB) pct_apply_kerne
         if (p.reward) p.reward[e] = reward;
         if (p.done) p.done[e] = (uint8_t)done;
         if (p.info) p.info[e] = info;
+        if (p.order) order_file(p.order, p.n_envs, e, h.n_box, h.n_ems);  // this env's slot in the next step's launches
         // record back to HBM: smem -> global via TMA bulk store
         tma_store_1d(ghot, hot, (uint32_t)sizeof(DEnvHot));
         if (STAB && p.mode == 1 && h.n_edge > 0) tma_store_1d(cold->e_st, st_sm, (uint32_t)min(h.n_edge, EDGE_STAGE) * (uint32_t)sizeof(Stack4));
@@ -922,7 +956,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) pct_candidates_kernel(co
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int slot = blockIdx.x * WARPS_PER_BLOCK + warp;
     if (slot >= p.n_envs) return;
-    const int e = (p.order && p.mode == 1) ? p.order[slot] : slot;
+    const int e = (p.order && p.mode == 1) ? order_lookup(p.order, p.n_envs, slot, lane) : slot;
     unsigned char *sm = smem_raw + (size_t)warp * LY::PER_WARP;
     DEnvHot *hot = (DEnvHot *)(sm + LY::HOT);
     SlotT *tabA = (SlotT *)(sm + LY::TAB_A_OFF), *tabB = (SlotT *)(sm + LY::TAB_B_OFF);
@@ -1055,7 +1089,7 @@ __global__ void __launch_bounds__(FEAS_THREADS, K3_MINB) pct_feas_emit_kernel(co
     constexpr int BITS = sizeof(SlotT) == 2 ? 4 : 8;
     __shared__ __align__(16) unsigned char sm[K3_SMEM];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int e = (p.order && p.mode == 1) ? p.order[blockIdx.x] : blockIdx.x;  // same heaviest-first permutation as K1 / K2
+    const int e = blockIdx.x;  // (round 1's heaviest-first permutation of this kernel went with the sorting pass; the legacy mode runs in env order)
     DEnvHot *hot = (DEnvHot *)sm;
     int16_t (*leaf)[6] = (int16_t (*)[6])(sm + sizeof(DEnvHot));
     uint64_t *mbar = (uint64_t *)(sm + sizeof(DEnvHot) + NL_MAX * 12);
@@ -1315,6 +1349,14 @@ __global__ void __launch_bounds__(32 * EMIT_WARPS) pct_emit_kernel(const DParams
     const int e = blockIdx.x * EMIT_WARPS + warp;
     // last kernel of the launch sequence that touches the walk pools (both walk kernels have completed: plain stream order): empty them for the next step
     if (blockIdx.x == 0 && threadIdx.x == 0 && p.walk_ctr) { *p.walk_ctr = 0; p.cont_ctr[0] = 0; p.cont_ctr[1] = 0; }
+    if (blockIdx.x == 0 && p.order) {
+        // ... and the last one of the step: the apply and candidates kernels have consumed this parity's buckets (both completed before the walk kernels
+        // started) and the apply kernel has filled the other parity's; empty the consumed ones and flip
+        const int par = *(volatile const int32_t *)p.order & 1;
+        if (threadIdx.x < ORD_BUCKETS) p.order[ORD_CNT + ORD_BUCKETS * par + threadIdx.x] = 0;
+        __syncthreads();
+        if (threadIdx.x == 0) { __threadfence(); *(volatile int32_t *)p.order = par ^ 1; }
+    }
     if (e >= p.n_envs) return;
     unsigned char *sm = smem + warp * EMIT_SM_PER_WARP;
     DEnvHot *hot = (DEnvHot *)sm;  // only the header and the boxes are staged
@@ -1382,34 +1424,6 @@ __global__ void __launch_bounds__(32 * EMIT_WARPS) pct_emit_kernel(const DParams
     // ---------------- cur_observation (D:bin3D.py:70-93) ----------------
     if constexpr (DELTA) write_obs_delta<OT, true, 2>(p, e, hot, cold, leaf, n_leaf, lane, 32);  // leaf rows: the rest was written by the candidates kernel
     else write_obs<OT, 2>(p, e, hot, cold, leaf, n_leaf, lane, 32);
-}
-
-// Block scheduling order.  A launch lasts as long as its slowest block, and blocks are dispatched in index order, so the
-// envs with the most expected work should get the lowest block indices (LPT rule).  One 1024-thread block counting-sorts
-// the envs by a work estimate read from the record headers: which = 0 -> order[0..n) for the NEXT step's apply kernel
-// (boxes already placed drive the real stability DFS and the EMS update), which = 1 -> order[n..2n) for feas_emit
-// (candidates x stack depth).
-__global__ void __launch_bounds__(1024) pct_order_kernel(const DEnvHot *hot, int n_envs, int32_t *order, int which) {
-    __shared__ int hist[64], base[64];
-    const int tid = threadIdx.x;
-    if (tid < 64) hist[tid] = 0;
-    __syncthreads();
-    for (int e = tid; e < n_envs; e += 1024) {
-        const DHdr &h = hot[e].h;
-        const int key = which ? min(63, (h.n_cand * (4 + h.n_box)) >> 6) : min(63, h.n_box + (h.n_ems >> 1));
-        atomicAdd(&hist[63 - key], 1);
-    }
-    __syncthreads();
-    if (tid == 0) {
-        int s = 0;
-        for (int b = 0; b < 64; b++) { base[b] = s; s += hist[b]; }
-    }
-    __syncthreads();
-    for (int e = tid; e < n_envs; e += 1024) {
-        const DHdr &h = hot[e].h;
-        const int key = which ? min(63, (h.n_cand * (4 + h.n_box)) >> 6) : min(63, h.n_box + (h.n_ems >> 1));
-        order[which * n_envs + atomicAdd(&base[63 - key], 1)] = e;
-    }
 }
 
 // uniform-random valid-leaf policy: reads only the record headers
@@ -1506,7 +1520,6 @@ static cudaError_t launch_t(const DParams &p_in, cudaStream_t st, cudaEvent_t *p
             if (err != cudaSuccess) return err;
         }
     }
-    if (p.order) pct_order_kernel<<<1, 1024, 0, st>>>(p.hot, p.n_envs, p.order, 0);
     if (prof) cudaEventRecord(prof[3], st);
     return cudaGetLastError();
 }
@@ -1518,8 +1531,8 @@ static cudaError_t launch_s(const DParams &p, cudaStream_t st, cudaEvent_t *prof
 
 // number of kernels one reset / step enqueues (for pct_kernel_launches): apply, candidates (+ classify), [walk], emit, order / pool reset
 int discrete_kernels_per_step(const DParams &p) {
-    if ((p.opt & PCT_OPT_K3_BLOCK) || !p.walkq) return 3 + (p.order ? 1 : 0);
-    return 3 + (p.setting != 2 ? 2 : 0) + (p.order ? 1 : 0);
+    if ((p.opt & PCT_OPT_K3_BLOCK) || !p.walkq) return 3;
+    return 3 + (p.setting != 2 ? 2 : 0);
 }
 
 cudaError_t launch_discrete(const DParams &p, cudaStream_t st, cudaEvent_t *prof) {

@@ -54,7 +54,7 @@ struct pct_env_batch {
     pct_step_info *d_info = nullptr;
     cudaStream_t own_stream = nullptr;
     void *dbg = nullptr;
-    int32_t *d_order = nullptr;   // block -> env permutations (LPT scheduling)
+    int32_t *d_order = nullptr;   // heaviest-first scheduling order: parity, bucket counts, per-bucket env lists (pct_discrete.cu order_lookup)
     pct::WalkItem *d_walkq = nullptr;  // [n_envs * CAND_MAX] pool of stability walks of the current step (pct_walk_kernel)
     int32_t *d_walk_ctr = nullptr;     // [n_envs] fill counters (index = first env of the launched range)
     pct::WalkCont *d_contq = nullptr;  // [n_envs * WALK_CONT_PER_ENV] continuations: light-prefix kernel -> pct_walk_kernel

@@ -47,8 +47,9 @@ struct EdgePool {
     Stack4 *st;            // [EDGE_MAX] load centre xyz + mass (global memory)
     Stack4 *st_sm;         // the first EDGE_STAGE loads, staged in shared memory by a TMA bulk copy
     int n;                 // current count (lane-local copy; the REAL path writes it back)
-    // support polygons (unshrunk hull vertices, x/y interleaved) of the placed boxes with >= 2 supports: the
-    // reference stores bottom_whole_contact_area per box at placement (D:space.py:378-379); CSR by box.
+    // support polygons (hull vertices already scaled down, x/y interleaved) of the placed boxes with >= 2 supports: the
+    // reference stores bottom_whole_contact_area per box at placement (D:space.py:378-379); CSR by box.  A box with exactly two
+    // supports has one more entry behind its vertices: the split direction of its load (split2_dir).
     uint16_t *poly_off;    // [NB_MAX + 2]
     double *poly;          // [POLY_MAX][2] global
     double *poly_sm;       // first POLY_STAGE vertices staged in shared memory

@@ -150,6 +150,35 @@ static __device__ __noinline__ bool pip_shrunk(const double *hx, const double *h
     return odd;
 }
 
+// The same test on a polygon that was shrunk when it was stored (store_shrunk): the placed boxes' bottom_whole_contact_area is the
+// scaled-down hull in the reference too (D:space.py:378-379), so a visit of a placed box only runs the edge loop.
+static __device__ __noinline__ bool pip_stored(const double *xy, int m, double lat, double lon) {
+    double jx = xy[2 * (m - 1)], jy = xy[2 * (m - 1) + 1];
+    bool odd = false;
+#pragma unroll 1
+    for (int i = 0; i < m; i++) {
+        const double ix = xy[2 * i], iy = xy[2 * i + 1];
+        const double a0 = ix - lat, a1 = iy - lon;
+        const double b0 = lat - jx, b1 = lon - jy;
+        const double m1 = a0 * b1, m2 = a1 * b0;
+        if (m1 - m2 == 0) return false;
+        if ((iy < lon && jy >= lon) || (jy < lon && iy >= lon)) {
+            if (cross_left(ix, iy, jx, jy, lat, lon)) odd = !odd;
+        }
+        jx = ix; jy = iy;
+    }
+    return odd;
+}
+
+// two supports: direction of the line through the two contact-rectangle centres divided by its squared length (D:space.py:383-392);
+// a function of the placed geometry only, so it is stored behind the polygon of a placed box with two supports.
+__device__ __forceinline__ void split2_dir(const double *px, const double *py, double &lx, double &ly) {
+    lx = px[0] - px[1]; ly = py[0] - py[1];
+    const double len = dsqrt(fma(ly, ly, lx * lx));
+    const double len2 = len * len;
+    lx = ddiv(lx, len2); ly = ddiv(ly, len2);
+}
+
 // Minimum-norm least squares (np.linalg.lstsq restatement: streaming Givens QR + one-sided Jacobi SVD,
 // identical operation order to oracle/pct_oracle_common.h po_ls_*).  ld = leading dimension of R and V.
 struct LsWork { double *R, *V, *y, *row, *x; int ld; };
@@ -504,11 +533,13 @@ static __device__ __noinline__ int stability_check(const G &g, const typename G:
 #pragma unroll 1
             for (int s = 0; s < k; s++) g.support(cur, sup_id[base + s], rect[s]);
             bool ok;
+            const double *split = nullptr;  // k == 2, placed box: the stored split direction
             const int pv = node == root_id ? 0 : (int)pool.poly_off[node], pm = node == root_id ? 0 : (int)pool.poly_off[node + 1] - pv;
             if (pm > 0 && (pv + pm <= POLY_STAGE || pv >= POLY_STAGE)) {
                 // a placed box: its support polygon was stored when it was placed
                 const double *xy = pool.poly_at(pv);
-                ok = pip_shrunk(xy, xy + 1, 2, pm, st.cx, st.cy);
+                ok = pip_stored(xy, pm - (k == 2), st.cx, st.cy);
+                if (k == 2) split = xy + 2 * (pm - 1);
             } else {
                 // combine_contact_points order: (x1,y1) (x1,y2) (x2,y1) (x2,y2); perturb x += y*1e-6 (convex_hull.py:43)
 #pragma unroll 1
@@ -522,11 +553,29 @@ static __device__ __noinline__ int stability_check(const G &g, const typename G:
                 }
                 const int m = hull_coords(px, py, 4 * k, hx, hy);
                 ok = pip_shrunk(hx, hy, 1, m, st.cx, st.cy);
-                if (real && ok && node == root_id && pool.n_poly + m <= POLY_MAX) {
-                    // the box being placed: remember its polygon (bottom_whole_contact_area, D:space.py:378-379)
+                if (real && ok && node == root_id && pool.n_poly + m + (k == 2) <= POLY_MAX) {
+                    // the box being placed: remember its shrunk polygon (bottom_whole_contact_area, D:space.py:378-379; same operations as
+                    // pip_shrunk) and, with two supports, the split direction behind it
+                    double sx = 0, sy = 0;
 #pragma unroll 1
-                    for (int i = 0; i < m; i++) { double *v = pool.poly_at(pool.n_poly + i); v[0] = hx[i]; v[1] = hy[i]; }
+                    for (int i = 0; i < m; i++) { sx += hx[i]; sy += hy[i]; }
+                    const double pcx = ddiv(sx, (double)m), pcy = ddiv(sy, (double)m);
+#pragma unroll 1
+                    for (int i = 0; i < m; i++) {
+                        double *v = pool.poly_at(pool.n_poly + i);
+                        double d = hx[i] - pcx;
+                        v[0] = hx[i] - d * 0.1;
+                        d = hy[i] - pcy;
+                        v[1] = hy[i] - d * 0.1;
+                    }
                     pool.n_poly += m;
+                    if (k == 2) {
+                        double cx2[2] = {(rect[0][0] + rect[0][2]) * 0.5, (rect[1][0] + rect[1][2]) * 0.5};
+                        double cy2[2] = {(rect[0][1] + rect[0][3]) * 0.5, (rect[1][1] + rect[1][3]) * 0.5};
+                        double *v = pool.poly_at(pool.n_poly);
+                        split2_dir(cx2, cy2, v[0], v[1]);
+                        pool.n_poly += 1;
+                    }
                 }
             }
             SEC(1);
@@ -549,10 +598,9 @@ static __device__ __noinline__ int stability_check(const G &g, const typename G:
                         py[s] = (rect[s][1] + rect[s][3]) * 0.5;
                     }
                     if (k == 2) {
-                        double lx = px[0] - px[1], ly = py[0] - py[1];
-                        const double len = dsqrt(fma(ly, ly, lx * lx));
-                        const double len2 = len * len;
-                        lx = ddiv(lx, len2); ly = ddiv(ly, len2);
+                        double lx, ly;
+                        if (split) { lx = split[0]; ly = split[1]; }
+                        else split2_dir(px, py, lx, ly);
                         sup_m[base + 0] = st.m * fabs(dot2(st.cx - px[1], st.cy - py[1], lx, ly));
                         sup_m[base + 1] = st.m * fabs(dot2(st.cx - px[0], st.cy - py[0], lx, ly));
                     } else {
@@ -670,6 +718,11 @@ static __device__ __noinline__ int stability_check(const G &g, const typename G:
 #ifndef PCT_STAT
 #define PCT_STAT(i)   // statistics hook of the host build (tests/host_emul/stab_host.cpp)
 #endif
+#ifndef PCT_PATH_VISIT  // host statistics: cost of a walk in total and along its longest root-to-leaf path (scratch/stats_paths.py)
+#define PCT_PATH_VISIT(c)
+#define PCT_PATH_PUSH(d)
+#define PCT_PATH_POP(d)
+#endif
 
 // stab_light: the LIGHT PREFIX of a feasibility walk — visits of nodes with no or one support (81 % of the walks of the BASELINE streams
 // consist of nothing else; host statistics, scratch/stats_farout.py): a rectangle test in registers and the centre-of-mass update, no frames,
@@ -683,6 +736,7 @@ static __device__ __forceinline__ int stab_light(const G &g, const typename G::N
     int node = NODE_NEW;
     Stack4 st;
     g.centre(root, st.cx, st.cy, st.cz);
+    st.cz = 0;
     st.m = root.mass;
 #pragma unroll 1
     for (;;) {
@@ -708,19 +762,20 @@ static __device__ __forceinline__ int stab_light(const G &g, const typename G::N
         g.node_box(sid0, sb);
         double ccx, ccy, ccz, mm = sb.mass;
         g.centre(sb, ccx, ccy, ccz);
-        ccx *= mm; ccy *= mm; ccz *= mm;
+        ccx *= mm; ccy *= mm;  // the z centre of a stack enters no decision (pip tests are 2-D) and a virtual walk stores nothing: not carried
+        (void)ccz;
 #pragma unroll 1
         for (int q = pool.first_in[sid0]; q != EDGE_NIL; q = pool.next[q]) {
             if (q == skip) continue;
             const Stack4 e = pool.load(q);
-            ccx += e.cx * e.m; ccy += e.cy * e.m; ccz += e.cz * e.m;
+            ccx += e.cx * e.m; ccy += e.cy * e.m;
             mm += e.m;
         }
         if (st.m != 0.0) {
-            ccx += st.cx * st.m; ccy += st.cy * st.m; ccz += st.cz * st.m;
+            ccx += st.cx * st.m; ccy += st.cy * st.m;
             mm += st.m;
         }
-        st.cx = ddiv(ccx, mm); st.cy = ddiv(ccy, mm); st.cz = ddiv(ccz, mm); st.m = mm;
+        st.cx = ddiv(ccx, mm); st.cy = ddiv(ccy, mm); st.m = mm;
         node = sid0;
     }
 }
@@ -734,10 +789,11 @@ static __device__ __noinline__ int stab_virtual(const G &g, const typename G::No
     typedef typename G::Node Node;
     StabFrame fr[STAB_DEPTH];
     uint8_t sup_id[STAB_SUP_POOL];
-    double sup_m[STAB_SUP_POOL];
+    double sup_m[STAB_SUP_POOL], sup_x[STAB_SUP_POOL], sup_y[STAB_SUP_POOL];  // load per support; contact-rectangle centres (split loads only)
     int depth = 0, node = NODE_NEW, base = 0;
     Stack4 st;
     g.centre(root, st.cx, st.cy, st.cz);
+    st.cz = 0;
     st.m = root.mass;
     if (start_node != NODE_NEW) { node = start_node; st = *start_st; }
     bool active = has_work, need_adv = false;
@@ -773,20 +829,14 @@ static __device__ __noinline__ int stab_virtual(const G &g, const typename G::No
                         StabFrame &f = fr[depth - 1];
                         if (f.i == f.k) { depth--; continue; }
                         const int s = f.i++;
+                        PCT_PATH_POP(depth - 1);
                         child = sup_id[f.base + s];
                         const int parent = f.node;
                         skip = (parent == NODE_NEW) ? EDGE_NIL : (int)f.eoff + s;
                         st = f.st;
                         vm = sup_m[f.base + s];
                         vx = st.cx; vy = st.cy;
-                        if (!f.whole) {  // the load sits at the centre of this support's contact rectangle with the parent
-                            Node par;
-                            if (parent != NODE_NEW) g.node_box(parent, par);
-                            else par = root;
-                            double r[4];
-                            g.support(par, child, r);
-                            vx = (r[0] + r[2]) * 0.5; vy = (r[1] + r[3]) * 0.5;
-                        }
+                        if (!f.whole) { vx = sup_x[f.base + s]; vy = sup_y[f.base + s]; }  // the load sits at the centre of this support's contact rectangle with the parent
                         base = f.base + f.k;
                         if (s == f.k - 1) { depth--; base = f.base; }  // tail call: the parent frame is finished
                         break;
@@ -798,19 +848,20 @@ static __device__ __noinline__ int stab_virtual(const G &g, const typename G::No
                 g.node_box(child, sb);
                 double ccx, ccy, ccz, mm = sb.mass;
                 g.centre(sb, ccx, ccy, ccz);
-                ccx *= mm; ccy *= mm; ccz *= mm;
+                ccx *= mm; ccy *= mm;  // z: see stab_light
+                (void)ccz;
 #pragma unroll 1
                 for (int q = pool.first_in[child]; q != EDGE_NIL; q = pool.next[q]) {
                     if (q == skip) continue;  // `involved` path member: its real load is replaced by the virtual one
                     const Stack4 e = pool.load(q);
-                    ccx += e.cx * e.m; ccy += e.cy * e.m; ccz += e.cz * e.m;
+                    ccx += e.cx * e.m; ccy += e.cy * e.m;
                     mm += e.m;
                 }
                 if (vm != 0.0) {  // zero-mass virtual loads add +0.0 to every sum: skipped (exact)
-                    ccx += vx * vm; ccy += vy * vm; ccz += st.cz * vm;
+                    ccx += vx * vm; ccy += vy * vm;
                     mm += vm;
                 }
-                st.cx = ddiv(ccx, mm); st.cy = ddiv(ccy, mm); st.cz = ddiv(ccz, mm); st.m = mm;
+                st.cx = ddiv(ccx, mm); st.cy = ddiv(ccy, mm); st.m = mm;
                 node = child;
                 need_adv = false;
             }
@@ -820,6 +871,7 @@ static __device__ __noinline__ int stab_virtual(const G &g, const typename G::No
             if (k >= 2) { heavy = true; break; }
             child = -1;
             PCT_STAT(k);  // 0 / 1: light visits
+            PCT_PATH_VISIT(k ? 1.0 : 0.1);
             if (k == 1) {
                 const int sid0 = (node == NODE_NEW) ? (int)(sup_pack & 0xFFu) : (int)pool.lower[eoff];
                 Node cur;
@@ -850,6 +902,7 @@ static __device__ __noinline__ int stab_virtual(const G &g, const typename G::No
         if (heavy) {
             PCT_STAT(node == NODE_NEW ? 2 : 3);  // heavy visits: root / placed box
             PCT_STAT(4 + (k < 8 ? k : 8));       // by number of supports
+            PCT_PATH_VISIT(node == NODE_NEW ? 6.0 : 3.5);
             Node cur;
             if (node != NODE_NEW) g.node_box(node, cur);
             else cur = root;
@@ -887,10 +940,12 @@ static __device__ __noinline__ int stab_virtual(const G &g, const typename G::No
                 }
 #pragma unroll 1
                 for (int s = 0; s < k; s++) g.support(cur, sup_id[base + s], rect[s]);
+                const double *split = nullptr;  // k == 2, placed box: the stored split direction
                 const int pv = node == NODE_NEW ? 0 : (int)pool.poly_off[node], pm = node == NODE_NEW ? 0 : (int)pool.poly_off[node + 1] - pv;
                 if (pm > 0 && (pv + pm <= POLY_STAGE || pv >= POLY_STAGE)) {
-                    const double *xy = pool.poly_at(pv);  // a placed box: its support polygon was stored when it was placed
-                    ok = pip_shrunk(xy, xy + 1, 2, pm, st.cx, st.cy);
+                    const double *xy = pool.poly_at(pv);  // a placed box: its shrunk support polygon was stored when it was placed
+                    ok = pip_stored(xy, pm - (k == 2), st.cx, st.cy);
+                    if (k == 2) split = xy + 2 * (pm - 1);
                 } else {
 #pragma unroll 1
                     for (int s = 0; s < k; s++) {
@@ -916,18 +971,18 @@ static __device__ __noinline__ int stab_virtual(const G &g, const typename G::No
                         whole = 0;
 #pragma unroll 1
                         for (int s = 0; s < k; s++) {
-                            px[s] = (rect[s][0] + rect[s][2]) * 0.5;
-                            py[s] = (rect[s][1] + rect[s][3]) * 0.5;
+                            sup_x[base + s] = px[s] = (rect[s][0] + rect[s][2]) * 0.5;
+                            sup_y[base + s] = py[s] = (rect[s][1] + rect[s][3]) * 0.5;
                         }
                         if (k == 2) {
-                            double lx = px[0] - px[1], ly = py[0] - py[1];
-                            const double len = dsqrt(fma(ly, ly, lx * lx));
-                            const double len2 = len * len;
-                            lx = ddiv(lx, len2); ly = ddiv(ly, len2);
+                            double lx, ly;
+                            if (split) { lx = split[0]; ly = split[1]; }
+                            else split2_dir(px, py, lx, ly);
                             sup_m[base + 0] = st.m * fabs(dot2(st.cx - px[1], st.cy - py[1], lx, ly));
                             sup_m[base + 1] = st.m * fabs(dot2(st.cx - px[0], st.cy - py[0], lx, ly));
                         } else {
                             PCT_STAT(14);
+                            PCT_PATH_VISIT(10.0);
                             double lR[KSUP_SMALL * KSUP_SMALL], lV[KSUP_SMALL * KSUP_SMALL], ly_[KSUP_SMALL], lrow[KSUP_SMALL], lx_[KSUP_SMALL];
                             LsWork w;
                             w.R = small ? lR : big->R; w.V = small ? lV : big->V; w.y = small ? ly_ : big->y;
@@ -945,6 +1000,7 @@ static __device__ __noinline__ int stab_virtual(const G &g, const typename G::No
             if (!ok) { active = false; result = 0; }
             else {
                 StabFrame &f = fr[depth++];
+                PCT_PATH_PUSH(depth - 1);
                 f.st = st; f.node = (uint8_t)node; f.base = (uint8_t)base; f.k = (uint8_t)k; f.i = 0; f.whole = (uint8_t)whole;
                 f.eoff = (uint8_t)eoff;
                 child = -1;

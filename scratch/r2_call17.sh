@@ -1,0 +1,20 @@
+#!/bin/bash
+# Round 2, GPU call 17: scheduling order without the sorting pass (bucket lists filed by the apply kernel), idle-lane prefetch in the continuation kernel (A/B), no z in virtual walks
+O=gpurun_out/r2_c17; mkdir -p $O
+( timeout 900 python -m pytest tests -m gpu -x -q --tb=short ) > $O/tests.log 2>&1; echo "tests rc=$?" | tee $O/summary.txt; tail -3 $O/tests.log | tee -a $O/summary.txt
+B="python bench.py --steps 400 --warmup 200 --e2e-steps 50 --skip-cpu --skip-configs"
+for rep in 1 2; do
+PCT_B200_LIB=scratch/variants/lib_nopf.so timeout 200 $B > $O/bench_head_nopf$rep.log 2>&1
+timeout 200 $B > $O/bench_head_new$rep.log 2>&1
+PCT_B200_LPT=0 timeout 200 $B > $O/bench_head_new_nolpt$rep.log 2>&1
+done
+timeout 200 $B --continuous > $O/bench_cont_new.log 2>&1
+python - <<'PY' | tee -a gpurun_out/r2_c17/summary.txt
+import glob, json
+for f in sorted(glob.glob("gpurun_out/r2_c17/bench_*.log")):
+    for line in open(f):
+        if line.startswith("{"):
+            j = json.loads(line)
+            print("%-28s value %.2fM  e2e %.2fM  ms/step %.4f  kernels %s" % (f.split("/")[-1][:-4], j["value"] / 1e6, j["e2e"]["value"] / 1e6,
+                  j["ms_per_step"], j["roofline"].get("all_kernels_ms")))
+PY

@@ -19,6 +19,11 @@ static inline double __longlong_as_double(long long v) { double d; memcpy(&d, &v
 static long long g_far_out = 0, g_walks = 0;  // statistics of the quick reject (sh_stats)
 static long long g_stat[32];
 #define PCT_STAT(i) g_stat[(i)]++
+static double g_path_cur = 0, g_path_tot = 0, g_path_max = 0, g_path_fr[64];
+#define PCT_PATH_VISIT(c) do { g_path_cur += (c); g_path_tot += (c); if (g_path_cur > g_path_max) g_path_max = g_path_cur; } while (0)
+#define PCT_PATH_PUSH(d) (g_path_fr[(d)] = g_path_cur)
+#define PCT_PATH_POP(d) (g_path_cur = g_path_fr[(d)])
+static double g_last_path[3];  // the last continuation walk: total cost, cost of its longest root-to-leaf path, result
 static int g_use_v2 = 0;  // sh_use_v2: route the virtual checks through stab_virtual (the warp-convergent restatement used by the round-2 feasibility kernels)
 #include <cuda_runtime.h>
 #ifndef __noinline__
@@ -93,7 +98,12 @@ int sh_virtual(StabHost *h, int x, int y, int z, int lx, int ly, double density,
         if (far_out) { g_far_out++; return 0; }
         int node = NODE_NEW; Stack4 st{};
         ok = stab_light<GeomD>(g, root, k, pack, pool, node, st);
-        if (ok == 2) { g_walks++; ok = stab_virtual<GeomD>(g, root, k, pack, pool, &h->big, &h->lock, fl, true, 0xffffffffu, node, &st); }
+        if (ok == 2) {
+            g_walks++;
+            g_path_cur = g_path_tot = g_path_max = 0;
+            ok = stab_virtual<GeomD>(g, root, k, pack, pool, &h->big, &h->lock, fl, true, 0xffffffffu, node, &st);
+            g_last_path[0] = g_path_tot; g_last_path[1] = g_path_max; g_last_path[2] = ok;
+        } else g_last_path[0] = g_last_path[1] = 0;
     } else if (g_use_v2 == 2) ok = stab_virtual<GeomD>(g, root, -1, 0, pool, &h->big, &h->lock, fl, true, 0xffffffffu);
     else ok = stability_check<false, GeomD>(g, root, pool, &h->big, &h->lock, 0, fl) != 0;
     h->flags |= fl;
@@ -103,6 +113,7 @@ void sh_use_v2(int on) { g_use_v2 = on; }
 double sh_around6(double v) { return around6(v); }
 long long sh_hash_double(double v, int loop) { return (long long)(loop ? hash_double_loop(v) : hash_double(v)); }  // _Py_HashDouble: integer restatement / frexp loop  // the device's np.around(v, 6) (fast division by 1e6, pct_geom_continuous.cuh)
 void sh_stats(long long *out2) { out2[0] = g_far_out; out2[1] = g_walks; }
+void sh_last_path(double *out3) { memcpy(out3, g_last_path, sizeof g_last_path); }
 void sh_stats_visits(long long *out32) { memcpy(out32, g_stat, sizeof g_stat); }
 
 // Space.drop_box (D:space.py:347-391) as pct_apply_kernel performs it: 1 = placed, 0 = rejected (the episode ends)
