@@ -99,6 +99,8 @@ int pct_create(const pct_config *cfg, int32_t n_envs, int32_t device, pct_handle
     if (const char *kv = getenv("PCT_B200_K3")) h->k3_block = strcmp(kv, "block") == 0;
     if (const char *wv = getenv("PCT_B200_WALK_LANES_TALL")) { h->walk_lanes_tall = atoi(wv); if (h->walk_lanes_tall < 1) h->walk_lanes_tall = 1; if (h->walk_lanes_tall > 32) h->walk_lanes_tall = 32; }
     if (const char *ev = getenv("PCT_B200_EMIT_PDL")) h->no_emit_pdl = atoi(ev) == 0;
+    if (const char *wv = getenv("PCT_B200_WALK")) h->walk_fork = strcmp(wv, "seq") != 0;  // seq: the sequential continuation kernel (A/B)
+    if (const char *wv = getenv("PCT_B200_WALK_BLOCKS")) { h->walk_blocks = atoi(wv); if (h->walk_blocks < 1) h->walk_blocks = 1; if (h->walk_blocks > 8) h->walk_blocks = 8; }
     if (const char *wv = getenv("PCT_B200_WALK_LANES")) { h->walk_lanes = atoi(wv); if (h->walk_lanes < 1) h->walk_lanes = 1; if (h->walk_lanes > 32) h->walk_lanes = 32; }
     if (cfg->setting == 2) h->alias_mode = false;  // no stability check, no load entries
     if ((h->obs_delta || h->alias_mode) && e == cudaSuccess) {
@@ -131,8 +133,11 @@ int pct_create(const pct_config *cfg, int32_t n_envs, int32_t device, pct_handle
                 if (e == cudaSuccess) e = cudaMalloc(&h->d_walk_ctr, sizeof(int32_t) * (size_t)n_envs);
                 if (e == cudaSuccess) e = cudaMemset(h->d_walk_ctr, 0, sizeof(int32_t) * (size_t)n_envs);
                 if (e == cudaSuccess) e = cudaMalloc(&h->d_contq, sizeof(WalkCont) * (size_t)WALK_CONT_PER_ENV * (size_t)n_envs);
-                if (e == cudaSuccess) e = cudaMalloc(&h->d_cont_ctr, sizeof(int32_t) * ((size_t)n_envs + 1));
-                if (e == cudaSuccess) e = cudaMemset(h->d_cont_ctr, 0, sizeof(int32_t) * ((size_t)n_envs + 1));
+                if (e == cudaSuccess) e = cudaMalloc(&h->d_cont_ctr, sizeof(int32_t) * 4 * ((size_t)n_envs + 1));  // four counters per (possible) env range
+                if (e == cudaSuccess) e = cudaMemset(h->d_cont_ctr, 0, sizeof(int32_t) * 4 * ((size_t)n_envs + 1));
+                if (e == cudaSuccess) e = cudaMalloc(&h->d_piece_ready, sizeof(int32_t) * (size_t)WALK_CONT_PER_ENV * (size_t)n_envs);
+                if (e == cudaSuccess) e = cudaMemset(h->d_piece_ready, 0, sizeof(int32_t) * (size_t)WALK_CONT_PER_ENV * (size_t)n_envs);
+                if (e == cudaSuccess) e = cudaMalloc(&h->d_walk_pend, sizeof(int32_t) * (size_t)CAND_MAX * (size_t)n_envs);
             }
             h->lpt = !h->k3_block;   // heaviest-env-first block order (pct_discrete.cu, order_lookup / order_file); PCT_B200_LPT=0 disables
             if (const char *lv = getenv("PCT_B200_LPT")) h->lpt = atoi(lv) != 0 && !h->k3_block;
@@ -168,7 +173,7 @@ void pct_destroy(pct_handle h) {
     cudaSetDevice(h->device);
     if (h->cfg.domain == PCT_CONTINUOUS) continuous_destroy(h);
     cudaFree(h->d_order);
-    cudaFree(h->d_walkq); cudaFree(h->d_walk_ctr); cudaFree(h->d_contq); cudaFree(h->d_cont_ctr);
+    cudaFree(h->d_walkq); cudaFree(h->d_walk_ctr); cudaFree(h->d_contq); cudaFree(h->d_cont_ctr); cudaFree(h->d_piece_ready); cudaFree(h->d_walk_pend);
     cudaFree(h->d_hstate); cudaFree(h->d_hstate_c); cudaFree(h->d_query_c); cudaFree(h->d_query); cudaFree(h->d_aux);
     cudaFree(h->d_ready);
     cudaFree(h->d_hot); cudaFree(h->d_cold); cudaFree(h->d_item_set); cudaFree(h->d_stream);
@@ -268,8 +273,11 @@ static int launch_range(pct_handle h, int mode, int off, int cnt, const void *ac
     p.walkq = h->d_walkq ? h->d_walkq + (size_t)off * CAND_MAX : nullptr;  // env ranges stepped concurrently (pct_step_host's staged path) own disjoint slices
     p.walk_ctr = h->d_walk_ctr ? h->d_walk_ctr + off : nullptr;
     p.contq = h->d_contq ? h->d_contq + (size_t)off * WALK_CONT_PER_ENV : nullptr;
-    p.cont_ctr = h->d_cont_ctr ? h->d_cont_ctr + off : nullptr;
+    p.cont_ctr = h->d_cont_ctr ? h->d_cont_ctr + 4 * (size_t)off : nullptr;
     p.walk_lanes = h->walk_lanes; p.walk_lanes_tall = h->walk_lanes_tall;
+    p.walk_fork = h->walk_fork ? 1 : 0; p.walk_blocks = h->walk_blocks;
+    p.piece_ready = h->d_piece_ready ? h->d_piece_ready + (size_t)off * WALK_CONT_PER_ENV : nullptr;
+    p.walk_pend = h->d_walk_pend ? h->d_walk_pend + (size_t)off * CAND_MAX : nullptr;
     CK(h, launch_discrete(p, gs, prof));
     h->launches += discrete_kernels_per_step(p);
     return PCT_OK;

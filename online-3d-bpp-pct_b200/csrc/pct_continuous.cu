@@ -113,6 +113,7 @@ __device__ __forceinline__ void cand_tuple(uint16_t code, const double (*ems)[6]
     if (q & 2) { t[1] = m[4] - sy; t[4] = m[4]; } else { t[1] = m[1]; t[4] = m[1] + sy; }
     t[2] = m[2]; t[5] = m[2] + sz;
 }
+__device__ __noinline__ uint64_t hash_double_call(double v) { return hash_double(v); }  // one copy of the routine for the three call sites of the candidates kernel
 __device__ __noinline__ uint64_t cand_hash_c(const double t[6]) {
     uint64_t l[6];
 #pragma unroll 1
@@ -219,10 +220,33 @@ __device__ __noinline__ int genems_warp_c(CEnv *ev, const int n0, const double l
     // (ncu r2, profiles/r2_cont_head.txt: 30 % of this kernel's stall samples on that line); the intermediate list is staged in shared memory first
     // (lists longer than CE_STAGE entries — not seen on the BASELINE streams — keep reading the record).
     const bool staged = n <= CE_STAGE;
-    if (staged)
+    // Every EMS coordinate is a 6-decimal value (the container's corners or an np.around(.., 6) result), so v -> rint(v * 1e6) is an order-preserving
+    // bijection onto integers; for bins up to 1.048575 they fit 20 bits and the six comparisons of a containment test become two 64-bit subtractions on
+    // packed fields with guard bits (the discrete kernel's trick; ncu r2: this loop was 21 % of the kernel's instructions).  Any coordinate that is not
+    // exactly such a value (checked per entry) sends the whole list through the float64 comparisons.
+    constexpr uint64_t GUARD = (1ull << 20) | (1ull << 41) | (1ull << 62);
+    uint64_t *pk = (uint64_t *)&stage[0][0];
+    bool packed = staged;
+    if (packed) {
+        bool good = true;
+#pragma unroll 1
+        for (int i = lane; i < n; i += 32) {
+            uint64_t w2[2] = {0, 0};
+#pragma unroll
+            for (int t = 0; t < 6; t++) {
+                const double v = tmp[i][t], k = rint(v * 1e6);
+                good = good && k >= 0.0 && k < 1048576.0 && around6(v) == v;
+                w2[t / 3] |= (uint64_t)(long long)k << (21 * (t % 3));
+            }
+            pk[2 * i] = w2[0]; pk[2 * i + 1] = w2[1];
+        }
+        packed = __all_sync(FULL, good);
+        __syncwarp();
+    }
+    if (staged && !packed)
         for (int t = lane; t < n * 6; t += 32) (&stage[0][0])[t] = (&tmp[0][0])[t];
     __syncwarp();
-    const double (*src)[6] = staged ? stage : tmp;
+    const double (*src)[6] = (staged && !packed) ? stage : tmp;
     int w = 0;
     const int nch2 = (n + 31) >> 5;
 #pragma unroll 1
@@ -234,10 +258,19 @@ __device__ __noinline__ int genems_warp_c(CEnv *ev, const int n0, const double l
 #pragma unroll
             for (int t = 0; t < 6; t++) a[t] = src[i][t];
             int hit = 0;
+            if (packed) {
+                const uint64_t alo = pk[2 * i] | GUARD, ahi = pk[2 * i + 1];
+#pragma unroll 4
+                for (int j = 0; j < n; j++) {
+                    const ulonglong2 b = *(const ulonglong2 *)(pk + 2 * j);
+                    hit |= (int)(j != i && (((alo - b.x) & ((b.y | GUARD) - ahi) & GUARD) == GUARD));
+                }
+            } else {
 #pragma unroll 2
-            for (int j = 0; j < n; j++) {
-                const double *b = src[j];
-                hit |= (int)(j != i && a[0] >= b[0] && a[1] >= b[1] && a[2] >= b[2] && a[3] <= b[3] && a[4] <= b[4] && a[5] <= b[5]);
+                for (int j = 0; j < n; j++) {
+                    const double *b = src[j];
+                    hit |= (int)(j != i && a[0] >= b[0] && a[1] >= b[1] && a[2] >= b[2] && a[3] <= b[3] && a[4] <= b[4] && a[5] <= b[5]);
+                }
             }
             keep = !hit;
         }
@@ -266,7 +299,7 @@ __global__ void __launch_bounds__(64) pctc_apply_kernel(const CParams p) {
     const int e = blockIdx.x * 2 + warp;
     if (e >= p.n_envs) return;
     __shared__ int lock_s[2];
-    __shared__ double ems_stage[2][CE_STAGE][6];
+    __shared__ __align__(16) double ems_stage[2][CE_STAGE][6];
     int *lock = &lock_s[warp];
     CEnv *ev = p.env + e;
     CHdr &h = ev->h;
@@ -442,19 +475,37 @@ __global__ void __launch_bounds__(32) pctc_candidates_kernel(const CParams p) {
         bool valid = false;
         uint64_t hash = 0;
         uint16_t code = 0;
+        // The four corners of one (EMS, orientation) are four adjacent lanes and their 6-tuples draw on ten distinct coordinates (x: m0, m0 + sx, m3 - sx,
+        // m3; y alike; z: m2, m2 + sz): every lane hashes two or three of them (_Py_HashDouble, the expensive part) and the group exchanges the results,
+        // instead of six hashes per lane (ncu r2: 17 % of this kernel's instructions).  Same expressions as cand_tuple, so the same bits.
+        uint64_t h0 = 0, h1 = 0, h2 = 0;
+        const int q = r & 3;
         if (r < raw) {
-            const int q = r & 3, er = r >> 2, rot = er % R, ei = er / R;
+            const int er = r >> 2, rot = er % R, ei = er / R;
             double sx, sy, sz;
             if (rot_dims_c(nb, rot, sx, sy, sz)) {
                 const double *m = ev->ems[ei];
                 if (m[3] - m[0] + 1e-6 >= sx && m[4] - m[1] + 1e-6 >= sy && m[5] - m[2] + 1e-6 >= sz) {
                     valid = true;
                     code = (uint16_t)((ei << 5) | (rot << 2) | q);
-                    double t6[6];
-                    cand_tuple(code, ev->ems, nb, t6);
-                    hash = cand_hash_c(t6);
+                    double v0, v1, v2 = 0;
+                    if (q == 0) { v0 = m[0]; v1 = m[0] + sx; v2 = m[2]; }
+                    else if (q == 1) { v0 = m[3] - sx; v1 = m[3]; v2 = m[2] + sz; }
+                    else if (q == 2) { v0 = m[1]; v1 = m[1] + sy; }
+                    else { v0 = m[4] - sy; v1 = m[4]; }
+                    h0 = hash_double_call(v0);
+                    h1 = hash_double_call(v1);
+                    if (q < 2) h2 = hash_double_call(v2);
                 }
             }
+        }
+        {
+            const int gb = lane & ~3, lx = gb + (q & 1), ly = gb + 2 + (q >> 1);
+            uint64_t l6[6];
+            l6[0] = __shfl_sync(FULL, h0, lx); l6[3] = __shfl_sync(FULL, h1, lx);
+            l6[1] = __shfl_sync(FULL, h0, ly); l6[4] = __shfl_sync(FULL, h1, ly);
+            l6[2] = __shfl_sync(FULL, h2, gb); l6[5] = __shfl_sync(FULL, h2, gb + 1);
+            if (valid) hash = tuple_hash6(l6);
         }
         // already present? (read-only probe; present keys sit on their own probe sequence)
         if (valid) {

@@ -1283,6 +1283,27 @@ __global__ void __launch_bounds__(32 * LIGHT_WARPS, LIGHT_MINB) pct_walk_light_k
         if (has && res != 2) walk_done(&v.cold->n_pending);
         // continuations: walks high up in the bin descend through the deepest support DAGs (host statistics: resting height >= 0.6 H -> up to 8 heavy
         // visits, below -> at most 2), so they are pooled apart (from the END of the pool) and get fewer lanes per warp in pct_walk_kernel
+        if (p.walk_fork) {  // fork-join continuation kernel: one queue of pieces, "enter `node` with the stack st"
+            const uint32_t pm = __ballot_sync(FULL, res == 2);
+            if (pm) {
+                int qb = 0;
+                if (lane == 0) { qb = atomicAdd(p.cont_ctr, __popc(pm)); atomicAdd(p.cont_ctr + 2, __popc(pm)); }
+                qb = __shfl_sync(FULL, qb, 0);
+                if (res == 2) {
+                    const int idx = qb + __popc(pm & ((1u << lane) - 1));
+                    if (idx < cap) {
+                        p.walk_pend[i] = 1;
+                        ((WalkPiece *)p.contq)[idx] = WalkPiece{(uint32_t)i, (uint8_t)node, (uint8_t)EDGE_NIL, 0, 0, st.cx, st.cy, st.m};
+                        p.piece_ready[idx] = 1;  // (the consumer kernel starts after this one has completed: plain stores)
+                    } else {
+                        atomicSub(p.cont_ctr + 2, 1);
+                        atomicOr(const_cast<int32_t *>(&v.hot->h.flags), PCT_FLAG_CAND_OVERFLOW);
+                        walk_done(&v.cold->n_pending);
+                    }
+                }
+            }
+            continue;
+        }
         const bool tall = (int)it.mh * 5 >= p.H * 3;
         const uint32_t ps = __ballot_sync(FULL, res == 2 && !tall), pt = __ballot_sync(FULL, res == 2 && tall);
         if (ps | pt) {
@@ -1336,6 +1357,99 @@ __global__ void __launch_bounds__(32 * WALK_WARPS, WALK_MINB) pct_walk_kernel(co
     }
 }
 
+// walk, stage 2, fork-join form (default): the queue holds PIECES of walks (stab_piece: one chain of visits; a node with k >= 2 supports keeps
+// its first subtree and publishes the other k - 1 as new pieces), persistent warps take up to `walk_lanes` pieces at a time until no piece is left
+// or running.  A walk's verdict is the AND over its pieces: walk_pend[item] counts them, the piece that brings it to zero sets the feasibility bit
+// (unless one failed) and releases the env's n_pending.  The kernel's duration is the longest root-to-floor PATH of a walk instead of the sum over
+// its visits (host statistics, scratch/stats_paths.py).  Only the first WALK_KEEP blocks per SM stay to the end; the others leave as soon as they find
+// the queue empty, so the emit kernel's blocks (programmatic dependents, each waiting for ITS env) get SM slots during the tail.
+#ifndef WALK_KEEP
+#define WALK_KEEP 2
+#endif
+struct PieceFork {
+    WalkPiece *q;
+    int32_t *ready, *ctr, *pend;
+    uint32_t item;
+    int cap;
+    bool overflow;
+    __device__ __forceinline__ void operator()(int child, int skip, double vx, double vy, double vm) {
+        const int slot = atomicAdd(ctr, 1);
+        if (slot >= cap) { overflow = true; return; }
+        atomicAdd(pend, 1);      // before the parent's own decrement: the walk cannot complete in between
+        atomicAdd(ctr + 2, 1);
+        q[slot] = WalkPiece{item, (uint8_t)child, (uint8_t)skip, 1, 0, vx, vy, vm};
+        __threadfence();
+        *(volatile int32_t *)(ready + slot) = 1;
+    }
+};
+__global__ void __launch_bounds__(32 * WALK_WARPS, WALK_MINB) pct_walk_fork_kernel(const DParams p, int n_sm) {
+    const int lane = threadIdx.x & 31;
+    const int cap = p.n_envs * WALK_CONT_PER_ENV;
+    const int L = p.walk_lanes;
+    const bool keep = (int)blockIdx.x < n_sm * WALK_KEEP;
+    WalkPiece *q = (WalkPiece *)p.contq;
+    pdl_launch_dependents();  // the emit kernel's blocks may become resident; each waits for ITS env's last walk
+#pragma unroll 1
+    for (;;) {
+        int n = 0, h0 = 0;
+        if (lane == 0) {
+            int spins = 0;
+#pragma unroll 1
+            for (;;) {
+                const int h = *(volatile const int32_t *)(p.cont_ctr + 1);
+                const int a = min(*(volatile const int32_t *)p.cont_ctr, cap);
+                n = min(a - h, L);
+                if (n > 0) {
+                    if (atomicCAS(p.cont_ctr + 1, h, h + n) == h) { h0 = h; break; }
+                    continue;
+                }
+                n = -1;
+                if (!keep || *(volatile const int32_t *)(p.cont_ctr + 2) <= 0) break;  // nothing queued: leave (kept blocks: only once nothing is running either)
+                __nanosleep(spins < 64 ? 200 : 2000);
+                if (++spins > (1 << 20)) break;  // bounded (never seen): whatever is still queued is taken by the warps that are still working
+            }
+        }
+        n = __shfl_sync(FULL, n, 0);
+        h0 = __shfl_sync(FULL, h0, 0);
+        if (n < 0) break;
+        if (lane < n) {
+            const int slot = h0 + lane;
+            int spins = 0;
+            while (*(volatile const int32_t *)(p.piece_ready + slot) == 0 && ++spins < (1 << 24)) { }  // allocated, being written
+            __threadfence();
+            const WalkPiece pc = q[slot];
+            p.piece_ready[slot] = 0;
+            const WalkItem it = p.walkq[pc.item];
+            const WalkView v = walk_view(p, it, true);
+            int32_t *pend = p.walk_pend + pc.item;
+            int fl = 0, ok = 0;
+            if (!(*(volatile const int32_t *)pend & WALK_FAILED)) {  // a failed sibling has already decided the walk
+                PieceFork fork{q, p.piece_ready, p.cont_ctr, pend, pc.item, cap, false};
+                ok = stab_piece<GeomD>(v.g, v.root, (int)it.k, it.pack, v.pool, &v.cold->big, &v.cold->lock, fl, (int)pc.node, (int)pc.kind, (int)pc.skip,
+                                       pc.a, pc.b, pc.c, fork);
+                if (fork.overflow) { fl |= PCT_FLAG_CAND_OVERFLOW; ok = 0; }  // never silent: the candidate stays infeasible and the env is flagged
+            }
+            if (fl) atomicOr(const_cast<int32_t *>(&v.hot->h.flags), fl);
+            if (!ok) atomicOr(pend, WALK_FAILED);
+            __threadfence();
+            const int r = atomicSub(pend, 1);
+            if ((r & (WALK_FAILED - 1)) == 1) {  // the walk's last piece
+                if (!(r & WALK_FAILED)) atomicOr(&v.cold->fbits[it.c >> 5], 1u << (it.c & 31));
+                walk_done(&v.cold->n_pending);
+            }
+            atomicSub(p.cont_ctr + 2, 1);
+        }
+        __syncwarp();
+    }
+    // last warp out empties the pools for the next step (every other warp has finished, the light-prefix kernel completed before this one started)
+    if (lane == 0) {
+        __threadfence();
+        if (atomicAdd(p.cont_ctr + 3, 1) == (int)(gridDim.x * WALK_WARPS) - 1) {
+            *p.walk_ctr = 0; p.cont_ctr[0] = 0; p.cont_ctr[1] = 0; p.cont_ctr[2] = 0; p.cont_ctr[3] = 0;
+        }
+    }
+}
+
 constexpr int EMIT_WARPS = 4;
 constexpr int EMIT_STAGE = sizeof(DHdr) + NB_MAX * 12;  // header + placed boxes: all the observation needs from the hot record
 constexpr int EMIT_SM_PER_WARP = EMIT_STAGE + NL_MAX * 12 + 48;
@@ -1348,7 +1462,7 @@ __global__ void __launch_bounds__(32 * EMIT_WARPS) pct_emit_kernel(const DParams
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int e = blockIdx.x * EMIT_WARPS + warp;
     // last kernel of the launch sequence that touches the walk pools (both walk kernels have completed: plain stream order): empty them for the next step
-    if (blockIdx.x == 0 && threadIdx.x == 0 && p.walk_ctr) { *p.walk_ctr = 0; p.cont_ctr[0] = 0; p.cont_ctr[1] = 0; }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && p.walk_ctr && !p.walk_fork) { *p.walk_ctr = 0; p.cont_ctr[0] = 0; p.cont_ctr[1] = 0; }  // (the fork-join kernel's counters are live while this kernel starts: its last warp empties them)
     if (blockIdx.x == 0 && p.order) {
         // ... and the last one of the step: the apply and candidates kernels have consumed this parity's buckets (both completed before the walk kernels
         // started) and the apply kernel has filled the other parity's; empty the consumed ones and flip
@@ -1506,7 +1620,8 @@ static cudaError_t launch_t(const DParams &p_in, cudaStream_t st, cudaEvent_t *p
         if (p.ready && prof) cudaEventRecord(prof[2], st);
         if (STAB) {
             pct_walk_light_kernel<<<n_sm * LIGHT_MINB, 32 * LIGHT_WARPS, 0, st>>>(p);
-            pct_walk_kernel<<<n_sm * WALK_MINB, 32 * WALK_WARPS, 0, st>>>(p);  // one resident wave (every block starts at once: the emit kernel may follow)
+            if (p.walk_fork) pct_walk_fork_kernel<<<n_sm * max(1, min(p.walk_blocks, WALK_MINB)), 32 * WALK_WARPS, 0, st>>>(p, n_sm);  // one resident wave, persistent warps
+            else pct_walk_kernel<<<n_sm * WALK_MINB, 32 * WALK_WARPS, 0, st>>>(p);  // one resident wave (every block starts at once: the emit kernel may follow)
         }
         const int eb = (p.n_envs + EMIT_WARPS - 1) / EMIT_WARPS;
         {   // programmatic dependent of the continuation kernel (setting 2: of the candidates kernel, whose blocks never trigger early -> plain order)

@@ -59,6 +59,9 @@ struct pct_env_batch {
     int32_t *d_walk_ctr = nullptr;     // [n_envs] fill counters (index = first env of the launched range)
     pct::WalkCont *d_contq = nullptr;  // [n_envs * WALK_CONT_PER_ENV] continuations: light-prefix kernel -> pct_walk_kernel
     int32_t *d_cont_ctr = nullptr;
+    int32_t *d_piece_ready = nullptr, *d_walk_pend = nullptr;  // fork-join walks: per-slot publication flags, per-walk piece counters
+    bool walk_fork = true;             // fork-join continuation kernel (PCT_B200_WALK=seq: the sequential one)
+    int walk_blocks = 6;               // its blocks per SM (PCT_B200_WALK_BLOCKS)
     int walk_lanes_tall = 4;           // ... of the tall walks (resting height >= 0.6 H: the longest chains), PCT_B200_WALK_LANES_TALL
     int walk_lanes = 16;               // continuations per warp of pct_walk_kernel (PCT_B200_WALK_LANES; few long serial chains: more warps beat fuller warps)
     bool lpt = false;

@@ -154,6 +154,7 @@ struct WalkCont {
     Stack4 st;
 };
 static_assert(sizeof(WalkCont) == 40, "queue entry");
+constexpr int WALK_FAILED = 1 << 30;
 constexpr int WALK_CONT_PER_ENV = 256;  // capacity of the continuation pool = n_envs x this (mean use: 3 per env); overflow -> PCT_FLAG_CAND_OVERFLOW
 
 struct DParams {
@@ -199,6 +200,13 @@ struct DParams {
     WalkCont *contq;    // [n_envs * WALK_CONT_PER_ENV] walks the light-prefix kernel hands to the continuation kernel
     int32_t *cont_ctr;  // [2]: continuations pooled from the front (ordinary) / from the end (tall walks) of contq
     int32_t walk_lanes, walk_lanes_tall; // continuations per warp of pct_walk_kernel (1..32): ordinary / tall (resting height >= 0.6 H) walks
+    // fork-join walks (pct_walk_fork_kernel, the default; PCT_B200_WALK=seq selects the sequential continuation kernel): contq holds WalkPiece entries,
+    // cont_ctr = {allocated, taken, outstanding}; piece_ready[slot] = 1 once the slot's piece is written (cleared by its consumer);
+    // walk_pend[item] = pieces of the walk still running (+ WALK_FAILED once one of them failed)
+    int32_t walk_fork;
+    int32_t walk_blocks;   // blocks per SM of the fork-join kernel (1..8)
+    int32_t *piece_ready;
+    int32_t *walk_pend;
     int32_t opt;     // opt-in variants served by `aux`: PCT_OPT_DELTA (K3 delta observation writes), PCT_OPT_ALIAS (K1 object semantics of the loads)
 };
 constexpr int PCT_OPT_DELTA = 1, PCT_OPT_ALIAS = 2, PCT_OPT_K3_BLOCK = 4, PCT_OPT_NO_EMIT_PDL = 8;  // K3_BLOCK: round 1's block-per-env feasibility kernel (A/B)

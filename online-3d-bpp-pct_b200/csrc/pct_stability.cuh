@@ -31,6 +31,10 @@
 namespace pct {
 
 static __device__ __noinline__ double ddiv(double a, double b) { return a / b; }
+// two / three quotients by the same divisor in ONE routine: the independent Newton chains interleave, so the second and third division cost
+// issue slots but (almost) no extra latency on the serial chain of a walk (each is the same correctly rounded a / d as ddiv)
+static __device__ __noinline__ void ddiv2(double a, double b, double d, double &qa, double &qb) { qa = a / d; qb = b / d; }
+static __device__ __noinline__ void ddiv3(double a, double b, double c, double d, double &qa, double &qb, double &qc) { qa = a / d; qb = b / d; qc = c / d; }
 static __device__ __noinline__ double dsqrt(double a) { return sqrt(a); }
 __device__ __forceinline__ double dot2(double u0, double u1, double v0, double v1) { return fma(u1, v1, u0 * v0); }
 
@@ -123,7 +127,8 @@ static __device__ __noinline__ bool pip_shrunk(const double *hx, const double *h
     double sx = 0, sy = 0;
 #pragma unroll 1
     for (int i = 0; i < m; i++) { sx += hx[i * stride]; sy += hy[i * stride]; }
-    const double cx = ddiv(sx, (double)m), cy = ddiv(sy, (double)m);
+    double cx, cy;
+    ddiv2(sx, sy, (double)m, cx, cy);
     double jx, jy;
     {
         double v = hx[(m - 1) * stride], d = v - cx;
@@ -176,7 +181,7 @@ __device__ __forceinline__ void split2_dir(const double *px, const double *py, d
     lx = px[0] - px[1]; ly = py[0] - py[1];
     const double len = dsqrt(fma(ly, ly, lx * lx));
     const double len2 = len * len;
-    lx = ddiv(lx, len2); ly = ddiv(ly, len2);
+    ddiv2(lx, ly, len2, lx, ly);
 }
 
 // Minimum-norm least squares (np.linalg.lstsq restatement: streaming Givens QR + one-sided Jacobi SVD,
@@ -411,7 +416,7 @@ static __device__ __noinline__ void alias_recompute(const G &g, EdgePoolA &pa, i
         mm += e.m;
     }
     Stack4 &d = pa.box_st[box];
-    d.cx = ddiv(cx, mm); d.cy = ddiv(cy, mm); d.cz = ddiv(cz, mm); d.m = mm;
+    ddiv3(cx, cy, cz, mm, d.cx, d.cy, d.cz); d.m = mm;
 }
 // SET_EDGE bookkeeping of edge q (upper box `upper`, supporting box `lower`): kind of the entry, then the support's eager recompute
 template <class G>
@@ -559,7 +564,8 @@ static __device__ __noinline__ int stability_check(const G &g, const typename G:
                     double sx = 0, sy = 0;
 #pragma unroll 1
                     for (int i = 0; i < m; i++) { sx += hx[i]; sy += hy[i]; }
-                    const double pcx = ddiv(sx, (double)m), pcy = ddiv(sy, (double)m);
+                    double pcx, pcy;
+                    ddiv2(sx, sy, (double)m, pcx, pcy);
 #pragma unroll 1
                     for (int i = 0; i < m; i++) {
                         double *v = pool.poly_at(pool.n_poly + i);
@@ -687,7 +693,7 @@ static __device__ __noinline__ int stability_check(const G &g, const typename G:
             ccx += vx * vm; ccy += vy * vm; ccz += st.cz * vm;
             mm += vm;
         }
-        st.cx = ddiv(ccx, mm); st.cy = ddiv(ccy, mm); st.cz = ddiv(ccz, mm); st.m = mm;
+        ddiv3(ccx, ccy, ccz, mm, st.cx, st.cy, st.cz); st.m = mm;
         node = child;
         DBG_VISIT();
         SEC(4);
@@ -775,7 +781,7 @@ static __device__ __forceinline__ int stab_light(const G &g, const typename G::N
             ccx += st.cx * st.m; ccy += st.cy * st.m;
             mm += st.m;
         }
-        st.cx = ddiv(ccx, mm); st.cy = ddiv(ccy, mm); st.m = mm;
+        ddiv2(ccx, ccy, mm, st.cx, st.cy); st.m = mm;
         node = sid0;
     }
 }
@@ -861,7 +867,7 @@ static __device__ __noinline__ int stab_virtual(const G &g, const typename G::No
                     ccx += vx * vm; ccy += vy * vm;
                     mm += vm;
                 }
-                st.cx = ddiv(ccx, mm); st.cy = ddiv(ccy, mm); st.m = mm;
+                ddiv2(ccx, ccy, mm, st.cx, st.cy); st.m = mm;
                 node = child;
                 need_adv = false;
             }
@@ -1009,6 +1015,190 @@ static __device__ __noinline__ int stab_virtual(const G &g, const typename G::No
         }
     }
     return result;
+}
+
+
+// ---- fork-join form of the read-only walk (round 2, pct_walk_fork_kernel) -----------------------------------------------------------------------
+// calculated_impact_virtual is a conjunction over the support DAG below the placement: a node with k >= 2 supports passes iff its own polygon
+// test passes AND every support subtree passes, and a read-only walk has no side effects — so the k subtrees are independent.  stab_piece runs ONE
+// chain of the walk: it visits nodes, follows single supports itself (tail calls) and, at a node with k >= 2 supports, keeps the first subtree and
+// hands the other k - 1 to `fork` as new pieces; the walk's verdict is the AND over its pieces (the reference's depth-first order only decides
+// which failing subtree is seen first).  No frames and no per-depth arrays are left: the state of a piece is (node, stack).  The longest walk of a step
+// (what the continuation kernel's duration was) shrinks from the SUM over its visits to its longest root-to-floor path (host statistics,
+// scratch/stats_paths.py: 51 -> 34 visit units at the 99.99 % quantile).
+// A piece is either "enter `node` with the stack (a, b, c) = (cx, cy, mass)" (kind 0) or "the load (a, b, c) = (x, y, mass) arrives on `node`
+// in place of the stored edge `skip`: combine (calculate_new_com), then enter" (kind 1).
+struct WalkPiece {
+    uint32_t item;           // index of the WalkItem (the candidate placement this piece belongs to)
+    uint8_t node, skip, kind, pad_;
+    double a, b, c;
+};
+static_assert(sizeof(WalkPiece) == 32, "queue entry");
+
+template <class G, class Fork>
+static __device__ __noinline__ int stab_piece(const G &g, const typename G::Node &root, int k_root, uint32_t sup_pack, const EdgePool &pool,
+                                              BigScratch *big, int *lock, int &flags, int node, int kind, int skip, double pa, double pb, double pc,
+                                              Fork &fork) {
+    typedef typename G::Node Node;
+    Stack4 st;
+    st.cx = pa; st.cy = pb; st.cz = 0; st.m = pc;
+    bool need_com = kind != 0;
+    int child = node;
+    double vx = pa, vy = pb, vm = pc;
+#pragma unroll 1
+    for (;;) {
+        if (need_com) {
+            // calculate_new_com of `child` (D:space.py:51-71) under the virtual load (vx, vy, vm); z: see stab_light
+            Node sb;
+            g.node_box(child, sb);
+            double ccx, ccy, ccz, mm = sb.mass;
+            g.centre(sb, ccx, ccy, ccz);
+            ccx *= mm; ccy *= mm;
+            (void)ccz;
+#pragma unroll 1
+            for (int q = pool.first_in[child]; q != EDGE_NIL; q = pool.next[q]) {
+                if (q == skip) continue;  // `involved` path member: its real load is replaced by the virtual one
+                const Stack4 e = pool.load(q);
+                ccx += e.cx * e.m; ccy += e.cy * e.m;
+                mm += e.m;
+            }
+            if (vm != 0.0) {  // zero-mass virtual loads add +0.0 to every sum: skipped (exact)
+                ccx += vx * vm; ccy += vy * vm;
+                mm += vm;
+            }
+            ddiv2(ccx, ccy, mm, st.cx, st.cy); st.m = mm;
+            node = child;
+        }
+        need_com = true;
+        // ENTER(node, st)
+        int k, eoff;
+        if (node == NODE_NEW) { k = k_root; eoff = pool.n; }
+        else { eoff = (int)pool.off[node]; k = (int)pool.off[node + 1] - eoff; }
+        if (k == 0) return 1;  // rests on the floor
+        Node cur;
+        if (node != NODE_NEW) g.node_box(node, cur);
+        else cur = root;
+        if (k == 1) {
+            PCT_STAT(1);
+            PCT_PATH_VISIT(1.0);
+            const int sid0 = (node == NODE_NEW) ? (int)(sup_pack & 0xFFu) : (int)pool.lower[eoff];
+            double r0[4];
+            g.support(cur, sid0, r0);
+            const double t1 = r0[1] * 1e-6, t2 = r0[3] * 1e-6;
+            const bool fast = (r0[0] + t1 < r0[0] + t2) && (r0[0] + t2 < r0[2] + t1) && (r0[2] + t1 < r0[2] + t2);
+            bool ok;
+            if (fast) ok = pip_rect(r0[0], r0[1], r0[2], r0[3], t1, t2, st.cx, st.cy);
+            else {
+                double px[4] = {r0[0] + t1, r0[0] + t2, r0[2] + t1, r0[2] + t2}, py[4] = {r0[1], r0[3], r0[1], r0[3]};
+                double hx[8], hy[8];
+                const int m = hull_coords(px, py, 4, hx, hy);
+                ok = pip_shrunk(hx, hy, 1, m, st.cx, st.cy);
+            }
+            if (!ok) return 0;
+            child = sid0;  // the whole stack goes to the single support
+            skip = (node == NODE_NEW) ? EDGE_NIL : eoff;
+            vx = st.cx; vy = st.cy; vm = st.m;
+            continue;
+        }
+        // ---------------- k >= 2 supports: polygon test, load split, fork ----------------
+        PCT_STAT(node == NODE_NEW ? 2 : 3);
+        PCT_STAT(4 + (k < 8 ? k : 8));
+        PCT_PATH_VISIT(node == NODE_NEW ? 6.0 : 3.5);
+        uint8_t sup_id[KSUP_MAX];
+        double sup_m[KSUP_MAX];
+        if (k > KSUP_MAX) { flags |= PCT_FLAG_SUPPORT_OVERFLOW; return 0; }
+        if (node == NODE_NEW) {
+            if (k <= 4) {
+#pragma unroll 1
+                for (int j = 0; j < k; j++) sup_id[j] = (uint8_t)((sup_pack >> (8 * j)) & 0xFFu);
+            } else {
+                int kk = 0;
+                const int limit = g.n_boxes();
+                double r[4];
+#pragma unroll 1
+                for (int t = 0; t < limit && kk < k; t++)
+                    if (g.support(cur, t, r)) sup_id[kk++] = (uint8_t)t;
+            }
+        } else {
+#pragma unroll 1
+            for (int j = 0; j < k; j++) sup_id[j] = pool.lower[eoff + j];
+        }
+        int whole = 2;
+        bool ok;
+        double lrect[KSUP_SMALL][4], lpx[4 * KSUP_SMALL], lpy[4 * KSUP_SMALL], lhx[8 * KSUP_SMALL], lhy[8 * KSUP_SMALL];
+        const bool small = k <= KSUP_SMALL;
+        double (*rect)[4] = lrect;
+        double *px = lpx, *py = lpy, *hx = lhx, *hy = lhy;
+        if (!small) {  // rare: serialise the lanes of this env on the per-env HBM scratch
+            while (atomicCAS(lock, 0, 1) != 0) { }
+            __threadfence_block();
+            rect = big->rect; px = big->px; py = big->py; hx = big->hx; hy = big->hy;
+        }
+#pragma unroll 1
+        for (int s = 0; s < k; s++) g.support(cur, sup_id[s], rect[s]);
+        const double *split = nullptr;  // k == 2, placed box: the stored split direction
+        const int pv = node == NODE_NEW ? 0 : (int)pool.poly_off[node], pm = node == NODE_NEW ? 0 : (int)pool.poly_off[node + 1] - pv;
+        if (pm > 0 && (pv + pm <= POLY_STAGE || pv >= POLY_STAGE)) {
+            const double *xy = pool.poly_at(pv);  // a placed box: its shrunk support polygon was stored when it was placed
+            ok = pip_stored(xy, pm - (k == 2), st.cx, st.cy);
+            if (k == 2) split = xy + 2 * (pm - 1);
+        } else {
+#pragma unroll 1
+            for (int s = 0; s < k; s++) {
+                const double x1 = rect[s][0], y1 = rect[s][1], x2 = rect[s][2], y2 = rect[s][3];
+                const double t1 = y1 * 1e-6, t2 = y2 * 1e-6;
+                px[4 * s + 0] = x1 + t1; py[4 * s + 0] = y1;
+                px[4 * s + 1] = x1 + t2; py[4 * s + 1] = y2;
+                px[4 * s + 2] = x2 + t1; py[4 * s + 2] = y1;
+                px[4 * s + 3] = x2 + t2; py[4 * s + 3] = y2;
+            }
+            const int m = hull_coords(px, py, 4 * k, hx, hy);
+            ok = pip_shrunk(hx, hy, 1, m, st.cx, st.cy);
+        }
+        if (ok) {
+            int direct = -1;
+#pragma unroll 1
+            for (int s = 0; s < k; s++)
+                if (g.strictly_inside(st.cx, st.cy, rect[s])) { direct = s; break; }
+            if (direct >= 0) {
+#pragma unroll 1
+                for (int s = 0; s < k; s++) sup_m[s] = (s == direct) ? st.m : 0.0;
+            } else {
+                whole = 0;
+#pragma unroll 1
+                for (int s = 0; s < k; s++) {
+                    px[s] = (rect[s][0] + rect[s][2]) * 0.5;
+                    py[s] = (rect[s][1] + rect[s][3]) * 0.5;
+                }
+                if (k == 2) {
+                    double lx, ly;
+                    if (split) { lx = split[0]; ly = split[1]; }
+                    else split2_dir(px, py, lx, ly);
+                    sup_m[0] = st.m * fabs(dot2(st.cx - px[1], st.cy - py[1], lx, ly));
+                    sup_m[1] = st.m * fabs(dot2(st.cx - px[0], st.cy - py[0], lx, ly));
+                } else {
+                    PCT_STAT(14);
+                    PCT_PATH_VISIT(10.0);
+                    double lR[KSUP_SMALL * KSUP_SMALL], lV[KSUP_SMALL * KSUP_SMALL], ly_[KSUP_SMALL], lrow[KSUP_SMALL], lx_[KSUP_SMALL];
+                    LsWork w;
+                    w.R = small ? lR : big->R; w.V = small ? lV : big->V; w.y = small ? ly_ : big->y;
+                    w.row = small ? lrow : big->row; w.x = small ? lx_ : big->x; w.ld = small ? KSUP_SMALL : KSUP_MAX;
+                    lstsq_ratios(w, k, px, py, st.cx, st.cy);
+#pragma unroll 1
+                    for (int s = 0; s < k; s++) sup_m[s] = st.m * w.x[s];
+                }
+            }
+            // the subtrees of supports 1 .. k-1 become pieces of their own; support 0 is followed here
+#pragma unroll 1
+            for (int s = 1; s < k; s++)
+                fork((int)sup_id[s], (node == NODE_NEW) ? EDGE_NIL : eoff + s, whole ? st.cx : px[s], whole ? st.cy : py[s], sup_m[s]);
+            vx = whole ? st.cx : px[0]; vy = whole ? st.cy : py[0]; vm = sup_m[0];
+        }
+        if (!small) { __threadfence_block(); atomicExch(lock, 0); }
+        if (!ok) return 0;
+        child = sup_id[0];
+        skip = (node == NODE_NEW) ? EDGE_NIL : eoff;
+    }
 }
 
 

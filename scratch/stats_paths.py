@@ -14,7 +14,7 @@ for f in ("sh_destroy", "sh_reset", "sh_flags"): getattr(L, f).argtypes = [C.c_v
 L.sh_virtual.argtypes = [C.c_void_p] + [C.c_int] * 5 + [C.c_double, C.POINTER(C.c_int)]
 L.sh_place.argtypes = [C.c_void_p] + [C.c_int] * 5 + [C.c_double]
 L.sh_set_alias.argtypes = [C.c_void_p, C.c_int]; L.sh_set_holder.argtypes = [C.c_void_p, C.c_int]; L.sh_use_v2.argtypes = [C.c_int]
-L.sh_use_v2(3)
+L.sh_use_v2(int(sys.argv[3]) if len(sys.argv) > 3 else 3)
 E, STEPS = int(sys.argv[1]) if len(sys.argv) > 1 else 96, int(sys.argv[2]) if len(sys.argv) > 2 else 150
 setting = 1
 tot = np.zeros((E, STEPS)); path = np.zeros((E, STEPS)); allw = []
@@ -28,11 +28,12 @@ for env_id in range(E):
         for p, f in zip(cand, feas):
             if f < 0:
                 continue
-            got = L.sh_virtual(h, int(p[3] - p[0]), int(p[4] - p[1]), int(p[5] - p[2]), int(p[0]), int(p[1]), env.next_den, None)
+            mh = C.c_int()
+            got = L.sh_virtual(h, int(p[3] - p[0]), int(p[4] - p[1]), int(p[5] - p[2]), int(p[0]), int(p[1]), env.next_den, C.byref(mh))
             assert got == f
             L.sh_last_path(out)
             if out[0] > 0:
-                allw.append((out[0], out[1]))
+                allw.append((out[0], out[1], mh.value, env_id, t))
                 if out[0] > tot[env_id, t]: tot[env_id, t] = out[0]
                 if out[1] > path[env_id, t]: path[env_id, t] = out[1]
         _, row = policy_pick(o, 80, 50, 4321, env_id, t)
@@ -49,3 +50,13 @@ for q in (0.5, 0.9, 0.99, 0.999, 0.9999, 1.0):
     print("  quantile %.4f: total %.1f  path %.1f" % (q, np.quantile(a[:, 0], q), np.quantile(a[:, 1], q)))
 mt, mp = tot.max(axis=0), path.max(axis=0)
 print("per step, max over %d envs: total mean %.1f (max %.1f) | longest path mean %.1f (max %.1f) | ratio of means %.2f" % (E, mt.mean(), mt.max(), mp.mean(), mp.max(), mt.mean() / mp.mean()))
+
+# which walks are the longest?  cost by resting height of the candidate (the continuation kernel deals walks by this key)
+print("resting height: walks per env-step, mean cost, 99.9 % cost, max cost")
+for mh in range(1, 10):
+    sel = a[a[:, 2] == mh]
+    if len(sel):
+        print("  mh %d: %.3f walks/env-step  mean %.1f  q999 %.1f  max %.1f" % (mh, len(sel) / (E * STEPS), sel[:, 0].mean(), np.quantile(sel[:, 0], 0.999), sel[:, 0].max()))
+for thr in (15, 20, 25):
+    sel = a[a[:, 0] >= thr]
+    print("  walks with cost >= %d: %.4f per env-step; resting heights %s" % (thr, len(sel) / (E * STEPS), np.bincount(sel[:, 2].astype(int), minlength=10).tolist()))

@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <vector>
 #include <cstdlib>
 using std::max;
 using std::min;
@@ -24,6 +25,7 @@ static double g_path_cur = 0, g_path_tot = 0, g_path_max = 0, g_path_fr[64];
 #define PCT_PATH_PUSH(d) (g_path_fr[(d)] = g_path_cur)
 #define PCT_PATH_POP(d) (g_path_cur = g_path_fr[(d)])
 static double g_last_path[3];  // the last continuation walk: total cost, cost of its longest root-to-leaf path, result
+static long long g_pieces = 0;
 static int g_use_v2 = 0;  // sh_use_v2: route the virtual checks through stab_virtual (the warp-convergent restatement used by the round-2 feasibility kernels)
 #include <cuda_runtime.h>
 #ifndef __noinline__
@@ -76,6 +78,7 @@ int sh_n_boxes(StabHost *h) { return h->n_box; }
 int sh_virtual(StabHost *h, int x, int y, int z, int lx, int ly, double density, int *mh_out) {
     const int mh = rest_height(h->box, 0, h->n_box, 1, lx, ly, lx + x, ly + y);
     if (mh_out) *mh_out = mh;
+    g_last_path[0] = g_last_path[1] = 0;
     if (lx + x > h->W || ly + y > h->L) return 0;
     if (mh + z > h->H) return 0;
     if (h->setting == 2 || mh == 0) return 1;
@@ -104,6 +107,31 @@ int sh_virtual(StabHost *h, int x, int y, int z, int lx, int ly, double density,
             ok = stab_virtual<GeomD>(g, root, k, pack, pool, &h->big, &h->lock, fl, true, 0xffffffffu, node, &st);
             g_last_path[0] = g_path_tot; g_last_path[1] = g_path_max; g_last_path[2] = ok;
         } else g_last_path[0] = g_last_path[1] = 0;
+    } else if (g_use_v2 == 4) {  // fork-join form (pct_walk_fork_kernel): light prefix, then pieces from a queue, verdict = AND over the pieces
+        int k; uint32_t pack; bool far_out;
+        const int mh2 = rest_height_supports(h->box, h->n_box, lx, ly, lx + x, ly + y, k, pack, far_out);
+        if (mh2 != mh) { h->flags |= 1 << 20; return -1; }
+        if (far_out) { g_far_out++; return 0; }
+        int node = NODE_NEW; Stack4 st{};
+        ok = stab_light<GeomD>(g, root, k, pack, pool, node, st);
+        if (ok == 2) {
+            g_walks++;
+            std::vector<WalkPiece> q;
+            q.push_back(WalkPiece{0u, (uint8_t)node, (uint8_t)EDGE_NIL, 0, 0, st.cx, st.cy, st.m});
+            struct Fork {
+                std::vector<WalkPiece> *q;
+                void operator()(int child, int skip, double vx, double vy, double vm) { q->push_back(WalkPiece{0u, (uint8_t)child, (uint8_t)skip, 1, 0, vx, vy, vm}); }
+            } fork{&q};
+            ok = 1;
+            double longest = 0, total = 0;
+            for (size_t i = 0; i < q.size(); i++) {  // every piece runs (the kernel runs them concurrently)
+                const WalkPiece pc = q[i];
+                g_path_cur = g_path_tot = g_path_max = 0;
+                if (!stab_piece<GeomD>(g, root, k, pack, pool, &h->big, &h->lock, fl, (int)pc.node, (int)pc.kind, (int)pc.skip, pc.a, pc.b, pc.c, fork)) ok = 0;
+                total += g_path_tot; if (g_path_tot > longest) longest = g_path_tot;
+            }
+            g_last_path[0] = total; g_last_path[1] = longest; g_last_path[2] = ok; g_pieces += (long long)q.size();
+        }
     } else if (g_use_v2 == 2) ok = stab_virtual<GeomD>(g, root, -1, 0, pool, &h->big, &h->lock, fl, true, 0xffffffffu);
     else ok = stability_check<false, GeomD>(g, root, pool, &h->big, &h->lock, 0, fl) != 0;
     h->flags |= fl;
@@ -113,6 +141,7 @@ void sh_use_v2(int on) { g_use_v2 = on; }
 double sh_around6(double v) { return around6(v); }
 long long sh_hash_double(double v, int loop) { return (long long)(loop ? hash_double_loop(v) : hash_double(v)); }  // _Py_HashDouble: integer restatement / frexp loop  // the device's np.around(v, 6) (fast division by 1e6, pct_geom_continuous.cuh)
 void sh_stats(long long *out2) { out2[0] = g_far_out; out2[1] = g_walks; }
+long long sh_pieces() { return g_pieces; }
 void sh_last_path(double *out3) { memcpy(out3, g_last_path, sizeof g_last_path); }
 void sh_stats_visits(long long *out32) { memcpy(out32, g_stat, sizeof g_stat); }
 

@@ -114,8 +114,9 @@ def _drive(L, env, setting, container, nb, nl, seed, env_id, steps, alias=True):
 
 
 # routine: 0 = stability_check<false> (K1's twin, heuristics, round 1's block kernel), 1 = stab_virtual with the supports of the fused
-# resting-height scan, 2 = stab_virtual scanning the supports itself, 3 = stab_light + stab_virtual continuation (what the round-2 walk kernels run)
-@pytest.mark.parametrize("routine", [0, 1, 2, 3], ids=["stability_check", "stab_virtual_fused", "stab_virtual_scan", "light_then_continuation"])
+# resting-height scan, 2 = stab_virtual scanning the supports itself, 3 = stab_light + stab_virtual continuation (the sequential walk kernels),
+# 4 = stab_light + stab_piece pieces from a queue, verdict = AND (the fork-join walk kernel)
+@pytest.mark.parametrize("routine", [0, 1, 2, 3, 4], ids=["stability_check", "stab_virtual_fused", "stab_virtual_scan", "light_then_continuation", "fork_join"])
 @pytest.mark.parametrize("setting", [1, 3, 2])
 def test_device_stability_source_follows_the_oracle(lib, setting, routine):
     lib.sh_use_v2(routine)
@@ -128,7 +129,7 @@ def test_device_stability_source_follows_the_oracle(lib, setting, routine):
     assert tot > 20000
 
 
-@pytest.mark.parametrize("routine", [0, 1, 3], ids=["stability_check", "stab_virtual_fused", "light_then_continuation"])
+@pytest.mark.parametrize("routine", [0, 1, 3, 4], ids=["stability_check", "stab_virtual_fused", "light_then_continuation", "fork_join"])
 @pytest.mark.parametrize("name", ["big_s1", "dense16_s1", "flat_s1", "holders_s1"])
 def test_device_stability_source_on_other_configurations(lib, name, routine):
     lib.sh_use_v2(routine)
