@@ -99,7 +99,8 @@ int pct_create(const pct_config *cfg, int32_t n_envs, int32_t device, pct_handle
     if (const char *kv = getenv("PCT_B200_K3")) h->k3_block = strcmp(kv, "block") == 0;
     if (const char *wv = getenv("PCT_B200_WALK_LANES_TALL")) { h->walk_lanes_tall = atoi(wv); if (h->walk_lanes_tall < 1) h->walk_lanes_tall = 1; if (h->walk_lanes_tall > 32) h->walk_lanes_tall = 32; }
     if (const char *ev = getenv("PCT_B200_EMIT_PDL")) h->no_emit_pdl = atoi(ev) == 0;
-    if (const char *wv = getenv("PCT_B200_WALK")) h->walk_fork = strcmp(wv, "seq") != 0;  // seq: the sequential continuation kernel (A/B)
+    if (const char *wv = getenv("PCT_B200_WALK")) h->walk_fork = strcmp(wv, "fork") == 0;  // fork: the fork-join continuation kernel (A/B; default: sequential walks)
+    if (const char *wv = getenv("PCT_B200_WALK_KEEP")) { h->walk_keep = atoi(wv); if (h->walk_keep < 1) h->walk_keep = 1; }
     if (const char *wv = getenv("PCT_B200_WALK_BLOCKS")) { h->walk_blocks = atoi(wv); if (h->walk_blocks < 1) h->walk_blocks = 1; if (h->walk_blocks > 8) h->walk_blocks = 8; }
     if (const char *wv = getenv("PCT_B200_WALK_LANES")) { h->walk_lanes = atoi(wv); if (h->walk_lanes < 1) h->walk_lanes = 1; if (h->walk_lanes > 32) h->walk_lanes = 32; }
     if (cfg->setting == 2) h->alias_mode = false;  // no stability check, no load entries
@@ -132,11 +133,12 @@ int pct_create(const pct_config *cfg, int32_t n_envs, int32_t device, pct_handle
                 e = cudaMalloc(&h->d_walkq, sizeof(WalkItem) * (size_t)CAND_MAX * (size_t)n_envs);
                 if (e == cudaSuccess) e = cudaMalloc(&h->d_walk_ctr, sizeof(int32_t) * (size_t)n_envs);
                 if (e == cudaSuccess) e = cudaMemset(h->d_walk_ctr, 0, sizeof(int32_t) * (size_t)n_envs);
-                if (e == cudaSuccess) e = cudaMalloc(&h->d_contq, sizeof(WalkCont) * (size_t)WALK_CONT_PER_ENV * (size_t)n_envs);
-                if (e == cudaSuccess) e = cudaMalloc(&h->d_cont_ctr, sizeof(int32_t) * 4 * ((size_t)n_envs + 1));  // four counters per (possible) env range
-                if (e == cudaSuccess) e = cudaMemset(h->d_cont_ctr, 0, sizeof(int32_t) * 4 * ((size_t)n_envs + 1));
-                if (e == cudaSuccess) e = cudaMalloc(&h->d_piece_ready, sizeof(int32_t) * (size_t)WALK_CONT_PER_ENV * (size_t)n_envs);
-                if (e == cudaSuccess) e = cudaMemset(h->d_piece_ready, 0, sizeof(int32_t) * (size_t)WALK_CONT_PER_ENV * (size_t)n_envs);
+                static_assert(sizeof(WalkPiece) * WALK_PIECES_PER_ENV >= sizeof(WalkCont) * WALK_CONT_PER_ENV, "one allocation serves both continuation kernels");
+                if (e == cudaSuccess) e = cudaMalloc((void **)&h->d_contq, sizeof(WalkPiece) * (size_t)WALK_PIECES_PER_ENV * (size_t)n_envs);
+                if (e == cudaSuccess) e = cudaMalloc(&h->d_cont_ctr, sizeof(int32_t) * 8 * ((size_t)n_envs + 1));  // eight counters per (possible) env range
+                if (e == cudaSuccess) e = cudaMemset(h->d_cont_ctr, 0, sizeof(int32_t) * 8 * ((size_t)n_envs + 1));
+                if (e == cudaSuccess) e = cudaMalloc(&h->d_piece_ready, sizeof(int32_t) * (size_t)WALK_PIECES_PER_ENV * (size_t)n_envs);
+                if (e == cudaSuccess) e = cudaMemset(h->d_piece_ready, 0, sizeof(int32_t) * (size_t)WALK_PIECES_PER_ENV * (size_t)n_envs);
                 if (e == cudaSuccess) e = cudaMalloc(&h->d_walk_pend, sizeof(int32_t) * (size_t)CAND_MAX * (size_t)n_envs);
             }
             h->lpt = !h->k3_block;   // heaviest-env-first block order (pct_discrete.cu, order_lookup / order_file); PCT_B200_LPT=0 disables
@@ -272,11 +274,11 @@ static int launch_range(pct_handle h, int mode, int off, int cnt, const void *ac
     }
     p.walkq = h->d_walkq ? h->d_walkq + (size_t)off * CAND_MAX : nullptr;  // env ranges stepped concurrently (pct_step_host's staged path) own disjoint slices
     p.walk_ctr = h->d_walk_ctr ? h->d_walk_ctr + off : nullptr;
-    p.contq = h->d_contq ? h->d_contq + (size_t)off * WALK_CONT_PER_ENV : nullptr;
-    p.cont_ctr = h->d_cont_ctr ? h->d_cont_ctr + 4 * (size_t)off : nullptr;
+    p.contq = h->d_contq ? (WalkCont *)((char *)h->d_contq + (size_t)off * WALK_PIECES_PER_ENV * sizeof(WalkPiece)) : nullptr;  // an env range's slice of the pool
+    p.cont_ctr = h->d_cont_ctr ? h->d_cont_ctr + 8 * (size_t)off : nullptr;
     p.walk_lanes = h->walk_lanes; p.walk_lanes_tall = h->walk_lanes_tall;
-    p.walk_fork = h->walk_fork ? 1 : 0; p.walk_blocks = h->walk_blocks;
-    p.piece_ready = h->d_piece_ready ? h->d_piece_ready + (size_t)off * WALK_CONT_PER_ENV : nullptr;
+    p.walk_fork = h->walk_fork ? 1 : 0; p.walk_blocks = h->walk_blocks; p.walk_keep = h->walk_keep; p.piece_cap = cnt * WALK_PIECES_PER_ENV;
+    p.piece_ready = h->d_piece_ready ? h->d_piece_ready + (size_t)off * WALK_PIECES_PER_ENV : nullptr;
     p.walk_pend = h->d_walk_pend ? h->d_walk_pend + (size_t)off * CAND_MAX : nullptr;
     CK(h, launch_discrete(p, gs, prof));
     h->launches += discrete_kernels_per_step(p);

@@ -15,6 +15,7 @@
 #include "pct_kernels.h"
 #include "pct_handle.h"
 #include "pct_geom_continuous.cuh"
+#include "pct_walkq.cuh"
 
 namespace pct {
 
@@ -87,6 +88,8 @@ struct CParams {
     WalkCont *contq;
     int32_t *cont_ctr;
     int32_t walk_lanes, walk_lanes_tall;
+    int32_t walk_fork, walk_blocks, walk_keep, piece_cap;   // fork-join continuation kernel (see DParams)
+    int32_t *piece_ready, *walk_pend;
     int32_t delta;   // delta observation rows (DEnvAux::obs_prev), emit kernel only
     DEnvAux *aux;    // per-env state of the ALIAS apply kernel (EdgePoolA arrays), nullptr with PCT_B200_ALIAS=0 / setting 2
 };
@@ -742,6 +745,28 @@ __global__ void __launch_bounds__(128, 4) pctc_walk_light_kernel(const CParams p
         if (has) res = stab_light<GeomC>(v.g, v.root, it.k, it.pack, v.pool, node, st);
         if (res == 1) atomicOr(&v.ev->fbits[it.c >> 5], 1u << (it.c & 31));
         if (has && res != 2) { __threadfence(); atomicSub(&v.ev->n_pending, 1); }
+        if (p.walk_fork) {  // fork-join continuation kernel: one queue of pieces (pct_walkq.cuh)
+            const uint32_t pm = __ballot_sync(FULL, res == 2);
+            if (pm) {
+                const PieceQueue pq{(WalkPiece *)p.contq, p.piece_ready, p.cont_ctr, p.piece_cap};
+                int qb = 0;
+                if (lane == 0) qb = pq_reserve_initial(pq, __popc(pm));
+                qb = __shfl_sync(FULL, qb, 0);
+                if (res == 2) {
+                    const int idx = qb + __popc(pm & ((1u << lane) - 1));
+                    if (idx < pq.cap) {
+                        p.walk_pend[i] = 1;
+                        pq.q[idx] = WalkPiece{(uint32_t)i, (uint8_t)node, (uint8_t)EDGE_NIL, 0, 0, st.cx, st.cy, st.m};
+                    } else {
+                        atomicOr(&v.ev->h.flags, PCT_FLAG_CAND_OVERFLOW);
+                        __threadfence();
+                        atomicSub(&v.ev->n_pending, 1);
+                        pq_piece_done(pq);
+                    }
+                }
+            }
+            continue;
+        }
         const bool tall = it.mh >= 0.6 * p.H;  // the longest chains: pooled from the end, fewer lanes per warp (see pct_discrete.cu)
         const uint32_t ps = __ballot_sync(FULL, res == 2 && !tall), pt = __ballot_sync(FULL, res == 2 && tall);
         if (ps | pt) {
@@ -790,6 +815,74 @@ __global__ void __launch_bounds__(64, 8) pctc_walk_kernel(const CParams p) {
     }
 }
 
+// fork-join form of the continuation kernel: see pct_walk_fork_kernel (pct_discrete.cu) and pct_walkq.cuh — same protocol, continuous geometry
+struct PieceForkC {
+    PieceQueue pq;
+    int32_t *pend;
+    uint32_t item;
+    int n_init;
+    bool overflow;
+    __device__ __forceinline__ void operator()(int child, int skip, double vx, double vy, double vm) {
+        if (!pq_fork(pq, n_init, pend, WalkPiece{item, (uint8_t)child, (uint8_t)skip, 1, 0, vx, vy, vm})) overflow = true;
+    }
+};
+__device__ __forceinline__ void run_piece_c(const CParams &p, const PieceQueue &pq, int n_init, int slot) {
+    const WalkPiece pc = pq.q[slot];
+    if (slot >= n_init) pq.ready[slot] = 0;
+    const WalkItemC it = p.walkq[pc.item];
+    const WalkViewC v = walk_view_c(p, it, true);
+    int32_t *pend = p.walk_pend + pc.item;
+    int fl = 0, ok = 0;
+    if (!(*(volatile const int32_t *)pend & WALK_FAILED)) {
+        PieceForkC fork{pq, pend, pc.item, n_init, false};
+        ok = stab_piece<GeomC>(v.g, v.root, it.k, it.pack, v.pool, &v.ev->big, &v.ev->lock, fl, (int)pc.node, (int)pc.kind, (int)pc.skip, pc.a, pc.b, pc.c, fork);
+        if (fork.overflow) { fl |= PCT_FLAG_CAND_OVERFLOW; ok = 0; }
+    }
+    if (fl) atomicOr(&v.ev->h.flags, fl);
+    if (!ok) atomicOr(pend, WALK_FAILED);
+    __threadfence();
+    const int r = atomicSub(pend, 1);
+    if ((r & (WALK_FAILED - 1)) == 1) {
+        if (!(r & WALK_FAILED)) atomicOr(&v.ev->fbits[it.c >> 5], 1u << (it.c & 31));
+        __threadfence();
+        atomicSub(&v.ev->n_pending, 1);
+    }
+    pq_piece_done(pq);
+}
+__global__ void __launch_bounds__(64, 8) pctc_walk_fork_kernel(const CParams p) {
+    const int lane = threadIdx.x & 31;
+    const int wid = blockIdx.x * 2 + (threadIdx.x >> 5), n_warps = gridDim.x * 2;
+    const PieceQueue pq{(WalkPiece *)p.contq, p.piece_ready, p.cont_ctr, p.piece_cap};
+    const int n_init = min(*(volatile const int32_t *)(pq.ctr + PQ_NINIT), pq.cap);
+    const int L = p.walk_lanes;
+    pdl_launch_dependents();
+    if (n_init > 0) {
+#pragma unroll 1
+        for (int b = wid * L; b < n_init; b += n_warps * L) {
+            if (lane < L && b + lane < n_init) run_piece_c(p, pq, n_init, b + lane);
+            __syncwarp();
+        }
+        const bool keep = wid < p.walk_keep;
+#pragma unroll 1
+        for (;;) {
+            int t0 = -1;
+            if (lane == 0 && (keep || *(volatile const int32_t *)(pq.ctr + PQ_ALLOC) - *(volatile const int32_t *)(pq.ctr + PQ_HEAD) > 0))
+                t0 = atomicAdd(pq.ctr + PQ_HEAD, L);
+            t0 = __shfl_sync(FULL, t0, 0);
+            if (t0 < 0) break;
+            bool fin = false;
+            if (lane < L) {
+                const int slot = n_init + t0 + lane;
+                if (pq_wait(pq, slot)) run_piece_c(p, pq, n_init, slot);
+                else fin = true;
+            }
+            __syncwarp();
+            if (__any_sync(FULL, fin)) break;
+        }
+    }
+    if (lane == 0) pq_warp_exit(pq, n_warps, p.walk_ctr);
+}
+
 template <typename OT> __device__ __noinline__ void write_obs_c(const CParams &p, int e, const CEnv *ev, const double (*leaf)[6], int n_leaf, int tid, int nthreads);
 template <typename OT> __device__ __noinline__ void write_obs_c_delta(const CParams &p, int e, const CEnv *ev, const double (*leaf)[6], int n_leaf, int tid, int nthreads);
 
@@ -802,7 +895,7 @@ __global__ void __launch_bounds__(64) pctc_emit_kernel(const CParams p) {
     CEnv *ev = p.env + e;
     const CHdr &h = ev->h;
     const double nb[3] = {h.next_box[0], h.next_box[1], h.next_box[2]};
-    if (e == 0 && tid == 0) { *p.walk_ctr = 0; p.cont_ctr[0] = 0; p.cont_ctr[1] = 0; }  // every walk-kernel block has read them (programmatic dependency): empty the pools for the next step
+    if (e == 0 && tid == 0 && !p.walk_fork) { *p.walk_ctr = 0; p.cont_ctr[0] = 0; p.cont_ctr[1] = 0; }  // every walk-kernel block has read them (programmatic dependency): empty the pools for the next step
     if (tid == 0) {  // may run while this env's walks are still in flight (programmatic dependent of the continuation kernel)
         int spins = 0;
         while (*(volatile const int32_t *)&ev->n_pending > 0) {
@@ -1030,9 +1123,13 @@ int continuous_create(pct_env_batch *h) {
     if (e == cudaSuccess) e = cudaMemset(h->d_ready, 0, sizeof(int32_t) * 2 * (size_t)h->n_envs);
     if (e == cudaSuccess && !h->k3_block) {  // pools of the round-2 walk kernels (worst-case capacity for the walks; only the used prefix is touched)
         e = cudaMalloc(&h->c_walkq, sizeof(WalkItemC) * (size_t)CAND_MAX * (size_t)h->n_envs);
-        if (e == cudaSuccess) e = cudaMalloc(&h->d_walk_ctr, sizeof(int32_t) * 4);  // [0] walk pool, [1] / [2] continuation pool (ordinary / tall)
-        if (e == cudaSuccess) e = cudaMemset(h->d_walk_ctr, 0, sizeof(int32_t) * 4);
-        if (e == cudaSuccess) e = cudaMalloc(&h->d_contq, sizeof(WalkCont) * (size_t)WALK_CONT_PER_ENV * (size_t)h->n_envs);
+        if (e == cudaSuccess) e = cudaMalloc(&h->d_walk_ctr, sizeof(int32_t) * 16);  // [0] walk pool, [1..] continuation pool counters (sequential kernel: ordinary / tall; fork-join: pct_walkq.cuh)
+        if (e == cudaSuccess) e = cudaMemset(h->d_walk_ctr, 0, sizeof(int32_t) * 16);
+        if (e == cudaSuccess) e = cudaMalloc(&h->d_piece_ready, sizeof(int32_t) * (size_t)WALK_PIECES_PER_ENV * (size_t)h->n_envs);
+        if (e == cudaSuccess) e = cudaMemset(h->d_piece_ready, 0, sizeof(int32_t) * (size_t)WALK_PIECES_PER_ENV * (size_t)h->n_envs);
+        if (e == cudaSuccess) e = cudaMalloc(&h->d_walk_pend, sizeof(int32_t) * (size_t)CAND_MAX * (size_t)h->n_envs);
+        static_assert(sizeof(WalkPiece) * WALK_PIECES_PER_ENV >= sizeof(WalkCont) * WALK_CONT_PER_ENV, "one allocation serves both continuation kernels");
+        if (e == cudaSuccess) e = cudaMalloc(&h->d_contq, sizeof(WalkPiece) * (size_t)WALK_PIECES_PER_ENV * (size_t)h->n_envs);
     }
     if (e != cudaSuccess) { h->err = std::string("continuous_create: ") + cudaGetErrorString(e); return PCT_ERR_CUDA; }
     return PCT_OK;
@@ -1080,6 +1177,8 @@ int continuous_launch(pct_env_batch *h, int mode, const void *actions, int actio
     h->fill_pending = false;
     if (pooled) {
         p.walkq = (WalkItemC *)h->c_walkq; p.walk_ctr = h->d_walk_ctr; p.contq = h->d_contq; p.cont_ctr = h->d_walk_ctr + 1; p.walk_lanes = h->walk_lanes; p.walk_lanes_tall = h->walk_lanes_tall;
+        p.walk_fork = h->walk_fork ? 1 : 0; p.walk_blocks = h->walk_blocks; p.walk_keep = h->walk_keep; p.piece_cap = p.n_envs * WALK_PIECES_PER_ENV;
+        p.piece_ready = h->d_piece_ready; p.walk_pend = h->d_walk_pend;
     }
     cfg.gridDim = dim3(p.n_envs); cfg.blockDim = dim3(32);
     cudaLaunchKernelEx(&cfg, pctc_candidates_kernel, p);
@@ -1088,7 +1187,8 @@ int continuous_launch(pct_env_batch *h, int mode, const void *actions, int actio
         if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
         if (stab) {
             pctc_walk_light_kernel<<<n_sm * 4, 128, 0, st>>>(p);
-            pctc_walk_kernel<<<n_sm * 8, 64, 0, st>>>(p);  // one resident wave
+            if (p.walk_fork) pctc_walk_fork_kernel<<<n_sm * max(1, min(p.walk_blocks, 8)), 64, 0, st>>>(p);  // one resident wave
+            else pctc_walk_kernel<<<n_sm * 8, 64, 0, st>>>(p);  // one resident wave
         }
         {
             cudaLaunchAttribute at2[1];

@@ -26,6 +26,7 @@
 #include "pct_stability.cuh"
 #include "pct_kernels.h"
 #include "pct_geom.cuh"
+#include "pct_walkq.cuh"
 
 namespace pct {
 
@@ -1283,22 +1284,22 @@ __global__ void __launch_bounds__(32 * LIGHT_WARPS, LIGHT_MINB) pct_walk_light_k
         if (has && res != 2) walk_done(&v.cold->n_pending);
         // continuations: walks high up in the bin descend through the deepest support DAGs (host statistics: resting height >= 0.6 H -> up to 8 heavy
         // visits, below -> at most 2), so they are pooled apart (from the END of the pool) and get fewer lanes per warp in pct_walk_kernel
-        if (p.walk_fork) {  // fork-join continuation kernel: one queue of pieces, "enter `node` with the stack st"
+        if (p.walk_fork) {  // fork-join continuation kernel: one queue of pieces, "enter `node` with the stack st" (pct_walkq.cuh)
             const uint32_t pm = __ballot_sync(FULL, res == 2);
             if (pm) {
+                const PieceQueue pq{(WalkPiece *)p.contq, p.piece_ready, p.cont_ctr, p.piece_cap};
                 int qb = 0;
-                if (lane == 0) { qb = atomicAdd(p.cont_ctr, __popc(pm)); atomicAdd(p.cont_ctr + 2, __popc(pm)); }
+                if (lane == 0) qb = pq_reserve_initial(pq, __popc(pm));
                 qb = __shfl_sync(FULL, qb, 0);
                 if (res == 2) {
                     const int idx = qb + __popc(pm & ((1u << lane) - 1));
-                    if (idx < cap) {
+                    if (idx < pq.cap) {
                         p.walk_pend[i] = 1;
-                        ((WalkPiece *)p.contq)[idx] = WalkPiece{(uint32_t)i, (uint8_t)node, (uint8_t)EDGE_NIL, 0, 0, st.cx, st.cy, st.m};
-                        p.piece_ready[idx] = 1;  // (the consumer kernel starts after this one has completed: plain stores)
-                    } else {
-                        atomicSub(p.cont_ctr + 2, 1);
+                        pq.q[idx] = WalkPiece{(uint32_t)i, (uint8_t)node, (uint8_t)EDGE_NIL, 0, 0, st.cx, st.cy, st.m};
+                    } else {  // never silent: the candidate stays infeasible and the env is flagged
                         atomicOr(const_cast<int32_t *>(&v.hot->h.flags), PCT_FLAG_CAND_OVERFLOW);
                         walk_done(&v.cold->n_pending);
+                        pq_piece_done(pq);
                     }
                 }
             }
@@ -1357,97 +1358,82 @@ __global__ void __launch_bounds__(32 * WALK_WARPS, WALK_MINB) pct_walk_kernel(co
     }
 }
 
-// walk, stage 2, fork-join form (default): the queue holds PIECES of walks (stab_piece: one chain of visits; a node with k >= 2 supports keeps
-// its first subtree and publishes the other k - 1 as new pieces), persistent warps take up to `walk_lanes` pieces at a time until no piece is left
-// or running.  A walk's verdict is the AND over its pieces: walk_pend[item] counts them, the piece that brings it to zero sets the feasibility bit
-// (unless one failed) and releases the env's n_pending.  The kernel's duration is the longest root-to-floor PATH of a walk instead of the sum over
-// its visits (host statistics, scratch/stats_paths.py).  Only the first WALK_KEEP blocks per SM stay to the end; the others leave as soon as they find
-// the queue empty, so the emit kernel's blocks (programmatic dependents, each waiting for ITS env) get SM slots during the tail.
-#ifndef WALK_KEEP
-#define WALK_KEEP 2
-#endif
+// walk, stage 2, fork-join form (opt-in, PCT_B200_WALK=fork): the queue holds PIECES of walks (stab_piece: one chain of visits; a node with k >= 2 supports keeps
+// its first subtree and publishes the other k - 1 as new pieces; protocol: pct_walkq.cuh).  A walk's verdict is the AND over its pieces:
+// walk_pend[item] counts them, the piece that brings it to zero sets the feasibility bit (unless one failed) and releases the env's n_pending.
+// The critical chain of a step's longest walk becomes its longest root-to-floor PATH instead of the sum over its visits (host statistics,
+// scratch/stats_paths.py: 51 -> 34 visit units at the 99.99 % quantile) — and the stage does not get faster (B200, 4096 envs: walk + emit group 0.180 ms
+// against 0.171 ms, whatever the number of helper warps, blocks per SM or pieces per warp): the continuation stage is bound by the issue rate of a few
+// hundred divergent, latency-bound warps (warp instructions = thread instructions / 4.8 lanes, ~10 cycles each), not by its longest walk.  Kept as an
+// opt-in because it is the measured answer to "would independent subtrees on separate lanes help?" and is parity-tested (tests/test_gpu_walk_fork.py).
 struct PieceFork {
-    WalkPiece *q;
-    int32_t *ready, *ctr, *pend;
+    PieceQueue pq;
+    int32_t *pend;
     uint32_t item;
-    int cap;
+    int n_init;
     bool overflow;
     __device__ __forceinline__ void operator()(int child, int skip, double vx, double vy, double vm) {
-        const int slot = atomicAdd(ctr, 1);
-        if (slot >= cap) { overflow = true; return; }
-        atomicAdd(pend, 1);      // before the parent's own decrement: the walk cannot complete in between
-        atomicAdd(ctr + 2, 1);
-        q[slot] = WalkPiece{item, (uint8_t)child, (uint8_t)skip, 1, 0, vx, vy, vm};
-        __threadfence();
-        *(volatile int32_t *)(ready + slot) = 1;
+        if (!pq_fork(pq, n_init, pend, WalkPiece{item, (uint8_t)child, (uint8_t)skip, 1, 0, vx, vy, vm})) overflow = true;
     }
 };
-__global__ void __launch_bounds__(32 * WALK_WARPS, WALK_MINB) pct_walk_fork_kernel(const DParams p, int n_sm) {
+// one piece: the chain of visits, then the walk's AND-reduction (walk_pend) and the queue's bookkeeping
+__device__ __forceinline__ void run_piece(const DParams &p, const PieceQueue &pq, int n_init, int slot) {
+    const WalkPiece pc = pq.q[slot];
+    if (slot >= n_init) pq.ready[slot] = 0;
+    const WalkItem it = p.walkq[pc.item];
+    const WalkView v = walk_view(p, it, true);
+    int32_t *pend = p.walk_pend + pc.item;
+    int fl = 0, ok = 0;
+    if (!(*(volatile const int32_t *)pend & WALK_FAILED)) {  // a failed sibling has already decided the walk
+        PieceFork fork{pq, pend, pc.item, n_init, false};
+        ok = stab_piece<GeomD>(v.g, v.root, (int)it.k, it.pack, v.pool, &v.cold->big, &v.cold->lock, fl, (int)pc.node, (int)pc.kind, (int)pc.skip,
+                               pc.a, pc.b, pc.c, fork);
+        if (fork.overflow) { fl |= PCT_FLAG_CAND_OVERFLOW; ok = 0; }  // never silent: the candidate stays infeasible and the env is flagged
+    }
+    if (fl) atomicOr(const_cast<int32_t *>(&v.hot->h.flags), fl);
+    if (!ok) atomicOr(pend, WALK_FAILED);
+    __threadfence();
+    const int r = atomicSub(pend, 1);
+    if ((r & (WALK_FAILED - 1)) == 1) {  // the walk's last piece
+        if (!(r & WALK_FAILED)) atomicOr(&v.cold->fbits[it.c >> 5], 1u << (it.c & 31));
+        walk_done(&v.cold->n_pending);
+    }
+    pq_piece_done(pq);
+}
+__global__ void __launch_bounds__(32 * WALK_WARPS, WALK_MINB) pct_walk_fork_kernel(const DParams p) {
     const int lane = threadIdx.x & 31;
-    const int cap = p.n_envs * WALK_CONT_PER_ENV;
+    const int wid = blockIdx.x * WALK_WARPS + (threadIdx.x >> 5), n_warps = gridDim.x * WALK_WARPS;
+    const PieceQueue pq{(WalkPiece *)p.contq, p.piece_ready, p.cont_ctr, p.piece_cap};
+    const int n_init = min(*(volatile const int32_t *)(pq.ctr + PQ_NINIT), pq.cap);  // written by the light-prefix kernel only (completed)
     const int L = p.walk_lanes;
-    const bool keep = (int)blockIdx.x < n_sm * WALK_KEEP;
-    WalkPiece *q = (WalkPiece *)p.contq;
     pdl_launch_dependents();  // the emit kernel's blocks may become resident; each waits for ITS env's last walk
+    if (n_init > 0) {
+        // the light-prefix kernel's pieces: dealt statically
 #pragma unroll 1
-    for (;;) {
-        int n = 0, h0 = 0;
-        if (lane == 0) {
-            int spins = 0;
+        for (int b = wid * L; b < n_init; b += n_warps * L) {
+            if (lane < L && b + lane < n_init) run_piece(p, pq, n_init, b + lane);
+            __syncwarp();
+        }
+        // forked pieces: tickets
+        const bool keep = wid < p.walk_keep;
 #pragma unroll 1
-            for (;;) {
-                const int h = *(volatile const int32_t *)(p.cont_ctr + 1);
-                const int a = min(*(volatile const int32_t *)p.cont_ctr, cap);
-                n = min(a - h, L);
-                if (n > 0) {
-                    if (atomicCAS(p.cont_ctr + 1, h, h + n) == h) { h0 = h; break; }
-                    continue;
-                }
-                n = -1;
-                if (!keep || *(volatile const int32_t *)(p.cont_ctr + 2) <= 0) break;  // nothing queued: leave (kept blocks: only once nothing is running either)
-                __nanosleep(spins < 64 ? 200 : 2000);
-                if (++spins > (1 << 20)) break;  // bounded (never seen): whatever is still queued is taken by the warps that are still working
+        for (;;) {
+            int t0 = -1;
+            if (lane == 0 && (keep || *(volatile const int32_t *)(pq.ctr + PQ_ALLOC) - *(volatile const int32_t *)(pq.ctr + PQ_HEAD) > 0))
+                t0 = atomicAdd(pq.ctr + PQ_HEAD, L);
+            t0 = __shfl_sync(FULL, t0, 0);
+            if (t0 < 0) break;  // not a helper and nothing unclaimed in the queue: leave (SM slots for the emit kernel)
+            bool fin = false;
+            if (lane < L) {
+                const int slot = n_init + t0 + lane;
+                if (pq_wait(pq, slot)) run_piece(p, pq, n_init, slot);
+                else fin = true;
             }
-        }
-        n = __shfl_sync(FULL, n, 0);
-        h0 = __shfl_sync(FULL, h0, 0);
-        if (n < 0) break;
-        if (lane < n) {
-            const int slot = h0 + lane;
-            int spins = 0;
-            while (*(volatile const int32_t *)(p.piece_ready + slot) == 0 && ++spins < (1 << 24)) { }  // allocated, being written
-            __threadfence();
-            const WalkPiece pc = q[slot];
-            p.piece_ready[slot] = 0;
-            const WalkItem it = p.walkq[pc.item];
-            const WalkView v = walk_view(p, it, true);
-            int32_t *pend = p.walk_pend + pc.item;
-            int fl = 0, ok = 0;
-            if (!(*(volatile const int32_t *)pend & WALK_FAILED)) {  // a failed sibling has already decided the walk
-                PieceFork fork{q, p.piece_ready, p.cont_ctr, pend, pc.item, cap, false};
-                ok = stab_piece<GeomD>(v.g, v.root, (int)it.k, it.pack, v.pool, &v.cold->big, &v.cold->lock, fl, (int)pc.node, (int)pc.kind, (int)pc.skip,
-                                       pc.a, pc.b, pc.c, fork);
-                if (fork.overflow) { fl |= PCT_FLAG_CAND_OVERFLOW; ok = 0; }  // never silent: the candidate stays infeasible and the env is flagged
-            }
-            if (fl) atomicOr(const_cast<int32_t *>(&v.hot->h.flags), fl);
-            if (!ok) atomicOr(pend, WALK_FAILED);
-            __threadfence();
-            const int r = atomicSub(pend, 1);
-            if ((r & (WALK_FAILED - 1)) == 1) {  // the walk's last piece
-                if (!(r & WALK_FAILED)) atomicOr(&v.cold->fbits[it.c >> 5], 1u << (it.c & 31));
-                walk_done(&v.cold->n_pending);
-            }
-            atomicSub(p.cont_ctr + 2, 1);
-        }
-        __syncwarp();
-    }
-    // last warp out empties the pools for the next step (every other warp has finished, the light-prefix kernel completed before this one started)
-    if (lane == 0) {
-        __threadfence();
-        if (atomicAdd(p.cont_ctr + 3, 1) == (int)(gridDim.x * WALK_WARPS) - 1) {
-            *p.walk_ctr = 0; p.cont_ctr[0] = 0; p.cont_ctr[1] = 0; p.cont_ctr[2] = 0; p.cont_ctr[3] = 0;
+            __syncwarp();
+            if (__any_sync(FULL, fin)) break;  // a lane saw the end of all work
         }
     }
+    if (lane == 0) pq_warp_exit(pq, n_warps, p.walk_ctr);
 }
 
 constexpr int EMIT_WARPS = 4;
@@ -1620,7 +1606,7 @@ static cudaError_t launch_t(const DParams &p_in, cudaStream_t st, cudaEvent_t *p
         if (p.ready && prof) cudaEventRecord(prof[2], st);
         if (STAB) {
             pct_walk_light_kernel<<<n_sm * LIGHT_MINB, 32 * LIGHT_WARPS, 0, st>>>(p);
-            if (p.walk_fork) pct_walk_fork_kernel<<<n_sm * max(1, min(p.walk_blocks, WALK_MINB)), 32 * WALK_WARPS, 0, st>>>(p, n_sm);  // one resident wave, persistent warps
+            if (p.walk_fork) pct_walk_fork_kernel<<<n_sm * max(1, min(p.walk_blocks, WALK_MINB)), 32 * WALK_WARPS, 0, st>>>(p);  // one resident wave
             else pct_walk_kernel<<<n_sm * WALK_MINB, 32 * WALK_WARPS, 0, st>>>(p);  // one resident wave (every block starts at once: the emit kernel may follow)
         }
         const int eb = (p.n_envs + EMIT_WARPS - 1) / EMIT_WARPS;

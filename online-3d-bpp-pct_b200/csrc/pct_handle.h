@@ -60,8 +60,9 @@ struct pct_env_batch {
     pct::WalkCont *d_contq = nullptr;  // [n_envs * WALK_CONT_PER_ENV] continuations: light-prefix kernel -> pct_walk_kernel
     int32_t *d_cont_ctr = nullptr;
     int32_t *d_piece_ready = nullptr, *d_walk_pend = nullptr;  // fork-join walks: per-slot publication flags, per-walk piece counters
-    bool walk_fork = true;             // fork-join continuation kernel (PCT_B200_WALK=seq: the sequential one)
+    bool walk_fork = false;            // PCT_B200_WALK=fork: fork-join continuation kernel (pct_walkq.cuh) instead of the sequential one — measured equal-to-slower, kept as an opt-in
     int walk_blocks = 6;               // its blocks per SM (PCT_B200_WALK_BLOCKS)
+    int walk_keep = 296;               // its warps that stay as helpers for forked pieces (PCT_B200_WALK_KEEP)
     int walk_lanes_tall = 4;           // ... of the tall walks (resting height >= 0.6 H: the longest chains), PCT_B200_WALK_LANES_TALL
     int walk_lanes = 16;               // continuations per warp of pct_walk_kernel (PCT_B200_WALK_LANES; few long serial chains: more warps beat fuller warps)
     bool lpt = false;

@@ -154,7 +154,16 @@ struct WalkCont {
     Stack4 st;
 };
 static_assert(sizeof(WalkCont) == 40, "queue entry");
+// A piece of a walk in the fork-join form (stab_piece, pct_stability.cuh): "enter `node` with the stack (a, b, c) = (cx, cy, mass)" (kind 0) or "the load
+// (a, b, c) = (x, y, mass) arrives on `node` in place of the stored edge `skip`: combine, then enter" (kind 1)
+struct WalkPiece {
+    uint32_t item;           // index of the WalkItem (the candidate placement this piece belongs to)
+    uint8_t node, skip, kind, pad_;
+    double a, b, c;
+};
+static_assert(sizeof(WalkPiece) == 32, "queue entry");
 constexpr int WALK_FAILED = 1 << 30;
+constexpr int WALK_PIECES_PER_ENV = 1024;  // capacity of the fork-join piece queue = n_envs x this (32 B entries; mean use ~5 per env); overflow -> PCT_FLAG_CAND_OVERFLOW
 constexpr int WALK_CONT_PER_ENV = 256;  // capacity of the continuation pool = n_envs x this (mean use: 3 per env); overflow -> PCT_FLAG_CAND_OVERFLOW
 
 struct DParams {
@@ -200,11 +209,13 @@ struct DParams {
     WalkCont *contq;    // [n_envs * WALK_CONT_PER_ENV] walks the light-prefix kernel hands to the continuation kernel
     int32_t *cont_ctr;  // [2]: continuations pooled from the front (ordinary) / from the end (tall walks) of contq
     int32_t walk_lanes, walk_lanes_tall; // continuations per warp of pct_walk_kernel (1..32): ordinary / tall (resting height >= 0.6 H) walks
-    // fork-join walks (pct_walk_fork_kernel, the default; PCT_B200_WALK=seq selects the sequential continuation kernel): contq holds WalkPiece entries,
-    // cont_ctr = {allocated, taken, outstanding}; piece_ready[slot] = 1 once the slot's piece is written (cleared by its consumer);
+    // fork-join walks (pct_walk_fork_kernel, opt-in with PCT_B200_WALK=fork; the default is the sequential continuation kernel): contq holds WalkPiece entries,
+    // cont_ctr = the queue's counters (pct_walkq.cuh); piece_ready[slot] = 1 once the slot's piece is written (cleared by its consumer);
     // walk_pend[item] = pieces of the walk still running (+ WALK_FAILED once one of them failed)
     int32_t walk_fork;
     int32_t walk_blocks;   // blocks per SM of the fork-join kernel (1..8)
+    int32_t walk_keep;     // its warps that stay as helpers for forked pieces until the step's walks are done (the others leave when the fork queue is empty)
+    int32_t piece_cap;     // entries of contq / piece_ready in this launch (WALK_PIECES_PER_ENV per env)
     int32_t *piece_ready;
     int32_t *walk_pend;
     int32_t opt;     // opt-in variants served by `aux`: PCT_OPT_DELTA (K3 delta observation writes), PCT_OPT_ALIAS (K1 object semantics of the loads)

@@ -1028,12 +1028,7 @@ static __device__ __noinline__ int stab_virtual(const G &g, const typename G::No
 // scratch/stats_paths.py: 51 -> 34 visit units at the 99.99 % quantile).
 // A piece is either "enter `node` with the stack (a, b, c) = (cx, cy, mass)" (kind 0) or "the load (a, b, c) = (x, y, mass) arrives on `node`
 // in place of the stored edge `skip`: combine (calculate_new_com), then enter" (kind 1).
-struct WalkPiece {
-    uint32_t item;           // index of the WalkItem (the candidate placement this piece belongs to)
-    uint8_t node, skip, kind, pad_;
-    double a, b, c;
-};
-static_assert(sizeof(WalkPiece) == 32, "queue entry");
+// (struct WalkPiece: pct_kernels.h)
 
 template <class G, class Fork>
 static __device__ __noinline__ int stab_piece(const G &g, const typename G::Node &root, int k_root, uint32_t sup_pack, const EdgePool &pool,

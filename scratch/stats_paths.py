@@ -60,3 +60,6 @@ for mh in range(1, 10):
 for thr in (15, 20, 25):
     sel = a[a[:, 0] >= thr]
     print("  walks with cost >= %d: %.4f per env-step; resting heights %s" % (thr, len(sel) / (E * STEPS), np.bincount(sel[:, 2].astype(int), minlength=10).tolist()))
+if len(sys.argv) > 3 and sys.argv[3] == "4":
+    L.sh_pieces.restype = C.c_longlong
+    print("fork-join: %d pieces for %d continuation walks (%.2f per walk)" % (L.sh_pieces(), len(a), L.sh_pieces() / len(a)))

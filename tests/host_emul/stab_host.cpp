@@ -229,7 +229,7 @@ int shc_virtual(StabHostC *h, const double t6[6], double density) {
     EdgePool pool = pool_of(h);  // the read-only check knows snapshots only, in both semantics (like pct_feas_emit_kernel)
     int fl = 0;
     int ok;
-    if (g_use_v2 == 3) {  // as the round-2 continuous kernels run it: supports + quick reject (classification), light prefix, continuation
+    if (g_use_v2 == 3 || g_use_v2 == 4) {  // as the round-2 continuous kernels run it: supports + quick reject (classification), light prefix, continuation (4: fork-join pieces)
         int k = 0; uint32_t pack = 0; double r[4], X1 = 0, Y1 = 0, X2 = 0, Y2 = 0;
         for (int t = 0; t < h->n_box; t++) {
             if (!g.support(root, t, r)) continue;
@@ -242,7 +242,20 @@ int shc_virtual(StabHostC *h, const double t6[6], double density) {
         if (k > 0 && (cx < X1 - margin || cx > X2 + margin || cy < Y1 - margin || cy > Y2 + margin)) { g_far_out++; return 0; }
         int node = NODE_NEW; Stack4 st{};
         ok = stab_light<GeomC>(g, root, k, pack, pool, node, st);
-        if (ok == 2) { g_walks++; ok = stab_virtual<GeomC>(g, root, k, pack, pool, &h->big, &h->lock, fl, true, 0xffffffffu, node, &st); }
+        if (ok == 2 && g_use_v2 == 4) {
+            g_walks++;
+            std::vector<WalkPiece> q;
+            q.push_back(WalkPiece{0u, (uint8_t)node, (uint8_t)EDGE_NIL, 0, 0, st.cx, st.cy, st.m});
+            struct Fork {
+                std::vector<WalkPiece> *q;
+                void operator()(int child, int skip, double vx, double vy, double vm) { q->push_back(WalkPiece{0u, (uint8_t)child, (uint8_t)skip, 1, 0, vx, vy, vm}); }
+            } fork{&q};
+            ok = 1;
+            for (size_t i = 0; i < q.size(); i++) {
+                const WalkPiece pc = q[i];
+                if (!stab_piece<GeomC>(g, root, k, pack, pool, &h->big, &h->lock, fl, (int)pc.node, (int)pc.kind, (int)pc.skip, pc.a, pc.b, pc.c, fork)) ok = 0;
+            }
+        } else if (ok == 2) { g_walks++; ok = stab_virtual<GeomC>(g, root, k, pack, pool, &h->big, &h->lock, fl, true, 0xffffffffu, node, &st); }
     } else ok = g_use_v2 ? stab_virtual<GeomC>(g, root, -1, 0, pool, &h->big, &h->lock, fl, true, 0xffffffffu)
                          : (int)(stability_check<false, GeomC>(g, root, pool, &h->big, &h->lock, 0, fl) != 0);
     h->flags |= fl;

@@ -225,7 +225,7 @@ def _drive_c(L, env, setting, container, seed, env_id, steps, alias=True):
     return n_virtual
 
 
-@pytest.mark.parametrize("routine", [0, 2, 3], ids=["stability_check", "stab_virtual_scan", "classify_light_continuation"])
+@pytest.mark.parametrize("routine", [0, 2, 3, 4], ids=["stability_check", "stab_virtual_scan", "classify_light_continuation", "fork_join"])
 @pytest.mark.parametrize("setting", [1, 3, 2])
 def test_device_stability_source_follows_the_continuous_oracle(lib, setting, routine):
     from pct_oracle import OracleContinuous, make_continuous_stream
