@@ -11,15 +11,17 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-src = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out", "r2_final")
+src = sys.argv[1] if len(sys.argv) > 1 and not sys.argv[1].startswith("--") else os.path.join(ROOT, "gpurun_out", "r2_final")
 note = sys.argv[2] if len(sys.argv) > 2 else subprocess.run(["git", "-C", ROOT, "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip()
 P = os.path.join(ROOT, "profiles")
 
-for a, b in (("bench_default.json", "r2_final_bench.json"), ("bench_driver_flags.json", "r2_final_bench_driver_flags.json"),
-             ("bench_reference.json", "r2_final_bench_reference.json")):
-    line = [l for l in open(os.path.join(src, a)).read().splitlines() if l.startswith("{")][-1]
-    json.loads(line)
-    open(os.path.join(P, b), "w").write(line + "\n")
+TRAFFIC_ONLY = "--traffic-only" in sys.argv  # on the GPU box, between the ncu captures and the bench runs: bench.py then reports the traffic of THIS build
+if not TRAFFIC_ONLY:
+    for a, b in (("bench_default.json", "r2_final_bench.json"), ("bench_driver_flags.json", "r2_final_bench_driver_flags.json"),
+                 ("bench_reference.json", "r2_final_bench_reference.json")):
+        line = [l for l in open(os.path.join(src, a)).read().splitlines() if l.startswith("{")][-1]
+        json.loads(line)
+        open(os.path.join(P, b), "w").write(line + "\n")
 
 traffic = {"commit": note, "file": "r2_head_pct_*.txt", "kernels": {}}
 for k in ("pct_apply", "pct_candidates", "pct_walk_light", "pct_walk_kernel", "pct_emit"):
@@ -34,6 +36,9 @@ for k in ("pct_apply", "pct_candidates", "pct_walk_light", "pct_walk_kernel", "p
             traffic["kernels"][name] = d
 traffic["step_total_dram_bytes"] = sum(v["dram_bytes_per_launch"] for v in traffic["kernels"].values())
 json.dump(traffic, open(os.path.join(P, "traffic.json"), "w"), indent=1)
+if TRAFFIC_ONLY:
+    print(json.dumps({k: v["dram_bytes_per_launch"] for k, v in traffic["kernels"].items()}), traffic["step_total_dram_bytes"])
+    sys.exit(0)
 
 out = subprocess.run([sys.executable, os.path.join(ROOT, "scratch", "ncu_summary.py"), os.path.join(src, "cont_head.ncu-rep"), "20"], capture_output=True, text=True).stdout
 open(os.path.join(P, "r2_cont_head_final.txt"), "w").write("# ncu --set full, five consecutive launches of the continuous kernels (bench.py --continuous, 4096 envs, setting 2), %s\n" % note + out)

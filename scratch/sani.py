@@ -34,3 +34,13 @@ obs_u=np.empty((n,b.obs_len),dtype=np.float32)  # unpinned: staged path
 for t in range(4): b.step_host(obs_u,rew,done,info,leaf_idx=idx)
 b.close()
 print("sanitizer workload done")
+# round 2, later: the opt-in fork-join continuation kernel (device-side piece queue), both domains
+os.environ["PCT_B200_WALK"] = "fork"
+b=pct_b200.PctBatch(40, 1, item_set=items, seed=8); b.reset()
+for t in range(25): b.step(leaf_idx=b.random_policy(9,t))
+torch.cuda.synchronize(); b.close()
+b=pct_b200.PctBatch(16, 1, container_size=(1.0,1.0,1.0), continuous=True, sample_from_distribution=True, seed=4); b.reset()
+for t in range(12): b.step(leaf_idx=b.random_policy(9,t))
+torch.cuda.synchronize(); b.close()
+del os.environ["PCT_B200_WALK"]
+print("sanitizer workload (fork-join) done")
