@@ -1,6 +1,7 @@
 #!/bin/bash
 # Round 2, 2-GPU call: multi-GPU parity tests on real GPUs + bench at N = 2 (weak scaling line with config 5's per-GPU load and the timed all-gather)
 O=gpurun_out/r2_multi2; mkdir -p $O
+export PCT_B200_LIB=$PWD/scratch/variants/lib_final.so
 nvidia-smi -L > $O/gpus.txt
 ( timeout 900 python -m pytest tests/test_gpu_multi.py -m gpu -q --tb=short ) > $O/tests.log 2>&1; echo "tests rc=$?" | tee $O/summary.txt; tail -4 $O/tests.log | tee -a $O/summary.txt
 ( timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 300 --warmup 100 ) > $O/bench_n2.json 2> $O/bench_n2.err; echo "bench n2 rc=$?" | tee -a $O/summary.txt
