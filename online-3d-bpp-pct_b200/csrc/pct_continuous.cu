@@ -787,8 +787,7 @@ __global__ void __launch_bounds__(128, 4) pctc_walk_light_kernel(const CParams p
     }
 }
 
-__global__ void __launch_bounds__(64, 8) pctc_walk_kernel(const CParams p, int slab_lanes) {
-    extern __shared__ __align__(16) double walk_slab[];  // hull scratch of the walk lanes (stab_virtual), see pct_walk_kernel
+__global__ void __launch_bounds__(64, 8) pctc_walk_kernel(const CParams p) {
     const int lane = threadIdx.x & 31;
     const int cap = p.n_envs * WALK_CONT_PER_ENV;
     const int n_short = min(*(volatile const int32_t *)p.cont_ctr, cap / 2), n_tall = min(*(volatile const int32_t *)(p.cont_ctr + 1), cap / 2);
@@ -809,8 +808,7 @@ __global__ void __launch_bounds__(64, 8) pctc_walk_kernel(const CParams p, int s
         if (has) { ct = p.contq[tw ? cap - 1 - i : i]; it = p.walkq[ct.item]; }
         const WalkViewC v = walk_view_c(p, it, has);
         int fl = 0;
-        const bool ok = stab_virtual<GeomC>(v.g, v.root, it.k, it.pack, v.pool, &v.ev->big, &v.ev->lock, fl, has, mask, has ? (int)ct.node : NODE_NEW, &ct.st,
-                                            slab_lanes ? walk_slab + ((threadIdx.x >> 5) * slab_lanes + lane) * STAB_SLAB_DOUBLES : nullptr) != 0;
+        const bool ok = stab_virtual<GeomC>(v.g, v.root, it.k, it.pack, v.pool, &v.ev->big, &v.ev->lock, fl, has, mask, has ? (int)ct.node : NODE_NEW, &ct.st) != 0;
         if (has && ok) atomicOr(&v.ev->fbits[it.c >> 5], 1u << (it.c & 31));
         if (has && fl) atomicOr(&v.ev->h.flags, fl);
         if (has) { __threadfence(); atomicSub(&v.ev->n_pending, 1); }
@@ -1190,11 +1188,7 @@ int continuous_launch(pct_env_batch *h, int mode, const void *actions, int actio
         if (stab) {
             pctc_walk_light_kernel<<<n_sm * 4, 128, 0, st>>>(p);
             if (p.walk_fork) pctc_walk_fork_kernel<<<n_sm * max(1, min(p.walk_blocks, 8)), 64, 0, st>>>(p);  // one resident wave
-            else {
-                int slab_lanes = max(p.walk_lanes, p.walk_lanes_tall);
-                if (slab_lanes > 16) slab_lanes = 0;
-                pctc_walk_kernel<<<n_sm * 8, 64, (size_t)2 * slab_lanes * STAB_SLAB_DOUBLES * sizeof(double), st>>>(p, slab_lanes);  // one resident wave
-            }
+            else pctc_walk_kernel<<<n_sm * 8, 64, 0, st>>>(p);  // one resident wave
         }
         {
             cudaLaunchAttribute at2[1];

@@ -1329,8 +1329,7 @@ __global__ void __launch_bounds__(32 * LIGHT_WARPS, LIGHT_MINB) pct_walk_light_k
 // machine to the end of the walk.  Only `p.walk_lanes` lanes of a warp carry a walk (default 8): there are few continuations (3 per env) and each
 // is a long serial chain, so a full warp of them (ncu r2, profiles/r2_walk_two_stage_32lanes.txt: 400 warps on 592 schedulers, 20 k instructions
 // per warp, SMs 4 % occupied, 116 us) is latency-bound on the SUM of its lanes' divergent paths; fewer walks per warp = more warps, shorter chains.
-__global__ void __launch_bounds__(32 * WALK_WARPS, WALK_MINB) pct_walk_kernel(const DParams p, int slab_lanes) {
-    extern __shared__ __align__(16) double walk_slab[];  // [WALK_WARPS * walk lanes][STAB_SLAB_DOUBLES]: hull scratch of the lanes (stab_virtual)
+__global__ void __launch_bounds__(32 * WALK_WARPS, WALK_MINB) pct_walk_kernel(const DParams p) {
     const int lane = threadIdx.x & 31;
     const int cap = p.n_envs * WALK_CONT_PER_ENV;
     const int n_short = min(*(volatile const int32_t *)p.cont_ctr, cap / 2), n_tall = min(*(volatile const int32_t *)(p.cont_ctr + 1), cap / 2);
@@ -1352,7 +1351,7 @@ __global__ void __launch_bounds__(32 * WALK_WARPS, WALK_MINB) pct_walk_kernel(co
         const WalkView v = walk_view(p, it, has);
         int fl = 0;
         const bool ok = stab_virtual<GeomD>(v.g, v.root, (int)it.k, it.pack, v.pool, &v.cold->big, &v.cold->lock, fl, has, mask,
-                                            has ? (int)ct.node : NODE_NEW, &ct.st, slab_lanes ? walk_slab + ((threadIdx.x >> 5) * slab_lanes + lane) * STAB_SLAB_DOUBLES : nullptr) != 0;
+                                            has ? (int)ct.node : NODE_NEW, &ct.st) != 0;
         if (has && ok) atomicOr(&v.cold->fbits[it.c >> 5], 1u << (it.c & 31));
         if (has && fl) atomicOr(const_cast<int32_t *>(&v.hot->h.flags), fl);
         if (has) walk_done(&v.cold->n_pending);
@@ -1608,11 +1607,7 @@ static cudaError_t launch_t(const DParams &p_in, cudaStream_t st, cudaEvent_t *p
         if (STAB) {
             pct_walk_light_kernel<<<n_sm * LIGHT_MINB, 32 * LIGHT_WARPS, 0, st>>>(p);
             if (p.walk_fork) pct_walk_fork_kernel<<<n_sm * max(1, min(p.walk_blocks, WALK_MINB)), 32 * WALK_WARPS, 0, st>>>(p);  // one resident wave
-            else {
-                int slab_lanes = max(p.walk_lanes, p.walk_lanes_tall);  // a shared-memory slab per walk lane (hull scratch, stab_virtual); wider warps keep the stack
-                if (slab_lanes > 16) slab_lanes = 0;
-                pct_walk_kernel<<<n_sm * WALK_MINB, 32 * WALK_WARPS, (size_t)WALK_WARPS * slab_lanes * STAB_SLAB_DOUBLES * sizeof(double), st>>>(p, slab_lanes);  // one resident wave (every block starts at once: the emit kernel may follow)
-            }
+            else pct_walk_kernel<<<n_sm * WALK_MINB, 32 * WALK_WARPS, 0, st>>>(p);  // one resident wave (every block starts at once: the emit kernel may follow)
         }
         const int eb = (p.n_envs + EMIT_WARPS - 1) / EMIT_WARPS;
         {   // programmatic dependent of the continuation kernel (setting 2: of the candidates kernel, whose blocks never trigger early -> plain order)

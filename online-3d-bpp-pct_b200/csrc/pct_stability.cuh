@@ -187,8 +187,6 @@ __device__ __forceinline__ void split2_dir(const double *px, const double *py, d
 // Minimum-norm least squares (np.linalg.lstsq restatement: streaming Givens QR + one-sided Jacobi SVD,
 // identical operation order to oracle/pct_oracle_common.h po_ls_*).  ld = leading dimension of R and V.
 struct LsWork { double *R, *V, *y, *row, *x; int ld; };
-constexpr int STAB_SLAB_K = 4;                          // supports covered by a lane's shared-memory slab in the walk kernels
-constexpr int STAB_SLAB_DOUBLES = 28 * STAB_SLAB_K + 1;   // rect 4k + px 4k + py 4k + hx 8k + hy 8k, + 1: an odd stride keeps the lanes on distinct banks
 
 static __device__ __noinline__ void ls_add_row(const LsWork &w, int k, double rhs) {
 #pragma unroll 1
@@ -793,7 +791,7 @@ static __device__ __forceinline__ int stab_light(const G &g, const typename G::N
 template <class G>
 static __device__ __noinline__ int stab_virtual(const G &g, const typename G::Node &root, int k_root, uint32_t sup_pack, const EdgePool &pool,
                                                 BigScratch *big, int *lock, int &flags, bool has_work, unsigned mask,
-                                                int start_node = NODE_NEW, const Stack4 *start_st = nullptr, double *slab = nullptr) {
+                                                int start_node = NODE_NEW, const Stack4 *start_st = nullptr) {
     typedef typename G::Node Node;
     StabFrame fr[STAB_DEPTH];
     uint8_t sup_id[STAB_SUP_POOL];
@@ -941,11 +939,6 @@ static __device__ __noinline__ int stab_virtual(const G &g, const typename G::No
                 const bool small = k <= KSUP_SMALL;
                 double (*rect)[4] = lrect;
                 double *px = lpx, *py = lpy, *hx = lhx, *hy = lhy;
-                if (slab != nullptr && k <= STAB_SLAB_K) {
-                    // the walk kernels hand every lane a shared-memory slab for the contact rectangles and the hull of a visit with <= 4 supports
-                    // (96 % of them): the sort and the chain scan of hull_coords then run on shared memory instead of the local-memory stack
-                    rect = (double (*)[4])slab; px = slab + 4 * STAB_SLAB_K; py = px + 4 * STAB_SLAB_K; hx = py + 4 * STAB_SLAB_K; hy = hx + 8 * STAB_SLAB_K;
-                }
                 if (!small) {  // rare: serialise the lanes of this env on the per-env HBM scratch
                     while (atomicCAS(lock, 0, 1) != 0) { }
                     __threadfence_block();
