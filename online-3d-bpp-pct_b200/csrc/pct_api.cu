@@ -133,13 +133,14 @@ int pct_create(const pct_config *cfg, int32_t n_envs, int32_t device, pct_handle
                 e = cudaMalloc(&h->d_walkq, sizeof(WalkItem) * (size_t)CAND_MAX * (size_t)n_envs);
                 if (e == cudaSuccess) e = cudaMalloc(&h->d_walk_ctr, sizeof(int32_t) * (size_t)n_envs);
                 if (e == cudaSuccess) e = cudaMemset(h->d_walk_ctr, 0, sizeof(int32_t) * (size_t)n_envs);
-                static_assert(sizeof(WalkPiece) * WALK_PIECES_PER_ENV >= sizeof(WalkCont) * WALK_CONT_PER_ENV, "one allocation serves both continuation kernels");
-                if (e == cudaSuccess) e = cudaMalloc((void **)&h->d_contq, sizeof(WalkPiece) * (size_t)WALK_PIECES_PER_ENV * (size_t)n_envs);
+                // continuation pool: WalkCont entries for the sequential kernel, the (larger) piece queue + its flags and per-walk counters only with PCT_B200_WALK=fork
+                h->contq_env_bytes = h->walk_fork ? sizeof(WalkPiece) * (size_t)WALK_PIECES_PER_ENV : sizeof(WalkCont) * (size_t)WALK_CONT_PER_ENV;
+                if (e == cudaSuccess) e = cudaMalloc((void **)&h->d_contq, h->contq_env_bytes * (size_t)n_envs);
                 if (e == cudaSuccess) e = cudaMalloc(&h->d_cont_ctr, sizeof(int32_t) * 8 * ((size_t)n_envs + 1));  // eight counters per (possible) env range
                 if (e == cudaSuccess) e = cudaMemset(h->d_cont_ctr, 0, sizeof(int32_t) * 8 * ((size_t)n_envs + 1));
-                if (e == cudaSuccess) e = cudaMalloc(&h->d_piece_ready, sizeof(int32_t) * (size_t)WALK_PIECES_PER_ENV * (size_t)n_envs);
-                if (e == cudaSuccess) e = cudaMemset(h->d_piece_ready, 0, sizeof(int32_t) * (size_t)WALK_PIECES_PER_ENV * (size_t)n_envs);
-                if (e == cudaSuccess) e = cudaMalloc(&h->d_walk_pend, sizeof(int32_t) * (size_t)CAND_MAX * (size_t)n_envs);
+                if (e == cudaSuccess && h->walk_fork) e = cudaMalloc(&h->d_piece_ready, sizeof(int32_t) * (size_t)WALK_PIECES_PER_ENV * (size_t)n_envs);
+                if (e == cudaSuccess && h->walk_fork) e = cudaMemset(h->d_piece_ready, 0, sizeof(int32_t) * (size_t)WALK_PIECES_PER_ENV * (size_t)n_envs);
+                if (e == cudaSuccess && h->walk_fork) e = cudaMalloc(&h->d_walk_pend, sizeof(int32_t) * (size_t)CAND_MAX * (size_t)n_envs);
             }
             h->lpt = !h->k3_block;   // heaviest-env-first block order (pct_discrete.cu, order_lookup / order_file); PCT_B200_LPT=0 disables
             if (const char *lv = getenv("PCT_B200_LPT")) h->lpt = atoi(lv) != 0 && !h->k3_block;
@@ -274,7 +275,7 @@ static int launch_range(pct_handle h, int mode, int off, int cnt, const void *ac
     }
     p.walkq = h->d_walkq ? h->d_walkq + (size_t)off * CAND_MAX : nullptr;  // env ranges stepped concurrently (pct_step_host's staged path) own disjoint slices
     p.walk_ctr = h->d_walk_ctr ? h->d_walk_ctr + off : nullptr;
-    p.contq = h->d_contq ? (WalkCont *)((char *)h->d_contq + (size_t)off * WALK_PIECES_PER_ENV * sizeof(WalkPiece)) : nullptr;  // an env range's slice of the pool
+    p.contq = h->d_contq ? (WalkCont *)((char *)h->d_contq + (size_t)off * h->contq_env_bytes) : nullptr;  // an env range's slice of the pool
     p.cont_ctr = h->d_cont_ctr ? h->d_cont_ctr + 8 * (size_t)off : nullptr;
     p.walk_lanes = h->walk_lanes; p.walk_lanes_tall = h->walk_lanes_tall;
     p.walk_fork = h->walk_fork ? 1 : 0; p.walk_blocks = h->walk_blocks; p.walk_keep = h->walk_keep; p.piece_cap = cnt * WALK_PIECES_PER_ENV;

@@ -1125,11 +1125,11 @@ int continuous_create(pct_env_batch *h) {
         e = cudaMalloc(&h->c_walkq, sizeof(WalkItemC) * (size_t)CAND_MAX * (size_t)h->n_envs);
         if (e == cudaSuccess) e = cudaMalloc(&h->d_walk_ctr, sizeof(int32_t) * 16);  // [0] walk pool, [1..] continuation pool counters (sequential kernel: ordinary / tall; fork-join: pct_walkq.cuh)
         if (e == cudaSuccess) e = cudaMemset(h->d_walk_ctr, 0, sizeof(int32_t) * 16);
-        if (e == cudaSuccess) e = cudaMalloc(&h->d_piece_ready, sizeof(int32_t) * (size_t)WALK_PIECES_PER_ENV * (size_t)h->n_envs);
-        if (e == cudaSuccess) e = cudaMemset(h->d_piece_ready, 0, sizeof(int32_t) * (size_t)WALK_PIECES_PER_ENV * (size_t)h->n_envs);
-        if (e == cudaSuccess) e = cudaMalloc(&h->d_walk_pend, sizeof(int32_t) * (size_t)CAND_MAX * (size_t)h->n_envs);
-        static_assert(sizeof(WalkPiece) * WALK_PIECES_PER_ENV >= sizeof(WalkCont) * WALK_CONT_PER_ENV, "one allocation serves both continuation kernels");
-        if (e == cudaSuccess) e = cudaMalloc(&h->d_contq, sizeof(WalkPiece) * (size_t)WALK_PIECES_PER_ENV * (size_t)h->n_envs);
+        if (e == cudaSuccess && h->walk_fork) e = cudaMalloc(&h->d_piece_ready, sizeof(int32_t) * (size_t)WALK_PIECES_PER_ENV * (size_t)h->n_envs);
+        if (e == cudaSuccess && h->walk_fork) e = cudaMemset(h->d_piece_ready, 0, sizeof(int32_t) * (size_t)WALK_PIECES_PER_ENV * (size_t)h->n_envs);
+        if (e == cudaSuccess && h->walk_fork) e = cudaMalloc(&h->d_walk_pend, sizeof(int32_t) * (size_t)CAND_MAX * (size_t)h->n_envs);
+        h->contq_env_bytes = h->walk_fork ? sizeof(WalkPiece) * (size_t)WALK_PIECES_PER_ENV : sizeof(WalkCont) * (size_t)WALK_CONT_PER_ENV;
+        if (e == cudaSuccess) e = cudaMalloc((void **)&h->d_contq, h->contq_env_bytes * (size_t)h->n_envs);
     }
     if (e != cudaSuccess) { h->err = std::string("continuous_create: ") + cudaGetErrorString(e); return PCT_ERR_CUDA; }
     return PCT_OK;

@@ -59,6 +59,7 @@ struct pct_env_batch {
     int32_t *d_walk_ctr = nullptr;     // [n_envs] fill counters (index = first env of the launched range)
     pct::WalkCont *d_contq = nullptr;  // [n_envs * WALK_CONT_PER_ENV] continuations: light-prefix kernel -> pct_walk_kernel
     int32_t *d_cont_ctr = nullptr;
+    size_t contq_env_bytes = 0;        // bytes of d_contq per env (WalkCont pool / WalkPiece queue)
     int32_t *d_piece_ready = nullptr, *d_walk_pend = nullptr;  // fork-join walks: per-slot publication flags, per-walk piece counters
     bool walk_fork = false;            // PCT_B200_WALK=fork: fork-join continuation kernel (pct_walkq.cuh) instead of the sequential one — measured equal-to-slower, kept as an opt-in
     int walk_blocks = 6;               // its blocks per SM (PCT_B200_WALK_BLOCKS)

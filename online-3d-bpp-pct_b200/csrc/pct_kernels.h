@@ -28,9 +28,18 @@ constexpr int STAB_DEPTH = 14;   // DFS depth (levels of boxes on top of each ot
 constexpr int STAB_SUP_POOL = 48;
 constexpr int EDGE_MAX = 255;    // load edges per env; positions are uint8, 255 = NIL
 constexpr int EDGE_NIL = 255;
-constexpr int EDGE_STAGE = 64;
-constexpr int POLY_MAX = 256;     // stored support-polygon vertices per env (boxes with >= 2 supports)
-constexpr int POLY_STAGE = 96;    // vertices staged in shared memory   // loads staged in shared memory (serial DFS reads would otherwise be HBM-latency bound)
+// Staging areas of the apply kernel.  Small on purpose: its descent runs on ONE lane per warp, so every hot word of that lane's local-memory stack
+// costs a whole 128-byte L1 line; 64 loads + 96 vertices per warp put the kernel at the 164 KB shared-memory carve-out (92 KB of L1), 16 + 32 at
+// the 132 KB one (124 KB of L1): apply kernel 0.1126 -> 0.1075 ms (B200, 4096 envs; r2_c25).  Entries beyond the staged ones are read from L1 / L2.
+#ifndef PCT_EDGE_STAGE
+#define PCT_EDGE_STAGE 16
+#endif
+#ifndef PCT_POLY_STAGE
+#define PCT_POLY_STAGE 32
+#endif
+constexpr int EDGE_STAGE = PCT_EDGE_STAGE;    // loads staged in shared memory by the apply kernel (serial descent reads would otherwise be HBM-latency bound)
+constexpr int POLY_MAX = 256;                 // stored support-polygon vertices per env (boxes with >= 2 supports)
+constexpr int POLY_STAGE = PCT_POLY_STAGE;    // vertices staged in shared memory
 
 struct Stack4 { double cx, cy, cz, m; };
 
