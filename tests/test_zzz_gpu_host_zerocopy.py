@@ -28,7 +28,8 @@ def _drive(n, setting, steps, pinned, continuous=False):
         nvalid = (obs.reshape(n, -1, 9)[:, b.nb:b.nb + b.nl, 8] == 1).sum(1)
         idx[:] = (rng.randint(0, 1 << 30, n) % np.maximum(nvalid, 1)).astype(np.int32)
         b.step_host(obs, rew, done, info, leaf_idx=idx)
-        out.append(np.concatenate([obs.ravel(), rew, done.astype(np.float32), info[:, :2].ravel().astype(np.float32)]))
+        # every byte of the info records too (as 16-bit halves, exact in float32)
+        out.append(np.concatenate([obs.ravel(), rew, done.astype(np.float32), info.view(np.uint16).ravel().astype(np.float32)]))
     b.close()
     return out
 
