@@ -1326,9 +1326,9 @@ __global__ void __launch_bounds__(32 * LIGHT_WARPS, LIGHT_MINB) pct_walk_light_k
 }
 
 // walk, stage 2: the continuations — every lane starts with the heavy visit its walk stopped at, then runs the general light / heavy state
-// machine to the end of the walk.  Only `p.walk_lanes` lanes of a warp carry a walk (default 8): there are few continuations (3 per env) and each
-// is a long serial chain, so a full warp of them (ncu r2, profiles/r2_walk_two_stage_32lanes.txt: 400 warps on 592 schedulers, 20 k instructions
-// per warp, SMs 4 % occupied, 116 us) is latency-bound on the SUM of its lanes' divergent paths; fewer walks per warp = more warps, shorter chains.
+// machine to the end of the walk.  Only `p.walk_lanes` lanes of a warp carry a walk (default 16; 4 for the walks resting at >= 0.6 H): there are few
+// continuations (3 per env) and each is a long serial chain; a full warp of them (ncu r2, profiles/r2_walk_two_stage_32lanes.txt: 400 warps on 592
+// schedulers, 20 k instructions per warp, 116 us) leaves too few warps, 4-8 per warp multiply the warp instructions (measured sweep: DESIGN.md 5d).
 __global__ void __launch_bounds__(32 * WALK_WARPS, WALK_MINB) pct_walk_kernel(const DParams p) {
     const int lane = threadIdx.x & 31;
     const int cap = p.n_envs * WALK_CONT_PER_ENV;
