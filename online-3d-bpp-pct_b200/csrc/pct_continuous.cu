@@ -304,6 +304,8 @@ __global__ void __launch_bounds__(64) pctc_apply_kernel(const CParams p) {
     __shared__ int lock_s[2];
     __shared__ __align__(16) double ems_stage[2][CE_STAGE][6];
     int *lock = &lock_s[warp];
+    static_assert(sizeof(StabScratch) <= sizeof(double) * CE_STAGE * 6, "the descent's scratch fits the EMS stage");
+    StabScratch *scr = (StabScratch *)&ems_stage[warp][0][0];  // the descent's working arrays: aliased onto the EMS stage, which only GENEMS (after the descent) uses
     CEnv *ev = p.env + e;
     CHdr &h = ev->h;
     if (p.ready) pdl_launch_dependents();
@@ -375,13 +377,13 @@ __global__ void __launch_bounds__(64) pctc_apply_kernel(const CParams p) {
                                                                  ev->poly_off, &ev->poly[0][0], &ev->poly[0][0], h.n_poly};
                         DEnvAux *ax = p.aux + e;
                         pool.box_st = ax->box_st; pool.e_upper = ax->e_upper; pool.e_alias = ax->e_alias;
-                        res = stability_check<true, GeomC, true>(g, root, pool, &ev->big, lock, n_box0, fl);
+                        res = stability_check<true, GeomC, true>(g, root, pool, &ev->big, lock, n_box0, fl, nullptr, scr);
                         if (!res) alias_sync_loads(pool);
                         h.n_edge = pool.n; h.n_poly = pool.n_poly;
                     } else {
                     EdgePool pool{ev->e_lower, ev->e_next, ev->e_off, ev->first_in, ev->last_in, ev->e_st, ev->e_st, h.n_edge,
                                   ev->poly_off, &ev->poly[0][0], &ev->poly[0][0], h.n_poly};
-                    res = stability_check<true, GeomC>(g, root, pool, &ev->big, lock, n_box0, fl);
+                    res = stability_check<true, GeomC>(g, root, pool, &ev->big, lock, n_box0, fl, nullptr, scr);
                     h.n_edge = pool.n; h.n_poly = pool.n_poly;
                     }
                     h.flags |= fl;

@@ -744,12 +744,16 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, K1_MINB) pct_apply_kerne
     const int e = (p.order && p.mode == 1) ? order_lookup(p.order, p.n_envs, slot, lane) : slot;  // heaviest envs first (longest-processing-time-first)
     unsigned char *sm = smem_raw + (size_t)warp * K1_SM_PER_WARP;
     DEnvHot *hot = (DEnvHot *)sm;
+    // per-warp layout: record | EMS temp (3 KB) | packed EMS temp (2 KB) | mbarrier + lock | staged loads | staged polygons.  The two EMS areas are
+    // only used by GENEMS, after the descent: the descent's working arrays (StabScratch, 4 KB) are aliased onto them
     int16_t (*ems_tmp)[6] = (int16_t (*)[6])(sm + sizeof(DEnvHot));
-    uint64_t *mbar = (uint64_t *)(sm + sizeof(DEnvHot) + EMS_TMP_MAX * 12);
+    uint2 *ems_pk = (uint2 *)(sm + sizeof(DEnvHot) + EMS_TMP_MAX * 12);
+    static_assert(sizeof(StabScratch) <= EMS_TMP_MAX * 12 + EMS_TMP_MAX * 8 && sizeof(DEnvHot) % 8 == 0, "the descent's scratch fits the EMS temp areas");
+    StabScratch *scr = (StabScratch *)ems_tmp;
+    uint64_t *mbar = (uint64_t *)(sm + sizeof(DEnvHot) + EMS_TMP_MAX * 12 + EMS_TMP_MAX * 8);
     int *lock = (int *)(mbar + 1);
-    Stack4 *st_sm = (Stack4 *)(sm + sizeof(DEnvHot) + EMS_TMP_MAX * 12 + 16);
+    Stack4 *st_sm = (Stack4 *)(sm + sizeof(DEnvHot) + EMS_TMP_MAX * 12 + EMS_TMP_MAX * 8 + 16);
     double *poly_sm = (double *)(st_sm + EDGE_STAGE);
-    uint2 *ems_pk = (uint2 *)(poly_sm + 2 * POLY_STAGE);
     DEnvHot *ghot = p.hot + e;
     DEnvCold *cold = p.cold + e;
     DHdr &h = hot->h;
@@ -865,14 +869,14 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, K1_MINB) pct_apply_kerne
                                                                  hot->poly_off, &cold->poly[0][0], poly_sm, h.n_poly};
                         DEnvAux *ax = p.aux + e;
                         pool.box_st = ax->box_st; pool.e_upper = ax->e_upper; pool.e_alias = ax->e_alias;
-                        res = stability_check<true, GeomD, true>(g, root, pool, &cold->big, lock, n_box0, fl);
+                        res = stability_check<true, GeomD, true>(g, root, pool, &cold->big, lock, n_box0, fl, nullptr, scr);
                         if (!res) alias_sync_loads(pool);
                         h.n_edge = pool.n;
                         h.n_poly = pool.n_poly;
                     } else {
                     EdgePool pool{hot->e_lower, hot->e_next, hot->e_off, hot->first_in, hot->last_in, cold->e_st, st_sm, h.n_edge,
                                   hot->poly_off, &cold->poly[0][0], poly_sm, h.n_poly};
-                    res = stability_check<true, GeomD>(g, root, pool, &cold->big, lock, n_box0, fl);
+                    res = stability_check<true, GeomD>(g, root, pool, &cold->big, lock, n_box0, fl, nullptr, scr);
                     h.n_edge = pool.n;
                     h.n_poly = pool.n_poly;
                     }

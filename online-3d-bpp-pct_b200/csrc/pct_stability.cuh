@@ -442,15 +442,27 @@ static __device__ __noinline__ void alias_sync_loads(EdgePoolA &pa) {
 #ifdef PCT_PHASE_TIMERS
 __device__ long long *g_prof_dummy;
 #endif
+// Working arrays of one descent.  A lane-local instance lives on the local-memory stack; the apply kernel, whose descent runs on ONE lane per warp,
+// hands in a per-warp instance in shared memory instead (aliased onto its EMS scratch, which is idle during the descent): on the stack every hot word
+// of that single lane costs a whole 128-byte L1 line.
+struct StabScratch {
+    StabFrame fr[STAB_DEPTH];
+    double sup_m[STAB_SUP_POOL];
+    double rect[KSUP_SMALL][4], px[4 * KSUP_SMALL], py[4 * KSUP_SMALL], hx[8 * KSUP_SMALL], hy[8 * KSUP_SMALL];
+    double R[KSUP_SMALL * KSUP_SMALL], V[KSUP_SMALL * KSUP_SMALL], y[KSUP_SMALL], row[KSUP_SMALL], x[KSUP_SMALL];
+    uint8_t sup_id[STAB_SUP_POOL];
+};
 template <bool REAL, class G, bool ALIAS = false>
 static __device__ __noinline__ int stability_check(const G &g, const typename G::Node &root, EdgePool &pool, BigScratch *big, int *lock,
-                                            const int new_id, int &flags, long long *g_prof_out = nullptr) {
+                                            const int new_id, int &flags, long long *g_prof_out = nullptr, StabScratch *scr = nullptr) {
     typedef typename G::Node Node;
     constexpr bool real = REAL;  // REAL: load-propagating update of a committed placement; else read-only feasibility check
     constexpr bool alias = REAL && ALIAS;  // object semantics of the reference's load entries; `pool` is an EdgePoolA then
-    StabFrame fr[STAB_DEPTH];
-    uint8_t sup_id[STAB_SUP_POOL];
-    double sup_m[STAB_SUP_POOL];
+    StabScratch local_scr;  // untouched (no cache footprint) when the caller provides one
+    StabScratch &S = scr ? *scr : local_scr;
+    StabFrame *fr = S.fr;
+    uint8_t *sup_id = S.sup_id;
+    double *sup_m = S.sup_m;
     const int root_id = real ? new_id : NODE_NEW;
     int depth = 0;            // number of pushed frames
     int node = root_id, base = 0;
@@ -526,10 +538,9 @@ static __device__ __noinline__ int stability_check(const G &g, const typename G:
             skip = (node == root_id) ? EDGE_NIL : eoff;
         } else if (k >= 2) {
             // ---------- general case: hull over all contact-rectangle corners ----------
-            double lrect[KSUP_SMALL][4], lpx[4 * KSUP_SMALL], lpy[4 * KSUP_SMALL], lhx[8 * KSUP_SMALL], lhy[8 * KSUP_SMALL];
             const bool small = k <= KSUP_SMALL;
-            double (*rect)[4] = lrect;
-            double *px = lpx, *py = lpy, *hx = lhx, *hy = lhy;
+            double (*rect)[4] = S.rect;
+            double *px = S.px, *py = S.py, *hx = S.hx, *hy = S.hy;
             if (!small) {  // rare: serialise the lanes of this env on the per-env HBM scratch
                 while (atomicCAS(lock, 0, 1) != 0) { }
                 __threadfence_block();
@@ -610,10 +621,9 @@ static __device__ __noinline__ int stability_check(const G &g, const typename G:
                         sup_m[base + 0] = st.m * fabs(dot2(st.cx - px[1], st.cy - py[1], lx, ly));
                         sup_m[base + 1] = st.m * fabs(dot2(st.cx - px[0], st.cy - py[0], lx, ly));
                     } else {
-                        double lR[KSUP_SMALL * KSUP_SMALL], lV[KSUP_SMALL * KSUP_SMALL], ly_[KSUP_SMALL], lrow[KSUP_SMALL], lx_[KSUP_SMALL];
                         LsWork w;
-                        w.R = small ? lR : big->R; w.V = small ? lV : big->V; w.y = small ? ly_ : big->y;
-                        w.row = small ? lrow : big->row; w.x = small ? lx_ : big->x; w.ld = small ? KSUP_SMALL : KSUP_MAX;
+                        w.R = small ? S.R : big->R; w.V = small ? S.V : big->V; w.y = small ? S.y : big->y;
+                        w.row = small ? S.row : big->row; w.x = small ? S.x : big->x; w.ld = small ? KSUP_SMALL : KSUP_MAX;
                         DBG_LS();
                         lstsq_ratios(w, k, px, py, st.cx, st.cy);
 #pragma unroll 1
