@@ -16,7 +16,7 @@ note = sys.argv[2] if len(sys.argv) > 2 else subprocess.run(["git", "-C", ROOT, 
 P = os.path.join(ROOT, "profiles")
 
 TRAFFIC_ONLY = "--traffic-only" in sys.argv  # on the GPU box, between the ncu captures and the bench runs: bench.py then reports the traffic of THIS build
-if not TRAFFIC_ONLY:
+if not TRAFFIC_ONLY and "--no-bench" not in sys.argv:  # --no-bench: the run was cut before its benches (keep the bench lines of the previous complete run)
     for a, b in (("bench_default.json", "r2_final_bench.json"), ("bench_driver_flags.json", "r2_final_bench_driver_flags.json"),
                  ("bench_reference.json", "r2_final_bench_reference.json")):
         line = [l for l in open(os.path.join(src, a)).read().splitlines() if l.startswith("{")][-1]
