@@ -378,7 +378,7 @@ int pct_step_host(pct_handle h, const void *h_actions, int32_t action_f64, const
     if (rc) return rc;
     const size_t osz = h->cfg.obs_dtype == PCT_F64 ? 8 : 4, asz = action_f64 ? 8 : 4;
     if (h->host_zero_copy) {
-        // Zero-copy observation delivery (opt-in, PCT_B200_HOST_ZEROCOPY=1): when h_obs is pinned (mapped under UVA) the feasibility
+        // Zero-copy observation delivery (the default; PCT_B200_HOST_ZEROCOPY=0 disables): when h_obs is pinned (mapped under UVA) the feasibility
         // kernel writes every env's observation straight into it over PCIe as that env finishes — no staging copy after the kernels
         // and no env-range pipeline; the whole batch runs as ONE launch sequence (overlapped mode, heaviest-env-first order).  The
         // observation is write-only for the kernels.  Actions and the small reward / done / info records keep their staged copies

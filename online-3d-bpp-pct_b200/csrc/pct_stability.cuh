@@ -398,7 +398,7 @@ static __device__ __noinline__ bool pip_rect(double x1, double y1, double x2, do
     return odd;
 }
 
-// ---- ALIAS variant helpers (opt-in; see EdgePoolA) ----------------------------------------------------------------------
+// ---- ALIAS variant helpers (the default since round 2; see EdgePoolA) ----------------------------------------------------------------------
 // calculate_new_com of a placed box under the reference's object semantics: entries that ARE the upper box's Stack object are read
 // through that box's current field, the others are the stored snapshots.  Same operation order as the lazy sum at the end of the DFS loop.
 template <class G>
